@@ -1,0 +1,147 @@
+// CPU emulation of the Griffin-Lim iteration kernel's lane program -- TEST INFRASTRUCTURE.
+//
+// Runs xd-tts_b200/csrc/gl_core.cuh (the very functions the CUDA kernel inlines) with the 32
+// lanes of a warp looped on the host and a "warp sync" between phases, so the index algebra
+// (FFT factorisation, exchange layouts, pairing, run boundaries, edge frames) can be checked
+// against the oracle in the GPU-less build container.  Never loaded by the product.
+//
+// build: g++ -O2 -shared -fPIC -I/usr/local/cuda/include -Ixd-tts_b200/csrc tests/emu/gl_emu.cpp
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "gl_core.cuh"
+#include "gl_tables.h"
+
+using namespace xdtts;
+
+template <int R3, int MODE, bool STORE_R, bool TRACK_MAX>
+static void emu_launch(GlParams p, bool reverse_order) {
+    typedef Geo<R3> G;
+    std::vector<float2> ex1(G::EX1), ex2(G::EX2);
+    std::vector<Lane<R3>> lanes(32);
+    for (int rr = 0; rr < p.n_runs; rr++) {
+        const int run_idx = reverse_order ? p.n_runs - 1 - rr : rr;
+        const GlRun r = p.runs[run_idx];
+        const int T = p.utt_T[r.utt];
+        const long foff = p.utt_foff[r.utt];
+        const long yoff = foff * G::H;
+        for (int l = 0; l < 32; l++) lane_reset<R3>(lanes[l]);
+        auto arrive = [&](int boundary) {
+            const unsigned old = p.flags[boundary]++;
+            if (old & 1u)
+                for (int l = 0; l < 32; l++) combine_boundary<R3, TRACK_MAX>(lanes[l], l, p, boundary);
+        };
+        for (int t = r.ta; t < r.tb; t++) {
+            const long frame = foff + t;
+            if (MODE != GL_MODE_INIT) {
+                for (int l = 0; l < 32; l++) phase_f1<R3>(lanes[l], l, p.y_in + yoff, T, t, p.pad_mode, p.tables, ex1.data());
+                for (int l = 0; l < 32; l++) phase_f2<R3>(lanes[l], l, p.tables, ex1.data(), ex2.data());
+            }
+            for (int l = 0; l < 32; l++) phase_f3<R3, MODE, STORE_R>(lanes[l], l, p, r.utt, T, t, frame, p.tables, ex2.data());
+            for (int l = 0; l < 32; l++) phase_f4<R3>(lanes[l], l, p.tables, ex2.data(), ex1.data());
+            bool sig = false;
+            for (int l = 0; l < 32; l++) {
+                phase_f5<R3>(lanes[l], l, p.tables, ex1.data());
+                float2 out[2 * G::NB];
+                ola_shift<R3>(lanes[l], out);
+                sig = emit_block<R3, TRACK_MAX>(lanes[l], l, p, run_idx, r, yoff, t, out);
+            }
+            if (sig) arrive(run_idx - 1);
+        }
+        bool sig = false;
+        for (int l = 0; l < 32; l++) sig = emit_tail<R3, TRACK_MAX>(lanes[l], l, p, run_idx, r, yoff, T);
+        if (sig) arrive(run_idx);
+        if (TRACK_MAX) {
+            float m = 0.f;
+            for (int l = 0; l < 32; l++) m = fmaxf(m, lanes[l].amax);
+            unsigned bits;
+            memcpy(&bits, &m, 4);
+            if (bits > p.amax[r.utt]) p.amax[r.utt] = bits;
+        }
+    }
+}
+
+template <int R3>
+static int emu_run(const float* s_mag, const float* turns, int T, int n_iter, float momentum, int run_frames, int pad_mode,
+                   unsigned long long seed, float* out, float* r_out, float* peak) {
+    typedef Geo<R3> G;
+    const int K = G::M + 1;
+    std::vector<GlRun> runs;
+    std::vector<int> foff;
+    build_runs(&T, 1, run_frames, &runs, &foff);
+    std::vector<float2> tab = build_tables<R3>();
+    std::vector<float> edge = build_edge_scale(G::N);
+    std::vector<float> S((size_t)T * G::M), Sn(T), tu((size_t)T * G::M), tn(T);
+    for (int t = 0; t < T; t++) {
+        for (int k = 0; k < G::M; k++) {
+            S[(size_t)t * G::M + k] = s_mag[(size_t)k * T + t];
+            if (turns) tu[(size_t)t * G::M + k] = turns[(size_t)k * T + t];
+        }
+        Sn[t] = s_mag[(size_t)G::M * T + t];
+        if (turns) tn[t] = turns[(size_t)G::M * T + t];
+    }
+    (void)K;
+    std::vector<float2> R((size_t)T * G::M, mk2(0.f, 0.f));
+    std::vector<float> ya((size_t)T * G::H, 0.f), yb((size_t)T * G::H, 0.f);
+    std::vector<float> halo((size_t)runs.size() * 6 * G::H, 0.f);
+    std::vector<unsigned> flags(runs.size(), 0u);
+    unsigned amax = 0;
+    GlParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_runs = (int)runs.size();
+    p.runs = runs.data();
+    p.utt_T = &T;
+    p.utt_foff = foff.data();
+    p.S = S.data();
+    p.S_nyq = Sn.data();
+    p.R = R.data();
+    p.halo = halo.data();
+    p.flags = flags.data();
+    p.amax = &amax;
+    p.edge_scale = edge.data();
+    p.tables = tab.data();
+    p.turns = turns ? tu.data() : nullptr;
+    p.turns_nyq = turns ? tn.data() : nullptr;
+    p.seed = seed;
+    p.utt_seed_base = 0;
+    p.alpha = momentum / (1.0f + momentum);
+    p.inv_n = 1.0f / (float)G::N;
+    p.pad_mode = pad_mode;
+    float* yin = ya.data();
+    float* yout = yb.data();
+    p.y_in = yin;
+    p.y_out = yout;
+    if (n_iter == 0) emu_launch<R3, GL_MODE_INIT, false, true>(p, false);
+    else emu_launch<R3, GL_MODE_INIT, false, false>(p, false);
+    for (int it = 1; it <= n_iter; it++) {
+        std::swap(yin, yout);
+        p.y_in = yin;
+        p.y_out = yout;
+        const bool last = (it == n_iter);
+        const bool rev = (it & 1);   // alternate the processing order: exercises both arrival orders
+        if (it == 1) {
+            if (last) emu_launch<R3, GL_MODE_FIRST, false, true>(p, rev);
+            else emu_launch<R3, GL_MODE_FIRST, true, false>(p, rev);
+        } else {
+            if (last) emu_launch<R3, GL_MODE_MID, false, true>(p, rev);
+            else emu_launch<R3, GL_MODE_MID, true, false>(p, rev);
+        }
+    }
+    memcpy(out, yout, sizeof(float) * (size_t)G::H * (T - 1));
+    if (r_out) memcpy(r_out, R.data(), sizeof(float2) * (size_t)T * G::M);
+    if (peak) memcpy(peak, &amax, 4);
+    return (int)runs.size();
+}
+
+extern "C" int emu_gl_from_mag(const float* s_mag, const float* turns, int K, int T, int n_iter, float momentum,
+                               int run_frames, int pad_mode, unsigned long long seed, float* out, float* r_out,
+                               float* peak) {
+    if (T < 4) return -1;
+    switch (K) {
+        case 257: return emu_run<4>(s_mag, turns, T, n_iter, momentum, run_frames, pad_mode, seed, out, r_out, peak);
+        case 513: return emu_run<8>(s_mag, turns, T, n_iter, momentum, run_frames, pad_mode, seed, out, r_out, peak);
+        case 1025: return emu_run<16>(s_mag, turns, T, n_iter, momentum, run_frames, pad_mode, seed, out, r_out, peak);
+    }
+    return -2;
+}

@@ -1,0 +1,631 @@
+// Griffin-Lim iteration core: the per-lane program of one warp that walks a run of
+// consecutive STFT frames of one utterance.
+//
+// Replaces the loop body of griffin_lim::GriffinLim::infer (external crate
+// griffin-lim 0.2.0 @ e6415314, called at /root/reference src/lib.rs:141, configured
+// at src/tacotron2/mod.rs:453-456; algorithm per SURVEY.md section 3.4 / appendix B):
+//
+//     rebuilt = stft(istft(S * angles));  angles = unit(rebuilt - alpha * tprev)
+//
+// fused "STFT-first" so that ONE kernel launch is one iteration:
+//
+//     R_i  = STFT(y_{i-1})                       Hann window, real FFT of N = 128*R3
+//     Y    = S * unit(R_i - alpha * R_{i-1})     momentum + projection onto |S|
+//     y_i  = ISTFT(Y)                            inverse real FFT, window, overlap-add
+//
+// Mapping.  One warp owns one frame at a time; the N-point real FFT is an M = N/2
+// point complex FFT on z[n] = x[2n] + i x[2n+1], factored M = 8 * 8 * R3 with all
+// butterflies in registers (VPL = M/32 complex values per lane) and two
+// shared-memory transposes per direction.  The last forward pass is arranged so
+// that every lane holds both bins k and M-k of each of its values, hence the
+// real-FFT split, the projection and the inverse split need no data exchange, and
+// the inverse transform is the exact transpose of the forward one (same lane
+// mapping, conjugated twiddles).  The windowed output of consecutive frames is
+// overlap-added in registers (hop = N/4: a lane owns the same sample offsets in
+// every hop block), so a finished hop block leaves the warp exactly once.
+//
+// Everything here is `__host__ __device__`: tests/emu/ runs the identical lane
+// program on the CPU (lanes looped, warp syncs between phases) to check the index
+// algebra without a GPU.  The product only ever calls it from gl_iter.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define XD_HD __host__ __device__ __forceinline__
+#else
+#define XD_HD inline
+#endif
+
+namespace xdtts {
+
+// ------------------------------------------------------------------ geometry
+template <int R3_>
+struct Geo {
+    static constexpr int R3 = R3_;            // radix of the last pass: 4, 8 or 16
+    static constexpr int M = 64 * R3;         // complex FFT length
+    static constexpr int N = 2 * M;           // n_fft
+    static constexpr int H = N / 4;           // hop (the fused path needs hop == n_fft/4)
+    static constexpr int VPL = 2 * R3;        // complex values per lane
+    static constexpr int NB = R3 / 4;         // radix-8 butterflies per lane in passes 1 and 2
+    static constexpr int LN3 = (R3 == 4) ? 2 : (R3 == 8 ? 3 : 4);
+    static constexpr int S1 = 8 * R3 + (R3 == 4 ? 4 : 8);  // exchange-1 row stride (per k1), bank-conflict free
+    static constexpr int S2 = 64 + 16 / R3;                // exchange-2 row stride (per n3), bank-conflict free
+    static constexpr int EX1 = 8 * S1;        // exchange-1 size, complex elements
+    static constexpr int EX2 = R3 * S2;       // exchange-2 size
+    static constexpr int EXW = EX1 + EX2;     // per-warp exchange scratch
+    // constant tables, float2 units, laid out [row][32 lanes]
+    static constexpr int TW1_OFF = 0;                     // W_M^{(lane+32 i) k1}, row i*7 + k1-1
+    static constexpr int TW2_OFF = TW1_OFF + 7 * NB * 32; // W_{8 R3}^{(lane & (R3-1)) k2}, row k2-1
+    static constexpr int RTW_OFF = TW2_OFF + 7 * 32;      // -i W_N^{k(lane,j)} / 2, row j
+    static constexpr int WIN_OFF = RTW_OFF + R3 * 32;     // (w[s], w[s+1]), row i*8 + n1
+    static constexpr int TAB = WIN_OFF + VPL * 32;
+};
+
+// bin held in pair slot j of a lane after the last forward pass (its partner is M - k)
+template <int R3>
+XD_HD int kslot(int lane, int j) {
+    if (lane) return lane + 64 * j;
+    return (j < R3 / 2) ? 64 * j : 32 + 64 * (j - R3 / 2);
+}
+
+// ------------------------------------------------------------------ complex helpers
+XD_HD float2 mk2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
+XD_HD float2 cadd(float2 a, float2 b) { return mk2(a.x + b.x, a.y + b.y); }
+XD_HD float2 csub(float2 a, float2 b) { return mk2(a.x - b.x, a.y - b.y); }
+XD_HD float2 cmul(float2 a, float2 b) { return mk2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+XD_HD float2 cmulc(float2 a, float2 b) { return mk2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a * conj(b)
+
+// cos(2 pi k / 16), sin(2 pi k / 16) as literals (no constexpr libm on device)
+XD_HD constexpr float cos16(int k) {
+    return k == 0 ? 1.f : k == 1 ? 0.92387953251128674f : k == 2 ? 0.70710678118654752f : k == 3 ? 0.38268343236508977f
+         : k == 4 ? 0.f : k == 5 ? -0.38268343236508977f : k == 6 ? -0.70710678118654752f : k == 7 ? -0.92387953251128674f : -1.f;
+}
+XD_HD constexpr float sin16(int k) {
+    return k == 0 ? 0.f : k == 1 ? 0.38268343236508977f : k == 2 ? 0.70710678118654752f : k == 3 ? 0.92387953251128674f
+         : k == 4 ? 1.f : k == 5 ? 0.92387953251128674f : k == 6 ? 0.70710678118654752f : k == 7 ? 0.38268343236508977f : 0.f;
+}
+
+// z * W_R^k (forward, e^{-2 pi i k / R}) or z * conj(W_R^k) (inverse); k < R/2, R <= 16
+template <int R, int K, bool INV>
+XD_HD float2 mulw(float2 z) {
+    constexpr float r = 0.70710678118654752f;
+    if constexpr (K == 0) {
+        return z;
+    } else if constexpr (4 * K == R) {
+        return INV ? mk2(-z.y, z.x) : mk2(z.y, -z.x);
+    } else if constexpr (8 * K == R) {
+        return INV ? mk2(r * (z.x - z.y), r * (z.x + z.y)) : mk2(r * (z.x + z.y), r * (z.y - z.x));
+    } else if constexpr (8 * K == 3 * R) {
+        return INV ? mk2(-r * (z.x + z.y), r * (z.x - z.y)) : mk2(r * (z.y - z.x), -r * (z.x + z.y));
+    } else {
+        constexpr int k16 = K * (16 / R);
+        constexpr float c = cos16(k16), s = sin16(k16);
+        return INV ? mk2(z.x * c - z.y * s, z.x * s + z.y * c) : mk2(z.x * c + z.y * s, z.y * c - z.x * s);
+    }
+}
+
+// in-register DFT of R points, natural order in and out (decimation in time, fully unrolled)
+template <int R, bool INV>
+struct Dft {
+    template <int K>
+    static XD_HD void combine(float2* x, const float2* e, const float2* o) {
+        if constexpr (K < R / 2) {
+            const float2 t = mulw<R, K, INV>(o[K]);
+            x[K] = cadd(e[K], t);
+            x[K + R / 2] = csub(e[K], t);
+            combine<K + 1>(x, e, o);
+        }
+    }
+    static XD_HD void run(float2* x) {
+        float2 e[R / 2], o[R / 2];
+#pragma unroll
+        for (int k = 0; k < R / 2; k++) { e[k] = x[2 * k]; o[k] = x[2 * k + 1]; }
+        Dft<R / 2, INV>::run(e);
+        Dft<R / 2, INV>::run(o);
+        combine<0>(x, e, o);
+    }
+};
+template <bool INV>
+struct Dft<2, INV> {
+    static XD_HD void run(float2* x) {
+        const float2 a = x[0], b = x[1];
+        x[0] = cadd(a, b);
+        x[1] = csub(a, b);
+    }
+};
+
+// ------------------------------------------------------------------ parameters
+enum { GL_MODE_INIT = 0, GL_MODE_FIRST = 1, GL_MODE_MID = 2 };  // + flags below
+enum { GL_PAD_REFLECT = 0, GL_PAD_CONSTANT = 1 };
+
+struct GlRun {   // one warp's work: frames [ta, tb) of utterance utt
+    int utt, ta, tb, pad;
+};
+
+struct GlParams {
+    int n_runs;
+    const GlRun* runs;
+    const int* utt_T;        // frames per utterance
+    const int* utt_foff;     // first frame row of the utterance in S / R; its samples start at foff * H
+    const float* y_in;       // waveform of the previous iteration
+    float* y_out;            // waveform of this iteration
+    const float* S;          // [frames][M] magnitudes, bins 0..M-1
+    const float* S_nyq;      // [frames]    magnitude of bin M
+    float2* R;               // [frames][M] rebuilt spectrum, updated in place; slot 0 = (Re R[0], Re R[M])
+    float* halo;             // [n_runs][2][3*H] partial overlap-add sums at run boundaries
+    unsigned* flags;         // [n_runs] arrival counters of the boundary to the right of each run
+    unsigned* amax;          // [n_utt] max |y| as float bits (last iteration only)
+    const float* edge_scale; // [2][H] 1 / window-sum-square of the first / last hop block
+    const float2* tables;    // Geo::TAB constants
+    const float* turns;      // INIT: [frames][M] initial phase in turns, or null -> hashed from seed
+    const float* turns_nyq;  // INIT: [frames]
+    unsigned long long seed; // INIT: seed of the counter-based phase generator
+    int utt_seed_base;       // INIT: global index of utterance 0 (so shards draw distinct phases)
+    float alpha;             // momentum / (1 + momentum)
+    float inv_n;             // 1 / n_fft
+    int pad_mode;
+};
+
+// counter-based uniform in [0,1): top 24 bits of splitmix64 (bit-identical to oracle phase_turns)
+XD_HD float phase_turn(unsigned long long seed, int utt, int k_bins, int t, int k) {
+    const unsigned long long G = 0x9E3779B97F4A7C15ull;
+    unsigned long long z = seed + G * (unsigned long long)(utt + 1);
+    z += G * ((unsigned long long)t * (unsigned long long)k_bins + (unsigned long long)k + 1ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (float)(z >> 40) * 5.9604644775390625e-8f;
+}
+
+XD_HD void sincos_turns(float u, float* s, float* c) {
+#if defined(__CUDA_ARCH__)
+    sincospif(2.0f * u, s, c);
+#else
+    const double th = 6.283185307179586476925286766559 * (double)u;
+    *s = (float)sin(th);
+    *c = (float)cos(th);
+#endif
+}
+
+XD_HD float rsqrt_pos(float m2) {
+#if defined(__CUDA_ARCH__)
+    return m2 > 0.f ? rsqrtf(m2) : 0.f;
+#else
+    return m2 > 0.f ? 1.0f / sqrtf(m2) : 0.f;
+#endif
+}
+
+// streaming global accesses (state that is touched once per launch must not evict the waveform from L1)
+template <typename T>
+XD_HD T ld_stream(const T* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+template <typename T>
+XD_HD void st_stream(T* p, T v) {
+#if defined(__CUDA_ARCH__)
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+template <typename T>
+XD_HD T ld_l2(const T* p) {   // bypass L1: data written by another SM during this launch
+#if defined(__CUDA_ARCH__)
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+
+// ------------------------------------------------------------------ per-lane state
+template <int R3>
+struct Lane {
+    float2 v[Geo<R3>::VPL];          // FFT working set
+    float2 acc[3][2 * Geo<R3>::NB];  // overlap-add sums of the three unfinished hop blocks
+    float amax;
+};
+
+XD_HD int reflect_index(int j, int len) {
+    if (j < 0) j = -j;
+    if (j >= len) j = 2 * (len - 1) - j;
+    return j;
+}
+
+// F1: frame t of the previous waveform -> window -> pass 1 (radix 8 over n1) -> exchange 1
+template <int R3>
+XD_HD void phase_f1(Lane<R3>& L, int lane, const float* y, int T, int t, int pad_mode, const float2* tab, float2* ex1) {
+    typedef Geo<R3> G;
+    const int base = (t - 2) * G::H;
+    const bool edge = (t < 2) || (t >= T - 2);
+    const int len = G::H * (T - 1);
+#pragma unroll
+    for (int i = 0; i < G::NB; i++) {
+#pragma unroll
+        for (int n1 = 0; n1 < 8; n1++) {
+            const int s = 16 * R3 * n1 + 2 * (lane + 32 * i);
+            float2 x;
+            if (!edge) {
+                x = *reinterpret_cast<const float2*>(y + base + s);
+            } else {
+                const int j0 = base + s, j1 = j0 + 1;
+                if (pad_mode == GL_PAD_REFLECT) {
+                    x.x = y[reflect_index(j0, len)];
+                    x.y = y[reflect_index(j1, len)];
+                } else {
+                    x.x = (j0 >= 0 && j0 < len) ? y[j0] : 0.f;
+                    x.y = (j1 >= 0 && j1 < len) ? y[j1] : 0.f;
+                }
+            }
+            const float2 w = tab[G::WIN_OFF + (i * 8 + n1) * 32 + lane];
+            L.v[i * 8 + n1] = mk2(x.x * w.x, x.y * w.y);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < G::NB; i++) {
+        Dft<8, false>::run(&L.v[i * 8]);
+#pragma unroll
+        for (int k1 = 0; k1 < 8; k1++) {
+            float2 z = L.v[i * 8 + k1];
+            if (k1) z = cmul(z, tab[G::TW1_OFF + (i * 7 + k1 - 1) * 32 + lane]);
+            ex1[k1 * G::S1 + lane + 32 * i] = z;
+        }
+    }
+}
+
+// F2: pass 2 (radix 8 over n2) -> exchange 2
+template <int R3>
+XD_HD void phase_f2(Lane<R3>& L, int lane, const float2* tab, const float2* ex1, float2* ex2) {
+    typedef Geo<R3> G;
+    const int n3 = lane & (R3 - 1);
+#pragma unroll
+    for (int i = 0; i < G::NB; i++) {
+        const int k1 = (lane >> G::LN3) + (32 / R3) * i;
+#pragma unroll
+        for (int n2 = 0; n2 < 8; n2++) L.v[i * 8 + n2] = ex1[k1 * G::S1 + R3 * n2 + n3];
+    }
+#pragma unroll
+    for (int i = 0; i < G::NB; i++) {
+        const int k1 = (lane >> G::LN3) + (32 / R3) * i;
+        Dft<8, false>::run(&L.v[i * 8]);
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++) {
+            float2 z = L.v[i * 8 + k2];
+            if (k2) z = cmul(z, tab[G::TW2_OFF + (k2 - 1) * 32 + lane]);
+            ex2[n3 * G::S2 + k1 + 8 * k2] = z;
+        }
+    }
+}
+
+// lane 0 holds the two self-paired butterflies (k mod 64 == 0 and == 32); permute its
+// registers so that "slot j pairs A[j] with B[R3-1-j]" holds for it as for every other lane
+template <int R3>
+XD_HD void lane0_fix(float2* v, bool l0) {
+    float2 A[R3], B[R3];
+#pragma unroll
+    for (int i = 0; i < R3; i++) { A[i] = v[i]; B[i] = v[R3 + i]; }
+#pragma unroll
+    for (int i = 0; i < R3 / 2; i++) {
+        if (l0) v[R3 / 2 + i] = B[i];           // A'[R3/2+i] = B[i]
+        if (l0) v[R3 + i] = B[R3 / 2 + i];      // B'[i]      = B[R3/2+i]
+    }
+#pragma unroll
+    for (int i = R3 / 2; i < R3 - 1; i++)
+        if (l0) v[R3 + i] = A[i + 1];           // B'[i]      = A[i+1]
+    if (l0) v[R3 + R3 - 1] = A[R3 / 2];         // B'[R3-1]   = A[R3/2]
+}
+template <int R3>
+XD_HD void lane0_unfix(float2* v, bool l0) {
+    float2 A[R3], B[R3];   // the primed arrays
+#pragma unroll
+    for (int i = 0; i < R3; i++) { A[i] = v[i]; B[i] = v[R3 + i]; }
+#pragma unroll
+    for (int i = 0; i < R3 / 2; i++) {
+        if (l0) v[R3 + i] = A[R3 / 2 + i];          // B[i]        = A'[R3/2+i]
+        if (l0) v[R3 + R3 / 2 + i] = B[i];          // B[R3/2+i]   = B'[i]
+    }
+#pragma unroll
+    for (int i = R3 / 2; i < R3 - 1; i++)
+        if (l0) v[i + 1] = B[i];                    // A[i+1]      = B'[i]
+    if (l0) v[R3 / 2] = B[R3 - 1];                  // A[R3/2]     = B'[R3-1]
+}
+
+// F3: pass 3 (radix R3 over n3) -> real-FFT split -> momentum + projection -> inverse split
+//     -> inverse pass 1 -> exchange 2 (in place)
+template <int R3, int MODE, bool STORE_R>
+XD_HD void phase_f3(Lane<R3>& L, int lane, const GlParams& p, int utt, int T, int t, long frame, const float2* tab,
+                    float2* ex2) {
+    typedef Geo<R3> G;
+    const bool l0 = (lane == 0);
+    const int qA = lane, qB = lane ? 64 - lane : 32;
+    float2* A = &L.v[0];
+    float2* B = &L.v[R3];
+    const float* Srow = p.S + frame * G::M;
+    float2* Rrow = p.R + frame * G::M;
+
+    // issue the state loads first so that they overlap the last forward pass
+    float sa[R3], sb[R3];
+    float2 pa[R3], pb[R3];
+    float s_nyq = 0.f;
+#pragma unroll
+    for (int j = 0; j < R3; j++) {
+        const int ka = kslot<R3>(lane, j);
+        const int kb = (l0 && j == 0) ? G::M / 2 : G::M - ka;
+        sa[j] = ld_stream(Srow + ka);
+        sb[j] = ld_stream(Srow + kb);
+        if (MODE == GL_MODE_MID) {
+            pa[j] = ld_stream(Rrow + ka);
+            pb[j] = ld_stream(Rrow + kb);
+        }
+    }
+    if (l0) s_nyq = ld_stream(p.S_nyq + frame);
+
+    if (MODE != GL_MODE_INIT) {
+#pragma unroll
+        for (int n3 = 0; n3 < R3; n3++) {
+            A[n3] = ex2[n3 * G::S2 + qA];
+            B[n3] = ex2[n3 * G::S2 + qB];
+        }
+        Dft<R3, false>::run(A);
+        Dft<R3, false>::run(B);
+        lane0_fix<R3>(L.v, l0);
+    }
+
+#pragma unroll
+    for (int j = 0; j < R3; j++) {
+        const int ka = kslot<R3>(lane, j);
+        const int kb = (l0 && j == 0) ? G::M / 2 : G::M - ka;
+        const float2 C = tab[G::RTW_OFF + j * 32 + lane];   // -i W_N^k / 2
+        float2 Ya, Yb;
+        if (MODE != GL_MODE_INIT) {
+            const float2 a = A[j], b = B[R3 - 1 - j];
+            // X[k] = E + W^k O,  X[M-k] = conj(E - W^k O),  E = (a + conj b)/2,  O = (a - conj b)/(2i)
+            const float2 s = mk2(a.x + b.x, a.y - b.y);
+            const float2 d = mk2(a.x - b.x, a.y + b.y);
+            const float2 tt = cmul(C, d);
+            float2 Ra = mk2(0.5f * s.x + tt.x, 0.5f * s.y + tt.y);
+            float2 Rb = mk2(0.5f * s.x - tt.x, tt.y - 0.5f * s.y);
+            if (j == 0 && l0) {   // bins 0 and M are real and share one slot; bin M/2 pairs with itself
+                Ra = mk2(a.x + a.y, a.x - a.y);
+                Rb = mk2(b.x, -b.y);
+            }
+            float2 ua = Ra, ub = Rb;
+            if (MODE == GL_MODE_MID) {
+                ua = mk2(Ra.x - p.alpha * pa[j].x, Ra.y - p.alpha * pa[j].y);
+                ub = mk2(Rb.x - p.alpha * pb[j].x, Rb.y - p.alpha * pb[j].y);
+            }
+            if (STORE_R) {
+                st_stream(Rrow + ka, Ra);
+                st_stream(Rrow + kb, Rb);
+            }
+            const float ga = sa[j] * p.inv_n * rsqrt_pos(ua.x * ua.x + ua.y * ua.y);
+            const float gb = sb[j] * p.inv_n * rsqrt_pos(ub.x * ub.x + ub.y * ub.y);
+            Ya = mk2(ua.x * ga, ua.y * ga);
+            Yb = mk2(ub.x * gb, ub.y * gb);
+            if (j == 0 && l0) {
+                const float y0 = ua.x > 0.f ? 1.f : (ua.x < 0.f ? -1.f : 0.f);
+                const float ym = ua.y > 0.f ? 1.f : (ua.y < 0.f ? -1.f : 0.f);
+                Ya = mk2(y0 * sa[0] * p.inv_n, ym * s_nyq * p.inv_n);
+            }
+        } else {
+            float ta_, tb_, tn_ = 0.f;
+            if (p.turns) {
+                ta_ = p.turns[frame * G::M + ka];
+                tb_ = p.turns[frame * G::M + kb];
+                if (j == 0 && l0) tn_ = p.turns_nyq[frame];
+            } else {
+                ta_ = phase_turn(p.seed, p.utt_seed_base + utt, G::M + 1, t, ka);
+                tb_ = phase_turn(p.seed, p.utt_seed_base + utt, G::M + 1, t, kb);
+                if (j == 0 && l0) tn_ = phase_turn(p.seed, p.utt_seed_base + utt, G::M + 1, t, G::M);
+            }
+            float sn, cs;
+            sincos_turns(ta_, &sn, &cs);
+            Ya = mk2(sa[j] * p.inv_n * cs, sa[j] * p.inv_n * sn);
+            sincos_turns(tb_, &sn, &cs);
+            Yb = mk2(sb[j] * p.inv_n * cs, sb[j] * p.inv_n * sn);
+            if (j == 0 && l0) {   // the inverse real FFT ignores the imaginary part of bins 0 and M
+                sincos_turns(tn_, &sn, &cs);
+                Ya = mk2(Ya.x, s_nyq * p.inv_n * cs);
+            }
+        }
+        // Z[k] = E' + i O',  Z[M-k] = conj(E' - i O'),  E' = Ya + conj Yb,  O' = conj(W^k) (Ya - conj Yb)
+        const float2 s2 = mk2(Ya.x + Yb.x, Ya.y - Yb.y);
+        const float2 d2 = mk2(Ya.x - Yb.x, Ya.y + Yb.y);
+        const float2 D = mk2(2.f * C.x, -2.f * C.y);       // i conj(W_N^k)
+        const float2 t2 = cmul(D, d2);
+        float2 Za = mk2(s2.x + t2.x, s2.y + t2.y);
+        float2 Zb = mk2(s2.x - t2.x, t2.y - s2.y);
+        if (j == 0 && l0) {
+            Za = mk2(Ya.x + Ya.y, Ya.x - Ya.y);
+            Zb = mk2(2.f * Yb.x, -2.f * Yb.y);
+        }
+        A[j] = Za;
+        B[R3 - 1 - j] = Zb;
+    }
+    lane0_unfix<R3>(L.v, l0);
+    Dft<R3, true>::run(A);
+    Dft<R3, true>::run(B);
+#pragma unroll
+    for (int n3 = 0; n3 < R3; n3++) {
+        ex2[n3 * G::S2 + qA] = A[n3];
+        ex2[n3 * G::S2 + qB] = B[n3];
+    }
+}
+
+// F4: inverse pass 2 (radix 8 over k2) -> exchange 1
+template <int R3>
+XD_HD void phase_f4(Lane<R3>& L, int lane, const float2* tab, const float2* ex2, float2* ex1) {
+    typedef Geo<R3> G;
+    const int n3 = lane & (R3 - 1);
+#pragma unroll
+    for (int i = 0; i < G::NB; i++) {
+        const int k1 = (lane >> G::LN3) + (32 / R3) * i;
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++) {
+            float2 z = ex2[n3 * G::S2 + k1 + 8 * k2];
+            if (k2) z = cmulc(z, tab[G::TW2_OFF + (k2 - 1) * 32 + lane]);
+            L.v[i * 8 + k2] = z;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < G::NB; i++) {
+        const int k1 = (lane >> G::LN3) + (32 / R3) * i;
+        Dft<8, true>::run(&L.v[i * 8]);
+#pragma unroll
+        for (int n2 = 0; n2 < 8; n2++) ex1[k1 * G::S1 + R3 * n2 + n3] = L.v[i * 8 + n2];
+    }
+}
+
+// F5a: inverse pass 3 (radix 8 over k1) -> window; leaves frame samples in L.v
+template <int R3>
+XD_HD void phase_f5(Lane<R3>& L, int lane, const float2* tab, const float2* ex1) {
+    typedef Geo<R3> G;
+#pragma unroll
+    for (int i = 0; i < G::NB; i++) {
+#pragma unroll
+        for (int k1 = 0; k1 < 8; k1++) {
+            float2 z = ex1[k1 * G::S1 + lane + 32 * i];
+            if (k1) z = cmulc(z, tab[G::TW1_OFF + (i * 7 + k1 - 1) * 32 + lane]);
+            L.v[i * 8 + k1] = z;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < G::NB; i++) {
+        Dft<8, true>::run(&L.v[i * 8]);
+#pragma unroll
+        for (int n1 = 0; n1 < 8; n1++) {
+            const float2 w = tab[G::WIN_OFF + (i * 8 + n1) * 32 + lane];
+            L.v[i * 8 + n1] = mk2(L.v[i * 8 + n1].x * w.x, L.v[i * 8 + n1].y * w.y);
+        }
+    }
+}
+
+// element e of a hop block held by a lane: e = p * NB + i  <->  sample offset p*16*R3 + 64 i + 2 lane
+template <int R3>
+XD_HD int blk_off(int lane, int e) {
+    return (e / Geo<R3>::NB) * 16 * R3 + 64 * (e % Geo<R3>::NB) + 2 * lane;
+}
+
+// store one finished hop block (scaled by 1/window-sum-square) and track max |y|
+template <int R3, bool TRACK_MAX>
+XD_HD void store_block(Lane<R3>& L, int lane, const float2* blk, float* ydst, const float* scale_tab, float scale) {
+    typedef Geo<R3> G;
+#pragma unroll
+    for (int e = 0; e < 2 * G::NB; e++) {
+        const int off = blk_off<R3>(lane, e);
+        float2 o = blk[e];
+        if (scale_tab) {
+            o.x *= scale_tab[off];
+            o.y *= scale_tab[off + 1];
+        } else {
+            o.x *= scale;
+            o.y *= scale;
+        }
+        if (TRACK_MAX) L.amax = fmaxf(L.amax, fmaxf(fabsf(o.x), fabsf(o.y)));
+        *reinterpret_cast<float2*>(ydst + off) = o;
+    }
+}
+
+// F5b: overlap-add frame t into the register accumulators; returns in `out` the hop block
+// t-2, which has now received every frame of this run that touches it
+template <int R3>
+XD_HD void ola_shift(Lane<R3>& L, float2* out) {
+    typedef Geo<R3> G;
+    // frame sample s = 16 R3 n1 + 2 m + e lies in quarter n1 >> 1 at element (n1 & 1) * NB + i
+#pragma unroll
+    for (int e = 0; e < 2 * G::NB; e++) {
+        const int pbit = e / G::NB, i = e % G::NB;
+        const float2 q0 = L.v[i * 8 + 0 + pbit], q1 = L.v[i * 8 + 2 + pbit];
+        const float2 q2 = L.v[i * 8 + 4 + pbit], q3 = L.v[i * 8 + 6 + pbit];
+        out[e] = cadd(L.acc[0][e], q0);
+        L.acc[0][e] = cadd(L.acc[1][e], q1);
+        L.acc[1][e] = cadd(L.acc[2][e], q2);
+        L.acc[2][e] = q3;
+    }
+}
+
+// ------------------------------------------------------------------ run-level bookkeeping
+// A run [ta, tb) emits hop block b = t-2 after adding frame t.  The block has then seen frames
+// max(ta, t-3)..t; it is complete iff ta == 0 or t-3 >= ta.  The three incomplete blocks at the
+// head of a run (ta-2, ta-1, ta) and the three at its tail (tb-2, tb-1, tb) are written as raw
+// partial sums to halo[boundary][side]; whichever of the two neighbouring warps arrives second
+// adds left + right (fixed order -> deterministic) and stores the finished blocks.
+
+template <int R3>
+XD_HD float* halo_ptr(const GlParams& p, int boundary, int side, int blk) {
+    return p.halo + ((size_t)(boundary * 2 + side) * 3 + blk) * Geo<R3>::H;
+}
+
+template <int R3>
+XD_HD void store_partial(int lane, const float2* blk, float* dst) {
+#pragma unroll
+    for (int e = 0; e < 2 * Geo<R3>::NB; e++) *reinterpret_cast<float2*>(dst + blk_off<R3>(lane, e)) = blk[e];
+}
+
+// block t-2 after frame t (called by every lane); returns true when the caller must signal the
+// boundary to its left (third partial block written)
+template <int R3, bool TRACK_MAX>
+XD_HD bool emit_block(Lane<R3>& L, int lane, const GlParams& p, int run_idx, const GlRun& r, long yoff, int t,
+                      const float2* out) {
+    typedef Geo<R3> G;
+    const int b = t - 2;
+    if (b < 0) return false;
+    const bool complete = (r.ta == 0) || (t - 3 >= r.ta);
+    if (complete) {
+        store_block<R3, TRACK_MAX>(L, lane, out, p.y_out + yoff + (long)b * G::H, b == 0 ? p.edge_scale : nullptr,
+                                   2.0f / 3.0f);
+        return false;
+    }
+    store_partial<R3>(lane, out, halo_ptr<R3>(p, run_idx - 1, 1, t - r.ta));
+    return t == r.ta + 2;
+}
+
+// end of run; returns true when the caller must signal the boundary to its right
+template <int R3, bool TRACK_MAX>
+XD_HD bool emit_tail(Lane<R3>& L, int lane, const GlParams& p, int run_idx, const GlRun& r, long yoff, int T) {
+    typedef Geo<R3> G;
+    if (r.tb == T) {   // block T-2 is the last one; it is complete (frames T-3..T-1)
+        store_block<R3, TRACK_MAX>(L, lane, L.acc[0], p.y_out + yoff + (long)(T - 2) * G::H, p.edge_scale + G::H, 0.f);
+        return false;
+    }
+#pragma unroll
+    for (int q = 0; q < 3; q++) store_partial<R3>(lane, L.acc[q], halo_ptr<R3>(p, run_idx, 0, q));
+    return true;
+}
+
+// second arrival at `boundary` (between runs boundary and boundary+1): finish blocks tb-2..tb
+template <int R3, bool TRACK_MAX>
+XD_HD void combine_boundary(Lane<R3>& L, int lane, const GlParams& p, int boundary) {
+    typedef Geo<R3> G;
+    const GlRun r = p.runs[boundary];
+    const long yoff = (long)p.utt_foff[r.utt] * G::H;
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        const float* lp = halo_ptr<R3>(p, boundary, 0, q);
+        const float* rp = halo_ptr<R3>(p, boundary, 1, q);
+        float2 blk[2 * G::NB];
+#pragma unroll
+        for (int e = 0; e < 2 * G::NB; e++) {
+            const int off = blk_off<R3>(lane, e);
+            const float2 a = ld_l2(reinterpret_cast<const float2*>(lp + off));
+            const float2 c = ld_l2(reinterpret_cast<const float2*>(rp + off));
+            blk[e] = cadd(a, c);
+        }
+        store_block<R3, TRACK_MAX>(L, lane, blk, p.y_out + yoff + (long)(r.tb - 2 + q) * G::H, nullptr, 2.0f / 3.0f);
+    }
+}
+
+template <int R3>
+XD_HD void lane_reset(Lane<R3>& L) {
+#pragma unroll
+    for (int q = 0; q < 3; q++)
+#pragma unroll
+        for (int e = 0; e < 2 * Geo<R3>::NB; e++) L.acc[q][e] = mk2(0.f, 0.f);
+    L.amax = 0.f;
+}
+
+}  // namespace xdtts
