@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: Griffin-Lim vocoding of a batch of synthetic 80xT mels.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config cfg2|cfg5]
+
+One "step" = one pass of the path over one batch: mel -> linear lift (pseudo-inverse, clamp,
+^1.7) -> 60 Griffin-Lim iterations -> peak normalisation, for 32 utterances of 1000 frames
+(BASELINE.json configs[1]; n_fft 1024, hop 256).  Metric: audio frames/s = sum(T) / time.
+
+  value      whole-job frames/s with the mels already resident in HBM (device time, CUDA events
+             around every step on the library's stream, max over ranks)
+  e2e        the same through the public call (GriffinLim.infer_batch -> xdtts_gl_infer_batch) with
+             pinned HOST buffers: H2D of the mels and D2H of the waveforms inside the timed region
+  roofline   the steady-state iteration kernel: algorithmic bytes (20K+8H per frame)
+             / its mean launch duration (events around the launches, kernel-by-kernel run) vs the
+             measured HBM peak of MEASURED_PEAKS.json
+  cpu_baseline  the oracle's C/OpenMP port of the same step on this host's cores, bounded sample
+
+--impl reference times that CPU port (the reference's Rust crate cannot be built here:
+no cargo/rustc, crate not vendored -- DESIGN.md) as its own arm.
+N > 1: launched by torchrun, one rank per GPU, 32 utterances per rank (weak scaling), no
+data-path collective; ranks meet only at the barriers and the final all-reduce of the counters.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "xd-tts_b200"))
+
+CONFIGS = {
+    # name: (batch per GPU, frames, n_fft, iterations)
+    "cfg2": (32, 1000, 1024, 60),
+    "cfg5": (8, 8000, 2048, 60),
+}
+POWER, MOMENTUM, N_MELS, SR, FMAX = 1.7, 0.99, 80, 22050.0, 8000.0
+FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def workload_name(cfg, b, t, n_fft, it):
+    return "%s: batch=%d x [80x%d] synthetic ln-mels U(-8,0), pinv lift ^1.7 + Griffin-Lim %d iters, n_fft=%d hop=%d" % (
+        cfg, b, t, it, n_fft, n_fft // 4)
+
+
+def synth_batch(b, t, seed0):
+    from oracle.gl_oracle import synth_mel   # input generator only (shared with the tests)
+
+    return [synth_mel(seed0 + i, N_MELS, t) for i in range(b)]
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            for key in ("hbm_gbs", "hbm_gb_s", "hbm_GBps"):
+                if key in d:
+                    return float(d[key]), "measured (MEASURED_PEAKS.json %s)" % key
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(cfg):
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(cfg)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def pinned_array(lib, shape):
+    n = int(np.prod(shape))
+    ptr = lib.xdtts_host_alloc(n * 4)
+    if not ptr:
+        raise MemoryError("xdtts_host_alloc")
+    buf = (ctypes.c_float * n).from_address(ptr)
+    return np.frombuffer(buf, dtype=np.float32).reshape(shape), ptr
+
+
+# ------------------------------------------------------------------------------- CPU arm
+def cpu_arm(cfg, steps, warmup, sample_utts=None):
+    """Oracle C port (OpenMP) on this host: returns (frames/s, cores, kind, sample description, ms/step)."""
+    from oracle import c_oracle, gl_oracle as o
+
+    b, t, n_fft, it = CONFIGS[cfg]
+    c_oracle.build()
+    cores = c_oracle.num_threads()
+    basis = o.create_mel_filter_bank(SR, n_fft, N_MELS, 0.0, FMAX)
+    pinv = o.pinv_basis(basis).astype(np.float32)
+    k = n_fft // 2 + 1
+    # bounded sample of the workload: enough utterances to occupy every core, a few seconds per step
+    n = sample_utts or max(2, min(b, cores))
+    mels = np.stack(synth_batch(n, t, 1234))
+    turns = np.stack([o.phase_turns(0, i, k, t) for i in range(n)])
+    hop = n_fft // 4
+
+    def per_utt():      # OpenMP over the frames of one utterance (rayon-style, as the crate does)
+        for i in range(n):
+            c_oracle.infer(pinv, mels[i], turns[i], hop, POWER, it, MOMENTUM)
+
+    def per_batch():    # one thread per utterance
+        c_oracle.infer_batch(pinv, mels, turns, hop, POWER, it, MOMENTUM)
+
+    best = None
+    for name, fn in (("threads over utterances", per_batch), ("threads over frames", per_utt)):
+        fn()
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[1]:
+            best = (name, dt, fn)
+    name, _, fn = best
+    for _ in range(max(0, warmup - 1)):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    dt = (time.perf_counter() - t0) / steps
+    sample = "%d of %d utterances x %d frames x %d iters per step, C/OpenMP port of the oracle, %s" % (n, b, t, it, name)
+    return n * t / dt, cores, "port", sample, dt * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = args.config
+    b, t, n_fft, it = CONFIGS[cfg]
+    steps, warmup = args.steps, args.warmup
+    v, cores, kind, sample, ms = cpu_arm(cfg, steps, warmup)
+    line = {
+        "impl": "reference", "metric": "audio frames/sec", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(cfg, b, t, n_fft, it)},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference Rust crate (griffin-lim 0.2.0) cannot be built here (no cargo, not vendored): CPU arm is the oracle's C/OpenMP port",
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import __graft_entry__ as g
+
+    if not os.path.exists(g.LIB):
+        g.build_cuda()
+    from xdtts_b200 import _ffi, griffin_lim
+
+    lib = _ffi.load_library()
+    cfg = args.config
+    b, t, n_fft, it = CONFIGS[cfg]
+    hop, k = n_fft // 4, n_fft // 2 + 1
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    basis = griffin_lim.mel.create_mel_filter_bank(SR, n_fft, N_MELS, 0.0, FMAX)
+    voc = griffin_lim.GriffinLim.new(basis, n_fft - hop, POWER, it, MOMENTUM, seed=rank, device=local_rank)
+    mels = synth_batch(b, t, 1234 + rank * b)          # this rank's shard of the job
+    frames = b * t
+
+    # ---- device-resident arm: plan with the mels already in HBM
+    plan = voc.plan([t] * b)
+    plan.upload(0, mels)
+    info = plan.info()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        plan.run(0)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = lib.xdtts_kernel_launches()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(steps):
+        ms, _, _ = plan.run(0)
+        dev_ms += ms
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    launches = lib.xdtts_kernel_launches() - launches0
+    clocks = sampler.stop()
+
+    # ---- steady-state kernel duration, live, kernel-by-kernel run with events around the launches
+    iter_ms, iter_n = 0.0, 0
+    for _ in range(max(2, min(steps, 5))):
+        _, mi, n = plan.run(_ffi.RUN_NO_GRAPH)
+        iter_ms += mi
+        iter_n += n
+    kern_ms = iter_ms / max(iter_n, 1)
+
+    # ---- end to end through the public call, pinned host buffers
+    pin_in = [pinned_array(lib, (N_MELS, t)) for _ in range(b)]
+    for (a, _), m in zip(pin_in, mels):
+        a[...] = m
+    out_len = hop * (t - 1)
+    pin_out = [pinned_array(lib, (out_len,)) for _ in range(b)]
+    in_ptrs = _ffi.fptr_array([a for a, _ in pin_in])
+    out_ptrs = _ffi.fptr_array([a for a, _ in pin_out])
+    t_arr = (ctypes.c_int * b)(*([t] * b))
+
+    def e2e_step():
+        _ffi.check(lib.xdtts_gl_infer_batch(voc._h, in_ptrs, t_arr, b, None, out_ptrs))
+
+    for _ in range(warmup):
+        e2e_step()
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(steps):
+        e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t1) * 1e3
+    peak_ok = all(abs(float(np.abs(a).max()) - 1.0) < 1e-5 for a, _ in pin_out)
+
+    # ---- reduce over ranks: time = max, frames = sum
+    tt = torch.tensor([dev_ms, wall_ms, e2e_ms, kern_ms], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(frames), float(launches)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)     # the single collective of the job: the throughput counter
+    dev_ms, wall_ms, e2e_ms, kern_ms = [float(x) for x in tt.tolist()]
+    total_frames, total_launches = float(cnt[0]), int(cnt[1])
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        alg_bytes = frames * (20 * k + 8 * hop)      # per steady-state launch on one GPU
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+        line = {
+            "metric": "audio frames/sec", "value": total_frames * steps / (dev_ms * 1e-3), "unit": "frames/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": dev_ms / steps,
+            "wall_ms_per_step": wall_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(cfg, b, t, n_fft, it), "utterances_per_gpu": b,
+                       "l2": "no flush needed: per-step state %.0f MB > 126 MB L2" % ((20 * k + 8 * hop) * frames / 1e6),
+                       "runs": info["n_runs"], "run_frames": info["run_frames"], "ctas": info["ctas"]},
+            "e2e": {"value": total_frames * steps / (e2e_ms * 1e-3), "unit": "frames/s",
+                    "h2d_bytes_per_step": b * N_MELS * t * 4, "d2h_bytes_per_step": b * out_len * 4,
+                    "ms_per_step": e2e_ms / steps, "api": "xdtts_gl_infer_batch (pinned host buffers)",
+                    "peak_normalised_ok": peak_ok},
+            "gpu_launches": total_launches,
+            "roofline": {"bound": "hbm", "kernel": "gl_iter_kernel<MID> (one Griffin-Lim iteration)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(cfg), "peak_source": peak_src, "kernel_ms": kern_ms,
+                         "algorithmic_bytes_per_launch": alg_bytes},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            v, cores, kind, sample, _ = cpu_arm(cfg, 1, 1)
+            line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}
+        print(json.dumps(line))
+    for _, p in pin_in + pin_out:
+        lib.xdtts_host_free(p)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps == 10:
+            args.steps = 3
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,115 @@
+/* xdtts_b200.h -- C ABI of the B200 (sm_100a) vocoding + postnet back end for xd-tts.
+ *
+ * Drop-in boundary for the two calls XdTts::infer makes on its hot path
+ * (/root/reference src/lib.rs:110-159): `self.model.infer(input)` -> postnet tail
+ * (src/tacotron2/mod.rs:344-357) and `self.vocoder.infer(&spectrogram)` (src/lib.rs:141,
+ * griffin_lim::GriffinLim, external crate griffin-lim 0.2.0 @ e6415314, Cargo.lock:666-680).
+ * A Rust shim crate named `griffin-lim` binds these symbols (INTEGRATION.md shows it); the
+ * Python mirror in xd-tts_b200/xdtts_b200/ binds them through ctypes.
+ *
+ * Conventions: plain pointers and sizes only.  Host arrays are C-contiguous float32 in the
+ * reference's ndarray layouts: mel [n_mels, T], linear magnitude / phase [K, T] with
+ * K = n_fft/2 + 1, waveform [hop * (T - 1)].  The caller owns every host buffer, inputs and
+ * outputs; the library returns only opaque handles.  Every function returns 0 or a negative
+ * XDTTS_ERR_* code and never throws or aborts; xdtts_last_error() gives the message of the
+ * last failure on the calling thread (maps to anyhow::bail! in the shim).  Handles may be
+ * shared between threads (calls on one handle are serialised internally).
+ * There is NO CPU fallback: every entry point fails with XDTTS_ERR_CUDA when no sm_100 device
+ * is usable.
+ */
+#ifndef XDTTS_B200_H
+#define XDTTS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XDTTS_OK 0
+#define XDTTS_ERR_BAD_ARG (-1)     /* null pointer, non-finite or out-of-range parameter */
+#define XDTTS_ERR_SHAPE (-2)       /* T < 4, K != n_fft/2+1, wrong out_len ... */
+#define XDTTS_ERR_CUDA (-3)        /* CUDA runtime error, no usable sm_100 device */
+#define XDTTS_ERR_OOM (-4)
+#define XDTTS_ERR_UNSUPPORTED (-5) /* n_fft not in {512,1024,2048}, hop != n_fft/4, n_mels > 256 */
+
+/* Options whose value the un-vendored crate fixes internally (SURVEY.md section 7 "unknowns");
+ * defaults (all zero) are the librosa-0.9.2 behaviour the crate ports. */
+typedef struct xdtts_gl_opts {
+    int delog;               /* 0: exp (Tacotron2 ln-mel, default)  1: 10^x  2: mel is already linear */
+    int pad_mode;            /* 0: reflect (librosa 0.9.2 stft)     1: constant zero */
+    int normalise;           /* 0: peak-normalise to [-1,1] (caller scales by i16::MAX, src/lib.rs:155)  1: none */
+    int run_frames;          /* 0: auto.  Frames per warp run (tuning knob, >= 4) */
+    unsigned long long seed; /* seed of the random initial phase used when the caller passes none */
+} xdtts_gl_opts;
+
+typedef struct xdtts_gl xdtts_gl;           /* replaces griffin_lim::GriffinLim */
+typedef struct xdtts_gl_plan xdtts_gl_plan; /* device-resident batch: buffers + captured CUDA graph */
+
+/* griffin_lim::mel::create_mel_filter_bank(sr, n_fft, n_mels, fmin, fmax) (call site
+ * src/tacotron2/mod.rs:453): Slaney-scale, Slaney-normalised triangular filters (librosa
+ * filters.mel, htk=False, norm='slaney').  fmax < 0 means None (sr/2).  out: [n_mels, n_fft/2+1]. */
+int xdtts_mel_filter_bank(float sr, int n_fft, int n_mels, float fmin, float fmax, float* out);
+
+/* Moore-Penrose pseudo-inverse of a [rows, cols] row-major matrix -> out [cols, rows] (host, fp64
+ * one-sided Jacobi; stands in for the MKL lstsq/SVD the crate uses, Cargo.lock:1006).  This is
+ * the matrix the mel -> linear lift multiplies by. */
+int xdtts_pinv(const float* a, int rows, int cols, float* out);
+
+/* GriffinLim::new(mel_basis, noverlap, power, iter, momentum) (call site src/tacotron2/mod.rs:456).
+ * mel_basis: [n_mels, K] row-major; n_fft = 2 (K-1); hop = n_fft - noverlap.  Builds the
+ * pseudo-inverse of the basis once (host, fp64) and uploads constants to `device`. */
+int xdtts_gl_create(const float* mel_basis, int n_mels, int K, int noverlap, float power, int n_iter, float momentum,
+                    const xdtts_gl_opts* opts_or_null, int device, xdtts_gl** out);
+void xdtts_gl_destroy(xdtts_gl* h);
+
+/* hop * (T - 1), or a negative error */
+int xdtts_gl_out_len(const xdtts_gl* h, int T);
+/* copies the [K, n_mels] pseudo-inverse the lift uses (for parity checks) */
+int xdtts_gl_get_pinv(const xdtts_gl* h, float* out);
+
+/* GriffinLim::infer(&mel) (call site src/lib.rs:141): mel [n_mels, T] -> out [hop (T-1)].
+ * init_phase_or_null: [K, T] initial phase in turns, u in [0,1) (angle = 2 pi u); null draws
+ * u from the counter-based generator (splitmix64 of seed, utterance index, t*K + k). */
+int xdtts_gl_infer(xdtts_gl* h, const float* mel, int T, const float* init_phase_or_null, float* out, int out_len);
+/* B independent utterances in one pass (the reference loops; src/lib.rs:83-104).  init_phases
+ * may be null, or an array of B pointers (all non-null). */
+int xdtts_gl_infer_batch(xdtts_gl* h, const float* const* mels, const int* Ts, int B,
+                         const float* const* init_phases_or_null, float* const* outs);
+/* Same, starting from linear magnitudes [K, T] (skips the mel -> linear lift; rows a6-a8 only) */
+int xdtts_gl_from_mag_batch(xdtts_gl* h, const float* const* mags, const int* Ts, int B,
+                            const float* const* init_phases_or_null, float* const* outs);
+
+/* ---- device-resident plan: what the batch calls above use internally, exposed so that a
+ * pipeline (or the benchmark) can keep inputs and outputs in HBM and time the device work. */
+int xdtts_gl_plan_create(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out);
+void xdtts_gl_plan_destroy(xdtts_gl_plan* p);
+/* kind: 0 mel [n_mels,T], 1 magnitude [K,T], 2 initial phase [K,T]; srcs: B host pointers */
+int xdtts_gl_plan_upload(xdtts_gl_plan* p, int kind, const float* const* srcs);
+#define XDTTS_RUN_FROM_MAG 1    /* start from the uploaded magnitudes instead of lifting the mels */
+#define XDTTS_RUN_USE_PHASE 2   /* use the uploaded initial phase instead of the seeded generator */
+#define XDTTS_RUN_NO_GRAPH 4    /* launch kernel by kernel (needed for ms_iter) */
+/* Runs lift/transposes, the n_iter+1 Griffin-Lim launches and the normalisation on the plan's
+ * stream and waits.  ms_total: device time of the whole pass (CUDA events); ms_iter / n_iter_launches:
+ * summed device time and count of the steady-state iteration launches (only with NO_GRAPH). */
+int xdtts_gl_plan_run(xdtts_gl_plan* p, int flags, float* ms_total, float* ms_iter, int* n_iter_launches);
+int xdtts_gl_plan_download(xdtts_gl_plan* p, float* const* outs);
+/* debugging / parity: copy device state to host. what: 0 S [T_total][M] frame-major, 1 S Nyquist [T_total],
+ * 2 R [T_total][M][2]; n_floats must match. */
+int xdtts_gl_plan_peek(xdtts_gl_plan* p, int what, float* out, long long n_floats);
+/* geometry the plan chose: info[0]=n_runs, [1]=frames per run (max), [2]=CTAs, [3]=total frames */
+int xdtts_gl_plan_info(const xdtts_gl_plan* p, int* info4);
+
+/* pinned host memory for callers that want copy/compute overlap and full PCIe speed */
+void* xdtts_host_alloc(unsigned long long bytes);
+void xdtts_host_free(void* p);
+
+/* thread-local message of the last error returned on this thread ("" if none) */
+const char* xdtts_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long xdtts_kernel_launches(void);
+/* "xdtts_b200 <version> sm_100a" */
+const char* xdtts_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XDTTS_B200_H */

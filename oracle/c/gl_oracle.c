@@ -280,6 +280,19 @@ int oracle_infer(const float *pinv, const float *mel, const float *turns, int K,
     return 0;
 }
 
+/* B utterances of equal shape, one OpenMP thread per utterance (the inner loops then run
+ * serially: nested parallelism is off by default).  The better of this and the per-frame
+ * parallel form is what bench.py reports as the CPU arm. */
+int oracle_infer_batch(const float *pinv, const float *mels, const float *turns, int B, int K, int M, int T, int hop,
+                       float power, int n_iter, float momentum, int delog, int pad_constant, int normalise, float *outs) {
+    const size_t len = (size_t)hop * (T - 1);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int b = 0; b < B; b++)
+        oracle_infer(pinv, mels + (size_t)b * M * T, turns + (size_t)b * K * T, K, M, T, hop, power, n_iter, momentum,
+                     delog, pad_constant, normalise, outs + b * len);
+    return 0;
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -35,6 +35,9 @@ def lib():
         _lib.oracle_infer.argtypes = (
             [fp, fp, fp] + [ctypes.c_int] * 4 + [ctypes.c_float, ctypes.c_int, ctypes.c_float] + [ctypes.c_int] * 3 + [fp]
         )
+        _lib.oracle_infer_batch.argtypes = (
+            [fp, fp, fp] + [ctypes.c_int] * 5 + [ctypes.c_float, ctypes.c_int, ctypes.c_float] + [ctypes.c_int] * 3 + [fp]
+        )
         _lib.oracle_stft.argtypes = [fp] + [ctypes.c_int] * 4 + [fp]
         _lib.oracle_num_threads.restype = ctypes.c_int
     return _lib
@@ -71,6 +74,19 @@ def infer(pinv, mel, turns, hop, power, n_iter, momentum, delog=0, pad_constant=
     t = mel.shape[1]
     out = np.empty(hop * (t - 1), dtype=np.float32)
     lib().oracle_infer(_p(pinv), _p(mel), _p(turns), k, m, t, hop, power, n_iter, momentum, delog, pad_constant, normalise, _p(out))
+    return out
+
+
+def infer_batch(pinv, mels, turns, hop, power, n_iter, momentum, delog=0, pad_constant=0, normalise=0):
+    """mels [B, n_mels, T], turns [B, K, T] -> [B, hop*(T-1)], one thread per utterance."""
+    pinv = np.ascontiguousarray(pinv, dtype=np.float32)
+    mels = np.ascontiguousarray(mels, dtype=np.float32)
+    turns = np.ascontiguousarray(turns, dtype=np.float32)
+    k, m = pinv.shape
+    b, _, t = mels.shape
+    out = np.empty((b, hop * (t - 1)), dtype=np.float32)
+    lib().oracle_infer_batch(_p(pinv), _p(mels), _p(turns), b, k, m, t, hop, power, n_iter, momentum, delog, pad_constant,
+                             normalise, _p(out))
     return out
 
 

@@ -1,0 +1,154 @@
+"""CPU tests of the product's host side: the C ABI library loads and exports every symbol of
+include/xdtts_b200.h, host math (filterbank, pseudo-inverse), argument validation, and the kernel's
+lane program run by the CPU emulator against the oracle.  No CUDA compute here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import rel_rms
+from oracle import gl_oracle as o
+
+
+@pytest.fixture(scope="module")
+def lib(built):
+    from xdtts_b200 import _ffi
+
+    return _ffi.load_library()
+
+
+def test_library_exports_every_declared_symbol(lib, built):
+    from xdtts_b200 import _ffi
+
+    hdr = open(os.path.join(os.path.dirname(built.__file__), "include", "xdtts_b200.h")).read()
+    declared = set(re.findall(r"\b(xdtts_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "header parse failed"
+    for name in declared:
+        assert hasattr(lib, name), "missing export %s" % name
+    assert declared == set(_ffi.SIGNATURES), declared ^ set(_ffi.SIGNATURES)
+    assert b"sm_100a" in lib.xdtts_version()
+
+
+def test_mel_filter_bank_matches_golden(lib, golden_dir):
+    from xdtts_b200 import griffin_lim
+
+    g = np.load(os.path.join(golden_dir, "melbank.npz"))
+    for n_fft in (1024, 2048):
+        fb = griffin_lim.mel.create_mel_filter_bank(22050.0, n_fft, 80, 0.0, 8000.0)
+        assert fb.shape == (80, n_fft // 2 + 1) and fb.dtype == np.float32
+        assert np.abs(fb - g["torchaudio_%d" % n_fft]).max() < 2e-7     # independent implementation
+        assert np.abs(fb - g["oracle_%d" % n_fft]).max() < 1e-8
+    # fmax = None -> sr/2
+    fb = griffin_lim.mel.create_mel_filter_bank(16000.0, 512, 40, 20.0, None)
+    assert np.abs(fb - o.create_mel_filter_bank(16000.0, 512, 40, 20.0, None)).max() < 1e-8
+
+
+def test_pinv_matches_numpy(lib):
+    from xdtts_b200 import griffin_lim
+
+    basis = o.create_mel_filter_bank(22050.0, 1024, 80, 0.0, 8000.0)
+    p = griffin_lim.pinv(basis)
+    ref = np.linalg.pinv(basis.astype(np.float64))
+    assert p.shape == (513, 80)
+    assert np.abs(p - ref).max() / np.abs(ref).max() < 1e-6
+    assert (p[0] == 0).all() and (p[372:] == 0).all()       # empty columns
+    # rank-deficient input (duplicated + zero row) still gives the Moore-Penrose inverse
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((6, 11)).astype(np.float32)
+    a[3] = a[1]
+    a[5] = 0
+    p = griffin_lim.pinv(a)
+    ref = np.linalg.pinv(a.astype(np.float64), rcond=1e-6)
+    assert np.abs(p - ref).max() < 1e-5
+
+
+def test_argument_validation_without_gpu(lib):
+    from xdtts_b200 import griffin_lim
+    from xdtts_b200._ffi import ERR_BAD_ARG, ERR_SHAPE, ERR_UNSUPPORTED, XdttsError
+
+    basis = o.create_mel_filter_bank(22050.0, 1024, 80, 0.0, 8000.0)
+    with pytest.raises(XdttsError) as e:
+        griffin_lim.GriffinLim.new(basis, 1024 - 200, 1.7, 30, 0.99)    # hop != n_fft/4
+    assert e.value.code == ERR_UNSUPPORTED
+    with pytest.raises(XdttsError) as e:
+        griffin_lim.GriffinLim.new(basis[:, :400], 768, 1.7, 30, 0.99)  # n_fft = 798
+    assert e.value.code == ERR_UNSUPPORTED
+    with pytest.raises(XdttsError) as e:
+        griffin_lim.GriffinLim.new(basis, 768, -1.0, 30, 0.99)
+    assert e.value.code == ERR_BAD_ARG
+    with pytest.raises(XdttsError) as e:
+        griffin_lim.GriffinLim.new(basis, 768, 1.7, 30, float("nan"))
+    assert e.value.code == ERR_BAD_ARG
+    with pytest.raises(XdttsError) as e:
+        griffin_lim.GriffinLim.new(basis[0], 768, 1.7, 30, 0.99)
+    assert e.value.code == ERR_SHAPE
+    bad = basis.copy()
+    bad[3, 7] = np.inf
+    with pytest.raises(XdttsError) as e:
+        griffin_lim.GriffinLim.new(bad, 768, 1.7, 30, 0.99)
+    assert e.value.code == ERR_BAD_ARG
+    with pytest.raises(XdttsError):
+        griffin_lim.mel.create_mel_filter_bank(22050.0, 1024, 80, 9000.0, 8000.0)
+    assert b"fmax" in lib.xdtts_last_error()
+
+
+def test_no_cpu_fallback(lib):
+    """Without a usable sm_100 device the product refuses to work instead of computing on the CPU."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from xdtts_b200 import griffin_lim
+    from xdtts_b200._ffi import ERR_CUDA, XdttsError
+
+    basis = o.create_mel_filter_bank(22050.0, 1024, 80, 0.0, 8000.0)
+    with pytest.raises(XdttsError) as e:
+        griffin_lim.GriffinLim.new(basis, 768, 1.7, 30, 0.99)
+    assert e.value.code == ERR_CUDA
+
+
+# ---------------------------------------------------------------- lane program (CPU emulation)
+@pytest.mark.parametrize("n_fft,hop,t", [(1024, 256, 37), (2048, 512, 21), (512, 128, 30)])
+def test_lane_program_matches_oracle(built, n_fft, hop, t):
+    from emu import emu
+
+    k = n_fft // 2 + 1
+    s = o.synth_speech_like_mag(5, n_fft, hop, t)
+    tu = o.phase_turns(9, 0, k, t)
+    for it in (0, 1, 3):
+        y64 = o.griffin_lim(s, tu, it, 0.99, n_fft, hop, dtype=np.float64)
+        for run_frames in (1000, 8, 4):     # one run; several runs; shortest legal runs
+            y, r, peak, n_runs = emu.gl_from_mag(s, tu, it, 0.99, run_frames)
+            assert rel_rms(y, y64) < 5e-7, (it, run_frames)
+            assert abs(peak - np.abs(y).max()) < 1e-6
+
+
+def test_lane_program_rebuilt_spectrum_and_options(built):
+    from emu import emu
+
+    n_fft, hop, t = 1024, 256, 16
+    s = o.synth_speech_like_mag(3, n_fft, hop, t)
+    tu = o.phase_turns(1, 0, 513, t)
+    # after 2 iterations R holds stft(y_0) (the last launch does not store): packed slot 0 = (R[0], R[M])
+    ck = {0: None}
+    o.griffin_lim(s, tu, 2, 0.99, n_fft, hop, dtype=np.float64, checkpoints=ck)
+    r_ref = o.stft(ck[0][0], n_fft, hop, dtype=np.float64).T           # [T, K]
+    _, r, _, _ = emu.gl_from_mag(s, tu, 2, 0.99, 5)
+    scale = np.abs(r_ref).max()
+    assert np.abs(r[:, 1:] - r_ref[:, 1:512]).max() / scale < 1e-6
+    assert np.abs(r[:, 0].real - r_ref[:, 0].real).max() / scale < 1e-6
+    assert np.abs(r[:, 0].imag - r_ref[:, 512].real).max() / scale < 1e-6
+    # constant (zero) padding variant
+    y64 = o.griffin_lim(s, tu, 2, 0.99, n_fft, hop, pad_mode=o.PAD_CONSTANT, dtype=np.float64)
+    y, _, _, _ = emu.gl_from_mag(s, tu, 2, 0.99, 6, pad_mode=1)
+    assert rel_rms(y, y64) < 5e-7
+    # momentum 0 (classic Griffin-Lim)
+    y64 = o.griffin_lim(s, tu, 3, 0.0, n_fft, hop, dtype=np.float64)
+    y, _, _, _ = emu.gl_from_mag(s, tu, 3, 0.0, 6)
+    assert rel_rms(y, y64) < 5e-7
+    # seeded phase generator == oracle's phase_turns
+    y_seed, _, _, _ = emu.gl_from_mag(s, None, 1, 0.99, 6, seed=1)
+    y_expl, _, _, _ = emu.gl_from_mag(s, tu, 1, 0.99, 6)
+    assert rel_rms(y_seed, y_expl) < 1e-6

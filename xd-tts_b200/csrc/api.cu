@@ -1,0 +1,633 @@
+// C ABI of libxdtts_b200 (include/xdtts_b200.h): handles, plans, CUDA-graph capture, error
+// plumbing.  Host-side equivalent of what griffin_lim::GriffinLim owns in the reference
+// (/root/reference src/tacotron2/mod.rs:441-458 builds it, src/lib.rs:141 calls it).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <atomic>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/xdtts_b200.h"
+#include "gl_host.h"
+#include "gl_tables.h"
+
+namespace xdtts {
+cudaError_t gl_launch_lift(const float*, const float*, const int*, const int*, int, int, int, int, float, int, float*,
+                           float*, cudaStream_t);
+cudaError_t gl_launch_to_frame_major(const float*, const int*, const int*, int, int, int, float*, float*, cudaStream_t);
+cudaError_t gl_launch_finish(const float*, const int*, const int*, const long long*, const unsigned*, int, int, int, int,
+                             float*, cudaStream_t);
+std::atomic<unsigned long long> g_launches{0};
+}  // namespace xdtts
+
+using namespace xdtts;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string tl_error;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    tl_error = buf;
+    return code;
+}
+
+#define CU(expr)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (expr);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(e_ == cudaErrorMemoryAllocation ? XDTTS_ERR_OOM : XDTTS_ERR_CUDA, "%s: %s", #expr, \
+                        cudaGetErrorString(e_));                                                      \
+    } while (0)
+
+extern "C" const char* xdtts_last_error(void) { return tl_error.c_str(); }
+extern "C" unsigned long long xdtts_kernel_launches(void) { return g_launches.load(); }
+extern "C" const char* xdtts_version(void) { return "xdtts_b200 0.1.0 sm_100a"; }
+
+extern "C" void* xdtts_host_alloc(unsigned long long bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        fail(XDTTS_ERR_OOM, "cudaHostAlloc(%llu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void xdtts_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------ host math
+// Slaney mel scale (librosa hz_to_mel / mel_to_hz, htk=False)
+static double hz_to_mel(double f) {
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+    return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp;
+}
+static double mel_to_hz(double m) {
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+    return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+extern "C" int xdtts_mel_filter_bank(float sr, int n_fft, int n_mels, float fmin, float fmax, float* out) {
+    if (!out) return fail(XDTTS_ERR_BAD_ARG, "mel_filter_bank: out is null");
+    if (!(sr > 0.f) || n_fft < 2 || n_mels < 1 || !(fmin >= 0.f)) return fail(XDTTS_ERR_BAD_ARG, "mel_filter_bank: bad parameter");
+    const double hi = fmax < 0.f ? 0.5 * (double)sr : (double)fmax;
+    if (!(hi > (double)fmin)) return fail(XDTTS_ERR_BAD_ARG, "mel_filter_bank: fmax <= fmin");
+    const int K = n_fft / 2 + 1;
+    std::vector<double> mel_f(n_mels + 2);
+    const double m_lo = hz_to_mel(fmin), m_hi = hz_to_mel(hi);
+    for (int i = 0; i < n_mels + 2; i++) mel_f[i] = mel_to_hz(m_lo + (m_hi - m_lo) * (double)i / (double)(n_mels + 1));
+    for (int i = 0; i < n_mels; i++) {
+        const double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
+        for (int k = 0; k < K; k++) {
+            const double f = 0.5 * (double)sr * (double)k / (double)(K - 1);
+            const double lower = (f - mel_f[i]) / (mel_f[i + 1] - mel_f[i]);
+            const double upper = (mel_f[i + 2] - f) / (mel_f[i + 2] - mel_f[i + 1]);
+            const double w = std::fmax(0.0, std::fmin(lower, upper));
+            out[(size_t)i * K + k] = (float)(w * enorm);
+        }
+    }
+    return XDTTS_OK;
+}
+
+// Moore-Penrose pseudo-inverse of B [m][n] (m <= n typical) by one-sided Jacobi (Hestenes) on the
+// rows of B, fp64: G B = W with orthogonal rows, |w_i| = sigma_i, G orthogonal, hence
+// pinv(B) = sum_i w_i^T g_i / sigma_i^2 over sigma_i > rcond * sigma_max.  Replaces the MKL
+// lstsq/SVD the crate reaches through ndarray-linalg (Cargo.lock:1006).  out: [n][m].
+static void pinv_rows(const float* B, int m, int n, std::vector<double>* out) {
+    std::vector<double> W((size_t)m * n), G((size_t)m * m, 0.0);
+    for (size_t i = 0; i < (size_t)m * n; i++) W[i] = (double)B[i];
+    for (int i = 0; i < m; i++) G[(size_t)i * m + i] = 1.0;
+    for (int sweep = 0; sweep < 60; sweep++) {
+        double off = 0.0;
+        for (int p = 0; p < m - 1; p++)
+            for (int q = p + 1; q < m; q++) {
+                double* wp = &W[(size_t)p * n];
+                double* wq = &W[(size_t)q * n];
+                double a = 0, b = 0, c = 0;
+                for (int k = 0; k < n; k++) { a += wp[k] * wp[k]; b += wq[k] * wq[k]; c += wp[k] * wq[k]; }
+                if (c == 0.0 || std::fabs(c) <= 1e-17 * std::sqrt(a * b)) continue;
+                off = std::fmax(off, std::fabs(c) / std::sqrt(a * b));
+                const double zeta = (b - a) / (2.0 * c);
+                const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+                const double cs = 1.0 / std::sqrt(1.0 + t * t), sn = cs * t;
+                for (int k = 0; k < n; k++) {
+                    const double x = wp[k], y = wq[k];
+                    wp[k] = cs * x - sn * y;
+                    wq[k] = sn * x + cs * y;
+                }
+                double* gp = &G[(size_t)p * m];
+                double* gq = &G[(size_t)q * m];
+                for (int k = 0; k < m; k++) {
+                    const double x = gp[k], y = gq[k];
+                    gp[k] = cs * x - sn * y;
+                    gq[k] = sn * x + cs * y;
+                }
+            }
+        if (off < 1e-15) break;
+    }
+    std::vector<double> s2(m);
+    double smax2 = 0.0;
+    for (int i = 0; i < m; i++) {
+        double a = 0;
+        for (int k = 0; k < n; k++) a += W[(size_t)i * n + k] * W[(size_t)i * n + k];
+        s2[i] = a;
+        smax2 = std::fmax(smax2, a);
+    }
+    const double rcond = 1e-15 * (double)(m > n ? m : n);   // numpy.linalg.pinv default
+    out->assign((size_t)n * m, 0.0);
+    for (int i = 0; i < m; i++) {
+        if (!(s2[i] > rcond * rcond * smax2) || s2[i] == 0.0) continue;
+        const double inv = 1.0 / s2[i];
+        for (int k = 0; k < n; k++) {
+            const double wk = W[(size_t)i * n + k] * inv;
+            if (wk == 0.0) continue;
+            for (int j = 0; j < m; j++) (*out)[(size_t)k * m + j] += wk * G[(size_t)i * m + j];
+        }
+    }
+}
+
+extern "C" int xdtts_pinv(const float* a, int rows, int cols, float* out) {
+    if (!a || !out || rows < 1 || cols < 1) return fail(XDTTS_ERR_BAD_ARG, "pinv: bad argument");
+    std::vector<double> pv;
+    pinv_rows(a, rows, cols, &pv);
+    for (size_t i = 0; i < pv.size(); i++) out[i] = (float)pv[i];
+    return XDTTS_OK;
+}
+
+// ------------------------------------------------------------------ handle
+struct xdtts_gl {
+    int device = 0, n_mels = 0, K = 0, n_fft = 0, hop = 0, n_iter = 0, sm_count = 148;
+    float power = 1.f, momentum = 0.f;
+    xdtts_gl_opts opts{};
+    std::vector<float> pinv;        // [K][n_mels] host copy
+    float* d_pinvT = nullptr;       // [n_mels][K]
+    float2* d_tables = nullptr;
+    float* d_edge = nullptr;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::vector<xdtts_gl_plan*> cache;   // plans owned by the batch entry points
+};
+
+struct xdtts_gl_plan {
+    xdtts_gl* h = nullptr;
+    int B = 0, max_T = 0, total_T = 0, run_frames = 0;
+    std::vector<int> Ts, foff;
+    std::vector<long long> out_off;
+    long long out_total = 0;
+    std::vector<GlRun> runs;
+    // device
+    GlRun* d_runs = nullptr;
+    int *d_T = nullptr, *d_foff = nullptr;
+    long long* d_out_off = nullptr;
+    float *d_mel = nullptr, *d_in_mag = nullptr, *d_in_phase = nullptr, *d_turns = nullptr, *d_turns_nyq = nullptr;
+    float *d_S = nullptr, *d_S_nyq = nullptr, *d_y[2] = {nullptr, nullptr}, *d_halo = nullptr, *d_out = nullptr;
+    float2* d_R = nullptr;
+    unsigned *d_flags = nullptr, *d_amax = nullptr;
+    // pinned staging for pageable callers
+    float *h_in = nullptr, *h_out = nullptr;
+    size_t h_in_floats = 0;
+    cudaGraphExec_t graphs[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+extern "C" int xdtts_gl_create(const float* mel_basis, int n_mels, int K, int noverlap, float power, int n_iter,
+                               float momentum, const xdtts_gl_opts* opts, int device, xdtts_gl** out) {
+    if (!out) return fail(XDTTS_ERR_BAD_ARG, "gl_create: out is null");
+    *out = nullptr;
+    if (!mel_basis) return fail(XDTTS_ERR_BAD_ARG, "gl_create: mel_basis is null");
+    if (n_mels < 1 || K < 2) return fail(XDTTS_ERR_SHAPE, "gl_create: mel_basis must be [n_mels >= 1, K >= 2], got [%d, %d]", n_mels, K);
+    if (n_mels > 256) return fail(XDTTS_ERR_UNSUPPORTED, "gl_create: n_mels = %d > 256", n_mels);
+    const int n_fft = 2 * (K - 1);
+    if (n_fft != 512 && n_fft != 1024 && n_fft != 2048)
+        return fail(XDTTS_ERR_UNSUPPORTED, "gl_create: n_fft = 2*(K-1) = %d, supported: 512, 1024, 2048", n_fft);
+    if (noverlap < 0 || noverlap >= n_fft) return fail(XDTTS_ERR_BAD_ARG, "gl_create: noverlap = %d not in [0, n_fft = %d)", noverlap, n_fft);
+    const int hop = n_fft - noverlap;
+    if (hop * 4 != n_fft) return fail(XDTTS_ERR_UNSUPPORTED, "gl_create: hop = n_fft - noverlap = %d, the fused kernel needs hop == n_fft/4 = %d", hop, n_fft / 4);
+    if (!(power > 0.f) || !std::isfinite(power)) return fail(XDTTS_ERR_BAD_ARG, "gl_create: power must be finite and > 0");
+    if (n_iter < 0) return fail(XDTTS_ERR_BAD_ARG, "gl_create: iter must be >= 0");
+    if (!(momentum >= 0.f) || !std::isfinite(momentum)) return fail(XDTTS_ERR_BAD_ARG, "gl_create: momentum must be finite and >= 0");
+    for (size_t i = 0; i < (size_t)n_mels * K; i++)
+        if (!std::isfinite(mel_basis[i])) return fail(XDTTS_ERR_BAD_ARG, "gl_create: mel_basis has a non-finite entry");
+    if (opts && (opts->delog < 0 || opts->delog > 2 || opts->pad_mode < 0 || opts->pad_mode > 1 || opts->normalise < 0 ||
+                 opts->normalise > 1 || opts->run_frames < 0))
+        return fail(XDTTS_ERR_BAD_ARG, "gl_create: option out of range");
+
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(XDTTS_ERR_CUDA, "gl_create: no CUDA device (this library has no CPU path)");
+    }
+    if (device < 0 || device >= n_dev) return fail(XDTTS_ERR_BAD_ARG, "gl_create: device %d of %d", device, n_dev);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(XDTTS_ERR_CUDA, "gl_create: device %d is sm_%d%d, this library is built for sm_100a only", device, prop.major, prop.minor);
+    CU(cudaSetDevice(device));
+
+    xdtts_gl* h = new (std::nothrow) xdtts_gl();
+    if (!h) return fail(XDTTS_ERR_OOM, "gl_create: out of host memory");
+    h->device = device; h->n_mels = n_mels; h->K = K; h->n_fft = n_fft; h->hop = hop; h->n_iter = n_iter;
+    h->power = power; h->momentum = momentum; h->sm_count = prop.multiProcessorCount;
+    if (opts) h->opts = *opts;
+
+    std::vector<double> pv;
+    pinv_rows(mel_basis, n_mels, K, &pv);
+    h->pinv.resize((size_t)K * n_mels);
+    std::vector<float> pT((size_t)n_mels * K);
+    for (int k = 0; k < K; k++)
+        for (int m = 0; m < n_mels; m++) {
+            const float v = (float)pv[(size_t)k * n_mels + m];
+            h->pinv[(size_t)k * n_mels + m] = v;
+            pT[(size_t)m * K + k] = v;
+        }
+    std::vector<float2> tab = n_fft == 512 ? build_tables<4>() : (n_fft == 1024 ? build_tables<8>() : build_tables<16>());
+    std::vector<float> edge = build_edge_scale(n_fft);
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_pinvT, pT.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_tables, tab.size() * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_edge, edge.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_pinvT, pT.data(), pT.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_tables, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_edge, edge.data(), edge.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = gl_prepare(n_fft);
+    if (e != cudaSuccess) {
+        xdtts_gl_destroy(h);
+        return fail(e == cudaErrorMemoryAllocation ? XDTTS_ERR_OOM : XDTTS_ERR_CUDA, "gl_create: %s", cudaGetErrorString(e));
+    }
+    *out = h;
+    return XDTTS_OK;
+}
+
+extern "C" void xdtts_gl_destroy(xdtts_gl* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (xdtts_gl_plan* p : h->cache) xdtts_gl_plan_destroy(p);
+    cudaFree(h->d_pinvT);
+    cudaFree(h->d_tables);
+    cudaFree(h->d_edge);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int xdtts_gl_out_len(const xdtts_gl* h, int T) {
+    if (!h) return fail(XDTTS_ERR_BAD_ARG, "gl_out_len: handle is null");
+    if (T < 4) return fail(XDTTS_ERR_SHAPE, "gl_out_len: T = %d, need >= 4 frames (reflect padding of n_fft/2 needs hop*(T-1) > n_fft/2)", T);
+    return h->hop * (T - 1);
+}
+
+extern "C" int xdtts_gl_get_pinv(const xdtts_gl* h, float* out) {
+    if (!h || !out) return fail(XDTTS_ERR_BAD_ARG, "gl_get_pinv: null argument");
+    memcpy(out, h->pinv.data(), h->pinv.size() * 4);
+    return XDTTS_OK;
+}
+
+// ------------------------------------------------------------------ plan
+extern "C" void xdtts_gl_plan_destroy(xdtts_gl_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->h->device);
+    for (auto& g : p->graphs)
+        if (g) cudaGraphExecDestroy(g);
+    for (auto& e : p->ev)
+        if (e) cudaEventDestroy(e);
+    cudaFree(p->d_runs); cudaFree(p->d_T); cudaFree(p->d_foff); cudaFree(p->d_out_off);
+    cudaFree(p->d_mel); cudaFree(p->d_in_mag); cudaFree(p->d_in_phase); cudaFree(p->d_turns); cudaFree(p->d_turns_nyq);
+    cudaFree(p->d_S); cudaFree(p->d_S_nyq); cudaFree(p->d_y[0]); cudaFree(p->d_y[1]); cudaFree(p->d_halo);
+    cudaFree(p->d_out); cudaFree(p->d_R); cudaFree(p->d_flags); cudaFree(p->d_amax);
+    if (p->h_in) cudaFreeHost(p->h_in);
+    if (p->h_out) cudaFreeHost(p->h_out);
+    delete p;
+}
+
+static int plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out) {
+    *out = nullptr;
+    if (!Ts || B < 1) return fail(XDTTS_ERR_BAD_ARG, "plan: need B >= 1 utterances");
+    long long total = 0;
+    for (int b = 0; b < B; b++) {
+        if (Ts[b] < 4) return fail(XDTTS_ERR_SHAPE, "plan: utterance %d has T = %d frames, need >= 4", b, Ts[b]);
+        total += Ts[b];
+    }
+    if (total * (long long)(h->K - 1) >= (1ll << 31)) return fail(XDTTS_ERR_SHAPE, "plan: %lld frames in one batch is too many (split it)", total);
+    CU(cudaSetDevice(h->device));
+    xdtts_gl_plan* p = new (std::nothrow) xdtts_gl_plan();
+    if (!p) return fail(XDTTS_ERR_OOM, "plan: out of host memory");
+    p->h = h; p->B = B; p->Ts.assign(Ts, Ts + B); p->total_T = (int)total;
+    for (int b = 0; b < B; b++) p->max_T = Ts[b] > p->max_T ? Ts[b] : p->max_T;
+    // frames per run: about one resident wave of warps over the whole batch
+    int rf = h->opts.run_frames;
+    if (const char* env = getenv("XDTTS_GL_RUN_FRAMES")) rf = atoi(env);
+    if (rf <= 0) {
+        const long long resident = (long long)h->sm_count * gl_resident_warps_per_sm(h->n_fft);
+        rf = (int)((total + resident - 1) / resident);
+        if (rf < 8) rf = 8;
+        if (rf > 64) rf = 64;
+    }
+    if (rf < 4) rf = 4;
+    p->run_frames = rf;
+    build_runs(Ts, B, rf, &p->runs, &p->foff);
+    p->out_off.resize(B);
+    for (int b = 0; b < B; b++) {
+        p->out_off[b] = p->out_total;
+        p->out_total += (long long)h->hop * (Ts[b] - 1);
+    }
+    const size_t M = (size_t)h->K - 1, H = (size_t)h->hop, TT = (size_t)total, nr = p->runs.size();
+    cudaError_t e = cudaSuccess;
+#define ALLOC(ptr, bytes) if (e == cudaSuccess) e = cudaMalloc((void**)&(ptr), (bytes))
+    ALLOC(p->d_runs, nr * sizeof(GlRun));
+    ALLOC(p->d_T, B * sizeof(int));
+    ALLOC(p->d_foff, B * sizeof(int));
+    ALLOC(p->d_out_off, B * sizeof(long long));
+    ALLOC(p->d_S, TT * M * 4);
+    ALLOC(p->d_S_nyq, TT * 4);
+    ALLOC(p->d_R, TT * M * sizeof(float2));
+    ALLOC(p->d_y[0], TT * H * 4);
+    ALLOC(p->d_y[1], TT * H * 4);
+    ALLOC(p->d_halo, nr * 6 * H * 4);
+    ALLOC(p->d_flags, nr * sizeof(unsigned));
+    ALLOC(p->d_amax, B * sizeof(unsigned));
+    ALLOC(p->d_out, (size_t)p->out_total * 4);
+#undef ALLOC
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_runs, p->runs.data(), nr * sizeof(GlRun), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_T, Ts, B * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_foff, p->foff.data(), B * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_out_off, p->out_off.data(), B * sizeof(long long), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(p->d_flags, 0, nr * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(p->d_R, 0, TT * M * sizeof(float2));
+    for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&p->ev[i]);
+    if (e != cudaSuccess) {
+        xdtts_gl_plan_destroy(p);
+        return fail(e == cudaErrorMemoryAllocation ? XDTTS_ERR_OOM : XDTTS_ERR_CUDA, "plan: %s", cudaGetErrorString(e));
+    }
+    *out = p;
+    return XDTTS_OK;
+}
+
+extern "C" int xdtts_gl_plan_create(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out) {
+    if (!h || !out) return fail(XDTTS_ERR_BAD_ARG, "plan_create: null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    return plan_build(h, Ts, B, out);
+}
+
+extern "C" int xdtts_gl_plan_info(const xdtts_gl_plan* p, int* info4) {
+    if (!p || !info4) return fail(XDTTS_ERR_BAD_ARG, "plan_info: null argument");
+    info4[0] = (int)p->runs.size();
+    info4[1] = p->run_frames;
+    info4[2] = ((int)p->runs.size() + gl_warps_per_cta() - 1) / gl_warps_per_cta();
+    info4[3] = p->total_T;
+    return XDTTS_OK;
+}
+
+static int plan_upload_locked(xdtts_gl_plan* p, int kind, const float* const* srcs) {
+    xdtts_gl* h = p->h;
+    if (!srcs) return fail(XDTTS_ERR_BAD_ARG, "plan_upload: srcs is null");
+    if (kind < 0 || kind > 2) return fail(XDTTS_ERR_BAD_ARG, "plan_upload: kind %d", kind);
+    for (int b = 0; b < p->B; b++)
+        if (!srcs[b]) return fail(XDTTS_ERR_BAD_ARG, "plan_upload: srcs[%d] is null", b);
+    CU(cudaSetDevice(h->device));
+    const size_t rows = kind == 0 ? (size_t)h->n_mels : (size_t)h->K;
+    float** dst = kind == 0 ? &p->d_mel : (kind == 1 ? &p->d_in_mag : &p->d_in_phase);
+    if (!*dst) CU(cudaMalloc((void**)dst, rows * (size_t)p->total_T * 4));
+    if (kind == 2 && !p->d_turns) {
+        CU(cudaMalloc((void**)&p->d_turns, (size_t)p->total_T * (h->K - 1) * 4));
+        CU(cudaMalloc((void**)&p->d_turns_nyq, (size_t)p->total_T * 4));
+    }
+    // pageable sources go through one pinned staging buffer so that the copy is a single async DMA
+    bool all_pinned = true;
+    for (int b = 0; b < p->B; b++) all_pinned = all_pinned && is_pinned(srcs[b]);
+    if (!all_pinned) {
+        const size_t need = rows * (size_t)p->total_T;
+        if (p->h_in_floats < need) {
+            if (p->h_in) cudaFreeHost(p->h_in);
+            p->h_in = nullptr; p->h_in_floats = 0;
+            CU(cudaHostAlloc((void**)&p->h_in, need * 4, cudaHostAllocDefault));
+            p->h_in_floats = need;
+        }
+        for (int b = 0; b < p->B; b++)
+            memcpy(p->h_in + rows * (size_t)p->foff[b], srcs[b], rows * (size_t)p->Ts[b] * 4);
+        CU(cudaMemcpyAsync(*dst, p->h_in, need * 4, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));   // the staging buffer is reused by the next upload
+    } else {
+        for (int b = 0; b < p->B; b++)
+            CU(cudaMemcpyAsync(*dst + rows * (size_t)p->foff[b], srcs[b], rows * (size_t)p->Ts[b] * 4, cudaMemcpyHostToDevice, h->stream));
+    }
+    return XDTTS_OK;
+}
+
+extern "C" int xdtts_gl_plan_upload(xdtts_gl_plan* p, int kind, const float* const* srcs) {
+    if (!p) return fail(XDTTS_ERR_BAD_ARG, "plan_upload: plan is null");
+    std::lock_guard<std::mutex> lk(p->h->mu);
+    return plan_upload_locked(p, kind, srcs);
+}
+
+// enqueue the whole pass on the handle's stream; ev[1]/ev[2] bracket the steady-state launches when timed
+static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid) {
+    xdtts_gl* h = p->h;
+    cudaStream_t s = h->stream;
+    const int M = h->K - 1;
+    const bool from_mag = flags & XDTTS_RUN_FROM_MAG, use_phase = flags & XDTTS_RUN_USE_PHASE;
+    CU(cudaMemsetAsync(p->d_amax, 0, p->B * sizeof(unsigned), s));
+    if (from_mag) {
+        CU(gl_launch_to_frame_major(p->d_in_mag, p->d_T, p->d_foff, p->B, p->max_T, h->K, p->d_S, p->d_S_nyq, s));
+    } else {
+        CU(gl_launch_lift(p->d_mel, h->d_pinvT, p->d_T, p->d_foff, p->B, p->max_T, h->n_mels, h->K, h->power, h->opts.delog, p->d_S, p->d_S_nyq, s));
+    }
+    g_launches++;
+    if (use_phase) {
+        CU(gl_launch_to_frame_major(p->d_in_phase, p->d_T, p->d_foff, p->B, p->max_T, h->K, p->d_turns, p->d_turns_nyq, s));
+        g_launches++;
+    }
+    GlParams gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.n_runs = (int)p->runs.size();
+    gp.runs = p->d_runs; gp.utt_T = p->d_T; gp.utt_foff = p->d_foff;
+    gp.S = p->d_S; gp.S_nyq = p->d_S_nyq; gp.R = p->d_R; gp.halo = p->d_halo; gp.flags = p->d_flags; gp.amax = p->d_amax;
+    gp.edge_scale = h->d_edge; gp.tables = h->d_tables;
+    gp.turns = use_phase ? p->d_turns : nullptr; gp.turns_nyq = use_phase ? p->d_turns_nyq : nullptr;
+    gp.seed = h->opts.seed; gp.utt_seed_base = 0;
+    gp.alpha = h->momentum / (1.0f + h->momentum);
+    gp.inv_n = 1.0f / (float)h->n_fft;
+    gp.pad_mode = h->opts.pad_mode;
+    (void)M;
+    gp.y_in = p->d_y[1]; gp.y_out = p->d_y[0];
+    CU(gl_launch_iteration(h->n_fft, GL_MODE_INIT, h->n_iter == 0, gp, s));
+    g_launches++;
+    int mids = 0;
+    for (int it = 1; it <= h->n_iter; it++) {
+        gp.y_in = p->d_y[(it - 1) & 1];
+        gp.y_out = p->d_y[it & 1];
+        const bool last = it == h->n_iter;
+        if (timed && it == 2) CU(cudaEventRecord(p->ev[1], s));
+        CU(gl_launch_iteration(h->n_fft, it == 1 ? GL_MODE_FIRST : GL_MODE_MID, last, gp, s));
+        g_launches++;
+        if (it >= 2 && !last) mids++;
+        if (timed && it == h->n_iter - 1 && it >= 2) CU(cudaEventRecord(p->ev[2], s));
+    }
+    CU(gl_launch_finish(p->d_y[h->n_iter & 1], p->d_T, p->d_foff, p->d_out_off, p->d_amax, p->B, p->max_T, h->hop,
+                        h->opts.normalise == 0, p->d_out, s));
+    g_launches++;
+    if (n_mid) *n_mid = mids;
+    return XDTTS_OK;
+}
+
+static int plan_run_locked(xdtts_gl_plan* p, int flags, float* ms_total, float* ms_iter, int* n_iter_launches) {
+    xdtts_gl* h = p->h;
+    CU(cudaSetDevice(h->device));
+    if ((flags & XDTTS_RUN_FROM_MAG) && !p->d_in_mag) return fail(XDTTS_ERR_BAD_ARG, "plan_run: FROM_MAG without uploaded magnitudes");
+    if (!(flags & XDTTS_RUN_FROM_MAG) && !p->d_mel) return fail(XDTTS_ERR_BAD_ARG, "plan_run: no mels uploaded");
+    if ((flags & XDTTS_RUN_USE_PHASE) && !p->d_in_phase) return fail(XDTTS_ERR_BAD_ARG, "plan_run: USE_PHASE without uploaded phase");
+    cudaStream_t s = h->stream;
+    int mids = 0;
+    if (ms_iter) *ms_iter = 0.f;
+    if (n_iter_launches) *n_iter_launches = 0;
+    if (flags & XDTTS_RUN_NO_GRAPH) {
+        CU(cudaEventRecord(p->ev[0], s));
+        int rc = plan_enqueue(p, flags, true, &mids);
+        if (rc) return rc;
+        CU(cudaEventRecord(p->ev[3], s));
+        CU(cudaStreamSynchronize(s));
+        if (ms_iter && mids > 0) CU(cudaEventElapsedTime(ms_iter, p->ev[1], p->ev[2]));
+        if (n_iter_launches) *n_iter_launches = mids;
+    } else {
+        const int gi = flags & 3;
+        if (!p->graphs[gi]) {
+            cudaGraph_t g = nullptr;
+            CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            const unsigned long long before = g_launches.load();
+            int rc = plan_enqueue(p, flags, false, nullptr);
+            g_launches = before;   // captured, not launched
+            cudaError_t e = cudaStreamEndCapture(s, &g);
+            if (rc) {
+                if (g) cudaGraphDestroy(g);
+                return rc;
+            }
+            if (e != cudaSuccess) return fail(XDTTS_ERR_CUDA, "plan_run: graph capture: %s", cudaGetErrorString(e));
+            e = cudaGraphInstantiate(&p->graphs[gi], g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) return fail(XDTTS_ERR_CUDA, "plan_run: graph instantiate: %s", cudaGetErrorString(e));
+        }
+        CU(cudaEventRecord(p->ev[0], s));
+        CU(cudaGraphLaunch(p->graphs[gi], s));
+        g_launches += (unsigned long long)(h->n_iter + 3 + ((flags & XDTTS_RUN_USE_PHASE) ? 1 : 0));
+        CU(cudaEventRecord(p->ev[3], s));
+        CU(cudaStreamSynchronize(s));
+    }
+    if (ms_total) CU(cudaEventElapsedTime(ms_total, p->ev[0], p->ev[3]));
+    return XDTTS_OK;
+}
+
+extern "C" int xdtts_gl_plan_run(xdtts_gl_plan* p, int flags, float* ms_total, float* ms_iter, int* n_iter_launches) {
+    if (!p) return fail(XDTTS_ERR_BAD_ARG, "plan_run: plan is null");
+    std::lock_guard<std::mutex> lk(p->h->mu);
+    return plan_run_locked(p, flags, ms_total, ms_iter, n_iter_launches);
+}
+
+static int plan_download_locked(xdtts_gl_plan* p, float* const* outs) {
+    xdtts_gl* h = p->h;
+    if (!outs) return fail(XDTTS_ERR_BAD_ARG, "plan_download: outs is null");
+    for (int b = 0; b < p->B; b++)
+        if (!outs[b]) return fail(XDTTS_ERR_BAD_ARG, "plan_download: outs[%d] is null", b);
+    CU(cudaSetDevice(h->device));
+    bool all_pinned = true;
+    for (int b = 0; b < p->B; b++) all_pinned = all_pinned && is_pinned(outs[b]);
+    if (all_pinned) {
+        for (int b = 0; b < p->B; b++)
+            CU(cudaMemcpyAsync(outs[b], p->d_out + p->out_off[b], (size_t)h->hop * (p->Ts[b] - 1) * 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    } else {
+        if (!p->h_out) CU(cudaHostAlloc((void**)&p->h_out, (size_t)p->out_total * 4, cudaHostAllocDefault));
+        CU(cudaMemcpyAsync(p->h_out, p->d_out, (size_t)p->out_total * 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (int b = 0; b < p->B; b++) memcpy(outs[b], p->h_out + p->out_off[b], (size_t)h->hop * (p->Ts[b] - 1) * 4);
+    }
+    return XDTTS_OK;
+}
+
+extern "C" int xdtts_gl_plan_download(xdtts_gl_plan* p, float* const* outs) {
+    if (!p) return fail(XDTTS_ERR_BAD_ARG, "plan_download: plan is null");
+    std::lock_guard<std::mutex> lk(p->h->mu);
+    return plan_download_locked(p, outs);
+}
+
+extern "C" int xdtts_gl_plan_peek(xdtts_gl_plan* p, int what, float* out, long long n_floats) {
+    if (!p || !out) return fail(XDTTS_ERR_BAD_ARG, "plan_peek: null argument");
+    std::lock_guard<std::mutex> lk(p->h->mu);
+    const long long M = p->h->K - 1, TT = p->total_T;
+    const void* src = what == 0 ? (const void*)p->d_S : (what == 1 ? (const void*)p->d_S_nyq : (const void*)p->d_R);
+    const long long n = what == 0 ? TT * M : (what == 1 ? TT : TT * M * 2);
+    if (what < 0 || what > 2 || n != n_floats) return fail(XDTTS_ERR_SHAPE, "plan_peek: what=%d expects %lld floats, got %lld", what, n, n_floats);
+    CU(cudaSetDevice(p->h->device));
+    CU(cudaStreamSynchronize(p->h->stream));
+    CU(cudaMemcpy(out, src, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return XDTTS_OK;
+}
+
+// ------------------------------------------------------------------ batch entry points
+static int batch_common(xdtts_gl* h, int kind, const float* const* ins, const int* Ts, int B,
+                        const float* const* phases, float* const* outs) {
+    if (!h) return fail(XDTTS_ERR_BAD_ARG, "infer: handle is null");
+    if (!ins || !Ts || !outs) return fail(XDTTS_ERR_BAD_ARG, "infer: null argument");
+    if (B < 1) return fail(XDTTS_ERR_BAD_ARG, "infer: B = %d", B);
+    std::lock_guard<std::mutex> lk(h->mu);
+    xdtts_gl_plan* p = nullptr;
+    for (xdtts_gl_plan* c : h->cache)
+        if (c->B == B && memcmp(c->Ts.data(), Ts, sizeof(int) * B) == 0) p = c;
+    if (!p) {
+        if (h->cache.size() >= 4) {   // small FIFO of shapes; buffers are large
+            xdtts_gl_plan_destroy(h->cache.front());
+            h->cache.erase(h->cache.begin());
+        }
+        int rc = plan_build(h, Ts, B, &p);
+        if (rc) return rc;
+        h->cache.push_back(p);
+    }
+    int rc = plan_upload_locked(p, kind, ins);
+    if (rc) return rc;
+    int flags = kind == 1 ? XDTTS_RUN_FROM_MAG : 0;
+    if (phases) {
+        rc = plan_upload_locked(p, 2, phases);
+        if (rc) return rc;
+        flags |= XDTTS_RUN_USE_PHASE;
+    }
+    rc = plan_run_locked(p, flags, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    return plan_download_locked(p, outs);
+}
+
+extern "C" int xdtts_gl_infer_batch(xdtts_gl* h, const float* const* mels, const int* Ts, int B,
+                                    const float* const* init_phases, float* const* outs) {
+    return batch_common(h, 0, mels, Ts, B, init_phases, outs);
+}
+
+extern "C" int xdtts_gl_from_mag_batch(xdtts_gl* h, const float* const* mags, const int* Ts, int B,
+                                       const float* const* init_phases, float* const* outs) {
+    return batch_common(h, 1, mags, Ts, B, init_phases, outs);
+}
+
+extern "C" int xdtts_gl_infer(xdtts_gl* h, const float* mel, int T, const float* init_phase, float* out, int out_len) {
+    if (!h) return fail(XDTTS_ERR_BAD_ARG, "infer: handle is null");
+    if (!mel || !out) return fail(XDTTS_ERR_BAD_ARG, "infer: null argument");
+    if (T < 4) return fail(XDTTS_ERR_SHAPE, "infer: T = %d, need >= 4 frames", T);
+    if (out_len != h->hop * (T - 1)) return fail(XDTTS_ERR_SHAPE, "infer: out_len = %d, expected hop*(T-1) = %d", out_len, h->hop * (T - 1));
+    const float* mels[1] = {mel};
+    const float* ph[1] = {init_phase};
+    float* outs[1] = {out};
+    return batch_common(h, 0, mels, &T, 1, init_phase ? ph : nullptr, outs);
+}

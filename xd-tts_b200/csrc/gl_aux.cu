@@ -1,0 +1,146 @@
+// Kernels either side of the Griffin-Lim iteration loop (all HBM-bound, one pass each):
+//   * mel -> linear lift   S = max(0, pinv(basis) . delog(mel)) ^ power     (step 1 of
+//     griffin_lim::GriffinLim::infer; the reference's call site is
+//     /root/reference src/lib.rs:141, its parameters come from src/tacotron2/mod.rs:453-456)
+//   * [K,T] row-major (the reference's ndarray layout) -> frame-major [T][M] + Nyquist column
+//   * peak normalisation of the final waveform (row a8; the caller scales by i16::MAX,
+//     src/lib.rs:153-155)
+#include <cuda_runtime.h>
+
+#include "gl_host.h"
+
+namespace xdtts {
+
+// ---------------------------------------------------------------- lift
+// grid (ceil(K/128), ceil(maxT/16), n_utt); thread <-> bin k, 16 frames per block.
+// Accumulates in fp64: the pseudo-inverse has 36% negative entries, an fp32 sum
+// loses ~1e-3 relative to cancellation; 2.6 GFLOP per 32x1000 batch is noise next to the loop.
+constexpr int LIFT_TT = 16;
+constexpr int LIFT_MAX_MELS = 256;
+
+__global__ void __launch_bounds__(128) gl_lift_kernel(const float* __restrict__ mel_arena, const float* __restrict__ pinvT,
+                                                      const int* __restrict__ utt_T, const int* __restrict__ utt_foff,
+                                                      int n_mels, int K, float power, int delog, float* __restrict__ S,
+                                                      float* __restrict__ S_nyq) {
+    __shared__ float e[LIFT_MAX_MELS * LIFT_TT];
+    const int u = blockIdx.z;
+    const int T = utt_T[u];
+    const int t0 = blockIdx.y * LIFT_TT;
+    if (t0 >= T) return;
+    const long foff = utt_foff[u];
+    const float* mel = mel_arena + foff * n_mels;   // [n_mels][T] row-major, as the caller passed it
+    for (int i = threadIdx.x; i < n_mels * LIFT_TT; i += 128) {
+        const int m = i / LIFT_TT, tt = i % LIFT_TT;
+        float v = 0.f;
+        if (t0 + tt < T) {
+            v = mel[(long)m * T + t0 + tt];
+            v = delog == 0 ? expf(v) : (delog == 1 ? powf(10.f, v) : v);
+        }
+        e[i] = v;
+    }
+    __syncthreads();
+    const int k = blockIdx.x * 128 + threadIdx.x;
+    if (k >= K) return;
+    double acc[LIFT_TT];
+#pragma unroll
+    for (int tt = 0; tt < LIFT_TT; tt++) acc[tt] = 0.0;
+    for (int m = 0; m < n_mels; m++) {
+        const double a = (double)pinvT[(long)m * K + k];
+        const float4* er = reinterpret_cast<const float4*>(e + m * LIFT_TT);
+#pragma unroll
+        for (int q = 0; q < LIFT_TT / 4; q++) {
+            const float4 x = er[q];
+            acc[4 * q + 0] += a * (double)x.x;
+            acc[4 * q + 1] += a * (double)x.y;
+            acc[4 * q + 2] += a * (double)x.z;
+            acc[4 * q + 3] += a * (double)x.w;
+        }
+    }
+    const int M = K - 1;
+#pragma unroll
+    for (int tt = 0; tt < LIFT_TT; tt++) {
+        if (t0 + tt >= T) break;
+        float s = (float)acc[tt];
+        s = s > 0.f ? (power == 1.0f ? s : powf(s, power)) : 0.f;
+        if (k < M) S[(foff + t0 + tt) * M + k] = s;
+        else S_nyq[foff + t0 + tt] = s;
+    }
+}
+
+cudaError_t gl_launch_lift(const float* mel_arena, const float* pinvT, const int* utt_T, const int* utt_foff, int n_utt,
+                           int max_T, int n_mels, int K, float power, int delog, float* S, float* S_nyq, cudaStream_t s) {
+    if (n_mels > LIFT_MAX_MELS) return cudaErrorInvalidValue;
+    dim3 grid((K + 127) / 128, (max_T + LIFT_TT - 1) / LIFT_TT, n_utt);
+    gl_lift_kernel<<<grid, 128, 0, s>>>(mel_arena, pinvT, utt_T, utt_foff, n_mels, K, power, delog, S, S_nyq);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- [K,T] -> frame-major
+// src arena: utterance u is a row-major [K][T_u] block at float offset foff[u]*K.
+__global__ void __launch_bounds__(256) gl_to_frame_major_kernel(const float* __restrict__ src_arena,
+                                                                const int* __restrict__ utt_T,
+                                                                const int* __restrict__ utt_foff, int K,
+                                                                float* __restrict__ dst, float* __restrict__ dst_nyq) {
+    __shared__ float tile[32][33];
+    const int u = blockIdx.z;
+    const int T = utt_T[u];
+    const int t0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+    if (t0 >= T) return;
+    const long foff = utt_foff[u];
+    const float* src = src_arena + foff * K;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int k = k0 + r, t = t0 + tx;
+        tile[r][tx] = (k < K && t < T) ? src[(long)k * T + t] : 0.f;
+    }
+    __syncthreads();
+    const int M = K - 1;
+    for (int r = ty; r < 32; r += 8) {
+        const int t = t0 + r, k = k0 + tx;
+        if (t < T && k < K) {
+            if (k < M) dst[(foff + t) * M + k] = tile[tx][r];
+            else dst_nyq[foff + t] = tile[tx][r];
+        }
+    }
+}
+
+cudaError_t gl_launch_to_frame_major(const float* src_arena, const int* utt_T, const int* utt_foff, int n_utt, int max_T,
+                                     int K, float* dst, float* dst_nyq, cudaStream_t s) {
+    dim3 grid((K + 31) / 32, (max_T + 31) / 32, n_utt);
+    gl_to_frame_major_kernel<<<grid, 256, 0, s>>>(src_arena, utt_T, utt_foff, K, dst, dst_nyq);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- finish
+// out arena: utterance u holds hop*(T_u-1) samples at out_off[u]; y holds them at foff[u]*hop.
+__global__ void __launch_bounds__(256) gl_finish_kernel(const float* __restrict__ y, const int* __restrict__ utt_T,
+                                                        const int* __restrict__ utt_foff,
+                                                        const long long* __restrict__ out_off,
+                                                        const unsigned* __restrict__ amax, int hop, int normalise,
+                                                        float* __restrict__ out) {
+    const int u = blockIdx.y;
+    const long len = (long)hop * (utt_T[u] - 1);
+    const float* src = y + (long)utt_foff[u] * hop;
+    float* dst = out + out_off[u];
+    const float m = __uint_as_float(amax[u]);
+    const bool norm = normalise && m > 0.f;
+    // 4 samples per thread; both offsets are multiples of hop (>= 128) so float4 is aligned
+    for (long i = ((long)blockIdx.x * 256 + threadIdx.x) * 4; i < len; i += (long)gridDim.x * 256 * 4) {
+        float4 v = *reinterpret_cast<const float4*>(src + i);
+        if (norm) { v.x /= m; v.y /= m; v.z /= m; v.w /= m; }
+        *reinterpret_cast<float4*>(dst + i) = v;
+    }
+}
+
+cudaError_t gl_launch_finish(const float* y, const int* utt_T, const int* utt_foff, const long long* out_off,
+                             const unsigned* amax, int n_utt, int max_T, int hop, int normalise, float* out,
+                             cudaStream_t s) {
+    int gx = (int)(((long)hop * max_T / 4 + 255) / 256);
+    if (gx > 64) gx = 64;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, n_utt);
+    gl_finish_kernel<<<grid, 256, 0, s>>>(y, utt_T, utt_foff, out_off, amax, hop, normalise, out);
+    return cudaGetLastError();
+}
+
+}  // namespace xdtts

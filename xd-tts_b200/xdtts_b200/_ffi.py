@@ -1,0 +1,106 @@
+"""ctypes binding of include/xdtts_b200.h (the same symbols a Rust/cgo/JNI shim would bind)."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libxdtts_b200.so")
+
+OK, ERR_BAD_ARG, ERR_SHAPE, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+RUN_FROM_MAG, RUN_USE_PHASE, RUN_NO_GRAPH = 1, 2, 4
+
+_CODE_NAMES = {
+    ERR_BAD_ARG: "BAD_ARG", ERR_SHAPE: "SHAPE", ERR_CUDA: "CUDA", ERR_OOM: "OOM", ERR_UNSUPPORTED: "UNSUPPORTED",
+}
+
+
+class XdttsError(RuntimeError):
+    """Raised for every non-zero return of the C ABI (the shim's anyhow::bail!)."""
+
+    def __init__(self, code, message):
+        super().__init__("xdtts_b200 error %s (%d): %s" % (_CODE_NAMES.get(code, "?"), code, message))
+        self.code = code
+        self.message = message
+
+
+class GlOpts(ctypes.Structure):
+    _fields_ = [
+        ("delog", ctypes.c_int),
+        ("pad_mode", ctypes.c_int),
+        ("normalise", ctypes.c_int),
+        ("run_frames", ctypes.c_int),
+        ("seed", ctypes.c_ulonglong),
+    ]
+
+
+_fp = ctypes.POINTER(ctypes.c_float)
+_fpp = ctypes.POINTER(_fp)
+_ip = ctypes.POINTER(ctypes.c_int)
+_vp = ctypes.c_void_p
+
+# every symbol include/xdtts_b200.h declares: (restype, argtypes)
+SIGNATURES = {
+    "xdtts_mel_filter_bank": (ctypes.c_int, [ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, _fp]),
+    "xdtts_pinv": (ctypes.c_int, [_fp, ctypes.c_int, ctypes.c_int, _fp]),
+    "xdtts_gl_create": (ctypes.c_int, [_fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
+                                       ctypes.c_float, ctypes.POINTER(GlOpts), ctypes.c_int, ctypes.POINTER(_vp)]),
+    "xdtts_gl_destroy": (None, [_vp]),
+    "xdtts_gl_out_len": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "xdtts_gl_get_pinv": (ctypes.c_int, [_vp, _fp]),
+    "xdtts_gl_infer": (ctypes.c_int, [_vp, _fp, ctypes.c_int, _fp, _fp, ctypes.c_int]),
+    "xdtts_gl_infer_batch": (ctypes.c_int, [_vp, _fpp, _ip, ctypes.c_int, _fpp, _fpp]),
+    "xdtts_gl_from_mag_batch": (ctypes.c_int, [_vp, _fpp, _ip, ctypes.c_int, _fpp, _fpp]),
+    "xdtts_gl_plan_create": (ctypes.c_int, [_vp, _ip, ctypes.c_int, ctypes.POINTER(_vp)]),
+    "xdtts_gl_plan_destroy": (None, [_vp]),
+    "xdtts_gl_plan_upload": (ctypes.c_int, [_vp, ctypes.c_int, _fpp]),
+    "xdtts_gl_plan_run": (ctypes.c_int, [_vp, ctypes.c_int, _fp, _fp, _ip]),
+    "xdtts_gl_plan_download": (ctypes.c_int, [_vp, _fpp]),
+    "xdtts_gl_plan_peek": (ctypes.c_int, [_vp, ctypes.c_int, _fp, ctypes.c_longlong]),
+    "xdtts_gl_plan_info": (ctypes.c_int, [_vp, _ip]),
+    "xdtts_host_alloc": (_vp, [ctypes.c_ulonglong]),
+    "xdtts_host_free": (None, [_vp]),
+    "xdtts_last_error": (ctypes.c_char_p, []),
+    "xdtts_kernel_launches": (ctypes.c_ulonglong, []),
+    "xdtts_version": (ctypes.c_char_p, []),
+}
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree CUDA library; fails loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "%s is missing: run `python __graft_entry__.py` (nvcc, sm_100a) first; there is no CPU fallback" % LIB_PATH
+            )
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise XdttsError(rc, load_library().xdtts_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+def version():
+    return load_library().xdtts_version().decode()
+
+
+def fptr(a):
+    return a.ctypes.data_as(_fp)
+
+
+def fptr_array(arrays):
+    arr = (_fp * len(arrays))()
+    for i, a in enumerate(arrays):
+        arr[i] = fptr(a)
+    return arr

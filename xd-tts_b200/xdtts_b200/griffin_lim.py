@@ -1,0 +1,192 @@
+"""Mirror of the `griffin_lim` crate surface that xd-tts uses (external crate griffin-lim 0.2.0,
+call sites /root/reference src/tacotron2/mod.rs:67-68,453,456 and src/lib.rs:5,35,51,141):
+
+    griffin_lim::mel::create_mel_filter_bank(f32, usize, usize, f32, Option<f32>) -> Array2<f32>
+    griffin_lim::GriffinLim::new(Array2<f32>, usize, f32, usize, f32) -> Result<GriffinLim>
+    GriffinLim::infer(&self, &Array2<f32>) -> Result<samples>
+
+plus the batch / device-plan entry points the B200 back end adds.  Shapes and argument order are
+the reference's; errors surface as XdttsError (anyhow::Error in the Rust shim).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import GlOpts, XdttsError, check, fptr, fptr_array, load_library
+
+DELOG_EXP, DELOG_POW10, DELOG_NONE = 0, 1, 2
+PAD_REFLECT, PAD_CONSTANT = 0, 1
+NORM_PEAK, NORM_NONE = 0, 1
+
+
+class mel:  # noqa: N801  (module-like namespace, as in griffin_lim::mel)
+    @staticmethod
+    def create_mel_filter_bank(sample_rate, n_fft, n_mels, fmin, fmax=None):
+        """[n_mels, n_fft//2+1] float32 Slaney filterbank (call site src/tacotron2/mod.rs:453)."""
+        lib = load_library()
+        out = np.empty((int(n_mels), int(n_fft) // 2 + 1), dtype=np.float32)
+        check(lib.xdtts_mel_filter_bank(float(sample_rate), int(n_fft), int(n_mels), float(fmin),
+                                        -1.0 if fmax is None else float(fmax), fptr(out)))
+        return out
+
+
+def pinv(a):
+    """Pseudo-inverse [cols, rows] of a row-major float32 matrix, as the lift uses it."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    out = np.empty((a.shape[1], a.shape[0]), dtype=np.float32)
+    check(load_library().xdtts_pinv(fptr(a), a.shape[0], a.shape[1], fptr(out)))
+    return out
+
+
+def _as_f32_2d(a, rows, what):
+    a = np.ascontiguousarray(a, dtype=np.float32)   # the shim's as_standard_layout()
+    if a.ndim != 2 or a.shape[0] != rows:
+        raise XdttsError(_ffi.ERR_SHAPE, "%s must be [%d, T], got %s" % (what, rows, a.shape))
+    return a
+
+
+class GriffinLim:
+    """Owns the device-side vocoder state (pseudo-inverse, twiddles, cached plans)."""
+
+    def __init__(self, handle, n_mels, k_bins, hop, n_iter):
+        self._h = handle
+        self.n_mels, self.k_bins, self.hop, self.n_iter = n_mels, k_bins, hop, n_iter
+
+    @classmethod
+    def new(cls, mel_basis, noverlap, power, iter, momentum, *, delog=DELOG_EXP, pad_mode=PAD_REFLECT,  # noqa: A002
+            normalise=NORM_PEAK, seed=0, run_frames=0, device=0):
+        """GriffinLim::new(mel_basis, noverlap, power, iter, momentum) (src/tacotron2/mod.rs:456)."""
+        lib = load_library()
+        basis = np.ascontiguousarray(mel_basis, dtype=np.float32)
+        if basis.ndim != 2:
+            raise XdttsError(_ffi.ERR_SHAPE, "mel_basis must be 2-D [n_mels, K]")
+        opts = GlOpts(int(delog), int(pad_mode), int(normalise), int(run_frames), int(seed))
+        h = ctypes.c_void_p()
+        check(lib.xdtts_gl_create(fptr(basis), basis.shape[0], basis.shape[1], int(noverlap), float(power), int(iter),
+                                  float(momentum), ctypes.byref(opts), int(device), ctypes.byref(h)))
+        n_fft = 2 * (basis.shape[1] - 1)
+        return cls(h, basis.shape[0], basis.shape[1], n_fft - int(noverlap), int(iter))
+
+    def close(self):
+        if self._h:
+            load_library().xdtts_gl_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def out_len(self, n_frames):
+        rc = load_library().xdtts_gl_out_len(self._h, int(n_frames))
+        if rc < 0:
+            check(rc)
+        return rc
+
+    def pinv(self):
+        out = np.empty((self.k_bins, self.n_mels), dtype=np.float32)
+        check(load_library().xdtts_gl_get_pinv(self._h, fptr(out)))
+        return out
+
+    def infer(self, mel_spectrogram, init_phase=None):
+        """GriffinLim::infer(&mel) (src/lib.rs:141): [n_mels, T] -> float32 samples [hop*(T-1)]."""
+        lib = load_library()
+        m = _as_f32_2d(mel_spectrogram, self.n_mels, "mel")
+        t = m.shape[1]
+        ph = None if init_phase is None else _as_f32_2d(init_phase, self.k_bins, "init_phase")
+        if ph is not None and ph.shape[1] != t:
+            raise XdttsError(_ffi.ERR_SHAPE, "init_phase has %d frames, mel has %d" % (ph.shape[1], t))
+        n = self.hop * (t - 1) if t >= 1 else 0
+        out = np.empty(max(n, 0), dtype=np.float32)
+        check(lib.xdtts_gl_infer(self._h, fptr(m), t, None if ph is None else fptr(ph), fptr(out), n))
+        return out
+
+    def _batch(self, fn, ins, rows, what, init_phases):
+        lib = load_library()
+        ins = [_as_f32_2d(a, rows, what) for a in ins]
+        ts = [a.shape[1] for a in ins]
+        outs = [np.empty(max(self.hop * (t - 1), 0), dtype=np.float32) for t in ts]
+        phs = None
+        if init_phases is not None:
+            phs = [_as_f32_2d(a, self.k_bins, "init_phase") for a in init_phases]
+            if [a.shape[1] for a in phs] != ts:
+                raise XdttsError(_ffi.ERR_SHAPE, "init_phases do not match the inputs' frame counts")
+        t_arr = (ctypes.c_int * len(ts))(*ts)
+        check(getattr(lib, fn)(self._h, fptr_array(ins), t_arr, len(ins), None if phs is None else fptr_array(phs),
+                               fptr_array(outs)))
+        return outs
+
+    def infer_batch(self, mels, init_phases=None):
+        """B utterances in one device pass (the reference loops over them, src/lib.rs:83-104)."""
+        return self._batch("xdtts_gl_infer_batch", mels, self.n_mels, "mel", init_phases)
+
+    def from_magnitude_batch(self, mags, init_phases=None):
+        """Griffin-Lim proper from linear magnitudes [K, T] (no mel -> linear lift)."""
+        return self._batch("xdtts_gl_from_mag_batch", mags, self.k_bins, "magnitude", init_phases)
+
+    def plan(self, frame_counts):
+        return GlPlan(self, frame_counts)
+
+
+class GlPlan:
+    """Device-resident batch (buffers + CUDA graph) for pipelines and benchmarking."""
+
+    def __init__(self, voc, frame_counts):
+        lib = load_library()
+        self.voc = voc
+        self.ts = [int(t) for t in frame_counts]
+        p = ctypes.c_void_p()
+        t_arr = (ctypes.c_int * len(self.ts))(*self.ts)
+        check(lib.xdtts_gl_plan_create(voc._h, t_arr, len(self.ts), ctypes.byref(p)))
+        self._p = p
+
+    def close(self):
+        if self._p:
+            load_library().xdtts_gl_plan_destroy(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        a = (ctypes.c_int * 4)()
+        check(load_library().xdtts_gl_plan_info(self._p, a))
+        return dict(n_runs=a[0], run_frames=a[1], ctas=a[2], total_frames=a[3])
+
+    def upload(self, kind, arrays):
+        rows = self.voc.n_mels if kind == 0 else self.voc.k_bins
+        arrays = [_as_f32_2d(a, rows, "input") for a in arrays]
+        if [a.shape[1] for a in arrays] != self.ts:
+            raise XdttsError(_ffi.ERR_SHAPE, "inputs do not match the plan's frame counts")
+        check(load_library().xdtts_gl_plan_upload(self._p, int(kind), fptr_array(arrays)))
+
+    def upload_ptrs(self, kind, ptr_array):
+        check(load_library().xdtts_gl_plan_upload(self._p, int(kind), ptr_array))
+
+    def run(self, flags=0):
+        """-> (ms_total, ms_iter, n_iter_launches), device times from CUDA events."""
+        a, b, n = ctypes.c_float(), ctypes.c_float(), ctypes.c_int()
+        check(load_library().xdtts_gl_plan_run(self._p, int(flags), ctypes.byref(a), ctypes.byref(b), ctypes.byref(n)))
+        return a.value, b.value, n.value
+
+    def download(self):
+        outs = [np.empty(self.voc.hop * (t - 1), dtype=np.float32) for t in self.ts]
+        check(load_library().xdtts_gl_plan_download(self._p, fptr_array(outs)))
+        return outs
+
+    def download_ptrs(self, ptr_array):
+        check(load_library().xdtts_gl_plan_download(self._p, ptr_array))
+
+    def peek(self, what):
+        m, tt = self.voc.k_bins - 1, sum(self.ts)
+        shape = {0: (tt, m), 1: (tt,), 2: (tt, m, 2)}[what]
+        out = np.empty(shape, dtype=np.float32)
+        check(load_library().xdtts_gl_plan_peek(self._p, what, fptr(out), out.size))
+        return out
