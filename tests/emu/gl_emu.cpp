@@ -34,8 +34,12 @@ static void emu_launch(GlParams p, bool reverse_order) {
         };
         for (int t = r.ta; t < r.tb; t++) {
             const long frame = foff + t;
+            for (int l = 0; l < 32; l++) phase_f0<R3, MODE>(lanes[l], l, p, frame);
             if (MODE != GL_MODE_INIT) {
-                for (int l = 0; l < 32; l++) phase_f1<R3>(lanes[l], l, p.y_in + yoff, T, t, p.pad_mode, p.tables, ex1.data());
+                const bool have_pref = (t > r.ta) && !frame_is_edge(t, T);
+                const bool fetch_next = (t + 1 < r.tb) && !frame_is_edge(t + 1, T);
+                for (int l = 0; l < 32; l++)
+                    phase_f1<R3>(lanes[l], l, p.y_in + yoff, T, t, p.pad_mode, have_pref, fetch_next, p.tables, ex1.data());
                 for (int l = 0; l < 32; l++) phase_f2<R3>(lanes[l], l, p.tables, ex1.data(), ex2.data());
             }
             for (int l = 0; l < 32; l++) phase_f3<R3, MODE, STORE_R>(lanes[l], l, p, r.utt, T, t, frame, p.tables, ex2.data());

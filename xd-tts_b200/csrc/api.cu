@@ -42,9 +42,28 @@ static int fail(int code, const char* fmt, ...) {
     return code;
 }
 
+static bool debug_on() {
+    static int v = -1;
+    if (v < 0) v = getenv("XDTTS_DEBUG") ? 1 : 0;
+    return v == 1;
+}
+
+// A CUDA error left behind by earlier work in this process (another library, an ignored return
+// in a destroy path) must not be blamed on -- or break -- the next launch: clear it on entry.
+static void clear_stale_error(const char* where) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess && debug_on()) fprintf(stderr, "[xdtts] %s: cleared stale CUDA error %s\n", where, cudaGetErrorName(e));
+}
+
 #define CU(expr)                                                                                      \
     do {                                                                                              \
         cudaError_t e_ = (expr);                                                                      \
+        if (debug_on()) {                                                                             \
+            cudaError_t pe_ = cudaPeekAtLastError();                                                  \
+            if (pe_ != cudaSuccess || e_ != cudaSuccess)                                              \
+                fprintf(stderr, "[xdtts] %s:%d %s -> %s (last error: %s)\n", __FILE__, __LINE__, #expr, \
+                        cudaGetErrorName(e_), cudaGetErrorName(pe_));                                 \
+        }                                                                                             \
         if (e_ != cudaSuccess)                                                                        \
             return fail(e_ == cudaErrorMemoryAllocation ? XDTTS_ERR_OOM : XDTTS_ERR_CUDA, "%s: %s", #expr, \
                         cudaGetErrorString(e_));                                                      \
@@ -327,6 +346,7 @@ static int plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out) {
     }
     if (total * (long long)(h->K - 1) >= (1ll << 31)) return fail(XDTTS_ERR_SHAPE, "plan: %lld frames in one batch is too many (split it)", total);
     CU(cudaSetDevice(h->device));
+    clear_stale_error(__func__);
     xdtts_gl_plan* p = new (std::nothrow) xdtts_gl_plan();
     if (!p) return fail(XDTTS_ERR_OOM, "plan: out of host memory");
     p->h = h; p->B = B; p->Ts.assign(Ts, Ts + B); p->total_T = (int)total;
@@ -397,6 +417,7 @@ extern "C" int xdtts_gl_plan_info(const xdtts_gl_plan* p, int* info4) {
 
 static int plan_upload_locked(xdtts_gl_plan* p, int kind, const float* const* srcs) {
     xdtts_gl* h = p->h;
+    clear_stale_error(__func__);
     if (!srcs) return fail(XDTTS_ERR_BAD_ARG, "plan_upload: srcs is null");
     if (kind < 0 || kind > 2) return fail(XDTTS_ERR_BAD_ARG, "plan_upload: kind %d", kind);
     for (int b = 0; b < p->B; b++)
@@ -489,6 +510,7 @@ static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid) {
 
 static int plan_run_locked(xdtts_gl_plan* p, int flags, float* ms_total, float* ms_iter, int* n_iter_launches) {
     xdtts_gl* h = p->h;
+    clear_stale_error(__func__);
     CU(cudaSetDevice(h->device));
     if ((flags & XDTTS_RUN_FROM_MAG) && !p->d_in_mag) return fail(XDTTS_ERR_BAD_ARG, "plan_run: FROM_MAG without uploaded magnitudes");
     if (!(flags & XDTTS_RUN_FROM_MAG) && !p->d_mel) return fail(XDTTS_ERR_BAD_ARG, "plan_run: no mels uploaded");
@@ -541,6 +563,7 @@ extern "C" int xdtts_gl_plan_run(xdtts_gl_plan* p, int flags, float* ms_total, f
 
 static int plan_download_locked(xdtts_gl_plan* p, float* const* outs) {
     xdtts_gl* h = p->h;
+    clear_stale_error(__func__);
     if (!outs) return fail(XDTTS_ERR_BAD_ARG, "plan_download: outs is null");
     for (int b = 0; b < p->B; b++)
         if (!outs[b]) return fail(XDTTS_ERR_BAD_ARG, "plan_download: outs[%d] is null", b);

@@ -227,6 +227,10 @@ template <int R3>
 struct Lane {
     float2 v[Geo<R3>::VPL];          // FFT working set
     float2 acc[3][2 * Geo<R3>::NB];  // overlap-add sums of the three unfinished hop blocks
+    float2 ynew[2 * Geo<R3>::NB];    // newest hop block of the NEXT frame, fetched one frame ahead
+    float sa[R3], sb[R3];            // |S| at this lane's bins k and M-k (issued at frame start, used in F3)
+    float2 pa[R3], pb[R3];           // previous rebuilt spectrum at the same bins
+    float s_nyq;
     float amax;
 };
 
@@ -236,23 +240,65 @@ XD_HD int reflect_index(int j, int len) {
     return j;
 }
 
-// F1: frame t of the previous waveform -> window -> pass 1 (radix 8 over n1) -> exchange 1
+// F0: issue this frame's state loads (S, previous R).  They are consumed in F3, two FFT passes
+// later, so their DRAM latency is covered by F1/F2 instead of stalling the warp.
+template <int R3, int MODE>
+XD_HD void phase_f0(Lane<R3>& L, int lane, const GlParams& p, long frame) {
+    typedef Geo<R3> G;
+    const bool l0 = (lane == 0);
+    const float* Srow = p.S + frame * G::M;
+    const float2* Rrow = p.R + frame * G::M;
+#pragma unroll
+    for (int j = 0; j < R3; j++) {
+        const int ka = kslot<R3>(lane, j);
+        const int kb = (l0 && j == 0) ? G::M / 2 : G::M - ka;
+        L.sa[j] = ld_stream(Srow + ka);
+        L.sb[j] = ld_stream(Srow + kb);
+        if (MODE == GL_MODE_MID) {
+            L.pa[j] = ld_stream(Rrow + ka);
+            L.pb[j] = ld_stream(Rrow + kb);
+        }
+    }
+    L.s_nyq = 0.f;
+    if (l0) L.s_nyq = ld_stream(p.S_nyq + frame);
+}
+
+XD_HD bool frame_is_edge(int t, int T) { return (t < 2) || (t >= T - 2); }
+
+// F1: frame t of the previous waveform -> window -> pass 1 (radix 8 over n1) -> exchange 1.
+// have_pref: L.ynew holds the frame's last hop block (fetched during the previous frame).
+// fetch_next: frame t+1 belongs to this run and is interior -> fetch its last hop block now.
 template <int R3>
-XD_HD void phase_f1(Lane<R3>& L, int lane, const float* y, int T, int t, int pad_mode, const float2* tab, float2* ex1) {
+XD_HD void phase_f1(Lane<R3>& L, int lane, const float* y, int T, int t, int pad_mode, bool have_pref, bool fetch_next,
+                    const float2* tab, float2* ex1) {
     typedef Geo<R3> G;
     const int base = (t - 2) * G::H;
-    const bool edge = (t < 2) || (t >= T - 2);
-    const int len = G::H * (T - 1);
+    if (!frame_is_edge(t, T)) {   // warp-uniform: all loads of the interior path are issued back to back
+        const float* yb = y + base + 2 * lane;
 #pragma unroll
-    for (int i = 0; i < G::NB; i++) {
+        for (int i = 0; i < G::NB; i++)
 #pragma unroll
-        for (int n1 = 0; n1 < 8; n1++) {
-            const int s = 16 * R3 * n1 + 2 * (lane + 32 * i);
-            float2 x;
-            if (!edge) {
-                x = *reinterpret_cast<const float2*>(y + base + s);
-            } else {
-                const int j0 = base + s, j1 = j0 + 1;
+            for (int n1 = 0; n1 < 6; n1++) L.v[i * 8 + n1] = *reinterpret_cast<const float2*>(yb + 16 * R3 * n1 + 64 * i);
+        if (have_pref) {
+#pragma unroll
+            for (int i = 0; i < G::NB; i++) {
+                L.v[i * 8 + 6] = L.ynew[i];
+                L.v[i * 8 + 7] = L.ynew[G::NB + i];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < G::NB; i++)
+#pragma unroll
+                for (int n1 = 6; n1 < 8; n1++) L.v[i * 8 + n1] = *reinterpret_cast<const float2*>(yb + 16 * R3 * n1 + 64 * i);
+        }
+    } else {
+        const int len = G::H * (T - 1);
+#pragma unroll
+        for (int i = 0; i < G::NB; i++) {
+#pragma unroll
+            for (int n1 = 0; n1 < 8; n1++) {
+                const int j0 = base + 16 * R3 * n1 + 2 * (lane + 32 * i), j1 = j0 + 1;
+                float2 x;
                 if (pad_mode == GL_PAD_REFLECT) {
                     x.x = y[reflect_index(j0, len)];
                     x.y = y[reflect_index(j1, len)];
@@ -260,13 +306,25 @@ XD_HD void phase_f1(Lane<R3>& L, int lane, const float* y, int T, int t, int pad
                     x.x = (j0 >= 0 && j0 < len) ? y[j0] : 0.f;
                     x.y = (j1 >= 0 && j1 < len) ? y[j1] : 0.f;
                 }
+                L.v[i * 8 + n1] = x;
             }
-            const float2 w = tab[G::WIN_OFF + (i * 8 + n1) * 32 + lane];
-            L.v[i * 8 + n1] = mk2(x.x * w.x, x.y * w.y);
+        }
+    }
+    if (fetch_next) {   // hop block (t+1)+1 of the trimmed signal = quarter 3 of frame t+1
+        const float* yn = y + base + G::H + 2 * lane;
+#pragma unroll
+        for (int i = 0; i < G::NB; i++) {
+            L.ynew[i] = *reinterpret_cast<const float2*>(yn + 16 * R3 * 6 + 64 * i);
+            L.ynew[G::NB + i] = *reinterpret_cast<const float2*>(yn + 16 * R3 * 7 + 64 * i);
         }
     }
 #pragma unroll
     for (int i = 0; i < G::NB; i++) {
+#pragma unroll
+        for (int n1 = 0; n1 < 8; n1++) {
+            const float2 w = tab[G::WIN_OFF + (i * 8 + n1) * 32 + lane];
+            L.v[i * 8 + n1] = mk2(L.v[i * 8 + n1].x * w.x, L.v[i * 8 + n1].y * w.y);
+        }
         Dft<8, false>::run(&L.v[i * 8]);
 #pragma unroll
         for (int k1 = 0; k1 < 8; k1++) {
@@ -344,25 +402,13 @@ XD_HD void phase_f3(Lane<R3>& L, int lane, const GlParams& p, int utt, int T, in
     const int qA = lane, qB = lane ? 64 - lane : 32;
     float2* A = &L.v[0];
     float2* B = &L.v[R3];
-    const float* Srow = p.S + frame * G::M;
     float2* Rrow = p.R + frame * G::M;
 
-    // issue the state loads first so that they overlap the last forward pass
-    float sa[R3], sb[R3];
-    float2 pa[R3], pb[R3];
-    float s_nyq = 0.f;
-#pragma unroll
-    for (int j = 0; j < R3; j++) {
-        const int ka = kslot<R3>(lane, j);
-        const int kb = (l0 && j == 0) ? G::M / 2 : G::M - ka;
-        sa[j] = ld_stream(Srow + ka);
-        sb[j] = ld_stream(Srow + kb);
-        if (MODE == GL_MODE_MID) {
-            pa[j] = ld_stream(Rrow + ka);
-            pb[j] = ld_stream(Rrow + kb);
-        }
-    }
-    if (l0) s_nyq = ld_stream(p.S_nyq + frame);
+    const float* sa = L.sa;
+    const float* sb = L.sb;
+    const float2* pa = L.pa;
+    const float2* pb = L.pb;
+    const float s_nyq = L.s_nyq;
 
     if (MODE != GL_MODE_INIT) {
 #pragma unroll

@@ -57,8 +57,11 @@ __global__ void __launch_bounds__(GL_WARPS * 32, (R3 == 16) ? 2 : 3) gl_iter_ker
 
     for (int t = r.ta; t < r.tb; t++) {
         const long frame = foff + t;
+        phase_f0<R3, MODE>(L, lane, p, frame);
         if (MODE != GL_MODE_INIT) {
-            phase_f1<R3>(L, lane, p.y_in + yoff, T, t, p.pad_mode, tab, ex1);
+            const bool have_pref = (t > r.ta) && !frame_is_edge(t, T);
+            const bool fetch_next = (t + 1 < r.tb) && !frame_is_edge(t + 1, T);
+            phase_f1<R3>(L, lane, p.y_in + yoff, T, t, p.pad_mode, have_pref, fetch_next, tab, ex1);
             __syncwarp();
             phase_f2<R3>(L, lane, tab, ex1, ex2);
             __syncwarp();
