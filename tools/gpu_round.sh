@@ -1,0 +1,20 @@
+#!/bin/bash
+# One gpurun call: GPU parity tests, bench lines, ncu launch list + one full capture of the top kernel.
+# Usage (from the repo root): gpurun --timeout 1500 -- 'bash tools/gpu_round.sh <tag>'
+tag=${1:-r01}
+out=gpurun_out/$tag
+mkdir -p $out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $out/gpu.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q > $out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $out/pytest_gpu.log
+tail -3 $out/pytest_gpu.log
+timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' > $out/smoke.log 2>&1; tail -1 $out/smoke.log
+timeout 600 python bench.py --steps 10 --warmup 3 > $out/bench_cfg2.json 2> $out/bench_cfg2.err; cat $out/bench_cfg2.json
+timeout 600 python bench.py --config cfg5 --steps 5 --warmup 3 --no-cpu > $out/bench_cfg5.json 2> $out/bench_cfg5.err; cat $out/bench_cfg5.json
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $out/bench_ref.json 2> $out/bench_ref.err; cat $out/bench_ref.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $out/launches_cfg2.csv \
+    python tools/prof_target.py cfg2 2 > $out/launches_cfg2.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gl_iter_kernel -s 20 -c 2 -f -o $out/prof_gl_iter_cfg2 \
+    python tools/prof_target.py cfg2 1 > $out/prof_cfg2.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gl_iter_kernel -s 20 -c 1 -f -o $out/prof_gl_iter_cfg5 \
+    python tools/prof_target.py cfg5 1 > $out/prof_cfg5.log 2>&1
+ls -la $out
