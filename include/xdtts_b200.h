@@ -98,6 +98,46 @@ int xdtts_gl_plan_peek(xdtts_gl_plan* p, int what, float* out, long long n_float
 /* geometry the plan chose: info[0]=n_runs, [1]=frames per run (max), [2]=CTAs, [3]=total frames */
 int xdtts_gl_plan_info(const xdtts_gl_plan* p, int* info4);
 
+/* ---- Tacotron2 postnet: replaces the `postnet` ort::Session (src/tacotron2/mod.rs:256-259 load,
+ * :344-357 run; output "mel_outputs_postnet").  out = mel + Postnet(mel), Postnet = n_layers x
+ * [Conv1d(k=5, pad=2, bias) -> BatchNorm1d(eval)], tanh after every layer but the last. */
+typedef struct xdtts_postnet_opts {
+    int precision; /* 0: bf16x3 split on the tensor cores (fp32-class, default)  1: single bf16 pass
+                      2: fp32 on the CUDA cores (strict parity / cross-check, slow) */
+} xdtts_postnet_opts;
+
+typedef struct xdtts_postnet xdtts_postnet;           /* the weights, folded and laid out for the device */
+typedef struct xdtts_postnet_plan xdtts_postnet_plan; /* device-resident batch */
+
+/* channels: n_layers+1 entries (Tacotron2: 80,512,512,512,512,80); ksize must be 5.
+ * conv_w[l]: [channels[l+1], channels[l], ksize] row-major (the ONNX initializer layout); conv_b[l]:
+ * [channels[l+1]] or null.  bn_*[l]: [channels[l+1]] each, or bn_gamma == null / bn_gamma[l] == null for
+ * a layer without BatchNorm.  BatchNorm is folded on the host in fp64. */
+int xdtts_postnet_create(int n_layers, const int* channels, int ksize, const float* const* conv_w,
+                         const float* const* conv_b, const float* const* bn_gamma, const float* const* bn_beta,
+                         const float* const* bn_mean, const float* const* bn_var, float eps,
+                         const xdtts_postnet_opts* opts_or_null, int device, xdtts_postnet** out);
+void xdtts_postnet_destroy(xdtts_postnet* h);
+/* mel [C, T] -> out [C, T] (C = channels[0]), host buffers, T >= 1 */
+int xdtts_postnet_infer(xdtts_postnet* h, const float* mel, int T, float* out);
+int xdtts_postnet_infer_batch(xdtts_postnet* h, const float* const* mels, const int* Ts, int B, float* const* outs);
+
+int xdtts_postnet_plan_create(xdtts_postnet* h, const int* Ts, int B, xdtts_postnet_plan** out);
+void xdtts_postnet_plan_destroy(xdtts_postnet_plan* p);
+int xdtts_postnet_plan_upload(xdtts_postnet_plan* p, const float* const* mels);
+/* feed_or_null: a vocoder plan of the same batch shape; the result is then written into that plan's
+ * mel arena (on the vocoder's stream) so that xdtts_gl_plan_run(feed, 0, ...) vocodes it without a
+ * host round trip.  ms_total: device time of the postnet (CUDA events). */
+int xdtts_postnet_plan_run(xdtts_postnet_plan* p, xdtts_gl_plan* feed_or_null, float* ms_total);
+int xdtts_postnet_plan_download(xdtts_postnet_plan* p, float* const* outs);
+
+/* The tail of XdTts::infer in one call (src/lib.rs:123 postnet tail of model.infer + :141 vocoder.infer):
+ * decoder mels [C, T_b] -> postnet -> mel-to-linear lift -> Griffin-Lim -> waveforms [hop (T_b - 1)].
+ * out_mels_or_null: B buffers [C, T_b] that receive "mel_outputs_postnet" (the --output-spectrogram dump). */
+int xdtts_tail_infer_batch(xdtts_postnet* pn, xdtts_gl* gl, const float* const* mels, const int* Ts, int B,
+                           const float* const* init_phases_or_null, float* const* out_mels_or_null,
+                           float* const* out_waves);
+
 /* pinned host memory for callers that want copy/compute overlap and full PCIe speed */
 void* xdtts_host_alloc(unsigned long long bytes);
 void xdtts_host_free(void* p);

@@ -1,0 +1,164 @@
+"""GPU parity tests of the postnet (Tacotron2 postnet session, /root/reference
+src/tacotron2/mod.rs:344-357) through the C ABI, against the numpy oracle (unfused BatchNorm, fp64)
+and the committed golden fixture (torch conv1d + batch_norm, tests/golden/postnet.npz).
+
+Tolerances (floating point path, stated per precision mode; values are ln-mels of magnitude ~1-8):
+  fp32 CUDA-core kernel   max abs error <= 1e-4   (SURVEY.md 8d gate 5 "fp32 path")
+  bf16x3 tensor-core      max abs error <= 2e-4   (three-pass split, fp32 accumulate in TMEM)
+  bf16 tensor-core        max abs error <= 6e-2   (single pass, 8-bit mantissa inputs)"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gl_oracle as o
+from oracle import postnet_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+TOL = {0: 2e-4, 1: 6e-2, 2: 1e-4}
+
+
+@pytest.fixture(scope="module")
+def taco(built):
+    from xdtts_b200 import tacotron2
+
+    return tacotron2
+
+
+@pytest.fixture(scope="module")
+def layers():
+    return po.synth_weights(seed=7)
+
+
+@pytest.mark.parametrize("precision", [2, 0, 1])
+def test_golden_fixture(taco, layers, golden_dir, precision):
+    g = np.load(os.path.join(golden_dir, "postnet.npz"))
+    post = taco.Postnet.from_layers(layers, precision=precision)
+    out = post.run(g["mel"])
+    assert out.shape == g["mel"].shape and out.dtype == np.float32 and np.isfinite(out).all()
+    assert np.abs(out - g["out_oracle64"]).max() < TOL[precision]
+    assert np.abs(out - g["out_torch32"]).max() < TOL[precision] + 2e-5
+    # the residual is really added: out - mel is the conv stack, not zero
+    assert np.abs(out - g["mel"]).max() > 1e-2
+
+
+@pytest.mark.parametrize("precision", [0, 2])
+@pytest.mark.parametrize("t", [1, 2, 5, 127, 128, 129, 300])
+def test_lengths_and_tile_edges(taco, layers, precision, t):
+    """T around the 128-row tile size, and shorter than the receptive field (21 frames)."""
+    mel = o.synth_mel(40 + t, 80, t)
+    post = taco.Postnet.from_layers(layers, precision=precision)
+    ref = po.postnet(mel, layers, dtype=np.float64)
+    out = post.run(mel)
+    assert np.abs(out - ref).max() < TOL[precision], t
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_ragged_batch_equals_single_calls(taco, layers, precision):
+    """Zero rows between stacked utterances are the conv padding: no leakage across utterances."""
+    ts = [3, 130, 17, 256, 64, 1, 99]
+    mels = [o.synth_mel(200 + i, 80, t) for i, t in enumerate(ts)]
+    post = taco.Postnet.from_layers(layers, precision=precision)
+    batch = post.run_batch(mels)
+    for m, b in zip(mels, batch):
+        single = post.run(m)
+        assert np.array_equal(single, b)
+        assert np.abs(b - po.postnet(m, layers, dtype=np.float64)).max() < TOL[precision]
+    again = post.run_batch(mels)       # buffers are reused: the gap rows must still be zero
+    for a, b in zip(batch, again):
+        assert np.array_equal(a, b)
+    longer = post.run_batch([o.synth_mel(1, 80, 400)])   # another shape in between, then back
+    assert longer[0].shape == (80, 400)
+    third = post.run_batch(mels)
+    for a, b in zip(batch, third):
+        assert np.array_equal(a, b)
+
+
+def test_tensor_path_agrees_with_cuda_core_path(taco, layers):
+    """On-device cross-check: tcgen05 bf16x3 vs the plain fp32 kernel on a cfg3-sized utterance."""
+    mel = o.synth_mel(77, 80, 1000)
+    a = taco.Postnet.from_layers(layers, precision=0).run(mel)
+    b = taco.Postnet.from_layers(layers, precision=2).run(mel)
+    assert np.abs(a - b).max() < 2e-4
+    c = taco.Postnet.from_layers(layers, precision=1).run(mel)
+    assert np.abs(c - b).max() < 6e-2
+    assert np.abs(c - b).max() > np.abs(a - b).max()       # the split really buys precision
+
+
+def test_other_architectures(taco):
+    """No BatchNorm / no bias, other channel counts (N tile of 128, 64-channel padding, one layer)."""
+    rng = np.random.default_rng(3)
+    for channels in ([32, 384, 32], [80, 80], [48, 64, 256, 48]):
+        layers = po.synth_weights(seed=11, channels=tuple(channels))
+        layers[0].pop("b")
+        for k in ("gamma", "beta", "mean", "var"):
+            layers[-1].pop(k)
+        mel = rng.uniform(-4, 1, (channels[0], 150)).astype(np.float32)
+        full = []
+        for l in layers:          # the oracle wants every key: identity BatchNorm / zero bias
+            c = l["w"].shape[0]
+            d = dict(w=l["w"], b=l.get("b", np.zeros(c, np.float32)), gamma=l.get("gamma", np.ones(c, np.float32)),
+                     beta=l.get("beta", np.zeros(c, np.float32)), mean=l.get("mean", np.zeros(c, np.float32)),
+                     var=l.get("var", np.ones(c, np.float32) - np.float32(po.BN_EPS)))
+            full.append(d)
+        ref = po.postnet(mel, full, dtype=np.float64)
+        for precision in (0, 2):
+            out = taco.Postnet.from_layers(layers, precision=precision).run(mel)
+            assert np.abs(out - ref).max() < TOL[precision], (channels, precision)
+
+
+def test_plan_feeds_vocoder_and_tail_call(taco, layers, built):
+    """postnet -> lift -> Griffin-Lim without leaving HBM == the two public calls chained on the host."""
+    from xdtts_b200 import griffin_lim
+
+    basis = o.create_mel_filter_bank(22050.0, 1024, 80, 0.0, 8000.0)
+    voc = griffin_lim.GriffinLim.new(basis, 768, 1.7, 8, 0.99, run_frames=8)
+    post = taco.Postnet.from_layers(layers, precision=0)
+    ts = [40, 150]
+    # decoder-like mels scaled so that postnet output stays in the ln-mel range
+    mels = [o.synth_mel(300 + i, 80, t) for i, t in enumerate(ts)]
+    phs = [o.phase_turns(5, i, 513, t) for i, t in enumerate(ts)]
+    waves, pmels = taco.infer_tail_batch(post, voc, mels, phs, return_mels=True)
+    chained_mels = post.run_batch(mels)
+    chained = voc.infer_batch(chained_mels, phs)
+    for a, b in zip(pmels, chained_mels):
+        assert np.array_equal(a, b)
+    for a, b, t in zip(waves, chained, ts):
+        assert a.shape == (256 * (t - 1),)
+        assert np.array_equal(a, b)
+    # and against the oracle end to end (fp64 postnet -> fp64 vocoder), same initial phase
+    for m, ph, w in zip(mels, phs, waves):
+        pm = po.postnet(m, layers, dtype=np.float64).astype(np.float32)
+        ref = o.infer(pm, basis, 768, 1.7, 8, 0.99, ph, dtype=np.float64)
+        assert float(np.sqrt(np.mean((w - ref) ** 2))) < 1e-3
+    # plan API: run(feed=...) then the vocoder plan
+    pp, gp = post.plan(ts), voc.plan(ts)
+    pp.upload(mels)
+    ms = pp.run(feed=gp)
+    assert ms > 0
+    gp.upload(2, phs)
+    gp.run(2)
+    for a, b in zip(gp.download(), waves):
+        assert np.array_equal(a, b)
+    single = taco.infer_tail(post, voc, mels[0], phs[0])
+    assert np.array_equal(single, waves[0])
+
+
+def test_errors(taco, layers):
+    from xdtts_b200._ffi import ERR_BAD_ARG, ERR_SHAPE, XdttsError
+
+    post = taco.Postnet.from_layers(layers)
+    with pytest.raises(XdttsError) as e:
+        post.run(np.zeros((79, 10), np.float32))
+    assert e.value.code == ERR_SHAPE
+    with pytest.raises(XdttsError) as e:
+        post.run(np.zeros((80, 0), np.float32))
+    assert e.value.code == ERR_SHAPE
+    out = post.run(np.zeros((80, 7), np.float32))           # zeros in -> the bias response, finite
+    assert np.isfinite(out).all()
+    p = post.plan([10])
+    with pytest.raises(XdttsError) as e:
+        p.upload([np.zeros((80, 11), np.float32)])
+    assert e.value.code == ERR_SHAPE
+    assert ERR_BAD_ARG < 0

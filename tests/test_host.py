@@ -152,3 +152,36 @@ def test_lane_program_rebuilt_spectrum_and_options(built):
     y_seed, _, _, _ = emu.gl_from_mag(s, None, 1, 0.99, 6, seed=1)
     y_expl, _, _, _ = emu.gl_from_mag(s, tu, 1, 0.99, 6)
     assert rel_rms(y_seed, y_expl) < 1e-6
+
+
+def test_postnet_argument_validation_without_gpu(lib):
+    from oracle import postnet_oracle as po
+    from xdtts_b200 import tacotron2
+    from xdtts_b200._ffi import ERR_BAD_ARG, ERR_CUDA, ERR_SHAPE, ERR_UNSUPPORTED, XdttsError
+
+    layers = po.synth_weights(seed=7)
+    with pytest.raises(XdttsError) as e:        # residual needs matching channel counts
+        tacotron2.Postnet.from_layers(layers[:2])
+    assert e.value.code == ERR_SHAPE
+    bad = po.synth_weights(seed=7, channels=(80, 100, 80))      # 100 is not a multiple of 16
+    with pytest.raises(XdttsError) as e:
+        tacotron2.Postnet.from_layers(bad)
+    assert e.value.code == ERR_UNSUPPORTED
+    k3 = [dict(l, w=l["w"][:, :, :3].copy()) for l in layers]
+    with pytest.raises(XdttsError) as e:
+        tacotron2.Postnet.from_layers(k3)
+    assert e.value.code == ERR_UNSUPPORTED
+    partial = [dict(l) for l in layers]
+    partial[1].pop("var")
+    with pytest.raises(XdttsError) as e:
+        tacotron2.Postnet.from_layers(partial)
+    assert e.value.code == ERR_BAD_ARG
+    with pytest.raises(XdttsError) as e:
+        tacotron2.Postnet.from_layers(layers, precision=7)
+    assert e.value.code == ERR_BAD_ARG
+    import torch
+
+    if not torch.cuda.is_available():
+        with pytest.raises(XdttsError) as e:    # valid arguments, no device: refuses, never computes on the CPU
+            tacotron2.Postnet.from_layers(layers)
+        assert e.value.code == ERR_CUDA

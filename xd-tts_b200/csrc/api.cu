@@ -14,7 +14,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/xdtts_b200.h"
+#include "api_internal.h"
 #include "gl_host.h"
 #include "gl_tables.h"
 
@@ -32,7 +32,8 @@ using namespace xdtts;
 // ------------------------------------------------------------------ errors
 static thread_local std::string tl_error;
 
-static int fail(int code, const char* fmt, ...) {
+namespace xdtts {
+int set_error(int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -42,7 +43,7 @@ static int fail(int code, const char* fmt, ...) {
     return code;
 }
 
-static bool debug_on() {
+bool debug_on() {
     static int v = -1;
     if (v < 0) v = getenv("XDTTS_DEBUG") ? 1 : 0;
     return v == 1;
@@ -50,24 +51,22 @@ static bool debug_on() {
 
 // A CUDA error left behind by earlier work in this process (another library, an ignored return
 // in a destroy path) must not be blamed on -- or break -- the next launch: clear it on entry.
-static void clear_stale_error(const char* where) {
+void clear_stale_error(const char* where) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess && debug_on()) fprintf(stderr, "[xdtts] %s: cleared stale CUDA error %s\n", where, cudaGetErrorName(e));
 }
 
-#define CU(expr)                                                                                      \
-    do {                                                                                              \
-        cudaError_t e_ = (expr);                                                                      \
-        if (debug_on()) {                                                                             \
-            cudaError_t pe_ = cudaPeekAtLastError();                                                  \
-            if (pe_ != cudaSuccess || e_ != cudaSuccess)                                              \
-                fprintf(stderr, "[xdtts] %s:%d %s -> %s (last error: %s)\n", __FILE__, __LINE__, #expr, \
-                        cudaGetErrorName(e_), cudaGetErrorName(pe_));                                 \
-        }                                                                                             \
-        if (e_ != cudaSuccess)                                                                        \
-            return fail(e_ == cudaErrorMemoryAllocation ? XDTTS_ERR_OOM : XDTTS_ERR_CUDA, "%s: %s", #expr, \
-                        cudaGetErrorString(e_));                                                      \
-    } while (0)
+bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+}  // namespace xdtts
+
+#define fail xdtts::set_error
 
 extern "C" const char* xdtts_last_error(void) { return tl_error.c_str(); }
 extern "C" unsigned long long xdtts_kernel_launches(void) { return g_launches.load(); }
@@ -183,51 +182,6 @@ extern "C" int xdtts_pinv(const float* a, int rows, int cols, float* out) {
     return XDTTS_OK;
 }
 
-// ------------------------------------------------------------------ handle
-struct xdtts_gl {
-    int device = 0, n_mels = 0, K = 0, n_fft = 0, hop = 0, n_iter = 0, sm_count = 148;
-    float power = 1.f, momentum = 0.f;
-    xdtts_gl_opts opts{};
-    std::vector<float> pinv;        // [K][n_mels] host copy
-    float* d_pinvT = nullptr;       // [n_mels][K]
-    float2* d_tables = nullptr;
-    float* d_edge = nullptr;
-    cudaStream_t stream = nullptr;
-    std::mutex mu;
-    std::vector<xdtts_gl_plan*> cache;   // plans owned by the batch entry points
-};
-
-struct xdtts_gl_plan {
-    xdtts_gl* h = nullptr;
-    int B = 0, max_T = 0, total_T = 0, run_frames = 0;
-    std::vector<int> Ts, foff;
-    std::vector<long long> out_off;
-    long long out_total = 0;
-    std::vector<GlRun> runs;
-    // device
-    GlRun* d_runs = nullptr;
-    int *d_T = nullptr, *d_foff = nullptr;
-    long long* d_out_off = nullptr;
-    float *d_mel = nullptr, *d_in_mag = nullptr, *d_in_phase = nullptr, *d_turns = nullptr, *d_turns_nyq = nullptr;
-    float *d_S = nullptr, *d_S_nyq = nullptr, *d_y[2] = {nullptr, nullptr}, *d_halo = nullptr, *d_out = nullptr;
-    float2* d_R = nullptr;
-    unsigned *d_flags = nullptr, *d_amax = nullptr;
-    // pinned staging for pageable callers
-    float *h_in = nullptr, *h_out = nullptr;
-    size_t h_in_floats = 0;
-    cudaGraphExec_t graphs[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-};
-
-static bool is_pinned(const void* p) {
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
-    }
-    return a.type == cudaMemoryTypeHost;
-}
-
 extern "C" int xdtts_gl_create(const float* mel_basis, int n_mels, int K, int noverlap, float power, int n_iter,
                                float momentum, const xdtts_gl_opts* opts, int device, xdtts_gl** out) {
     if (!out) return fail(XDTTS_ERR_BAD_ARG, "gl_create: out is null");
@@ -336,7 +290,7 @@ extern "C" void xdtts_gl_plan_destroy(xdtts_gl_plan* p) {
     delete p;
 }
 
-static int plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out) {
+int xdtts::gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out) {
     *out = nullptr;
     if (!Ts || B < 1) return fail(XDTTS_ERR_BAD_ARG, "plan: need B >= 1 utterances");
     long long total = 0;
@@ -403,7 +357,7 @@ static int plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out) {
 extern "C" int xdtts_gl_plan_create(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out) {
     if (!h || !out) return fail(XDTTS_ERR_BAD_ARG, "plan_create: null argument");
     std::lock_guard<std::mutex> lk(h->mu);
-    return plan_build(h, Ts, B, out);
+    return gl_plan_build(h, Ts, B, out);
 }
 
 extern "C" int xdtts_gl_plan_info(const xdtts_gl_plan* p, int* info4) {
@@ -415,7 +369,7 @@ extern "C" int xdtts_gl_plan_info(const xdtts_gl_plan* p, int* info4) {
     return XDTTS_OK;
 }
 
-static int plan_upload_locked(xdtts_gl_plan* p, int kind, const float* const* srcs) {
+int xdtts::gl_plan_upload_locked(xdtts_gl_plan* p, int kind, const float* const* srcs) {
     xdtts_gl* h = p->h;
     clear_stale_error(__func__);
     if (!srcs) return fail(XDTTS_ERR_BAD_ARG, "plan_upload: srcs is null");
@@ -455,7 +409,7 @@ static int plan_upload_locked(xdtts_gl_plan* p, int kind, const float* const* sr
 extern "C" int xdtts_gl_plan_upload(xdtts_gl_plan* p, int kind, const float* const* srcs) {
     if (!p) return fail(XDTTS_ERR_BAD_ARG, "plan_upload: plan is null");
     std::lock_guard<std::mutex> lk(p->h->mu);
-    return plan_upload_locked(p, kind, srcs);
+    return gl_plan_upload_locked(p, kind, srcs);
 }
 
 // enqueue the whole pass on the handle's stream; ev[1]/ev[2] bracket the steady-state launches when timed
@@ -508,7 +462,7 @@ static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid) {
     return XDTTS_OK;
 }
 
-static int plan_run_locked(xdtts_gl_plan* p, int flags, float* ms_total, float* ms_iter, int* n_iter_launches) {
+int xdtts::gl_plan_run_locked(xdtts_gl_plan* p, int flags, float* ms_total, float* ms_iter, int* n_iter_launches) {
     xdtts_gl* h = p->h;
     clear_stale_error(__func__);
     CU(cudaSetDevice(h->device));
@@ -558,10 +512,10 @@ static int plan_run_locked(xdtts_gl_plan* p, int flags, float* ms_total, float* 
 extern "C" int xdtts_gl_plan_run(xdtts_gl_plan* p, int flags, float* ms_total, float* ms_iter, int* n_iter_launches) {
     if (!p) return fail(XDTTS_ERR_BAD_ARG, "plan_run: plan is null");
     std::lock_guard<std::mutex> lk(p->h->mu);
-    return plan_run_locked(p, flags, ms_total, ms_iter, n_iter_launches);
+    return gl_plan_run_locked(p, flags, ms_total, ms_iter, n_iter_launches);
 }
 
-static int plan_download_locked(xdtts_gl_plan* p, float* const* outs) {
+int xdtts::gl_plan_download_locked(xdtts_gl_plan* p, float* const* outs) {
     xdtts_gl* h = p->h;
     clear_stale_error(__func__);
     if (!outs) return fail(XDTTS_ERR_BAD_ARG, "plan_download: outs is null");
@@ -586,7 +540,7 @@ static int plan_download_locked(xdtts_gl_plan* p, float* const* outs) {
 extern "C" int xdtts_gl_plan_download(xdtts_gl_plan* p, float* const* outs) {
     if (!p) return fail(XDTTS_ERR_BAD_ARG, "plan_download: plan is null");
     std::lock_guard<std::mutex> lk(p->h->mu);
-    return plan_download_locked(p, outs);
+    return gl_plan_download_locked(p, outs);
 }
 
 extern "C" int xdtts_gl_plan_peek(xdtts_gl_plan* p, int what, float* out, long long n_floats) {
@@ -602,13 +556,8 @@ extern "C" int xdtts_gl_plan_peek(xdtts_gl_plan* p, int what, float* out, long l
     return XDTTS_OK;
 }
 
-// ------------------------------------------------------------------ batch entry points
-static int batch_common(xdtts_gl* h, int kind, const float* const* ins, const int* Ts, int B,
-                        const float* const* phases, float* const* outs) {
-    if (!h) return fail(XDTTS_ERR_BAD_ARG, "infer: handle is null");
-    if (!ins || !Ts || !outs) return fail(XDTTS_ERR_BAD_ARG, "infer: null argument");
-    if (B < 1) return fail(XDTTS_ERR_BAD_ARG, "infer: B = %d", B);
-    std::lock_guard<std::mutex> lk(h->mu);
+// plan of this exact batch shape from the handle's small cache (built on a miss); h->mu held by the caller
+int xdtts::gl_cached_plan(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out) {
     xdtts_gl_plan* p = nullptr;
     for (xdtts_gl_plan* c : h->cache)
         if (c->B == B && memcmp(c->Ts.data(), Ts, sizeof(int) * B) == 0) p = c;
@@ -617,21 +566,47 @@ static int batch_common(xdtts_gl* h, int kind, const float* const* ins, const in
             xdtts_gl_plan_destroy(h->cache.front());
             h->cache.erase(h->cache.begin());
         }
-        int rc = plan_build(h, Ts, B, &p);
+        int rc = gl_plan_build(h, Ts, B, &p);
         if (rc) return rc;
         h->cache.push_back(p);
     }
-    int rc = plan_upload_locked(p, kind, ins);
+    *out = p;
+    return XDTTS_OK;
+}
+
+// device arena the lift reads: utterance u is a row-major [n_mels][T_u] block at float offset foff[u] * n_mels
+int xdtts::gl_plan_mel_arena(xdtts_gl_plan* p, float** out) {
+    if (!p->d_mel) {
+        CU(cudaSetDevice(p->h->device));
+        CU(cudaMalloc((void**)&p->d_mel, (size_t)p->h->n_mels * (size_t)p->total_T * 4));
+    }
+    *out = p->d_mel;
+    return XDTTS_OK;
+}
+
+// ------------------------------------------------------------------ batch entry points
+static int batch_common(xdtts_gl* h, int kind, const float* const* ins, const int* Ts, int B,
+                        const float* const* phases, float* const* outs) {
+    if (!h) return fail(XDTTS_ERR_BAD_ARG, "infer: handle is null");
+    if (!ins || !Ts || !outs) return fail(XDTTS_ERR_BAD_ARG, "infer: null argument");
+    if (B < 1) return fail(XDTTS_ERR_BAD_ARG, "infer: B = %d", B);
+    std::lock_guard<std::mutex> lk(h->mu);
+    xdtts_gl_plan* p = nullptr;
+    {
+        int rc = gl_cached_plan(h, Ts, B, &p);
+        if (rc) return rc;
+    }
+    int rc = gl_plan_upload_locked(p, kind, ins);
     if (rc) return rc;
     int flags = kind == 1 ? XDTTS_RUN_FROM_MAG : 0;
     if (phases) {
-        rc = plan_upload_locked(p, 2, phases);
+        rc = gl_plan_upload_locked(p, 2, phases);
         if (rc) return rc;
         flags |= XDTTS_RUN_USE_PHASE;
     }
-    rc = plan_run_locked(p, flags, nullptr, nullptr, nullptr);
+    rc = gl_plan_run_locked(p, flags, nullptr, nullptr, nullptr);
     if (rc) return rc;
-    return plan_download_locked(p, outs);
+    return gl_plan_download_locked(p, outs);
 }
 
 extern "C" int xdtts_gl_infer_batch(xdtts_gl* h, const float* const* mels, const int* Ts, int B,

@@ -1,0 +1,84 @@
+// Internals shared by the translation units that implement the C ABI (api.cu, postnet_api.cu):
+// error plumbing, the Griffin-Lim handle and plan layouts.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/xdtts_b200.h"
+#include "gl_core.cuh"
+
+namespace xdtts {
+extern std::atomic<unsigned long long> g_launches;
+// records the thread-local message returned by xdtts_last_error() and returns `code`
+int set_error(int code, const char* fmt, ...);
+bool debug_on();
+void clear_stale_error(const char* where);
+bool is_pinned(const void* p);
+}  // namespace xdtts
+
+#define CU(expr)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (expr);                                                                      \
+        if (xdtts::debug_on()) {                                                                      \
+            cudaError_t pe_ = cudaPeekAtLastError();                                                  \
+            if (pe_ != cudaSuccess || e_ != cudaSuccess)                                              \
+                fprintf(stderr, "[xdtts] %s:%d %s -> %s (last error: %s)\n", __FILE__, __LINE__, #expr, \
+                        cudaGetErrorName(e_), cudaGetErrorName(pe_));                                 \
+        }                                                                                             \
+        if (e_ != cudaSuccess)                                                                        \
+            return xdtts::set_error(e_ == cudaErrorMemoryAllocation ? XDTTS_ERR_OOM : XDTTS_ERR_CUDA, "%s: %s", #expr, \
+                                    cudaGetErrorString(e_));                                          \
+    } while (0)
+
+// ------------------------------------------------------------------ Griffin-Lim handle and plan
+struct xdtts_gl {
+    int device = 0, n_mels = 0, K = 0, n_fft = 0, hop = 0, n_iter = 0, sm_count = 148;
+    float power = 1.f, momentum = 0.f;
+    xdtts_gl_opts opts{};
+    std::vector<float> pinv;        // [K][n_mels] host copy
+    float* d_pinvT = nullptr;       // [n_mels][K]
+    float2* d_tables = nullptr;
+    float* d_edge = nullptr;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::vector<xdtts_gl_plan*> cache;   // plans owned by the batch entry points
+};
+
+struct xdtts_gl_plan {
+    xdtts_gl* h = nullptr;
+    int B = 0, max_T = 0, total_T = 0, run_frames = 0;
+    std::vector<int> Ts, foff;
+    std::vector<long long> out_off;
+    long long out_total = 0;
+    std::vector<xdtts::GlRun> runs;
+    // device
+    xdtts::GlRun* d_runs = nullptr;
+    int *d_T = nullptr, *d_foff = nullptr;
+    long long* d_out_off = nullptr;
+    float *d_mel = nullptr, *d_in_mag = nullptr, *d_in_phase = nullptr, *d_turns = nullptr, *d_turns_nyq = nullptr;
+    float *d_S = nullptr, *d_S_nyq = nullptr, *d_y[2] = {nullptr, nullptr}, *d_halo = nullptr, *d_out = nullptr;
+    float2* d_R = nullptr;
+    unsigned *d_flags = nullptr, *d_amax = nullptr;
+    // pinned staging for pageable callers
+    float *h_in = nullptr, *h_out = nullptr;
+    size_t h_in_floats = 0;
+    cudaGraphExec_t graphs[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+
+namespace xdtts {
+// the *_locked functions expect h->mu to be held
+int gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out);
+int gl_plan_upload_locked(xdtts_gl_plan* p, int kind, const float* const* srcs);
+int gl_plan_run_locked(xdtts_gl_plan* p, int flags, float* ms_total, float* ms_iter, int* n_iter_launches);
+int gl_plan_download_locked(xdtts_gl_plan* p, float* const* outs);
+int gl_cached_plan(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out);
+int gl_plan_mel_arena(xdtts_gl_plan* p, float** out);
+}  // namespace xdtts

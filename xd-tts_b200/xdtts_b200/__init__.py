@@ -13,4 +13,4 @@ The arithmetic runs only in the CUDA library; there is no CPU path.  Importing t
 does not need a GPU, creating a GriffinLim does.
 """
 from ._ffi import XdttsError, load_library, version  # noqa: F401
-from . import griffin_lim  # noqa: F401
+from . import griffin_lim, tacotron2  # noqa: F401

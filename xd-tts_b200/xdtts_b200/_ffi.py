@@ -24,6 +24,10 @@ class XdttsError(RuntimeError):
         self.message = message
 
 
+class PostnetOpts(ctypes.Structure):
+    _fields_ = [("precision", ctypes.c_int)]
+
+
 class GlOpts(ctypes.Structure):
     _fields_ = [
         ("delog", ctypes.c_int),
@@ -58,6 +62,17 @@ SIGNATURES = {
     "xdtts_gl_plan_download": (ctypes.c_int, [_vp, _fpp]),
     "xdtts_gl_plan_peek": (ctypes.c_int, [_vp, ctypes.c_int, _fp, ctypes.c_longlong]),
     "xdtts_gl_plan_info": (ctypes.c_int, [_vp, _ip]),
+    "xdtts_postnet_create": (ctypes.c_int, [ctypes.c_int, _ip, ctypes.c_int, _fpp, _fpp, _fpp, _fpp, _fpp, _fpp, ctypes.c_float,
+                                            ctypes.POINTER(PostnetOpts), ctypes.c_int, ctypes.POINTER(_vp)]),
+    "xdtts_postnet_destroy": (None, [_vp]),
+    "xdtts_postnet_infer": (ctypes.c_int, [_vp, _fp, ctypes.c_int, _fp]),
+    "xdtts_postnet_infer_batch": (ctypes.c_int, [_vp, _fpp, _ip, ctypes.c_int, _fpp]),
+    "xdtts_postnet_plan_create": (ctypes.c_int, [_vp, _ip, ctypes.c_int, ctypes.POINTER(_vp)]),
+    "xdtts_postnet_plan_destroy": (None, [_vp]),
+    "xdtts_postnet_plan_upload": (ctypes.c_int, [_vp, _fpp]),
+    "xdtts_postnet_plan_run": (ctypes.c_int, [_vp, _vp, _fp]),
+    "xdtts_postnet_plan_download": (ctypes.c_int, [_vp, _fpp]),
+    "xdtts_tail_infer_batch": (ctypes.c_int, [_vp, _vp, _fpp, _ip, ctypes.c_int, _fpp, _fpp, _fpp]),
     "xdtts_host_alloc": (_vp, [ctypes.c_ulonglong]),
     "xdtts_host_free": (None, [_vp]),
     "xdtts_last_error": (ctypes.c_char_p, []),
