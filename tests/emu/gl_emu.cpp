@@ -18,7 +18,8 @@ using namespace xdtts;
 template <int R3, int MODE, bool STORE_R, bool TRACK_MAX>
 static void emu_launch(GlParams p, bool reverse_order) {
     typedef Geo<R3> G;
-    std::vector<float2> ex1(G::EX1), ex2(G::EX2);
+    std::vector<float2> ex1(G::EX1), ex2(G::EX2), r_stg(G::M);
+    std::vector<float> s_stg(G::M);
     std::vector<Lane<R3>> lanes(32);
     for (int rr = 0; rr < p.n_runs; rr++) {
         const int run_idx = reverse_order ? p.n_runs - 1 - rr : rr;
@@ -32,17 +33,23 @@ static void emu_launch(GlParams p, bool reverse_order) {
             if (old & 1u)
                 for (int l = 0; l < 32; l++) combine_boundary<R3, TRACK_MAX>(lanes[l], l, p, boundary);
         };
+        for (int l = 0; l < 32; l++) stage_issue<R3, MODE>(lanes[l], l, p, foff + r.ta, s_stg.data(), r_stg.data(), nullptr);
+        bool pref = false;
         for (int t = r.ta; t < r.tb; t++) {
             const long frame = foff + t;
-            for (int l = 0; l < 32; l++) phase_f0<R3, MODE>(lanes[l], l, p, frame);
             if (MODE != GL_MODE_INIT) {
-                const bool have_pref = (t > r.ta) && !frame_is_edge(t, T);
-                const bool fetch_next = (t + 1 < r.tb) && !frame_is_edge(t + 1, T);
+                const bool fetch_next = (t + 1 < r.tb) && (t + 2 <= T - 2);
                 for (int l = 0; l < 32; l++)
-                    phase_f1<R3>(lanes[l], l, p.y_in + yoff, T, t, p.pad_mode, have_pref, fetch_next, p.tables, ex1.data());
+                    phase_f1<R3>(lanes[l], l, p.y_in + yoff, T, t, p.pad_mode, t == r.ta, pref, p.tables, ex1.data());
+                pref = fetch_next;
+                if (fetch_next)
+                    for (int l = 0; l < 32; l++) prefetch_next_block<R3>(lanes[l], l, p.y_in + yoff, T, t, p.pad_mode);
                 for (int l = 0; l < 32; l++) phase_f2<R3>(lanes[l], l, p.tables, ex1.data(), ex2.data());
             }
-            for (int l = 0; l < 32; l++) phase_f3<R3, MODE, STORE_R>(lanes[l], l, p, r.utt, T, t, frame, p.tables, ex2.data());
+            for (int l = 0; l < 32; l++)
+                phase_f3<R3, MODE, STORE_R>(lanes[l], l, p, r.utt, T, t, frame, p.tables, ex2.data(), s_stg.data(), r_stg.data());
+            if (t + 1 < r.tb)
+                for (int l = 0; l < 32; l++) stage_issue<R3, MODE>(lanes[l], l, p, frame + 1, s_stg.data(), r_stg.data(), nullptr);
             for (int l = 0; l < 32; l++) phase_f4<R3>(lanes[l], l, p.tables, ex2.data(), ex1.data());
             bool sig = false;
             for (int l = 0; l < 32; l++) {

@@ -313,6 +313,16 @@ int xdtts::gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out)
         rf = (int)((total + resident - 1) / resident);
         if (rf < 8) rf = 8;
         if (rf > 64) rf = 64;
+        // wave quantisation: lengthen the runs a little until the CTAs fit the resident set, or the
+        // last wave is at least 60% full (one straggler CTA would otherwise double the launch time)
+        const int wpc = gl_warps_per_cta(h->n_fft), res_ctas = h->sm_count * gl_ctas_per_sm(h->n_fft);
+        for (int tries = 0; tries < 16 && rf < 96; tries++, rf++) {
+            std::vector<GlRun> tmp_runs;
+            std::vector<int> tmp_foff;
+            build_runs(Ts, B, rf, &tmp_runs, &tmp_foff);
+            const int ctas = ((int)tmp_runs.size() + wpc - 1) / wpc, tail = ctas % res_ctas;
+            if (ctas <= res_ctas || tail == 0 || tail * 10 >= res_ctas * 6) break;
+        }
     }
     if (rf < 4) rf = 4;
     p->run_frames = rf;
@@ -364,7 +374,7 @@ extern "C" int xdtts_gl_plan_info(const xdtts_gl_plan* p, int* info4) {
     if (!p || !info4) return fail(XDTTS_ERR_BAD_ARG, "plan_info: null argument");
     info4[0] = (int)p->runs.size();
     info4[1] = p->run_frames;
-    info4[2] = ((int)p->runs.size() + gl_warps_per_cta() - 1) / gl_warps_per_cta();
+    info4[2] = ((int)p->runs.size() + gl_warps_per_cta(p->h->n_fft) - 1) / gl_warps_per_cta(p->h->n_fft);
     info4[3] = p->total_T;
     return XDTTS_OK;
 }

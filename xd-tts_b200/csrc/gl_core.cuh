@@ -226,11 +226,10 @@ XD_HD T ld_l2(const T* p) {   // bypass L1: data written by another SM during th
 template <int R3>
 struct Lane {
     float2 v[Geo<R3>::VPL];          // FFT working set
+    float2 raw[Geo<R3>::VPL];        // un-windowed samples of the current frame; three quarters carry over to the next
     float2 acc[3][2 * Geo<R3>::NB];  // overlap-add sums of the three unfinished hop blocks
     float2 ynew[2 * Geo<R3>::NB];    // newest hop block of the NEXT frame, fetched one frame ahead
-    float sa[R3], sb[R3];            // |S| at this lane's bins k and M-k (issued at frame start, used in F3)
-    float2 pa[R3], pb[R3];           // previous rebuilt spectrum at the same bins
-    float s_nyq;
+    float s_nyq;                     // |S| at the Nyquist bin of the frame whose state is staged (lane 0)
     float amax;
 };
 
@@ -240,90 +239,141 @@ XD_HD int reflect_index(int j, int len) {
     return j;
 }
 
-// F0: issue this frame's state loads (S, previous R).  They are consumed in F3, two FFT passes
-// later, so their DRAM latency is covered by F1/F2 instead of stalling the warp.
+// ------------------------------------------------------------------ state staging
+// S and the previous rebuilt spectrum of ONE frame are contiguous rows (4M and 8M bytes).  The warp
+// stages them in shared memory with two bulk asynchronous copies (cp.async.bulk, the TMA engine)
+// issued by lane 0 one frame ahead and signalled on the warp's mbarrier, so no lane holds state in
+// registers while the FFT passes run and the DRAM latency is off the warp's critical path.
+// The CPU emulator performs the same copy synchronously.
+#if defined(__CUDACC__)
+__device__ __forceinline__ unsigned smem_addr_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_addr_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr_u32(bar))
+                 : "memory");
+}
+#endif
+
+// issue the copies of `frame`'s state into the warp's staging area (call after every lane has
+// finished reading the previous contents: the caller puts a warp sync in between)
 template <int R3, int MODE>
-XD_HD void phase_f0(Lane<R3>& L, int lane, const GlParams& p, long frame) {
+XD_HD void stage_issue(Lane<R3>& L, int lane, const GlParams& p, long frame, float* s_stg, float2* r_stg,
+                       unsigned long long* bar) {
     typedef Geo<R3> G;
-    const bool l0 = (lane == 0);
-    const float* Srow = p.S + frame * G::M;
-    const float2* Rrow = p.R + frame * G::M;
-#pragma unroll
-    for (int j = 0; j < R3; j++) {
-        const int ka = kslot<R3>(lane, j);
-        const int kb = (l0 && j == 0) ? G::M / 2 : G::M - ka;
-        L.sa[j] = ld_stream(Srow + ka);
-        L.sb[j] = ld_stream(Srow + kb);
-        if (MODE == GL_MODE_MID) {
-            L.pa[j] = ld_stream(Rrow + ka);
-            L.pb[j] = ld_stream(Rrow + kb);
-        }
+    if (lane == 0) {
+        const float* Srow = p.S + frame * G::M;
+        const float2* Rrow = p.R + frame * G::M;
+#if defined(__CUDA_ARCH__)
+        mbar_expect_tx(bar, (unsigned)(G::M * (MODE == GL_MODE_MID ? 12 : 4)));
+        bulk_g2s(s_stg, Srow, (unsigned)(G::M * 4), bar);
+        if (MODE == GL_MODE_MID) bulk_g2s(r_stg, Rrow, (unsigned)(G::M * 8), bar);
+#else
+        (void)bar;
+        for (int k = 0; k < G::M; k++) s_stg[k] = Srow[k];
+        if (MODE == GL_MODE_MID)
+            for (int k = 0; k < G::M; k++) r_stg[k] = Rrow[k];
+#endif
+        L.s_nyq = ld_stream(p.S_nyq + frame);
     }
-    L.s_nyq = 0.f;
-    if (l0) L.s_nyq = ld_stream(p.S_nyq + frame);
+}
+
+XD_HD void stage_wait(unsigned long long* bar, unsigned parity) {
+#if defined(__CUDA_ARCH__)
+    mbar_wait(bar, parity);
+#else
+    (void)bar;
+    (void)parity;
+#endif
 }
 
 XD_HD bool frame_is_edge(int t, int T) { return (t < 2) || (t >= T - 2); }
 
-// F1: frame t of the previous waveform -> window -> pass 1 (radix 8 over n1) -> exchange 1.
-// have_pref: L.ynew holds the frame's last hop block (fetched during the previous frame).
-// fetch_next: frame t+1 belongs to this run and is interior -> fetch its last hop block now.
+// quarter qi (one hop block, H samples) of frame t of the padded previous waveform -> q[2 NB]
+// element (n1 & 1) * NB + i  <->  sample 16 R3 n1 + 2 (lane + 32 i), n1 = 2 qi + (n1 & 1)
 template <int R3>
-XD_HD void phase_f1(Lane<R3>& L, int lane, const float* y, int T, int t, int pad_mode, bool have_pref, bool fetch_next,
-                    const float2* tab, float2* ex1) {
+XD_HD void load_quarter(float2* q, int lane, const float* y, int T, int t, int qi, int pad_mode) {
     typedef Geo<R3> G;
-    const int base = (t - 2) * G::H;
-    if (!frame_is_edge(t, T)) {   // warp-uniform: all loads of the interior path are issued back to back
+    const int g = t - 2 + qi;                  // hop block of the trimmed signal
+    const int base = g * G::H;
+    if (g >= 0 && g <= T - 2) {                // warp-uniform: entirely inside the signal
         const float* yb = y + base + 2 * lane;
 #pragma unroll
-        for (int i = 0; i < G::NB; i++)
-#pragma unroll
-            for (int n1 = 0; n1 < 6; n1++) L.v[i * 8 + n1] = *reinterpret_cast<const float2*>(yb + 16 * R3 * n1 + 64 * i);
-        if (have_pref) {
-#pragma unroll
-            for (int i = 0; i < G::NB; i++) {
-                L.v[i * 8 + 6] = L.ynew[i];
-                L.v[i * 8 + 7] = L.ynew[G::NB + i];
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < G::NB; i++)
-#pragma unroll
-                for (int n1 = 6; n1 < 8; n1++) L.v[i * 8 + n1] = *reinterpret_cast<const float2*>(yb + 16 * R3 * n1 + 64 * i);
-        }
+        for (int e = 0; e < 2 * G::NB; e++)
+            q[e] = *reinterpret_cast<const float2*>(yb + 16 * R3 * (e / G::NB) + 64 * (e % G::NB));
     } else {
         const int len = G::H * (T - 1);
 #pragma unroll
-        for (int i = 0; i < G::NB; i++) {
-#pragma unroll
-            for (int n1 = 0; n1 < 8; n1++) {
-                const int j0 = base + 16 * R3 * n1 + 2 * (lane + 32 * i), j1 = j0 + 1;
-                float2 x;
-                if (pad_mode == GL_PAD_REFLECT) {
-                    x.x = y[reflect_index(j0, len)];
-                    x.y = y[reflect_index(j1, len)];
-                } else {
-                    x.x = (j0 >= 0 && j0 < len) ? y[j0] : 0.f;
-                    x.y = (j1 >= 0 && j1 < len) ? y[j1] : 0.f;
-                }
-                L.v[i * 8 + n1] = x;
+        for (int e = 0; e < 2 * G::NB; e++) {
+            const int j0 = base + 16 * R3 * (e / G::NB) + 64 * (e % G::NB) + 2 * lane, j1 = j0 + 1;
+            float2 x;
+            if (pad_mode == GL_PAD_REFLECT) {
+                x.x = y[reflect_index(j0, len)];
+                x.y = y[reflect_index(j1, len)];
+            } else {
+                x.x = (j0 >= 0 && j0 < len) ? y[j0] : 0.f;
+                x.y = (j1 >= 0 && j1 < len) ? y[j1] : 0.f;
             }
+            q[e] = x;
         }
     }
-    if (fetch_next) {   // hop block (t+1)+1 of the trimmed signal = quarter 3 of frame t+1
-        const float* yn = y + base + G::H + 2 * lane;
+}
+
+// F1: frame t of the previous waveform -> window -> pass 1 (radix 8 over n1) -> exchange 1.
+// The frame's samples live in L.raw: a frame shares three of its four hop blocks with its
+// predecessor, so only the newest block comes from memory (first: the run's first frame, which
+// loads all four; have_pref: L.ynew already holds the newest block, fetched during the previous frame).
+template <int R3>
+XD_HD void phase_f1(Lane<R3>& L, int lane, const float* y, int T, int t, int pad_mode, bool first, bool have_pref,
+                    const float2* tab, float2* ex1) {
+    typedef Geo<R3> G;
+    if (first) {
 #pragma unroll
-        for (int i = 0; i < G::NB; i++) {
-            L.ynew[i] = *reinterpret_cast<const float2*>(yn + 16 * R3 * 6 + 64 * i);
-            L.ynew[G::NB + i] = *reinterpret_cast<const float2*>(yn + 16 * R3 * 7 + 64 * i);
+        for (int qi = 0; qi < 4; qi++) {
+            float2 q[2 * G::NB];
+            load_quarter<R3>(q, lane, y, T, t, qi, pad_mode);
+#pragma unroll
+            for (int e = 0; e < 2 * G::NB; e++) L.raw[(e % G::NB) * 8 + 2 * qi + e / G::NB] = q[e];
         }
+    } else {
+#pragma unroll
+        for (int i = 0; i < G::NB; i++)
+#pragma unroll
+            for (int n1 = 0; n1 < 6; n1++) L.raw[i * 8 + n1] = L.raw[i * 8 + n1 + 2];
+        float2 q[2 * G::NB];
+        if (have_pref) {
+#pragma unroll
+            for (int e = 0; e < 2 * G::NB; e++) q[e] = L.ynew[e];
+        } else {
+            load_quarter<R3>(q, lane, y, T, t, 3, pad_mode);
+        }
+#pragma unroll
+        for (int e = 0; e < 2 * G::NB; e++) L.raw[(e % G::NB) * 8 + 6 + e / G::NB] = q[e];
     }
 #pragma unroll
     for (int i = 0; i < G::NB; i++) {
 #pragma unroll
         for (int n1 = 0; n1 < 8; n1++) {
             const float2 w = tab[G::WIN_OFF + (i * 8 + n1) * 32 + lane];
-            L.v[i * 8 + n1] = mk2(L.v[i * 8 + n1].x * w.x, L.v[i * 8 + n1].y * w.y);
+            L.v[i * 8 + n1] = mk2(L.raw[i * 8 + n1].x * w.x, L.raw[i * 8 + n1].y * w.y);
         }
         Dft<8, false>::run(&L.v[i * 8]);
 #pragma unroll
@@ -333,6 +383,14 @@ XD_HD void phase_f1(Lane<R3>& L, int lane, const float* y, int T, int t, int pad
             ex1[k1 * G::S1 + lane + 32 * i] = z;
         }
     }
+}
+
+// Fetch the newest hop block of frame t+1 (inside the signal by construction: fast path) one frame
+// ahead.  Issued AFTER the warp sync that follows F1: the loads then share no scoreboard wait with
+// the window multiply of frame t, which consumes the block fetched a frame earlier.
+template <int R3>
+XD_HD void prefetch_next_block(Lane<R3>& L, int lane, const float* y, int T, int t, int pad_mode) {
+    load_quarter<R3>(L.ynew, lane, y, T, t + 1, 3, pad_mode);
 }
 
 // F2: pass 2 (radix 8 over n2) -> exchange 2
@@ -396,7 +454,7 @@ XD_HD void lane0_unfix(float2* v, bool l0) {
 //     -> inverse pass 1 -> exchange 2 (in place)
 template <int R3, int MODE, bool STORE_R>
 XD_HD void phase_f3(Lane<R3>& L, int lane, const GlParams& p, int utt, int T, int t, long frame, const float2* tab,
-                    float2* ex2) {
+                    float2* ex2, const float* s_stg, const float2* r_stg) {
     typedef Geo<R3> G;
     const bool l0 = (lane == 0);
     const int qA = lane, qB = lane ? 64 - lane : 32;
@@ -404,10 +462,6 @@ XD_HD void phase_f3(Lane<R3>& L, int lane, const GlParams& p, int utt, int T, in
     float2* B = &L.v[R3];
     float2* Rrow = p.R + frame * G::M;
 
-    const float* sa = L.sa;
-    const float* sb = L.sb;
-    const float2* pa = L.pa;
-    const float2* pb = L.pb;
     const float s_nyq = L.s_nyq;
 
     if (MODE != GL_MODE_INIT) {
@@ -426,6 +480,7 @@ XD_HD void phase_f3(Lane<R3>& L, int lane, const GlParams& p, int utt, int T, in
         const int ka = kslot<R3>(lane, j);
         const int kb = (l0 && j == 0) ? G::M / 2 : G::M - ka;
         const float2 C = tab[G::RTW_OFF + j * 32 + lane];   // -i W_N^k / 2
+        const float sa_j = s_stg[ka], sb_j = s_stg[kb];      // staged |S| at bins k and M-k
         float2 Ya, Yb;
         if (MODE != GL_MODE_INIT) {
             const float2 a = A[j], b = B[R3 - 1 - j];
@@ -441,21 +496,22 @@ XD_HD void phase_f3(Lane<R3>& L, int lane, const GlParams& p, int utt, int T, in
             }
             float2 ua = Ra, ub = Rb;
             if (MODE == GL_MODE_MID) {
-                ua = mk2(Ra.x - p.alpha * pa[j].x, Ra.y - p.alpha * pa[j].y);
-                ub = mk2(Rb.x - p.alpha * pb[j].x, Rb.y - p.alpha * pb[j].y);
+                const float2 pa_j = r_stg[ka], pb_j = r_stg[kb];   // staged previous rebuilt spectrum
+                ua = mk2(Ra.x - p.alpha * pa_j.x, Ra.y - p.alpha * pa_j.y);
+                ub = mk2(Rb.x - p.alpha * pb_j.x, Rb.y - p.alpha * pb_j.y);
             }
             if (STORE_R) {
                 st_stream(Rrow + ka, Ra);
                 st_stream(Rrow + kb, Rb);
             }
-            const float ga = sa[j] * p.inv_n * rsqrt_pos(ua.x * ua.x + ua.y * ua.y);
-            const float gb = sb[j] * p.inv_n * rsqrt_pos(ub.x * ub.x + ub.y * ub.y);
+            const float ga = sa_j * p.inv_n * rsqrt_pos(ua.x * ua.x + ua.y * ua.y);
+            const float gb = sb_j * p.inv_n * rsqrt_pos(ub.x * ub.x + ub.y * ub.y);
             Ya = mk2(ua.x * ga, ua.y * ga);
             Yb = mk2(ub.x * gb, ub.y * gb);
             if (j == 0 && l0) {
                 const float y0 = ua.x > 0.f ? 1.f : (ua.x < 0.f ? -1.f : 0.f);
                 const float ym = ua.y > 0.f ? 1.f : (ua.y < 0.f ? -1.f : 0.f);
-                Ya = mk2(y0 * sa[0] * p.inv_n, ym * s_nyq * p.inv_n);
+                Ya = mk2(y0 * sa_j * p.inv_n, ym * s_nyq * p.inv_n);
             }
         } else {
             float ta_, tb_, tn_ = 0.f;
@@ -470,9 +526,9 @@ XD_HD void phase_f3(Lane<R3>& L, int lane, const GlParams& p, int utt, int T, in
             }
             float sn, cs;
             sincos_turns(ta_, &sn, &cs);
-            Ya = mk2(sa[j] * p.inv_n * cs, sa[j] * p.inv_n * sn);
+            Ya = mk2(sa_j * p.inv_n * cs, sa_j * p.inv_n * sn);
             sincos_turns(tb_, &sn, &cs);
-            Yb = mk2(sb[j] * p.inv_n * cs, sb[j] * p.inv_n * sn);
+            Yb = mk2(sb_j * p.inv_n * cs, sb_j * p.inv_n * sn);
             if (j == 0 && l0) {   // the inverse real FFT ignores the imaginary part of bins 0 and M
                 sincos_turns(tn_, &sn, &cs);
                 Ya = mk2(Ya.x, s_nyq * p.inv_n * cs);

@@ -18,7 +18,12 @@
 
 namespace xdtts {
 
-constexpr int GL_WARPS = 4;
+// warps per CTA and CTAs per SM by geometry: shared memory (tables + per-warp exchange and staging) is the limiter
+template <int R3>
+struct GlCfg {
+    static constexpr int WARPS = (R3 == 16) ? 7 : 4;
+    static constexpr int CTAS = (R3 == 16) ? 1 : 3;
+};
 
 template <int R3, bool TRACK_MAX>
 __device__ __forceinline__ void arrive(Lane<R3>& L, int lane, const GlParams& p, int boundary) {
@@ -33,19 +38,42 @@ __device__ __forceinline__ void arrive(Lane<R3>& L, int lane, const GlParams& p,
     }
 }
 
-template <int R3, int MODE, bool STORE_R, bool TRACK_MAX>
-__global__ void __launch_bounds__(GL_WARPS * 32, (R3 == 16) ? 2 : 3) gl_iter_kernel(const GlParams p) {
+// shared memory of one CTA, float2 units: [tables][per warp: exchange 1, exchange 2, staged S (M floats), staged R (M float2)]
+// followed by the mbarriers (one for the table copy, one per warp for its state staging)
+template <int R3>
+struct GlSmem {
     typedef Geo<R3> G;
+    static constexpr int WARPS = GlCfg<R3>::WARPS;
+    static constexpr int WARP = G::EXW + G::M / 2 + G::M;           // float2 per warp
+    static constexpr int BAR_OFF = G::TAB + WARPS * WARP;           // float2 units (8 bytes each)
+    static constexpr size_t BYTES = sizeof(float2) * (size_t)(BAR_OFF + 1 + WARPS);
+};
+
+template <int R3, int MODE, bool STORE_R, bool TRACK_MAX>
+__global__ void __launch_bounds__(GlCfg<R3>::WARPS * 32, GlCfg<R3>::CTAS) gl_iter_kernel(const GlParams p) {
+    typedef Geo<R3> G;
+    constexpr int GL_WARPS = GlCfg<R3>::WARPS;
     extern __shared__ __align__(16) float2 smem[];
     float2* tab = smem;
-    for (int i = threadIdx.x; i < G::TAB; i += GL_WARPS * 32) tab[i] = p.tables[i];
-    __syncthreads();
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + GlSmem<R3>::BAR_OFF);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i <= GL_WARPS; i++) mbar_init(&bars[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {   // constant tables: one bulk copy per CTA, awaited by each warp before its first use
+        mbar_expect_tx(&bars[0], (unsigned)(G::TAB * sizeof(float2)));
+        bulk_g2s(tab, p.tables, (unsigned)(G::TAB * sizeof(float2)), &bars[0]);
+    }
     const int run_idx = blockIdx.x * GL_WARPS + warp;
     if (run_idx >= p.n_runs) return;
-    float2* ex1 = smem + G::TAB + warp * G::EXW;
+    float2* ex1 = smem + G::TAB + warp * GlSmem<R3>::WARP;
     float2* ex2 = ex1 + G::EX1;
+    float* s_stg = reinterpret_cast<float*>(ex2 + G::EX2);
+    float2* r_stg = ex2 + G::EX2 + G::M / 2;
+    unsigned long long* bar = &bars[1 + warp];
 
     const GlRun r = p.runs[run_idx];
     const int T = p.utt_T[r.utt];
@@ -54,20 +82,25 @@ __global__ void __launch_bounds__(GL_WARPS * 32, (R3 == 16) ? 2 : 3) gl_iter_ker
 
     Lane<R3> L;
     lane_reset<R3>(L);
+    stage_issue<R3, MODE>(L, lane, p, foff + r.ta, s_stg, r_stg, bar);
+    stage_wait(&bars[0], 0);
 
+    bool pref = false;
     for (int t = r.ta; t < r.tb; t++) {
         const long frame = foff + t;
-        phase_f0<R3, MODE>(L, lane, p, frame);
         if (MODE != GL_MODE_INIT) {
-            const bool have_pref = (t > r.ta) && !frame_is_edge(t, T);
-            const bool fetch_next = (t + 1 < r.tb) && !frame_is_edge(t + 1, T);
-            phase_f1<R3>(L, lane, p.y_in + yoff, T, t, p.pad_mode, have_pref, fetch_next, tab, ex1);
+            const bool fetch_next = (t + 1 < r.tb) && (t + 2 <= T - 2);   // newest hop block of frame t+1 lies inside the signal
+            phase_f1<R3>(L, lane, p.y_in + yoff, T, t, p.pad_mode, t == r.ta, pref, tab, ex1);
+            pref = fetch_next;
             __syncwarp();
+            if (fetch_next) prefetch_next_block<R3>(L, lane, p.y_in + yoff, T, t, p.pad_mode);
             phase_f2<R3>(L, lane, tab, ex1, ex2);
             __syncwarp();
         }
-        phase_f3<R3, MODE, STORE_R>(L, lane, p, r.utt, T, t, frame, tab, ex2);
-        __syncwarp();
+        stage_wait(bar, (unsigned)(t - r.ta) & 1u);
+        phase_f3<R3, MODE, STORE_R>(L, lane, p, r.utt, T, t, frame, tab, ex2, s_stg, r_stg);
+        __syncwarp();   // every lane is done with the staged state (its values fed the stores above)
+        if (t + 1 < r.tb) stage_issue<R3, MODE>(L, lane, p, frame + 1, s_stg, r_stg, bar);
         phase_f4<R3>(L, lane, tab, ex2, ex1);
         __syncwarp();
         phase_f5<R3>(L, lane, tab, ex1);
@@ -89,7 +122,7 @@ __global__ void __launch_bounds__(GL_WARPS * 32, (R3 == 16) ? 2 : 3) gl_iter_ker
 
 template <int R3>
 static size_t gl_smem_bytes() {
-    return sizeof(float2) * (size_t)(Geo<R3>::TAB + GL_WARPS * Geo<R3>::EXW);
+    return GlSmem<R3>::BYTES;
 }
 
 template <int R3, int MODE, bool STORE_R, bool TRACK_MAX>
@@ -123,8 +156,9 @@ cudaError_t gl_prepare(int n_fft) {
 template <int R3, int MODE, bool STORE_R, bool TRACK_MAX>
 static cudaError_t launch_one(const GlParams& p, cudaStream_t s) {
     auto k = gl_iter_kernel<R3, MODE, STORE_R, TRACK_MAX>;
-    const int grid = (p.n_runs + GL_WARPS - 1) / GL_WARPS;
-    k<<<grid, GL_WARPS * 32, gl_smem_bytes<R3>(), s>>>(p);
+    constexpr int W = GlCfg<R3>::WARPS;
+    const int grid = (p.n_runs + W - 1) / W;
+    k<<<grid, W * 32, gl_smem_bytes<R3>(), s>>>(p);
     return cudaGetLastError();
 }
 
@@ -148,8 +182,12 @@ cudaError_t gl_launch_iteration(int n_fft, int mode, bool last, const GlParams& 
     return cudaErrorInvalidValue;
 }
 
-int gl_warps_per_cta() { return GL_WARPS; }
+int gl_warps_per_cta(int n_fft) { return n_fft == 2048 ? GlCfg<16>::WARPS : GlCfg<8>::WARPS; }
 
-int gl_resident_warps_per_sm(int n_fft) { return GL_WARPS * (n_fft == 2048 ? 2 : 3); }
+int gl_ctas_per_sm(int n_fft) { return n_fft == 2048 ? GlCfg<16>::CTAS : GlCfg<8>::CTAS; }
+
+int gl_resident_warps_per_sm(int n_fft) {
+    return n_fft == 2048 ? GlCfg<16>::WARPS * GlCfg<16>::CTAS : GlCfg<8>::WARPS * GlCfg<8>::CTAS;
+}
 
 }  // namespace xdtts

@@ -87,11 +87,12 @@ def load_library():
     """dlopen the in-tree CUDA library; fails loudly if it has not been built."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("XDTTS_B200_LIB", LIB_PATH)   # tuning builds (tools/build_variants.py) override the path
+        if not os.path.exists(path):
             raise ImportError(
-                "%s is missing: run `python __graft_entry__.py` (nvcc, sm_100a) first; there is no CPU fallback" % LIB_PATH
+                "%s is missing: run `python __graft_entry__.py` (nvcc, sm_100a) first; there is no CPU fallback" % path
             )
-        lib = ctypes.CDLL(LIB_PATH)
+        lib = ctypes.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype = res
