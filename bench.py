@@ -38,19 +38,47 @@ sys.path.insert(0, os.path.join(ROOT, "xd-tts_b200"))
 CONFIGS = {
     # name: (batch per GPU, frames, n_fft, iterations)
     "cfg2": (32, 1000, 1024, 60),
+    "cfg3": (32, 1000, 1024, 60),   # cfg2 preceded by the Tacotron2 postnet (BASELINE.json configs[2])
     "cfg5": (8, 8000, 2048, 60),
 }
+POSTNET_FLOP_PER_FRAME = 8683520.0   # 2 * 5 * (80*512 + 3*512*512 + 512*80)
+FALLBACK_BF16_TFLOPS = 1590.0        # B200_PROFILING.md fallback (burst)
 POWER, MOMENTUM, N_MELS, SR, FMAX = 1.7, 0.99, 80, 22050.0, 8000.0
 FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
 
 
 def workload_name(cfg, b, t, n_fft, it):
-    return "%s: batch=%d x [80x%d] synthetic ln-mels U(-8,0), pinv lift ^1.7 + Griffin-Lim %d iters, n_fft=%d hop=%d" % (
-        cfg, b, t, it, n_fft, n_fft // 4)
+    pre = "Tacotron2 postnet (5 conv, bf16x3 tensor cores) + " if cfg == "cfg3" else ""
+    return "%s: batch=%d x [80x%d] synthetic ln-mels U(-8,0), %spinv lift ^1.7 + Griffin-Lim %d iters, n_fft=%d hop=%d" % (
+        cfg, b, t, pre, it, n_fft, n_fft // 4)
+
+
+def measured_tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            if "bf16_tflops" in d:
+                return float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+        except Exception:
+            pass
+    return FALLBACK_BF16_TFLOPS, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
+
+
+def synth_postnet_layers():
+    from oracle.postnet_oracle import synth_weights   # weight generator only (the LFS weights are absent)
+
+    return synth_weights(seed=7)
+
+
+def bench_mel(i, t):
+    from oracle.gl_oracle import synth_mel   # input generator only (shared with the tests)
+
+    return synth_mel(1234 + i, N_MELS, t)    # utterance i of the job
 
 
 def synth_batch(b, t, seed0):
-    from oracle.gl_oracle import synth_mel   # input generator only (shared with the tests)
+    from oracle.gl_oracle import synth_mel
 
     return [synth_mel(seed0 + i, N_MELS, t) for i in range(b)]
 
@@ -153,12 +181,20 @@ def cpu_arm(cfg, steps, warmup, sample_utts=None):
     turns = np.stack([o.phase_turns(0, i, k, t) for i in range(n)])
     hop = n_fft // 4
 
+    layers = synth_postnet_layers() if cfg == "cfg3" else None
+
+    def cpu_postnet(m):   # numpy restatement of the ONNX graph (BLAS threads over the GEMMs), fp32
+        from oracle.postnet_oracle import postnet
+
+        return np.stack([postnet(x, layers, dtype=np.float32) for x in m]) if layers else m
+
     def per_utt():      # OpenMP over the frames of one utterance (rayon-style, as the crate does)
+        pm = cpu_postnet(mels)
         for i in range(n):
-            c_oracle.infer(pinv, mels[i], turns[i], hop, POWER, it, MOMENTUM)
+            c_oracle.infer(pinv, pm[i], turns[i], hop, POWER, it, MOMENTUM)
 
     def per_batch():    # one thread per utterance
-        c_oracle.infer_batch(pinv, mels, turns, hop, POWER, it, MOMENTUM)
+        c_oracle.infer_batch(pinv, cpu_postnet(mels), turns, hop, POWER, it, MOMENTUM)
 
     best = None
     for name, fn in (("threads over utterances", per_batch), ("threads over frames", per_utt)):
@@ -175,7 +211,8 @@ def cpu_arm(cfg, steps, warmup, sample_utts=None):
     for _ in range(steps):
         fn()
     dt = (time.perf_counter() - t0) / steps
-    sample = "%d of %d utterances x %d frames x %d iters per step, C/OpenMP port of the oracle, %s" % (n, b, t, it, name)
+    sample = "%d of %d utterances x %d frames x %d iters per step, C/OpenMP port of the oracle%s, %s" % (
+        n, b, t, it, " after the numpy/BLAS postnet" if layers else "", name)
     return n * t / dt, cores, "port", sample, dt * 1e3
 
 
@@ -221,7 +258,7 @@ def run_gpu(args):
 
     if not os.path.exists(g.LIB):
         g.build_cuda()
-    from xdtts_b200 import _ffi, griffin_lim
+    from xdtts_b200 import _ffi, griffin_lim, shard, tacotron2
 
     lib = _ffi.load_library()
     cfg = args.config
@@ -230,14 +267,29 @@ def run_gpu(args):
     steps, warmup = args.steps, max(args.warmup, 3)
 
     basis = griffin_lim.mel.create_mel_filter_bank(SR, n_fft, N_MELS, 0.0, FMAX)
-    voc = griffin_lim.GriffinLim.new(basis, n_fft - hop, POWER, it, MOMENTUM, seed=rank, device=local_rank)
-    mels = synth_batch(b, t, 1234 + rank * b)          # this rank's shard of the job
+    voc = griffin_lim.GriffinLim.new(basis, n_fft - hop, POWER, it, MOMENTUM, seed=shard.rank_seed(0, rank), device=local_rank)
+    # the job: world * b utterances (weak scaling: b per GPU); this rank vocodes its shard, no data crosses GPUs
+    mine = shard.shard_utterances([t] * (world * b), world, rank)
+    mels = [bench_mel(i, t) for i in mine]
+    b = len(mine)
     frames = b * t
 
     # ---- device-resident arm: plan with the mels already in HBM
     plan = voc.plan([t] * b)
-    plan.upload(0, mels)
     info = plan.info()
+    with_postnet = cfg == "cfg3"
+    post = pplan = None
+    if with_postnet or (world == 1 and n_fft == 1024):
+        post = tacotron2.Postnet.from_layers(synth_postnet_layers(), device=local_rank)
+        pplan = post.plan([t] * b)
+        pplan.upload(mels)
+    if not with_postnet:
+        plan.upload(0, mels)
+
+    def step():
+        """one pass of the path over the resident batch -> device milliseconds"""
+        ms_pn = pplan.run(feed=plan) if with_postnet else 0.0   # writes mel_outputs_postnet into the vocoder's arena
+        return ms_pn + plan.run(0)[0]
 
     def barrier():
         torch.cuda.synchronize()
@@ -246,7 +298,7 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     for _ in range(warmup):
-        plan.run(0)
+        step()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -254,8 +306,7 @@ def run_gpu(args):
     t0 = time.perf_counter()
     dev_ms = 0.0
     for _ in range(steps):
-        ms, _, _ = plan.run(0)
-        dev_ms += ms
+        dev_ms += step()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     launches = lib.xdtts_kernel_launches() - launches0
@@ -280,7 +331,10 @@ def run_gpu(args):
     t_arr = (ctypes.c_int * b)(*([t] * b))
 
     def e2e_step():
-        _ffi.check(lib.xdtts_gl_infer_batch(voc._h, in_ptrs, t_arr, b, None, out_ptrs))
+        if with_postnet:
+            _ffi.check(lib.xdtts_tail_infer_batch(post._h, voc._h, in_ptrs, t_arr, b, None, None, out_ptrs))
+        else:
+            _ffi.check(lib.xdtts_gl_infer_batch(voc._h, in_ptrs, t_arr, b, None, out_ptrs))
 
     for _ in range(warmup):
         e2e_step()
@@ -292,14 +346,17 @@ def run_gpu(args):
     e2e_ms = (time.perf_counter() - t1) * 1e3
     peak_ok = all(abs(float(np.abs(a).max()) - 1.0) < 1e-5 for a, _ in pin_out)
 
+    # ---- the tensor-core leg (BASELINE.json configs[2]): postnet alone, device time by CUDA events
+    pn_ms = None
+    if pplan is not None:
+        if not with_postnet:
+            for _ in range(3):
+                pplan.run()
+        pn_ms = min((pplan.run(feed=plan) if with_postnet else pplan.run()) for _ in range(5))
+
     # ---- reduce over ranks: time = max, frames = sum
-    tt = torch.tensor([dev_ms, wall_ms, e2e_ms, kern_ms], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([float(frames), float(launches)], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)     # the single collective of the job: the throughput counter
-    dev_ms, wall_ms, e2e_ms, kern_ms = [float(x) for x in tt.tolist()]
-    total_frames, total_launches = float(cnt[0]), int(cnt[1])
+    total_frames, total_launches, (dev_ms, wall_ms, e2e_ms, kern_ms) = shard.reduce_counters(
+        frames, launches, [dev_ms, wall_ms, e2e_ms, kern_ms], device="cuda")   # the single collective of the job
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -315,7 +372,8 @@ def run_gpu(args):
                        "runs": info["n_runs"], "run_frames": info["run_frames"], "ctas": info["ctas"]},
             "e2e": {"value": total_frames * steps / (e2e_ms * 1e-3), "unit": "frames/s",
                     "h2d_bytes_per_step": b * N_MELS * t * 4, "d2h_bytes_per_step": b * out_len * 4,
-                    "ms_per_step": e2e_ms / steps, "api": "xdtts_gl_infer_batch (pinned host buffers)",
+                    "ms_per_step": e2e_ms / steps,
+                    "api": ("xdtts_tail_infer_batch" if with_postnet else "xdtts_gl_infer_batch") + " (pinned host buffers)",
                     "peak_normalised_ok": peak_ok},
             "gpu_launches": total_launches,
             "roofline": {"bound": "hbm", "kernel": "gl_iter_kernel<MID> (one Griffin-Lim iteration)",
@@ -324,6 +382,14 @@ def run_gpu(args):
                          "algorithmic_bytes_per_launch": alg_bytes},
             "clocks": clocks,
         }
+        if pn_ms is not None:
+            tpeak, tsrc = measured_tensor_peak()
+            tf = POSTNET_FLOP_PER_FRAME * frames / (pn_ms * 1e-3) / 1e12
+            line["postnet"] = {"bound": "tensor", "kernel": "pn_conv_tc_kernel x5 + input staging (tcgen05 bf16x3: 3 MMA passes per layer)",
+                               "ms": pn_ms, "frames_per_s": frames / (pn_ms * 1e-3), "achieved": tf, "executed": 3 * tf,
+                               "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak, "frac_executed": 3 * tf / tpeak,
+                               "peak_source": tsrc, "algorithmic_flop_per_frame": POSTNET_FLOP_PER_FRAME,
+                               "in_timed_step": with_postnet}
         if world == 1 and not args.no_cpu:
             v, cores, kind, sample, _ = cpu_arm(cfg, 1, 1)
             line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}

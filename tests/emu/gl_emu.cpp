@@ -18,7 +18,10 @@ using namespace xdtts;
 template <int R3, int MODE, bool STORE_R, bool TRACK_MAX>
 static void emu_launch(GlParams p, bool reverse_order) {
     typedef Geo<R3> G;
-    std::vector<float2> ex1(G::EX1), ex2(G::EX2), r_stg(G::M);
+    // one buffer for both exchanges: the emulator always runs the aliased layout (a superset of the
+    // hazards of the two-buffer layout; phases are lane-sequential, i.e. warp-synchronous)
+    std::vector<float2> ex1(G::EX1 > G::EX2 ? G::EX1 : G::EX2), r_stg(G::M);
+    std::vector<float2>& ex2 = ex1;
     std::vector<float> s_stg(G::M);
     std::vector<Lane<R3>> lanes(32);
     for (int rr = 0; rr < p.n_runs; rr++) {
@@ -44,13 +47,15 @@ static void emu_launch(GlParams p, bool reverse_order) {
                 pref = fetch_next;
                 if (fetch_next)
                     for (int l = 0; l < 32; l++) prefetch_next_block<R3>(lanes[l], l, p.y_in + yoff, T, t, p.pad_mode);
-                for (int l = 0; l < 32; l++) phase_f2<R3>(lanes[l], l, p.tables, ex1.data(), ex2.data());
+                for (int l = 0; l < 32; l++) phase_f2_load<R3>(lanes[l], l, ex1.data());
+                for (int l = 0; l < 32; l++) phase_f2_store<R3>(lanes[l], l, p.tables, ex2.data());
             }
             for (int l = 0; l < 32; l++)
                 phase_f3<R3, MODE, STORE_R>(lanes[l], l, p, r.utt, T, t, frame, p.tables, ex2.data(), s_stg.data(), r_stg.data());
             if (t + 1 < r.tb)
                 for (int l = 0; l < 32; l++) stage_issue<R3, MODE>(lanes[l], l, p, frame + 1, s_stg.data(), r_stg.data(), nullptr);
-            for (int l = 0; l < 32; l++) phase_f4<R3>(lanes[l], l, p.tables, ex2.data(), ex1.data());
+            for (int l = 0; l < 32; l++) phase_f4_load<R3>(lanes[l], l, p.tables, ex2.data());
+            for (int l = 0; l < 32; l++) phase_f4_store<R3>(lanes[l], l, ex1.data());
             bool sig = false;
             for (int l = 0; l < 32; l++) {
                 phase_f5<R3>(lanes[l], l, p.tables, ex1.data());

@@ -9,6 +9,7 @@ timeout 900 python -m pytest tests -m gpu -x -q > $out/pytest_gpu.log 2>&1; echo
 tail -3 $out/pytest_gpu.log
 timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' > $out/smoke.log 2>&1; tail -1 $out/smoke.log
 timeout 600 python bench.py --steps 10 --warmup 3 > $out/bench_cfg2.json 2> $out/bench_cfg2.err; cat $out/bench_cfg2.json
+timeout 600 python bench.py --config cfg3 --steps 10 --warmup 3 > $out/bench_cfg3.json 2> $out/bench_cfg3.err; cat $out/bench_cfg3.json
 timeout 600 python bench.py --config cfg5 --steps 5 --warmup 3 --no-cpu > $out/bench_cfg5.json 2> $out/bench_cfg5.err; cat $out/bench_cfg5.json
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $out/bench_ref.json 2> $out/bench_ref.err; cat $out/bench_ref.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $out/launches_cfg2.csv \
@@ -17,4 +18,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:gl_i
     python tools/prof_target.py cfg2 1 > $out/prof_cfg2.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gl_iter_kernel -s 20 -c 1 -f -o $out/prof_gl_iter_cfg5 \
     python tools/prof_target.py cfg5 1 > $out/prof_cfg5.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:pn_conv_tc -s 1 -c 2 -f -o $out/prof_postnet_cfg3 \
+    python tools/prof_postnet.py 1 0 > $out/prof_postnet.log 2>&1
+timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_target.py > $out/sanitizer_memcheck.log 2>&1; tail -3 $out/sanitizer_memcheck.log
 ls -la $out

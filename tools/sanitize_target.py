@@ -1,0 +1,35 @@
+"""Small invocation of every kernel for compute-sanitizer (memcheck / racecheck / synccheck):
+
+    compute-sanitizer --tool memcheck python tools/sanitize_target.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "xd-tts_b200"))
+
+from oracle import gl_oracle as o  # noqa: E402
+from oracle import postnet_oracle as po  # noqa: E402
+from xdtts_b200 import griffin_lim, tacotron2  # noqa: E402
+
+layers = po.synth_weights(seed=7)
+for n_fft, ts in ((1024, [37, 4, 150]), (2048, [21, 9]), (512, [30])):
+    hop, k = n_fft // 4, n_fft // 2 + 1
+    basis = o.create_mel_filter_bank(22050.0, n_fft, 80, 0.0, 8000.0)
+    voc = griffin_lim.GriffinLim.new(basis, n_fft - hop, 1.7, 3, 0.99, run_frames=5)
+    mels = [o.synth_mel(i, 80, t) for i, t in enumerate(ts)]
+    ys = voc.infer_batch(mels)
+    ys2 = voc.infer_batch(mels, [o.phase_turns(0, i, k, t) for i, t in enumerate(ts)])
+    assert all(np.array_equal(a, b) for a, b in zip(ys, ys2))
+    if n_fft == 1024:
+        for prec in (0, 1, 2):
+            post = tacotron2.Postnet.from_layers(layers, precision=prec)
+            outs = post.run_batch(mels)
+            assert all(np.isfinite(x).all() for x in outs)
+        post = tacotron2.Postnet.from_layers(layers)
+        w = tacotron2.infer_tail_batch(post, voc, mels)
+        assert all(np.isfinite(x).all() for x in w)
+print("sanitize target ok")

@@ -393,9 +393,10 @@ XD_HD void prefetch_next_block(Lane<R3>& L, int lane, const float* y, int T, int
     load_quarter<R3>(L.ynew, lane, y, T, t + 1, 3, pad_mode);
 }
 
-// F2: pass 2 (radix 8 over n2) -> exchange 2
+// F2: pass 2 (radix 8 over n2) -> exchange 2.  Split into its read half and its write half so that
+// the two exchange buffers may share storage (a warp sync between the halves then orders them).
 template <int R3>
-XD_HD void phase_f2(Lane<R3>& L, int lane, const float2* tab, const float2* ex1, float2* ex2) {
+XD_HD void phase_f2_load(Lane<R3>& L, int lane, const float2* ex1) {
     typedef Geo<R3> G;
     const int n3 = lane & (R3 - 1);
 #pragma unroll
@@ -404,6 +405,11 @@ XD_HD void phase_f2(Lane<R3>& L, int lane, const float2* tab, const float2* ex1,
 #pragma unroll
         for (int n2 = 0; n2 < 8; n2++) L.v[i * 8 + n2] = ex1[k1 * G::S1 + R3 * n2 + n3];
     }
+}
+template <int R3>
+XD_HD void phase_f2_store(Lane<R3>& L, int lane, const float2* tab, float2* ex2) {
+    typedef Geo<R3> G;
+    const int n3 = lane & (R3 - 1);
 #pragma unroll
     for (int i = 0; i < G::NB; i++) {
         const int k1 = (lane >> G::LN3) + (32 / R3) * i;
@@ -558,9 +564,9 @@ XD_HD void phase_f3(Lane<R3>& L, int lane, const GlParams& p, int utt, int T, in
     }
 }
 
-// F4: inverse pass 2 (radix 8 over k2) -> exchange 1
+// F4: inverse pass 2 (radix 8 over k2) -> exchange 1 (read half / write half, as F2)
 template <int R3>
-XD_HD void phase_f4(Lane<R3>& L, int lane, const float2* tab, const float2* ex2, float2* ex1) {
+XD_HD void phase_f4_load(Lane<R3>& L, int lane, const float2* tab, const float2* ex2) {
     typedef Geo<R3> G;
     const int n3 = lane & (R3 - 1);
 #pragma unroll
@@ -573,6 +579,11 @@ XD_HD void phase_f4(Lane<R3>& L, int lane, const float2* tab, const float2* ex2,
             L.v[i * 8 + k2] = z;
         }
     }
+}
+template <int R3>
+XD_HD void phase_f4_store(Lane<R3>& L, int lane, float2* ex1) {
+    typedef Geo<R3> G;
+    const int n3 = lane & (R3 - 1);
 #pragma unroll
     for (int i = 0; i < G::NB; i++) {
         const int k1 = (lane >> G::LN3) + (32 / R3) * i;

@@ -19,10 +19,22 @@
 namespace xdtts {
 
 // warps per CTA and CTAs per SM by geometry: shared memory (tables + per-warp exchange and staging) is the limiter
+// (tuning builds override the defaults with -DXDTTS_GL8_WARPS=... etc., tools/build_variants.py)
+#ifndef XDTTS_GL8_WARPS
+#define XDTTS_GL8_WARPS 4
+#define XDTTS_GL8_CTAS 3
+#define XDTTS_GL8_ALIAS 0
+#endif
+#ifndef XDTTS_GL16_WARPS
+#define XDTTS_GL16_WARPS 4
+#define XDTTS_GL16_CTAS 2
+#define XDTTS_GL16_ALIAS 1
+#endif
 template <int R3>
 struct GlCfg {
-    static constexpr int WARPS = (R3 == 16) ? 7 : 4;
-    static constexpr int CTAS = (R3 == 16) ? 1 : 3;
+    static constexpr int WARPS = (R3 == 16) ? XDTTS_GL16_WARPS : XDTTS_GL8_WARPS;
+    static constexpr int CTAS = (R3 == 16) ? XDTTS_GL16_CTAS : XDTTS_GL8_CTAS;
+    static constexpr bool ALIAS = (R3 == 16) ? XDTTS_GL16_ALIAS : XDTTS_GL8_ALIAS;   // exchange 1 and 2 share storage
 };
 
 template <int R3, bool TRACK_MAX>
@@ -44,7 +56,8 @@ template <int R3>
 struct GlSmem {
     typedef Geo<R3> G;
     static constexpr int WARPS = GlCfg<R3>::WARPS;
-    static constexpr int WARP = G::EXW + G::M / 2 + G::M;           // float2 per warp
+    static constexpr int EX = GlCfg<R3>::ALIAS ? (G::EX1 > G::EX2 ? G::EX1 : G::EX2) : G::EXW;
+    static constexpr int WARP = EX + G::M / 2 + G::M;               // float2 per warp
     static constexpr int BAR_OFF = G::TAB + WARPS * WARP;           // float2 units (8 bytes each)
     static constexpr size_t BYTES = sizeof(float2) * (size_t)(BAR_OFF + 1 + WARPS);
 };
@@ -70,9 +83,10 @@ __global__ void __launch_bounds__(GlCfg<R3>::WARPS * 32, GlCfg<R3>::CTAS) gl_ite
     const int run_idx = blockIdx.x * GL_WARPS + warp;
     if (run_idx >= p.n_runs) return;
     float2* ex1 = smem + G::TAB + warp * GlSmem<R3>::WARP;
-    float2* ex2 = ex1 + G::EX1;
-    float* s_stg = reinterpret_cast<float*>(ex2 + G::EX2);
-    float2* r_stg = ex2 + G::EX2 + G::M / 2;
+    constexpr bool ALIAS = GlCfg<R3>::ALIAS;
+    float2* ex2 = ALIAS ? ex1 : ex1 + G::EX1;
+    float* s_stg = reinterpret_cast<float*>(ex1 + GlSmem<R3>::EX);
+    float2* r_stg = ex1 + GlSmem<R3>::EX + G::M / 2;
     unsigned long long* bar = &bars[1 + warp];
 
     const GlRun r = p.runs[run_idx];
@@ -94,14 +108,18 @@ __global__ void __launch_bounds__(GlCfg<R3>::WARPS * 32, GlCfg<R3>::CTAS) gl_ite
             pref = fetch_next;
             __syncwarp();
             if (fetch_next) prefetch_next_block<R3>(L, lane, p.y_in + yoff, T, t, p.pad_mode);
-            phase_f2<R3>(L, lane, tab, ex1, ex2);
+            phase_f2_load<R3>(L, lane, ex1);
+            if (ALIAS) __syncwarp();
+            phase_f2_store<R3>(L, lane, tab, ex2);
             __syncwarp();
         }
         stage_wait(bar, (unsigned)(t - r.ta) & 1u);
         phase_f3<R3, MODE, STORE_R>(L, lane, p, r.utt, T, t, frame, tab, ex2, s_stg, r_stg);
         __syncwarp();   // every lane is done with the staged state (its values fed the stores above)
         if (t + 1 < r.tb) stage_issue<R3, MODE>(L, lane, p, frame + 1, s_stg, r_stg, bar);
-        phase_f4<R3>(L, lane, tab, ex2, ex1);
+        phase_f4_load<R3>(L, lane, tab, ex2);
+        if (ALIAS) __syncwarp();
+        phase_f4_store<R3>(L, lane, ex1);
         __syncwarp();
         phase_f5<R3>(L, lane, tab, ex1);
         float2 out[2 * G::NB];
