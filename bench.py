@@ -220,6 +220,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host thread it can
+    if "TORCHELASTIC_RUN_ID" in os.environ or os.environ.get("OMP_NUM_THREADS") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     cfg = args.config
     b, t, n_fft, it = CONFIGS[cfg]
     steps, warmup = args.steps, args.warmup
