@@ -30,7 +30,10 @@ static void emu_launch(GlParams p, bool reverse_order) {
         const int T = p.utt_T[r.utt];
         const long foff = p.utt_foff[r.utt];
         const long yoff = foff * G::H;
-        for (int l = 0; l < 32; l++) lane_reset<R3>(lanes[l]);
+        for (int l = 0; l < 32; l++) {
+            lane_reset<R3>(lanes[l]);
+            lane_load_constants<R3>(lanes[l], l, p.tables);
+        }
         auto arrive = [&](int boundary) {
             const unsigned old = p.flags[boundary]++;
             if (old & 1u)

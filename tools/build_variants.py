@@ -19,9 +19,10 @@ procs = []
 for spec in sys.argv[1:]:
     r3, rest = spec.split(":")
     w, c, a = rest.split(",")
-    tag = "%s_%s_%s_%s" % (r3, w, c, a)
+    tag = "%s_%s_%s_%s%s" % (r3, w, c, a, os.environ.get("XDTTS_VARIANT_TAG", ""))
     obj = os.path.join(out_dir, "gl_iter_%s.o" % tag)
     defs = ["-DXDTTS_GL%s_WARPS=%s" % (r3, w), "-DXDTTS_GL%s_CTAS=%s" % (r3, c), "-DXDTTS_GL%s_ALIAS=%s" % (r3, a)]
+    defs += [d for d in os.environ.get("XDTTS_VARIANT_DEFS", "").split() if d]
     cmd = [g.NVCC] + g.NVCC_FLAGS + defs + ["-Xptxas", "-v", "-c", os.path.join(g.CSRC, "gl_iter.cu"), "-o", obj]
     procs.append((tag, obj, r3, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
 for tag, obj, r3, p in procs:

@@ -3,6 +3,7 @@
 // (/root/reference src/tacotron2/mod.rs:441-458 builds it, src/lib.rs:141 calls it).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -305,28 +306,29 @@ int xdtts::gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out)
     if (!p) return fail(XDTTS_ERR_OOM, "plan: out of host memory");
     p->h = h; p->B = B; p->Ts.assign(Ts, Ts + B); p->total_T = (int)total;
     for (int b = 0; b < B; b++) p->max_T = Ts[b] > p->max_T ? Ts[b] : p->max_T;
-    // frames per run: about one resident wave of warps over the whole batch
+    // Runs: one warp each.  A fixed run length (option / environment) gives results that do not depend on
+    // the batch; the automatic choice fills the resident warp slots of the device exactly once (as many
+    // runs as fit, utterances split in proportion to their length), or uses 64-frame runs over several
+    // waves when the batch is larger than that.
     int rf = h->opts.run_frames;
     if (const char* env = getenv("XDTTS_GL_RUN_FRAMES")) rf = atoi(env);
-    if (rf <= 0) {
+    if (rf > 0) {
+        if (rf < 4) rf = 4;
+        build_runs(Ts, B, rf, &p->runs, &p->foff);
+    } else {
         const long long resident = (long long)h->sm_count * gl_resident_warps_per_sm(h->n_fft);
-        rf = (int)((total + resident - 1) / resident);
-        if (rf < 8) rf = 8;
-        if (rf > 64) rf = 64;
-        // wave quantisation: lengthen the runs a little until the CTAs fit the resident set, or the
-        // last wave is at least 60% full (one straggler CTA would otherwise double the launch time)
-        const int wpc = gl_warps_per_cta(h->n_fft), res_ctas = h->sm_count * gl_ctas_per_sm(h->n_fft);
-        for (int tries = 0; tries < 16 && rf < 96; tries++, rf++) {
-            std::vector<GlRun> tmp_runs;
-            std::vector<int> tmp_foff;
-            build_runs(Ts, B, rf, &tmp_runs, &tmp_foff);
-            const int ctas = ((int)tmp_runs.size() + wpc - 1) / wpc, tail = ctas % res_ctas;
-            if (ctas <= res_ctas || tail == 0 || tail * 10 >= res_ctas * 6) break;
+        const long long target = total <= resident * 64 ? resident : (total + 63) / 64;
+        std::vector<int> counts(B);
+        for (int b = 0; b < B; b++) {
+            long long n = (long long)Ts[b] * target / total;   // floor: the sum never exceeds the target
+            if (n > Ts[b] / 8) n = Ts[b] / 8;                   // runs shorter than 8 frames pay too much halo traffic
+            counts[b] = n < 1 ? 1 : (int)n;
         }
+        build_runs_counts(Ts, B, counts.data(), &p->runs, &p->foff);
+        rf = 0;
+        for (const GlRun& r : p->runs) rf = std::max(rf, r.tb - r.ta);
     }
-    if (rf < 4) rf = 4;
     p->run_frames = rf;
-    build_runs(Ts, B, rf, &p->runs, &p->foff);
     p->out_off.resize(B);
     for (int b = 0; b < B; b++) {
         p->out_off[b] = p->out_total;

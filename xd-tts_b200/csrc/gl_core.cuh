@@ -37,6 +37,10 @@
 #define XD_HD inline
 #endif
 
+#ifndef XDTTS_GL_TW2_REGS
+#define XDTTS_GL_TW2_REGS(R3) ((R3) == 16)
+#endif
+
 namespace xdtts {
 
 // ------------------------------------------------------------------ geometry
@@ -60,6 +64,9 @@ struct Geo {
     static constexpr int RTW_OFF = TW2_OFF + 7 * 32;      // -i W_N^{k(lane,j)} / 2, row j
     static constexpr int WIN_OFF = RTW_OFF + R3 * 32;     // (w[s], w[s+1]), row i*8 + n1
     static constexpr int TAB = WIN_OFF + VPL * 32;
+    // keep the 7 pass-2 twiddles in registers for the whole run instead of re-reading them from shared
+    // memory twice per frame: measured faster at N = 2048 (cfg5 478 -> 461 us), slower at N = 1024 (98 -> 102 us)
+    static constexpr bool TW2_REGS = XDTTS_GL_TW2_REGS(R3_);
 };
 
 // bin held in pair slot j of a lane after the last forward pass (its partner is M - k)
@@ -229,6 +236,7 @@ struct Lane {
     float2 raw[Geo<R3>::VPL];        // un-windowed samples of the current frame; three quarters carry over to the next
     float2 acc[3][2 * Geo<R3>::NB];  // overlap-add sums of the three unfinished hop blocks
     float2 ynew[2 * Geo<R3>::NB];    // newest hop block of the NEXT frame, fetched one frame ahead
+    float2 tw2[7];                   // pass-2 twiddles W_{8 R3}^{(lane & (R3-1)) k2}, k2 = 1..7 (only when Geo::TW2_REGS)
     float s_nyq;                     // |S| at the Nyquist bin of the frame whose state is staged (lane 0)
     float amax;
 };
@@ -417,7 +425,7 @@ XD_HD void phase_f2_store(Lane<R3>& L, int lane, const float2* tab, float2* ex2)
 #pragma unroll
         for (int k2 = 0; k2 < 8; k2++) {
             float2 z = L.v[i * 8 + k2];
-            if (k2) z = cmul(z, tab[G::TW2_OFF + (k2 - 1) * 32 + lane]);
+            if (k2) z = cmul(z, G::TW2_REGS ? L.tw2[k2 - 1] : tab[G::TW2_OFF + (k2 - 1) * 32 + lane]);
             ex2[n3 * G::S2 + k1 + 8 * k2] = z;
         }
     }
@@ -575,7 +583,7 @@ XD_HD void phase_f4_load(Lane<R3>& L, int lane, const float2* tab, const float2*
 #pragma unroll
         for (int k2 = 0; k2 < 8; k2++) {
             float2 z = ex2[n3 * G::S2 + k1 + 8 * k2];
-            if (k2) z = cmulc(z, tab[G::TW2_OFF + (k2 - 1) * 32 + lane]);
+            if (k2) z = cmulc(z, G::TW2_REGS ? L.tw2[k2 - 1] : tab[G::TW2_OFF + (k2 - 1) * 32 + lane]);
             L.v[i * 8 + k2] = z;
         }
     }
@@ -729,6 +737,15 @@ XD_HD void combine_boundary(Lane<R3>& L, int lane, const GlParams& p, int bounda
             blk[e] = cadd(a, c);
         }
         store_block<R3, TRACK_MAX>(L, lane, blk, p.y_out + yoff + (long)(r.tb - 2 + q) * G::H, nullptr, 2.0f / 3.0f);
+    }
+}
+
+// after the constant tables have landed in shared memory
+template <int R3>
+XD_HD void lane_load_constants(Lane<R3>& L, int lane, const float2* tab) {
+    if (Geo<R3>::TW2_REGS) {
+#pragma unroll
+        for (int k2 = 1; k2 < 8; k2++) L.tw2[k2 - 1] = tab[Geo<R3>::TW2_OFF + (k2 - 1) * 32 + lane];
     }
 }
 

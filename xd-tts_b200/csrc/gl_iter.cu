@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(GlCfg<R3>::WARPS * 32, GlCfg<R3>::CTAS) gl_ite
     lane_reset<R3>(L);
     stage_issue<R3, MODE>(L, lane, p, foff + r.ta, s_stg, r_stg, bar);
     stage_wait(&bars[0], 0);
+    lane_load_constants<R3>(L, lane, tab);
 
     bool pref = false;
     for (int t = r.ta; t < r.tb; t++) {

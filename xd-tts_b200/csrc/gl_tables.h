@@ -58,6 +58,28 @@ inline std::vector<float> build_edge_scale(int N) {
     return e;
 }
 
+// split utterance u into counts[u] equal runs (each >= 4 frames so that a hop block is shared by at
+// most two runs); runs of one utterance are consecutive in the table
+inline void build_runs_counts(const int* T, int n_utt, const int* counts, std::vector<GlRun>* runs, std::vector<int>* foff) {
+    runs->clear();
+    foff->clear();
+    int f = 0;
+    for (int u = 0; u < n_utt; u++) {
+        foff->push_back(f);
+        f += T[u];
+        int n = counts[u] < 1 ? 1 : counts[u];
+        while (n > 1 && T[u] / n < 4) n--;
+        int t = 0;
+        for (int r = 0; r < n; r++) {
+            const int len = T[u] / n + (r < T[u] % n ? 1 : 0);
+            GlRun g;
+            g.utt = u; g.ta = t; g.tb = t + len; g.pad = 0;
+            runs->push_back(g);
+            t += len;
+        }
+    }
+}
+
 // split every utterance into runs of about `run_frames` frames (each >= 4 so that a hop block is
 // shared by at most two runs); runs of one utterance are consecutive in the table
 inline void build_runs(const int* T, int n_utt, int run_frames, std::vector<GlRun>* runs, std::vector<int>* foff) {
