@@ -78,6 +78,12 @@ int xdtts_gl_infer_batch(xdtts_gl* h, const float* const* mels, const int* Ts, i
 int xdtts_gl_from_mag_batch(xdtts_gl* h, const float* const* mags, const int* Ts, int B,
                             const float* const* init_phases_or_null, float* const* outs);
 
+/* As xdtts_gl_infer_batch, but returns 16-bit PCM: the caller's loop
+ * `wav.write_sample((sample * i16::MAX as f32) as i16)` (src/lib.rs:153-157: truncate toward zero,
+ * saturate, NaN -> 0) runs on the device, which halves the device -> host bytes. outs[b]: hop (T_b - 1) samples. */
+int xdtts_gl_infer_batch_pcm16(xdtts_gl* h, const float* const* mels, const int* Ts, int B,
+                               const float* const* init_phases_or_null, short* const* outs);
+
 /* ---- device-resident plan: what the batch calls above use internally, exposed so that a
  * pipeline (or the benchmark) can keep inputs and outputs in HBM and time the device work. */
 int xdtts_gl_plan_create(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out);
@@ -92,6 +98,7 @@ int xdtts_gl_plan_upload(xdtts_gl_plan* p, int kind, const float* const* srcs);
  * summed device time and count of the steady-state iteration launches (only with NO_GRAPH). */
 int xdtts_gl_plan_run(xdtts_gl_plan* p, int flags, float* ms_total, float* ms_iter, int* n_iter_launches);
 int xdtts_gl_plan_download(xdtts_gl_plan* p, float* const* outs);
+int xdtts_gl_plan_download_pcm16(xdtts_gl_plan* p, short* const* outs);   /* after a run: 16-bit PCM of the same waveforms */
 /* debugging / parity: copy device state to host. what: 0 S [T_total][M] frame-major, 1 S Nyquist [T_total],
  * 2 R [T_total][M][2]; n_floats must match. */
 int xdtts_gl_plan_peek(xdtts_gl_plan* p, int what, float* out, long long n_floats);
@@ -130,6 +137,21 @@ int xdtts_postnet_plan_upload(xdtts_postnet_plan* p, const float* const* mels);
  * host round trip.  ms_total: device time of the postnet (CUDA events). */
 int xdtts_postnet_plan_run(xdtts_postnet_plan* p, xdtts_gl_plan* feed_or_null, float* ms_total);
 int xdtts_postnet_plan_download(xdtts_postnet_plan* p, float* const* outs);
+
+/* Tacotron2::load for the postnet (src/tacotron2/mod.rs:256-259 opens postnet.onnx as an ort::Session):
+ * reads the Conv / BatchNormalization initializers out of the ONNX file (own protobuf wire-format
+ * reader, no ONNX Runtime) and builds the device postnet from them.  The graph is matched by
+ * structure (Conv nodes in order, the BatchNormalization consuming each Conv), not by tensor names. */
+int xdtts_postnet_create_from_onnx(const char* path, const xdtts_postnet_opts* opts_or_null, int device, xdtts_postnet** out);
+/* host-only access to the same reader (no GPU needed): layer shapes and tensors of a postnet.onnx */
+typedef struct xdtts_onnx_postnet xdtts_onnx_postnet;
+int xdtts_onnx_postnet_open(const char* path, xdtts_onnx_postnet** out);
+void xdtts_onnx_postnet_close(xdtts_onnx_postnet* m);
+int xdtts_onnx_postnet_n_layers(const xdtts_onnx_postnet* m);   /* >= 1, or a negative error */
+int xdtts_onnx_postnet_layer_info(const xdtts_onnx_postnet* m, int layer, int* cout, int* cin, int* ksize, int* has_bias,
+                                  int* has_bn, float* eps);
+/* which: 0 conv weight [cout, cin, k], 1 conv bias, 2 BN scale, 3 BN bias, 4 BN running mean, 5 BN running var */
+int xdtts_onnx_postnet_layer_copy(const xdtts_onnx_postnet* m, int layer, int which, float* out);
 
 /* The tail of XdTts::infer in one call (src/lib.rs:123 postnet tail of model.infer + :141 vocoder.infer):
  * decoder mels [C, T_b] -> postnet -> mel-to-linear lift -> Griffin-Lim -> waveforms [hop (T_b - 1)].

@@ -310,3 +310,14 @@ def synth_speech_like_mag(seed, n_fft, hop, n_frames, sr=22050.0):
     y = sum((1.0 / h) * np.sin(h * ph) for h in range(1, 30))
     y = y * (0.6 + 0.4 * np.sin(2 * np.pi * 1.7 * t)) + 0.02 * rng.standard_normal(n)
     return np.abs(stft(y, n_fft, hop, dtype=np.float64)).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------
+# 16-bit PCM -- the caller's loop, src/lib.rs:153-157:
+#     for sample in &audio { wav.write_sample((sample * i16::MAX as f32) as i16) }
+# Rust float -> int `as` casts truncate toward zero, saturate at the bounds and map NaN to 0.
+# ----------------------------------------------------------------------------
+def pcm16(y):
+    x = np.asarray(y, dtype=np.float32) * np.float32(32767.0)
+    x = np.where(np.isnan(x), np.float32(0.0), x)
+    return np.trunc(np.clip(x, -32768.0, 32767.0)).astype(np.int16)

@@ -216,3 +216,30 @@ def test_full_size_properties(gl):
     (y60,) = make(gl, 1024, 60, normalise=gl.NORM_NONE).from_magnitude_batch([s.astype(np.float32)], [ph])
     envelope = rel_rms(ref32, ref64)
     assert rel_rms(y60, ref64) < max(2 * envelope, 1e-4)
+
+
+def test_pcm16_matches_the_callers_cast(gl):
+    """src/lib.rs:153-157 on the device: bit-exact against the oracle's cast of the same f32 samples."""
+    voc = make(gl, 1024, 5, run_frames=8)
+    ts = [9, 64, 33]
+    mels = [o.synth_mel(50 + i, 80, t) for i, t in enumerate(ts)]
+    phs = [o.phase_turns(2, i, 513, t) for i, t in enumerate(ts)]
+    f32 = voc.infer_batch(mels, phs)
+    pcm = voc.infer_batch_pcm16(mels, phs)
+    for a, b in zip(f32, pcm):
+        assert b.dtype == np.int16 and b.shape == a.shape
+        assert np.array_equal(b, o.pcm16(a))
+        assert b.max() == 32767 or b.min() == -32767        # peak-normalised input reaches full scale
+    # un-normalised output beyond [-1, 1] saturates instead of wrapping
+    loud = make(gl, 1024, 2, normalise=gl.NORM_NONE)
+    big = [np.full((80, 12), 3.0, np.float32)]               # exp(3)^1.7 magnitudes -> |y| >> 1
+    y = loud.infer_batch(big)[0]
+    p = loud.infer_batch_pcm16(big)[0]
+    assert np.abs(y).max() > 1.0
+    assert np.array_equal(p, o.pcm16(y)) and p.max() == 32767 and p.min() == -32768
+    plan = voc.plan(ts)
+    plan.upload(0, mels)
+    plan.upload(2, phs)
+    plan.run(2)
+    for a, b in zip(plan.download_pcm16(), pcm):
+        assert np.array_equal(a, b)

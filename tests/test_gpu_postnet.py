@@ -162,3 +162,16 @@ def test_errors(taco, layers):
         p.upload([np.zeros((80, 11), np.float32)])
     assert e.value.code == ERR_SHAPE
     assert ERR_BAD_ARG < 0
+
+
+def test_load_from_onnx_file(taco, layers, tmp_path):
+    """Tacotron2::load's postnet session (src/tacotron2/mod.rs:256-259): same bits as passing the arrays."""
+    from onnx_writer import postnet_model
+
+    path = tmp_path / "postnet.onnx"
+    path.write_bytes(postnet_model(layers, eps=po.BN_EPS))
+    mel = o.synth_mel(9, 80, 200)
+    a = taco.Postnet.load(path).run(mel)
+    b = taco.Postnet.from_layers(layers).run(mel)
+    assert np.array_equal(a, b)
+    assert np.abs(a - po.postnet(mel, layers, dtype=np.float64)).max() < TOL[0]

@@ -185,3 +185,54 @@ def test_postnet_argument_validation_without_gpu(lib):
         with pytest.raises(XdttsError) as e:    # valid arguments, no device: refuses, never computes on the CPU
             tacotron2.Postnet.from_layers(layers)
         assert e.value.code == ERR_CUDA
+
+
+def test_onnx_postnet_reader(lib, tmp_path):
+    """The library's own protobuf reader recovers every initializer of a hand-encoded postnet.onnx."""
+    from onnx_writer import postnet_model
+    from oracle import postnet_oracle as po
+    from xdtts_b200 import tacotron2
+    from xdtts_b200._ffi import ERR_BAD_ARG, ERR_SHAPE, ERR_UNSUPPORTED, XdttsError
+
+    layers = po.synth_weights(seed=7)
+    for raw in (True, False):                       # raw_data and packed float_data encodings
+        path = tmp_path / ("postnet_%d.onnx" % raw)
+        path.write_bytes(postnet_model(layers, eps=1e-5, raw=raw))
+        got = tacotron2.read_onnx_postnet(path)
+        assert len(got) == 5
+        for a, b in zip(got, layers):
+            assert abs(a["eps"] - 1e-5) < 1e-12
+            for k in ("w", "b", "gamma", "beta", "mean", "var"):
+                assert a[k].shape == b[k].shape and np.array_equal(a[k], b[k]), k
+    # no BatchNormalization nodes (a fused export), no bias on one layer
+    nb = [dict(w=l["w"], b=l["b"]) for l in layers]
+    nb[2].pop("b")
+    path = tmp_path / "fused.onnx"
+    path.write_bytes(postnet_model(nb))
+    got = tacotron2.read_onnx_postnet(path)
+    assert all("gamma" not in l for l in got) and "b" not in got[2] and np.array_equal(got[4]["w"], layers[4]["w"])
+    # error paths: the LFS pointer the reference repo actually ships, garbage, a missing file, a broken graph
+    ptr = tmp_path / "pointer.onnx"
+    ptr.write_text("version https://git-lfs.github.com/spec/v1\noid sha256:7a65\nsize 17414016\n")
+    with pytest.raises(XdttsError) as e:
+        tacotron2.read_onnx_postnet(ptr)
+    assert e.value.code == ERR_BAD_ARG and "LFS" in e.value.message
+    junk = tmp_path / "junk.onnx"
+    junk.write_bytes(bytes(range(256)) * 4)
+    with pytest.raises(XdttsError):
+        tacotron2.read_onnx_postnet(junk)
+    with pytest.raises(XdttsError) as e:
+        tacotron2.read_onnx_postnet(tmp_path / "missing.onnx")
+    assert e.value.code == ERR_BAD_ARG
+    bad = [dict(l) for l in layers]
+    bad[1]["w"] = bad[1]["w"][:, :100].copy()      # layer 1 takes 100 channels, layer 0 makes 512
+    path = tmp_path / "bad.onnx"
+    path.write_bytes(postnet_model(bad))
+    with pytest.raises(XdttsError) as e:
+        tacotron2.read_onnx_postnet(path)
+    assert e.value.code == ERR_SHAPE
+    trunc = tmp_path / "trunc.onnx"
+    trunc.write_bytes(postnet_model(layers)[:200000])
+    with pytest.raises(XdttsError):
+        tacotron2.read_onnx_postnet(trunc)
+    assert ERR_UNSUPPORTED < 0

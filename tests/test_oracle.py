@@ -127,3 +127,10 @@ def test_postnet_golden(golden_dir):
         if i < 4:
             x = np.tanh(x)
     assert np.abs(g["mel"] + x - g["out_oracle64"]).max() < 2e-6
+
+
+def test_pcm16_cast_semantics():
+    """Rust `(sample * i16::MAX as f32) as i16` (src/lib.rs:155): truncation, saturation, NaN -> 0."""
+    y = np.array([0.0, 1.0, -1.0, 0.5, -0.5, 1.5, -1.5, 3.0517578e-05, -3.0517578e-05, np.nan, 0.99999, 2.0e-5], np.float32)
+    want = np.array([0, 32767, -32767, 16383, -16383, 32767, -32768, 0, 0, 0, 32766, 0], np.int16)
+    assert np.array_equal(o.pcm16(y), want)

@@ -25,6 +25,7 @@ cudaError_t gl_launch_lift(const float*, const float*, const int*, const int*, i
 cudaError_t gl_launch_to_frame_major(const float*, const int*, const int*, int, int, int, float*, float*, cudaStream_t);
 cudaError_t gl_launch_finish(const float*, const int*, const int*, const long long*, const unsigned*, int, int, int, int,
                              float*, cudaStream_t);
+cudaError_t gl_launch_pcm16(const float*, long long, short*, int, cudaStream_t);
 std::atomic<unsigned long long> g_launches{0};
 }  // namespace xdtts
 
@@ -285,7 +286,8 @@ extern "C" void xdtts_gl_plan_destroy(xdtts_gl_plan* p) {
     cudaFree(p->d_runs); cudaFree(p->d_T); cudaFree(p->d_foff); cudaFree(p->d_out_off);
     cudaFree(p->d_mel); cudaFree(p->d_in_mag); cudaFree(p->d_in_phase); cudaFree(p->d_turns); cudaFree(p->d_turns_nyq);
     cudaFree(p->d_S); cudaFree(p->d_S_nyq); cudaFree(p->d_y[0]); cudaFree(p->d_y[1]); cudaFree(p->d_halo);
-    cudaFree(p->d_out); cudaFree(p->d_R); cudaFree(p->d_flags); cudaFree(p->d_amax);
+    cudaFree(p->d_out); cudaFree(p->d_R); cudaFree(p->d_flags); cudaFree(p->d_amax); cudaFree(p->d_pcm);
+    if (p->h_pcm) cudaFreeHost(p->h_pcm);
     if (p->h_in) cudaFreeHost(p->h_in);
     if (p->h_out) cudaFreeHost(p->h_out);
     delete p;
@@ -555,6 +557,38 @@ extern "C" int xdtts_gl_plan_download(xdtts_gl_plan* p, float* const* outs) {
     return gl_plan_download_locked(p, outs);
 }
 
+// the caller's f32 -> i16 loop (src/lib.rs:153-157) on the device: halves the bytes that cross PCIe
+static int plan_download_pcm16_locked(xdtts_gl_plan* p, short* const* outs) {
+    xdtts_gl* h = p->h;
+    clear_stale_error(__func__);
+    if (!outs) return fail(XDTTS_ERR_BAD_ARG, "plan_download_pcm16: outs is null");
+    for (int b = 0; b < p->B; b++)
+        if (!outs[b]) return fail(XDTTS_ERR_BAD_ARG, "plan_download_pcm16: outs[%d] is null", b);
+    CU(cudaSetDevice(h->device));
+    if (!p->d_pcm) CU(cudaMalloc((void**)&p->d_pcm, (size_t)p->out_total * 2));
+    CU(gl_launch_pcm16(p->d_out, p->out_total, p->d_pcm, h->sm_count, h->stream));
+    g_launches++;
+    bool all_pinned = true;
+    for (int b = 0; b < p->B; b++) all_pinned = all_pinned && is_pinned(outs[b]);
+    if (all_pinned) {
+        for (int b = 0; b < p->B; b++)
+            CU(cudaMemcpyAsync(outs[b], p->d_pcm + p->out_off[b], (size_t)h->hop * (p->Ts[b] - 1) * 2, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    } else {
+        if (!p->h_pcm) CU(cudaHostAlloc((void**)&p->h_pcm, (size_t)p->out_total * 2, cudaHostAllocDefault));
+        CU(cudaMemcpyAsync(p->h_pcm, p->d_pcm, (size_t)p->out_total * 2, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (int b = 0; b < p->B; b++) memcpy(outs[b], p->h_pcm + p->out_off[b], (size_t)h->hop * (p->Ts[b] - 1) * 2);
+    }
+    return XDTTS_OK;
+}
+
+extern "C" int xdtts_gl_plan_download_pcm16(xdtts_gl_plan* p, short* const* outs) {
+    if (!p) return fail(XDTTS_ERR_BAD_ARG, "plan_download_pcm16: plan is null");
+    std::lock_guard<std::mutex> lk(p->h->mu);
+    return plan_download_pcm16_locked(p, outs);
+}
+
 extern "C" int xdtts_gl_plan_peek(xdtts_gl_plan* p, int what, float* out, long long n_floats) {
     if (!p || !out) return fail(XDTTS_ERR_BAD_ARG, "plan_peek: null argument");
     std::lock_guard<std::mutex> lk(p->h->mu);
@@ -598,9 +632,9 @@ int xdtts::gl_plan_mel_arena(xdtts_gl_plan* p, float** out) {
 
 // ------------------------------------------------------------------ batch entry points
 static int batch_common(xdtts_gl* h, int kind, const float* const* ins, const int* Ts, int B,
-                        const float* const* phases, float* const* outs) {
+                        const float* const* phases, float* const* outs, short* const* pcm_outs = nullptr) {
     if (!h) return fail(XDTTS_ERR_BAD_ARG, "infer: handle is null");
-    if (!ins || !Ts || !outs) return fail(XDTTS_ERR_BAD_ARG, "infer: null argument");
+    if (!ins || !Ts || (!outs && !pcm_outs)) return fail(XDTTS_ERR_BAD_ARG, "infer: null argument");
     if (B < 1) return fail(XDTTS_ERR_BAD_ARG, "infer: B = %d", B);
     std::lock_guard<std::mutex> lk(h->mu);
     xdtts_gl_plan* p = nullptr;
@@ -618,7 +652,12 @@ static int batch_common(xdtts_gl* h, int kind, const float* const* ins, const in
     }
     rc = gl_plan_run_locked(p, flags, nullptr, nullptr, nullptr);
     if (rc) return rc;
-    return gl_plan_download_locked(p, outs);
+    return pcm_outs ? plan_download_pcm16_locked(p, pcm_outs) : gl_plan_download_locked(p, outs);
+}
+
+extern "C" int xdtts_gl_infer_batch_pcm16(xdtts_gl* h, const float* const* mels, const int* Ts, int B,
+                                          const float* const* init_phases, short* const* outs) {
+    return batch_common(h, 0, mels, Ts, B, init_phases, nullptr, outs);
 }
 
 extern "C" int xdtts_gl_infer_batch(xdtts_gl* h, const float* const* mels, const int* Ts, int B,

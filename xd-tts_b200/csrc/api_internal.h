@@ -64,6 +64,8 @@ struct xdtts_gl_plan {
     float *d_mel = nullptr, *d_in_mag = nullptr, *d_in_phase = nullptr, *d_turns = nullptr, *d_turns_nyq = nullptr;
     float *d_S = nullptr, *d_S_nyq = nullptr, *d_y[2] = {nullptr, nullptr}, *d_halo = nullptr, *d_out = nullptr;
     float2* d_R = nullptr;
+    short* d_pcm = nullptr;          // 16-bit PCM copy of d_out (allocated on first use)
+    short* h_pcm = nullptr;
     unsigned *d_flags = nullptr, *d_amax = nullptr;
     // pinned staging for pageable callers
     float *h_in = nullptr, *h_out = nullptr;

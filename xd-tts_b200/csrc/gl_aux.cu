@@ -14,7 +14,9 @@ namespace xdtts {
 // ---------------------------------------------------------------- lift
 // grid (ceil(K/128), ceil(maxT/16), n_utt); thread <-> bin k, 16 frames per block.
 // Accumulates in fp64: the pseudo-inverse has 36% negative entries, an fp32 sum
-// loses ~1e-3 relative to cancellation; 2.6 GFLOP per 32x1000 batch is noise next to the loop.
+// loses ~1e-3 relative to cancellation.  The de-logged mel tile is converted to fp64 once, in shared
+// memory, so the inner loop is one coalesced load of the pseudo-inverse column and 16 DFMAs fed by
+// broadcast 128-bit shared loads; the kernel is bound by the fp64 pipe (1.3 G DFMA per 32x1000 batch).
 constexpr int LIFT_TT = 16;
 constexpr int LIFT_MAX_MELS = 256;
 
@@ -22,7 +24,7 @@ __global__ void __launch_bounds__(128) gl_lift_kernel(const float* __restrict__ 
                                                       const int* __restrict__ utt_T, const int* __restrict__ utt_foff,
                                                       int n_mels, int K, float power, int delog, float* __restrict__ S,
                                                       float* __restrict__ S_nyq) {
-    __shared__ float e[LIFT_MAX_MELS * LIFT_TT];
+    extern __shared__ __align__(16) double e[];   // [n_mels][LIFT_TT]
     const int u = blockIdx.z;
     const int T = utt_T[u];
     const int t0 = blockIdx.y * LIFT_TT;
@@ -36,7 +38,7 @@ __global__ void __launch_bounds__(128) gl_lift_kernel(const float* __restrict__ 
             v = mel[(long)m * T + t0 + tt];
             v = delog == 0 ? expf(v) : (delog == 1 ? powf(10.f, v) : v);
         }
-        e[i] = v;
+        e[i] = (double)v;
     }
     __syncthreads();
     const int k = blockIdx.x * 128 + threadIdx.x;
@@ -44,16 +46,16 @@ __global__ void __launch_bounds__(128) gl_lift_kernel(const float* __restrict__ 
     double acc[LIFT_TT];
 #pragma unroll
     for (int tt = 0; tt < LIFT_TT; tt++) acc[tt] = 0.0;
+    const float* col = pinvT + k;
+#pragma unroll 4
     for (int m = 0; m < n_mels; m++) {
-        const double a = (double)pinvT[(long)m * K + k];
-        const float4* er = reinterpret_cast<const float4*>(e + m * LIFT_TT);
+        const double a = (double)col[(long)m * K];
+        const double2* er = reinterpret_cast<const double2*>(e + m * LIFT_TT);
 #pragma unroll
-        for (int q = 0; q < LIFT_TT / 4; q++) {
-            const float4 x = er[q];
-            acc[4 * q + 0] += a * (double)x.x;
-            acc[4 * q + 1] += a * (double)x.y;
-            acc[4 * q + 2] += a * (double)x.z;
-            acc[4 * q + 3] += a * (double)x.w;
+        for (int q = 0; q < LIFT_TT / 2; q++) {
+            const double2 x = er[q];
+            acc[2 * q + 0] = fma(a, x.x, acc[2 * q + 0]);
+            acc[2 * q + 1] = fma(a, x.y, acc[2 * q + 1]);
         }
     }
     const int M = K - 1;
@@ -71,7 +73,8 @@ cudaError_t gl_launch_lift(const float* mel_arena, const float* pinvT, const int
                            int max_T, int n_mels, int K, float power, int delog, float* S, float* S_nyq, cudaStream_t s) {
     if (n_mels > LIFT_MAX_MELS) return cudaErrorInvalidValue;
     dim3 grid((K + 127) / 128, (max_T + LIFT_TT - 1) / LIFT_TT, n_utt);
-    gl_lift_kernel<<<grid, 128, 0, s>>>(mel_arena, pinvT, utt_T, utt_foff, n_mels, K, power, delog, S, S_nyq);
+    gl_lift_kernel<<<grid, 128, (size_t)n_mels * LIFT_TT * sizeof(double), s>>>(mel_arena, pinvT, utt_T, utt_foff, n_mels, K, power,
+                                                                               delog, S, S_nyq);
     return cudaGetLastError();
 }
 
@@ -140,6 +143,38 @@ cudaError_t gl_launch_finish(const float* y, const int* utt_T, const int* utt_fo
     if (gx < 1) gx = 1;
     dim3 grid(gx, n_utt);
     gl_finish_kernel<<<grid, 256, 0, s>>>(y, utt_T, utt_foff, out_off, amax, hop, normalise, out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- f32 -> 16-bit PCM
+// The caller's per-sample loop `(sample * i16::MAX as f32) as i16` (/root/reference src/lib.rs:153-157;
+// Rust float -> int `as` casts truncate toward zero, saturate, and map NaN to 0).  n is a multiple of 4
+// per utterance only up to alignment, so the tail is handled scalar.
+__device__ __forceinline__ short pcm16_of(float v) {
+    const float x = v * 32767.0f;
+    if (!(x == x)) return 0;
+    if (x >= 32767.0f) return 32767;
+    if (x <= -32768.0f) return -32768;
+    return (short)(int)x;   // truncation toward zero
+}
+
+__global__ void __launch_bounds__(256) gl_pcm16_kernel(const float* __restrict__ src, long long n, short* __restrict__ dst) {
+    const long long stride = (long long)gridDim.x * 256;
+    const long long n4 = n / 4;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += stride) {
+        const float4 v = reinterpret_cast<const float4*>(src)[i];
+        short4 o;
+        o.x = pcm16_of(v.x); o.y = pcm16_of(v.y); o.z = pcm16_of(v.z); o.w = pcm16_of(v.w);
+        reinterpret_cast<short4*>(dst)[i] = o;
+    }
+    for (long long i = n4 * 4 + (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) dst[i] = pcm16_of(src[i]);
+}
+
+cudaError_t gl_launch_pcm16(const float* src, long long n, short* dst, int sm_count, cudaStream_t s) {
+    long long blocks = (n / 4 + 255) / 256;
+    if (blocks > (long long)sm_count * 8) blocks = (long long)sm_count * 8;
+    if (blocks < 1) blocks = 1;
+    gl_pcm16_kernel<<<(int)blocks, 256, 0, s>>>(src, n, dst);
     return cudaGetLastError();
 }
 

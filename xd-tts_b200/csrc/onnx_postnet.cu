@@ -1,0 +1,340 @@
+// Reads the weights of the Tacotron2 postnet out of `postnet.onnx` -- the file the reference opens
+// with `Session::builder()?.commit_from_file(path.join("postnet.onnx"))`
+// (/root/reference src/tacotron2/mod.rs:256-259; 17.4 MB git-LFS object, models/tacotron2/postnet.onnx:1-3)
+// -- without ONNX Runtime or protobuf: a ~200-line reader of the protobuf wire format for the handful
+// of ModelProto / GraphProto / NodeProto / TensorProto fields that matter.
+//
+// The graph is matched structurally, not by initializer names (exporters rename them): every `Conv`
+// node in graph order is a layer (inputs X, W, B); a `BatchNormalization` node consuming the Conv's
+// output supplies (scale, B, mean, var) and the `epsilon` attribute; Tanh / Add / Identity / Dropout
+// nodes are what the device path implements itself.  Host-only code: usable (and tested) without a GPU.
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "api_internal.h"
+
+using namespace xdtts;
+#define fail xdtts::set_error
+
+namespace {
+
+struct Span {
+    const uint8_t* p;
+    const uint8_t* end;
+    bool ok = true;
+    bool done() const { return p >= end; }
+    uint64_t varint() {
+        uint64_t v = 0;
+        for (int shift = 0; shift < 64 && p < end; shift += 7) {
+            const uint8_t b = *p++;
+            v |= (uint64_t)(b & 0x7F) << shift;
+            if (!(b & 0x80)) return v;
+        }
+        ok = false;
+        return 0;
+    }
+    // reads one field header; returns false at the end or on a malformed stream
+    bool field(uint32_t* number, uint32_t* wire) {
+        if (done() || !ok) return false;
+        const uint64_t key = varint();
+        *number = (uint32_t)(key >> 3);
+        *wire = (uint32_t)(key & 7);
+        return ok;
+    }
+    Span bytes() {   // length-delimited payload
+        const uint64_t n = varint();
+        if (!ok || n > (uint64_t)(end - p)) {
+            ok = false;
+            return Span{end, end, false};
+        }
+        Span s{p, p + n};
+        p += n;
+        return s;
+    }
+    void skip(uint32_t wire) {
+        switch (wire) {
+            case 0: varint(); break;
+            case 1: if (end - p >= 8) p += 8; else ok = false; break;
+            case 2: bytes(); break;
+            case 5: if (end - p >= 4) p += 4; else ok = false; break;
+            default: ok = false;
+        }
+    }
+    std::string str() {
+        Span s = bytes();
+        return s.ok ? std::string((const char*)s.p, (size_t)(s.end - s.p)) : std::string();
+    }
+};
+
+struct Tensor {
+    std::vector<int64_t> dims;
+    int data_type = 0;   // 1 = FLOAT
+    std::vector<float> data;
+    bool external = false;
+    size_t count() const {
+        size_t n = 1;
+        for (int64_t d : dims) n *= (size_t)d;
+        return n;
+    }
+};
+
+struct Node {
+    std::string op;
+    std::vector<std::string> in, out;
+    float epsilon = 1e-5f;
+    int64_t group = 1;
+    std::vector<int64_t> pads, strides, dilations, kernel_shape;
+};
+
+bool parse_tensor(Span s, std::string* name, Tensor* t) {
+    uint32_t f, w;
+    const uint8_t* raw = nullptr;
+    size_t raw_n = 0;
+    while (s.field(&f, &w)) {
+        if (f == 1 && w == 0) t->dims.push_back((int64_t)s.varint());
+        else if (f == 1 && w == 2) { Span d = s.bytes(); while (!d.done() && d.ok) t->dims.push_back((int64_t)d.varint()); }
+        else if (f == 2 && w == 0) t->data_type = (int)s.varint();
+        else if (f == 4 && w == 2) {   // packed float_data
+            Span d = s.bytes();
+            const size_t n = (size_t)(d.end - d.p) / 4;
+            t->data.resize(n);
+            if (n) memcpy(t->data.data(), d.p, n * 4);
+        } else if (f == 4 && w == 5) { float v; if (s.end - s.p < 4) return false; memcpy(&v, s.p, 4); s.p += 4; t->data.push_back(v); }
+        else if (f == 8 && w == 2) *name = s.str();
+        else if (f == 9 && w == 2) { Span d = s.bytes(); raw = d.p; raw_n = (size_t)(d.end - d.p); }
+        else if (f == 14 && w == 0) t->external = s.varint() == 1;   // data_location = EXTERNAL
+        else s.skip(w);
+    }
+    if (!s.ok) return false;
+    if (raw && t->data_type == 1) {
+        t->data.resize(raw_n / 4);
+        if (raw_n) memcpy(t->data.data(), raw, raw_n / 4 * 4);
+    }
+    return true;
+}
+
+bool parse_attribute(Span s, Node* n) {
+    uint32_t f, w;
+    std::string name;
+    float fv = 0.f;
+    int64_t iv = 0;
+    std::vector<int64_t> ints;
+    while (s.field(&f, &w)) {
+        if (f == 1 && w == 2) name = s.str();
+        else if (f == 2 && w == 5) { if (s.end - s.p < 4) return false; memcpy(&fv, s.p, 4); s.p += 4; }
+        else if (f == 3 && w == 0) iv = (int64_t)s.varint();
+        else if (f == 8 && w == 0) ints.push_back((int64_t)s.varint());
+        else if (f == 8 && w == 2) { Span d = s.bytes(); while (!d.done() && d.ok) ints.push_back((int64_t)d.varint()); }
+        else s.skip(w);
+    }
+    if (!s.ok) return false;
+    if (name == "epsilon") n->epsilon = fv;
+    else if (name == "group") n->group = iv;
+    else if (name == "pads") n->pads = ints;
+    else if (name == "strides") n->strides = ints;
+    else if (name == "dilations") n->dilations = ints;
+    else if (name == "kernel_shape") n->kernel_shape = ints;
+    return true;
+}
+
+bool parse_node(Span s, Node* n) {
+    uint32_t f, w;
+    while (s.field(&f, &w)) {
+        if (f == 1 && w == 2) n->in.push_back(s.str());
+        else if (f == 2 && w == 2) n->out.push_back(s.str());
+        else if (f == 4 && w == 2) n->op = s.str();
+        else if (f == 5 && w == 2) { if (!parse_attribute(s.bytes(), n)) return false; }
+        else s.skip(w);
+    }
+    return s.ok;
+}
+
+struct Layer {
+    int cout = 0, cin = 0, k = 0;
+    std::vector<float> w, b, gamma, beta, mean, var;
+    float eps = 1e-5f;
+};
+
+}  // namespace
+
+struct xdtts_onnx_postnet {
+    std::vector<Layer> layers;
+    float eps = 1e-5f;
+};
+
+static bool all_equal(const std::vector<int64_t>& v, int64_t x) {
+    for (int64_t a : v)
+        if (a != x) return false;
+    return true;
+}
+
+extern "C" void xdtts_onnx_postnet_close(xdtts_onnx_postnet* m) { delete m; }
+
+extern "C" int xdtts_onnx_postnet_open(const char* path, xdtts_onnx_postnet** out) {
+    if (!out) return fail(XDTTS_ERR_BAD_ARG, "onnx_postnet_open: out is null");
+    *out = nullptr;
+    if (!path) return fail(XDTTS_ERR_BAD_ARG, "onnx_postnet_open: path is null");
+    FILE* fp = fopen(path, "rb");
+    if (!fp) return fail(XDTTS_ERR_BAD_ARG, "onnx_postnet_open: cannot open %s", path);
+    std::vector<uint8_t> buf;
+    fseek(fp, 0, SEEK_END);
+    const long size = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    if (size > 0) {
+        buf.resize((size_t)size);
+        if (fread(buf.data(), 1, (size_t)size, fp) != (size_t)size) buf.clear();
+    }
+    fclose(fp);
+    if (buf.empty()) return fail(XDTTS_ERR_BAD_ARG, "onnx_postnet_open: %s is empty or unreadable", path);
+    if (buf.size() < 200 && memcmp(buf.data(), "version https://git-lfs", 23) == 0)
+        return fail(XDTTS_ERR_BAD_ARG, "onnx_postnet_open: %s is a git-LFS pointer, not the model (run `git lfs pull`)", path);
+
+    // ModelProto: graph = field 7
+    Span model{buf.data(), buf.data() + buf.size()};
+    Span graph{nullptr, nullptr, false};
+    uint32_t f, w;
+    while (model.field(&f, &w)) {
+        if (f == 7 && w == 2) graph = model.bytes();
+        else model.skip(w);
+    }
+    if (!model.ok || !graph.ok || !graph.p) return fail(XDTTS_ERR_BAD_ARG, "onnx_postnet_open: %s is not an ONNX ModelProto with a graph", path);
+
+    std::map<std::string, Tensor> init;
+    std::vector<Node> nodes;
+    while (graph.field(&f, &w)) {
+        if (f == 1 && w == 2) {
+            Node n;
+            if (!parse_node(graph.bytes(), &n)) return fail(XDTTS_ERR_BAD_ARG, "onnx_postnet_open: malformed NodeProto");
+            nodes.push_back(std::move(n));
+        } else if (f == 5 && w == 2) {
+            std::string name;
+            Tensor t;
+            if (!parse_tensor(graph.bytes(), &name, &t)) return fail(XDTTS_ERR_BAD_ARG, "onnx_postnet_open: malformed TensorProto");
+            init[name] = std::move(t);
+        } else {
+            graph.skip(w);
+        }
+    }
+    if (!graph.ok) return fail(XDTTS_ERR_BAD_ARG, "onnx_postnet_open: malformed GraphProto");
+
+    auto get = [&](const std::string& name, size_t want, const char* what, std::vector<float>* dst) -> int {
+        auto it = init.find(name);
+        if (it == init.end()) return fail(XDTTS_ERR_BAD_ARG, "onnx_postnet_open: %s '%s' is not an initializer", what, name.c_str());
+        const Tensor& t = it->second;
+        if (t.external) return fail(XDTTS_ERR_UNSUPPORTED, "onnx_postnet_open: %s '%s' uses external data", what, name.c_str());
+        if (t.data_type != 1) return fail(XDTTS_ERR_UNSUPPORTED, "onnx_postnet_open: %s '%s' has data type %d, need FLOAT", what, name.c_str(), t.data_type);
+        if (t.data.size() != want || t.count() != want)
+            return fail(XDTTS_ERR_SHAPE, "onnx_postnet_open: %s '%s' has %zu values, expected %zu", what, name.c_str(), t.data.size(), want);
+        *dst = t.data;
+        return XDTTS_OK;
+    };
+
+    xdtts_onnx_postnet* m = new xdtts_onnx_postnet();
+    int rc = XDTTS_OK;
+    for (size_t i = 0; i < nodes.size() && rc == XDTTS_OK; i++) {
+        const Node& n = nodes[i];
+        if (n.op != "Conv") continue;
+        if (n.in.size() < 2 || n.out.empty()) { rc = fail(XDTTS_ERR_BAD_ARG, "onnx_postnet_open: Conv node without weights"); break; }
+        auto wt = init.find(n.in[1]);
+        if (wt == init.end() || wt->second.dims.size() != 3) { rc = fail(XDTTS_ERR_UNSUPPORTED, "onnx_postnet_open: Conv weight '%s' is not a 3-D initializer (Conv1d expected)", n.in[1].c_str()); break; }
+        Layer L;
+        L.cout = (int)wt->second.dims[0]; L.cin = (int)wt->second.dims[1]; L.k = (int)wt->second.dims[2];
+        if (n.group != 1 || (n.pads.empty() && L.k != 1) || !all_equal(n.strides, 1) || !all_equal(n.dilations, 1) || !all_equal(n.pads, L.k / 2) || (L.k & 1) == 0) {
+            rc = fail(XDTTS_ERR_UNSUPPORTED, "onnx_postnet_open: Conv '%s' is not a stride-1, dilation-1, same-padded, ungrouped convolution", n.in[1].c_str());
+            break;
+        }
+        rc = get(n.in[1], (size_t)L.cout * L.cin * L.k, "Conv weight", &L.w);
+        if (rc == XDTTS_OK && n.in.size() > 2 && !n.in[2].empty()) rc = get(n.in[2], (size_t)L.cout, "Conv bias", &L.b);
+        if (rc != XDTTS_OK) break;
+        for (const Node& bn : nodes) {   // the BatchNormalization that consumes this Conv's output, if any
+            if (bn.op != "BatchNormalization" || bn.in.size() < 5 || bn.in[0] != n.out[0]) continue;
+            rc = get(bn.in[1], (size_t)L.cout, "BatchNormalization scale", &L.gamma);
+            if (rc == XDTTS_OK) rc = get(bn.in[2], (size_t)L.cout, "BatchNormalization bias", &L.beta);
+            if (rc == XDTTS_OK) rc = get(bn.in[3], (size_t)L.cout, "BatchNormalization mean", &L.mean);
+            if (rc == XDTTS_OK) rc = get(bn.in[4], (size_t)L.cout, "BatchNormalization var", &L.var);
+            L.eps = bn.epsilon;
+            break;
+        }
+        if (rc == XDTTS_OK) m->layers.push_back(std::move(L));
+    }
+    if (rc == XDTTS_OK && m->layers.empty()) rc = fail(XDTTS_ERR_BAD_ARG, "onnx_postnet_open: %s has no Conv node", path);
+    for (size_t l = 1; rc == XDTTS_OK && l < m->layers.size(); l++) {
+        if (m->layers[l].cin != m->layers[l - 1].cout) rc = fail(XDTTS_ERR_SHAPE, "onnx_postnet_open: layer %zu takes %d channels, layer %zu makes %d", l, m->layers[l].cin, l - 1, m->layers[l - 1].cout);
+        if (m->layers[l].k != m->layers[0].k) rc = fail(XDTTS_ERR_UNSUPPORTED, "onnx_postnet_open: layers with different kernel sizes");
+    }
+    if (rc == XDTTS_OK) {
+        bool have = false;
+        for (const Layer& L : m->layers)
+            if (!L.gamma.empty()) {
+                if (have && L.eps != m->eps) rc = fail(XDTTS_ERR_UNSUPPORTED, "onnx_postnet_open: BatchNormalization nodes with different epsilon");
+                m->eps = L.eps;
+                have = true;
+            }
+    }
+    if (rc != XDTTS_OK) {
+        delete m;
+        return rc;
+    }
+    *out = m;
+    return XDTTS_OK;
+}
+
+extern "C" int xdtts_onnx_postnet_n_layers(const xdtts_onnx_postnet* m) {
+    if (!m) return fail(XDTTS_ERR_BAD_ARG, "onnx_postnet_n_layers: null");
+    return (int)m->layers.size();
+}
+
+extern "C" int xdtts_onnx_postnet_layer_info(const xdtts_onnx_postnet* m, int layer, int* cout, int* cin, int* ksize,
+                                             int* has_bias, int* has_bn, float* eps) {
+    if (!m || layer < 0 || layer >= (int)m->layers.size()) return fail(XDTTS_ERR_BAD_ARG, "onnx_postnet_layer_info: bad argument");
+    const Layer& L = m->layers[layer];
+    if (cout) *cout = L.cout;
+    if (cin) *cin = L.cin;
+    if (ksize) *ksize = L.k;
+    if (has_bias) *has_bias = !L.b.empty();
+    if (has_bn) *has_bn = !L.gamma.empty();
+    if (eps) *eps = L.eps;
+    return XDTTS_OK;
+}
+
+// which: 0 conv weight [cout, cin, k], 1 conv bias, 2 gamma, 3 beta, 4 running mean, 5 running var
+extern "C" int xdtts_onnx_postnet_layer_copy(const xdtts_onnx_postnet* m, int layer, int which, float* out) {
+    if (!m || !out || layer < 0 || layer >= (int)m->layers.size() || which < 0 || which > 5)
+        return fail(XDTTS_ERR_BAD_ARG, "onnx_postnet_layer_copy: bad argument");
+    const Layer& L = m->layers[layer];
+    const std::vector<float>* src[6] = {&L.w, &L.b, &L.gamma, &L.beta, &L.mean, &L.var};
+    if (src[which]->empty()) return fail(XDTTS_ERR_BAD_ARG, "onnx_postnet_layer_copy: layer %d has no tensor %d", layer, which);
+    memcpy(out, src[which]->data(), src[which]->size() * 4);
+    return XDTTS_OK;
+}
+
+// Tacotron2::load for the postnet session (src/tacotron2/mod.rs:256-259) straight onto the device
+extern "C" int xdtts_postnet_create_from_onnx(const char* path, const xdtts_postnet_opts* opts, int device, xdtts_postnet** out) {
+    if (!out) return fail(XDTTS_ERR_BAD_ARG, "postnet_create_from_onnx: out is null");
+    *out = nullptr;
+    xdtts_onnx_postnet* m = nullptr;
+    int rc = xdtts_onnx_postnet_open(path, &m);
+    if (rc) return rc;
+    const int n = (int)m->layers.size();
+    std::vector<int> ch(n + 1);
+    std::vector<const float*> w(n), b(n), g(n), be(n), mu(n), var(n);
+    ch[0] = m->layers[0].cin;
+    for (int l = 0; l < n; l++) {
+        const Layer& L = m->layers[l];
+        ch[l + 1] = L.cout;
+        w[l] = L.w.data();
+        b[l] = L.b.empty() ? nullptr : L.b.data();
+        g[l] = L.gamma.empty() ? nullptr : L.gamma.data();
+        be[l] = L.beta.empty() ? nullptr : L.beta.data();
+        mu[l] = L.mean.empty() ? nullptr : L.mean.data();
+        var[l] = L.var.empty() ? nullptr : L.var.data();
+    }
+    rc = xdtts_postnet_create(n, ch.data(), m->layers[0].k, w.data(), b.data(), g.data(), be.data(), mu.data(), var.data(),
+                              m->eps, opts, device, out);
+    delete m;
+    return rc;
+}

@@ -42,6 +42,8 @@ _fp = ctypes.POINTER(ctypes.c_float)
 _fpp = ctypes.POINTER(_fp)
 _ip = ctypes.POINTER(ctypes.c_int)
 _vp = ctypes.c_void_p
+_sp = ctypes.POINTER(ctypes.c_short)
+_spp = ctypes.POINTER(_sp)
 
 # every symbol include/xdtts_b200.h declares: (restype, argtypes)
 SIGNATURES = {
@@ -55,6 +57,8 @@ SIGNATURES = {
     "xdtts_gl_infer": (ctypes.c_int, [_vp, _fp, ctypes.c_int, _fp, _fp, ctypes.c_int]),
     "xdtts_gl_infer_batch": (ctypes.c_int, [_vp, _fpp, _ip, ctypes.c_int, _fpp, _fpp]),
     "xdtts_gl_from_mag_batch": (ctypes.c_int, [_vp, _fpp, _ip, ctypes.c_int, _fpp, _fpp]),
+    "xdtts_gl_infer_batch_pcm16": (ctypes.c_int, [_vp, _fpp, _ip, ctypes.c_int, _fpp, _spp]),
+    "xdtts_gl_plan_download_pcm16": (ctypes.c_int, [_vp, _spp]),
     "xdtts_gl_plan_create": (ctypes.c_int, [_vp, _ip, ctypes.c_int, ctypes.POINTER(_vp)]),
     "xdtts_gl_plan_destroy": (None, [_vp]),
     "xdtts_gl_plan_upload": (ctypes.c_int, [_vp, ctypes.c_int, _fpp]),
@@ -72,6 +76,12 @@ SIGNATURES = {
     "xdtts_postnet_plan_upload": (ctypes.c_int, [_vp, _fpp]),
     "xdtts_postnet_plan_run": (ctypes.c_int, [_vp, _vp, _fp]),
     "xdtts_postnet_plan_download": (ctypes.c_int, [_vp, _fpp]),
+    "xdtts_postnet_create_from_onnx": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(PostnetOpts), ctypes.c_int, ctypes.POINTER(_vp)]),
+    "xdtts_onnx_postnet_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    "xdtts_onnx_postnet_close": (None, [_vp]),
+    "xdtts_onnx_postnet_n_layers": (ctypes.c_int, [_vp]),
+    "xdtts_onnx_postnet_layer_info": (ctypes.c_int, [_vp, ctypes.c_int, _ip, _ip, _ip, _ip, _ip, _fp]),
+    "xdtts_onnx_postnet_layer_copy": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _fp]),
     "xdtts_tail_infer_batch": (ctypes.c_int, [_vp, _vp, _fpp, _ip, ctypes.c_int, _fpp, _fpp, _fpp]),
     "xdtts_host_alloc": (_vp, [ctypes.c_ulonglong]),
     "xdtts_host_free": (None, [_vp]),
@@ -113,6 +123,13 @@ def version():
 
 def fptr(a):
     return a.ctypes.data_as(_fp)
+
+
+def sptr_array(arrays):
+    arr = (_sp * len(arrays))()
+    for i, a in enumerate(arrays):
+        arr[i] = a.ctypes.data_as(_sp)
+    return arr
 
 
 def fptr_array(arrays):

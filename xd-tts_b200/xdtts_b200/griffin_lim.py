@@ -15,7 +15,7 @@ import ctypes
 import numpy as np
 
 from . import _ffi
-from ._ffi import GlOpts, XdttsError, check, fptr, fptr_array, load_library
+from ._ffi import GlOpts, XdttsError, check, fptr, fptr_array, load_library, sptr_array
 
 DELOG_EXP, DELOG_POW10, DELOG_NONE = 0, 1, 2
 PAD_REFLECT, PAD_CONSTANT = 0, 1
@@ -124,6 +124,22 @@ class GriffinLim:
         """B utterances in one device pass (the reference loops over them, src/lib.rs:83-104)."""
         return self._batch("xdtts_gl_infer_batch", mels, self.n_mels, "mel", init_phases)
 
+    def infer_batch_pcm16(self, mels, init_phases=None):
+        """infer_batch + the caller's `(sample * i16::MAX as f32) as i16` loop (src/lib.rs:153-157) on the device."""
+        lib = load_library()
+        ins = [_as_f32_2d(a, self.n_mels, "mel") for a in mels]
+        ts = [a.shape[1] for a in ins]
+        outs = [np.empty(max(self.hop * (t - 1), 0), dtype=np.int16) for t in ts]
+        phs = None
+        if init_phases is not None:
+            phs = [_as_f32_2d(a, self.k_bins, "init_phase") for a in init_phases]
+            if [a.shape[1] for a in phs] != ts:
+                raise XdttsError(_ffi.ERR_SHAPE, "init_phases do not match the inputs' frame counts")
+        t_arr = (ctypes.c_int * len(ts))(*ts)
+        check(lib.xdtts_gl_infer_batch_pcm16(self._h, fptr_array(ins), t_arr, len(ins),
+                                             None if phs is None else fptr_array(phs), sptr_array(outs)))
+        return outs
+
     def from_magnitude_batch(self, mags, init_phases=None):
         """Griffin-Lim proper from linear magnitudes [K, T] (no mel -> linear lift)."""
         return self._batch("xdtts_gl_from_mag_batch", mags, self.k_bins, "magnitude", init_phases)
@@ -179,6 +195,11 @@ class GlPlan:
     def download(self):
         outs = [np.empty(self.voc.hop * (t - 1), dtype=np.float32) for t in self.ts]
         check(load_library().xdtts_gl_plan_download(self._p, fptr_array(outs)))
+        return outs
+
+    def download_pcm16(self):
+        outs = [np.empty(self.voc.hop * (t - 1), dtype=np.int16) for t in self.ts]
+        check(load_library().xdtts_gl_plan_download_pcm16(self._p, sptr_array(outs)))
         return outs
 
     def download_ptrs(self, ptr_array):

@@ -84,6 +84,16 @@ class Postnet:
                                        ctypes.byref(h)))
         return cls(h, channels, int(precision))
 
+    @classmethod
+    def load(cls, path, *, precision=PRECISION_BF16X3, device=0):
+        """The postnet part of Tacotron2::load (src/tacotron2/mod.rs:256-259): `path` is postnet.onnx."""
+        lib = load_library()
+        opts = PostnetOpts(int(precision))
+        h = ctypes.c_void_p()
+        check(lib.xdtts_postnet_create_from_onnx(str(path).encode(), ctypes.byref(opts), int(device), ctypes.byref(h)))
+        layers = read_onnx_postnet(path)
+        return cls(h, [layers[0]["w"].shape[1]] + [l["w"].shape[0] for l in layers], int(precision))
+
     def close(self):
         if self._h:
             load_library().xdtts_postnet_destroy(self._h)
@@ -111,6 +121,35 @@ class Postnet:
 
     def plan(self, frame_counts):
         return PostnetPlan(self, frame_counts)
+
+
+def read_onnx_postnet(path):
+    """Layers of a postnet.onnx as `from_layers` takes them (host only; the library's own ONNX reader)."""
+    lib = load_library()
+    m = ctypes.c_void_p()
+    check(lib.xdtts_onnx_postnet_open(str(path).encode(), ctypes.byref(m)))
+    try:
+        n = lib.xdtts_onnx_postnet_n_layers(m)
+        if n < 0:
+            check(n)
+        layers = []
+        for i in range(n):
+            co, ci, k, hb, hbn = (ctypes.c_int() for _ in range(5))
+            eps = ctypes.c_float()
+            check(lib.xdtts_onnx_postnet_layer_info(m, i, ctypes.byref(co), ctypes.byref(ci), ctypes.byref(k), ctypes.byref(hb),
+                                                    ctypes.byref(hbn), ctypes.byref(eps)))
+            layer = {"eps": eps.value}
+            names = [("w", (co.value, ci.value, k.value), True), ("b", (co.value,), bool(hb.value))]
+            names += [(nm, (co.value,), bool(hbn.value)) for nm in ("gamma", "beta", "mean", "var")]
+            for which, (nm, shape, present) in enumerate(names):
+                if present:
+                    a = np.empty(shape, dtype=np.float32)
+                    check(lib.xdtts_onnx_postnet_layer_copy(m, i, which, fptr(a)))
+                    layer[nm] = a
+            layers.append(layer)
+        return layers
+    finally:
+        lib.xdtts_onnx_postnet_close(m)
 
 
 class PostnetPlan:
