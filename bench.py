@@ -65,21 +65,32 @@ def measured_tensor_peak():
     return FALLBACK_BF16_TFLOPS, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
 
 
-def synth_postnet_layers():
-    from oracle.postnet_oracle import synth_weights   # weight generator only (the LFS weights are absent)
+def synth_postnet_layers(seed=7, channels=(80, 512, 512, 512, 512, 80), ksize=5):
+    """Seeded random postnet (the LFS weights of the reference are absent): conv W ~ N(0, 1/sqrt(Cin k)),
+    b ~ N(0, 0.1); BatchNorm gamma ~ U(.5, 1.5), beta, mean ~ N(0, 0.1), var ~ U(.5, 1.5)."""
+    rng = np.random.default_rng(seed)
+    layers = []
+    for cin, cout in zip(channels[:-1], channels[1:]):
+        layers.append(dict(
+            w=(rng.standard_normal((cout, cin, ksize)) / np.sqrt(cin * ksize)).astype(np.float32),
+            b=(0.1 * rng.standard_normal(cout)).astype(np.float32),
+            gamma=rng.uniform(0.5, 1.5, cout).astype(np.float32),
+            beta=(0.1 * rng.standard_normal(cout)).astype(np.float32),
+            mean=(0.1 * rng.standard_normal(cout)).astype(np.float32),
+            var=rng.uniform(0.5, 1.5, cout).astype(np.float32)))
+    return layers
 
-    return synth_weights(seed=7)
+
+def synth_mel(seed, n_mels, n_frames):
+    """ln-mel in U(-8, 0), the range Tacotron2 emits: the benchmark's synthetic input."""
+    return np.random.default_rng(seed).uniform(-8.0, 0.0, (n_mels, n_frames)).astype(np.float32)
 
 
 def bench_mel(i, t):
-    from oracle.gl_oracle import synth_mel   # input generator only (shared with the tests)
-
     return synth_mel(1234 + i, N_MELS, t)    # utterance i of the job
 
 
 def synth_batch(b, t, seed0):
-    from oracle.gl_oracle import synth_mel
-
     return [synth_mel(seed0 + i, N_MELS, t) for i in range(b)]
 
 

@@ -1,13 +1,13 @@
 """Quick GPU check of a library build: parity on a small case + steady-state kernel time of cfg2 / cfg5.
 
-    [XDTTS_B200_LIB=path/to/variant.so] python tools/gl_quick.py [cfg2 cfg5 ...]
+    [XDTTS_B200_LIB=path/to/variant.so] python tests/gpu_tools/gl_quick.py [cfg2 cfg5 ...]
 """
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "xd-tts_b200"))
 

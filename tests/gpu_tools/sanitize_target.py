@@ -1,13 +1,13 @@
 """Small invocation of every kernel for compute-sanitizer (memcheck / racecheck / synccheck):
 
-    compute-sanitizer --tool memcheck python tools/sanitize_target.py
+    compute-sanitizer --tool memcheck python tests/gpu_tools/sanitize_target.py
 """
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "xd-tts_b200"))
 

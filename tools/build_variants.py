@@ -2,7 +2,7 @@
 exchange-buffer aliasing), written next to the product library so that they travel to the GPU box:
 
     python tools/build_variants.py 8:6,2,0 8:4,4,1 16:9,1,1 ...      # R3:WARPS,CTAS,ALIAS
-    XDTTS_B200_LIB=xd-tts_b200/xdtts_b200/_lib/variants/libxdtts_8_4_4_1.so python tools/gl_quick.py cfg2
+    XDTTS_B200_LIB=xd-tts_b200/xdtts_b200/_lib/variants/libxdtts_8_4_4_1.so python tests/gpu_tools/gl_quick.py cfg2
 """
 import os
 import subprocess

@@ -10,13 +10,12 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "xd-tts_b200"))
 
 import bench  # noqa: E402
-from oracle import postnet_oracle as po  # noqa: E402  (weights generator only)
 from xdtts_b200 import tacotron2  # noqa: E402
 
 passes = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 modes = [int(x) for x in sys.argv[2:]] or [0, 1]
 b, t = 32, 1000
-layers = po.synth_weights(seed=7)
+layers = bench.synth_postnet_layers()
 mels = bench.synth_batch(b, t, 1234)
 flop = 8683520.0 * b * t
 for prec in modes:
