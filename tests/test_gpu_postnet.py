@@ -175,3 +175,17 @@ def test_load_from_onnx_file(taco, layers, tmp_path):
     b = taco.Postnet.from_layers(layers).run(mel)
     assert np.array_equal(a, b)
     assert np.abs(a - po.postnet(mel, layers, dtype=np.float64)).max() < TOL[0]
+
+
+def test_cfg3_full_size_batch(taco, layers):
+    """BASELINE.json configs[2] shape (32 x 80x1000): tensor path vs the CUDA-core fp32 path on the whole batch,
+    and no cross-utterance leakage at full tile occupancy."""
+    b, t = 32, 1000
+    mels = [o.synth_mel(1234 + i, 80, t) for i in range(b)]
+    tc = taco.Postnet.from_layers(layers, precision=0)
+    outs = tc.run_batch(mels)
+    ref = taco.Postnet.from_layers(layers, precision=2).run_batch(mels)
+    worst = max(float(np.abs(a - r).max()) for a, r in zip(outs, ref))
+    assert worst < 2e-4, worst
+    assert np.array_equal(tc.run(mels[17]), outs[17])
+    assert np.abs(outs[5] - po.postnet(mels[5], layers, dtype=np.float64)).max() < TOL[0]
