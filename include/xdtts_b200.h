@@ -160,6 +160,13 @@ int xdtts_tail_infer_batch(xdtts_postnet* pn, xdtts_gl* gl, const float* const* 
                            const float* const* init_phases_or_null, float* const* out_mels_or_null,
                            float* const* out_waves);
 
+/* .npy I/O for [rows, cols] float32 arrays -- the format of the reference's spectrogram dump
+ * (ndarray_npy::write_npy, src/lib.rs:125-139, --output-spectrogram src/bin/app.rs:12-14).
+ * read: call with out == null to get the shape, then with a buffer of capacity >= rows*cols floats
+ * (1-D files read as [1, n]; Fortran-ordered files are transposed into C order). */
+int xdtts_npy_write_f32(const char* path, const float* data, int rows, int cols);
+int xdtts_npy_read_f32(const char* path, float* out_or_null, long long capacity, int* rows, int* cols);
+
 /* pinned host memory for callers that want copy/compute overlap and full PCIe speed */
 void* xdtts_host_alloc(unsigned long long bytes);
 void xdtts_host_free(void* p);

@@ -236,3 +236,33 @@ def test_onnx_postnet_reader(lib, tmp_path):
     with pytest.raises(XdttsError):
         tacotron2.read_onnx_postnet(trunc)
     assert ERR_UNSUPPORTED < 0
+
+
+def test_npy_io_matches_numpy(lib, tmp_path):
+    """The reference dumps mels with ndarray_npy::write_npy (src/lib.rs:132): our writer/reader interoperate with numpy."""
+    from xdtts_b200 import tacotron2
+    from xdtts_b200._ffi import ERR_BAD_ARG, ERR_UNSUPPORTED, XdttsError
+
+    rng = np.random.default_rng(1)
+    for shape in ((80, 200), (80, 1), (1, 7), (513, 33)):
+        a = rng.standard_normal(shape).astype(np.float32)
+        p = tmp_path / ("a_%d_%d.npy" % shape)
+        tacotron2.write_npy(p, a)
+        b = np.load(p)                                   # numpy reads what we wrote
+        assert b.dtype == np.float32 and b.shape == shape and np.array_equal(a, b)
+        assert (p.stat().st_size - a.nbytes) % 64 == 0   # header padded as numpy / ndarray-npy do
+        q = tmp_path / "np.npy"
+        np.save(q, a)                                    # we read what numpy wrote
+        assert np.array_equal(tacotron2.read_npy(q), a)
+        np.save(q, np.asfortranarray(a))
+        assert np.array_equal(tacotron2.read_npy(q), a)
+    np.save(tmp_path / "v.npy", np.arange(5, dtype=np.float32))
+    assert tacotron2.read_npy(tmp_path / "v.npy").shape == (1, 5)
+    np.save(tmp_path / "d.npy", np.zeros((2, 2)))
+    with pytest.raises(XdttsError) as e:
+        tacotron2.read_npy(tmp_path / "d.npy")           # float64 is not what the reference writes
+    assert e.value.code == ERR_UNSUPPORTED
+    (tmp_path / "junk.npy").write_bytes(b"not numpy at all")
+    with pytest.raises(XdttsError) as e:
+        tacotron2.read_npy(tmp_path / "junk.npy")
+    assert e.value.code == ERR_BAD_ARG

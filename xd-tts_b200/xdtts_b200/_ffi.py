@@ -83,6 +83,8 @@ SIGNATURES = {
     "xdtts_onnx_postnet_layer_info": (ctypes.c_int, [_vp, ctypes.c_int, _ip, _ip, _ip, _ip, _ip, _fp]),
     "xdtts_onnx_postnet_layer_copy": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _fp]),
     "xdtts_tail_infer_batch": (ctypes.c_int, [_vp, _vp, _fpp, _ip, ctypes.c_int, _fpp, _fpp, _fpp]),
+    "xdtts_npy_write_f32": (ctypes.c_int, [ctypes.c_char_p, _fp, ctypes.c_int, ctypes.c_int]),
+    "xdtts_npy_read_f32": (ctypes.c_int, [ctypes.c_char_p, _fp, ctypes.c_longlong, _ip, _ip]),
     "xdtts_host_alloc": (_vp, [ctypes.c_ulonglong]),
     "xdtts_host_free": (None, [_vp]),
     "xdtts_last_error": (ctypes.c_char_p, []),

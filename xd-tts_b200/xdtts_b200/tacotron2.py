@@ -123,6 +123,24 @@ class Postnet:
         return PostnetPlan(self, frame_counts)
 
 
+def write_npy(path, spectrogram):
+    """ndarray_npy::write_npy(path, &spectrogram) (src/lib.rs:132): the --output-spectrogram dump."""
+    a = np.ascontiguousarray(spectrogram, dtype=np.float32)
+    if a.ndim != 2:
+        raise XdttsError(_ffi.ERR_SHAPE, "spectrogram must be 2-D")
+    check(load_library().xdtts_npy_write_f32(str(path).encode(), fptr(a), a.shape[0], a.shape[1]))
+
+
+def read_npy(path):
+    """A mel dumped by the reference's `xd_tts --output-spectrogram` (or by numpy) -> float32 [rows, cols]."""
+    lib = load_library()
+    r, c = ctypes.c_int(), ctypes.c_int()
+    check(lib.xdtts_npy_read_f32(str(path).encode(), None, 0, ctypes.byref(r), ctypes.byref(c)))
+    out = np.empty((r.value, c.value), dtype=np.float32)
+    check(lib.xdtts_npy_read_f32(str(path).encode(), fptr(out), out.size, ctypes.byref(r), ctypes.byref(c)))
+    return out
+
+
 def read_onnx_postnet(path):
     """Layers of a postnet.onnx as `from_layers` takes them (host only; the library's own ONNX reader)."""
     lib = load_library()
