@@ -39,6 +39,8 @@ typedef struct xdtts_gl_opts {
     int normalise;           /* 0: peak-normalise to [-1,1] (caller scales by i16::MAX, src/lib.rs:155)  1: none */
     int run_frames;          /* 0: auto.  Frames per warp run (tuning knob, >= 4) */
     unsigned long long seed; /* seed of the random initial phase used when the caller passes none */
+    int persistent;          /* 0: one launch per iteration, CUDA graph (default; fastest at full occupancy)
+                                1: whole vocode in one cooperative launch when the batch fits one resident wave */
 } xdtts_gl_opts;
 
 typedef struct xdtts_gl xdtts_gl;           /* replaces griffin_lim::GriffinLim */
@@ -93,15 +95,23 @@ int xdtts_gl_plan_upload(xdtts_gl_plan* p, int kind, const float* const* srcs);
 #define XDTTS_RUN_FROM_MAG 1    /* start from the uploaded magnitudes instead of lifting the mels */
 #define XDTTS_RUN_USE_PHASE 2   /* use the uploaded initial phase instead of the seeded generator */
 #define XDTTS_RUN_NO_GRAPH 4    /* launch kernel by kernel (needed for ms_iter) */
-/* Runs lift/transposes, the n_iter+1 Griffin-Lim launches and the normalisation on the plan's
- * stream and waits.  ms_total: device time of the whole pass (CUDA events); ms_iter / n_iter_launches:
- * summed device time and count of the steady-state iteration launches (only with NO_GRAPH). */
+#define XDTTS_RUN_PER_LAUNCH 16 /* one launch per iteration even when the persistent single-launch kernel applies */
+/* Runs lift/transposes, Griffin-Lim and the normalisation on the plan's stream and waits: one launch per
+ * iteration, captured in a CUDA graph.  With opts.persistent = 1 and a batch that fits the device's resident
+ * warps in one wave (xdtts_gl_plan_is_persistent) the initial inverse transform and all n_iter iterations are
+ * instead ONE cooperative launch in which runs hand hop blocks to their neighbours through L2 flags
+ * (bit-identical results; measured equal or slower on B200); PER_LAUNCH overrides it per call.
+ * ms_total: device time of the whole pass (CUDA events).  With NO_GRAPH: ms_iter / n_iter_launches =
+ * device time and count of the Griffin-Lim launches it covers (the n_iter-2 steady-state launches, or the
+ * single persistent launch). */
 int xdtts_gl_plan_run(xdtts_gl_plan* p, int flags, float* ms_total, float* ms_iter, int* n_iter_launches);
 int xdtts_gl_plan_download(xdtts_gl_plan* p, float* const* outs);
 int xdtts_gl_plan_download_pcm16(xdtts_gl_plan* p, short* const* outs);   /* after a run: 16-bit PCM of the same waveforms */
 /* debugging / parity: copy device state to host. what: 0 S [T_total][M] frame-major, 1 S Nyquist [T_total],
  * 2 R [T_total][M][2]; n_floats must match. */
 int xdtts_gl_plan_peek(xdtts_gl_plan* p, int what, float* out, long long n_floats);
+/* 1 when xdtts_gl_plan_run uses the persistent single-launch kernel for this plan, 0 otherwise */
+int xdtts_gl_plan_is_persistent(const xdtts_gl_plan* p);
 /* geometry the plan chose: info[0]=n_runs, [1]=frames per run (max), [2]=CTAs, [3]=total frames */
 int xdtts_gl_plan_info(const xdtts_gl_plan* p, int* info4);
 

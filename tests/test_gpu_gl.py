@@ -287,3 +287,34 @@ def test_randomised_ragged_batches(gl):
             ref = o.griffin_lim(s, ph, it, mom, n_fft, hop, pad_mode=pad, dtype=np.float64)
             assert y.shape == (hop * (t - 1),)
             assert rel_rms(y, ref) < 3e-6, (trial, n_fft, ts, it, rf, pad, mom)
+
+
+def test_persistent_kernel_equals_per_iteration_launches_bitwise(gl):
+    """The single cooperative launch (runs synchronise with their neighbours through L2 flags) performs the
+    same arithmetic in the same order as one launch per iteration: identical bits, any shape, any run length."""
+    from xdtts_b200 import _ffi
+
+    for n_fft, ts, it, rf in ((1024, [200], 30, 0), (1024, [4, 9, 40, 5, 123, 17], 7, 4), (2048, [64, 31], 9, 6),
+                              (512, [77, 12], 12, 5), (1024, [1000] * 4, 20, 0), (1024, [50], 0, 0), (1024, [50], 1, 7)):
+        k = n_fft // 2 + 1
+        voc = make(gl, n_fft, it, run_frames=rf, persistent=True)
+        mels = [o.synth_mel(700 + i, 80, t) for i, t in enumerate(ts)]
+        phs = [o.phase_turns(9, i, k, t) for i, t in enumerate(ts)]
+        plan = voc.plan(ts)
+        assert plan.is_persistent()
+        plan.upload(0, mels)
+        plan.upload(2, phs)
+        plan.run(_ffi.RUN_USE_PHASE)
+        a = plan.download()
+        r_a = plan.peek(2)
+        plan.run(_ffi.RUN_USE_PHASE | _ffi.RUN_PER_LAUNCH)
+        b = plan.download()
+        r_b = plan.peek(2)
+        plan.run(_ffi.RUN_USE_PHASE | _ffi.RUN_PER_LAUNCH | _ffi.RUN_NO_GRAPH)
+        c = plan.download()
+        for x, y, z in zip(a, b, c):
+            assert np.array_equal(x, y) and np.array_equal(x, z), (n_fft, ts, it, rf)
+        assert np.array_equal(r_a, r_b)
+        plan.run(_ffi.RUN_USE_PHASE)               # and again: flags / counters are reusable
+        for x, y in zip(plan.download(), a):
+            assert np.array_equal(x, y)

@@ -203,7 +203,7 @@ extern "C" int xdtts_gl_create(const float* mel_basis, int n_mels, int K, int no
     for (size_t i = 0; i < (size_t)n_mels * K; i++)
         if (!std::isfinite(mel_basis[i])) return fail(XDTTS_ERR_BAD_ARG, "gl_create: mel_basis has a non-finite entry");
     if (opts && (opts->delog < 0 || opts->delog > 2 || opts->pad_mode < 0 || opts->pad_mode > 1 || opts->normalise < 0 ||
-                 opts->normalise > 1 || opts->run_frames < 0))
+                 opts->normalise > 1 || opts->run_frames < 0 || opts->persistent < 0 || opts->persistent > 1))
         return fail(XDTTS_ERR_BAD_ARG, "gl_create: option out of range");
 
     int n_dev = 0;
@@ -286,7 +286,7 @@ extern "C" void xdtts_gl_plan_destroy(xdtts_gl_plan* p) {
     cudaFree(p->d_runs); cudaFree(p->d_T); cudaFree(p->d_foff); cudaFree(p->d_out_off);
     cudaFree(p->d_mel); cudaFree(p->d_in_mag); cudaFree(p->d_in_phase); cudaFree(p->d_turns); cudaFree(p->d_turns_nyq);
     cudaFree(p->d_S); cudaFree(p->d_S_nyq); cudaFree(p->d_y[0]); cudaFree(p->d_y[1]); cudaFree(p->d_halo);
-    cudaFree(p->d_out); cudaFree(p->d_R); cudaFree(p->d_flags); cudaFree(p->d_amax); cudaFree(p->d_pcm);
+    cudaFree(p->d_out); cudaFree(p->d_R); cudaFree(p->d_flags); cudaFree(p->d_amax); cudaFree(p->d_pcm); cudaFree(p->d_done);
     if (p->h_pcm) cudaFreeHost(p->h_pcm);
     if (p->h_in) cudaFreeHost(p->h_in);
     if (p->h_out) cudaFreeHost(p->h_out);
@@ -323,7 +323,7 @@ int xdtts::gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out)
         std::vector<int> counts(B);
         for (int b = 0; b < B; b++) {
             long long n = (long long)Ts[b] * target / total;   // floor: the sum never exceeds the target
-            if (n > Ts[b] / 8) n = Ts[b] / 8;                   // runs shorter than 8 frames pay too much halo traffic
+            if (n > Ts[b] / 4) n = Ts[b] / 4;                   // a hop block may be shared by at most two runs
             counts[b] = n < 1 ? 1 : (int)n;
         }
         build_runs_counts(Ts, B, counts.data(), &p->runs, &p->foff);
@@ -331,6 +331,12 @@ int xdtts::gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out)
         for (const GlRun& r : p->runs) rf = std::max(rf, r.tb - r.ta);
     }
     p->run_frames = rf;
+    {   // persistent single-launch path: every run must be resident at once (checked again at launch)
+        const char* env = getenv("XDTTS_GL_PERSISTENT");
+        const long long resident = (long long)h->sm_count * gl_resident_warps_per_sm(h->n_fft);
+        const bool want = env ? atoi(env) != 0 : h->opts.persistent != 0;
+        p->use_persistent = want && (long long)p->runs.size() <= resident;
+    }
     p->out_off.resize(B);
     for (int b = 0; b < B; b++) {
         p->out_off[b] = p->out_total;
@@ -350,6 +356,7 @@ int xdtts::gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out)
     ALLOC(p->d_y[1], TT * H * 4);
     ALLOC(p->d_halo, nr * 6 * H * 4);
     ALLOC(p->d_flags, nr * sizeof(unsigned));
+    ALLOC(p->d_done, nr * sizeof(unsigned));
     ALLOC(p->d_amax, B * sizeof(unsigned));
     ALLOC(p->d_out, (size_t)p->out_total * 4);
 #undef ALLOC
@@ -372,6 +379,11 @@ extern "C" int xdtts_gl_plan_create(xdtts_gl* h, const int* Ts, int B, xdtts_gl_
     if (!h || !out) return fail(XDTTS_ERR_BAD_ARG, "plan_create: null argument");
     std::lock_guard<std::mutex> lk(h->mu);
     return gl_plan_build(h, Ts, B, out);
+}
+
+extern "C" int xdtts_gl_plan_is_persistent(const xdtts_gl_plan* p) {
+    if (!p) return fail(XDTTS_ERR_BAD_ARG, "plan_is_persistent: plan is null");
+    return p->use_persistent ? 1 : 0;
 }
 
 extern "C" int xdtts_gl_plan_info(const xdtts_gl_plan* p, int* info4) {
@@ -455,19 +467,37 @@ static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid) {
     gp.inv_n = 1.0f / (float)h->n_fft;
     gp.pad_mode = h->opts.pad_mode;
     (void)M;
-    gp.y_in = p->d_y[1]; gp.y_out = p->d_y[0];
-    CU(gl_launch_iteration(h->n_fft, GL_MODE_INIT, h->n_iter == 0, gp, s));
-    g_launches++;
     int mids = 0;
-    for (int it = 1; it <= h->n_iter; it++) {
-        gp.y_in = p->d_y[(it - 1) & 1];
-        gp.y_out = p->d_y[it & 1];
-        const bool last = it == h->n_iter;
-        if (timed && it == 2) CU(cudaEventRecord(p->ev[1], s));
-        CU(gl_launch_iteration(h->n_fft, it == 1 ? GL_MODE_FIRST : GL_MODE_MID, last, gp, s));
+    bool done = false;
+    if (p->use_persistent && !(flags & XDTTS_RUN_PER_LAUNCH)) {
+        gp.ybuf[0] = p->d_y[0]; gp.ybuf[1] = p->d_y[1]; gp.done = p->d_done; gp.n_iter = h->n_iter;
+        CU(cudaMemsetAsync(p->d_done, 0, p->runs.size() * sizeof(unsigned), s));
+        if (timed) CU(cudaEventRecord(p->ev[1], s));
+        bool fits = false;
+        CU(gl_launch_persistent(h->n_fft, gp, h->sm_count, s, &fits));
+        if (fits) {
+            if (timed) CU(cudaEventRecord(p->ev[2], s));
+            g_launches++;
+            mids = 1;
+            done = true;
+        } else {
+            p->use_persistent = false;   // does not fit this device after all: launch per iteration from now on
+        }
+    }
+    if (!done) {
+        gp.y_in = p->d_y[1]; gp.y_out = p->d_y[0];
+        CU(gl_launch_iteration(h->n_fft, GL_MODE_INIT, h->n_iter == 0, gp, s));
         g_launches++;
-        if (it >= 2 && !last) mids++;
-        if (timed && it == h->n_iter - 1 && it >= 2) CU(cudaEventRecord(p->ev[2], s));
+        for (int it = 1; it <= h->n_iter; it++) {
+            gp.y_in = p->d_y[(it - 1) & 1];
+            gp.y_out = p->d_y[it & 1];
+            const bool last = it == h->n_iter;
+            if (timed && it == 2) CU(cudaEventRecord(p->ev[1], s));
+            CU(gl_launch_iteration(h->n_fft, it == 1 ? GL_MODE_FIRST : GL_MODE_MID, last, gp, s));
+            g_launches++;
+            if (it >= 2 && !last) mids++;
+            if (timed && it == h->n_iter - 1 && it >= 2) CU(cudaEventRecord(p->ev[2], s));
+        }
     }
     CU(gl_launch_finish(p->d_y[h->n_iter & 1], p->d_T, p->d_foff, p->d_out_off, p->d_amax, p->B, p->max_T, h->hop,
                         h->opts.normalise == 0, p->d_out, s));
@@ -487,16 +517,17 @@ int xdtts::gl_plan_run_locked(xdtts_gl_plan* p, int flags, float* ms_total, floa
     int mids = 0;
     if (ms_iter) *ms_iter = 0.f;
     if (n_iter_launches) *n_iter_launches = 0;
-    if (flags & XDTTS_RUN_NO_GRAPH) {
+    const bool persistent = p->use_persistent && !(flags & XDTTS_RUN_PER_LAUNCH);
+    if ((flags & XDTTS_RUN_NO_GRAPH) || persistent) {   // the persistent path is 3-4 launches: no graph needed
         CU(cudaEventRecord(p->ev[0], s));
-        int rc = plan_enqueue(p, flags, true, &mids);
+        int rc = plan_enqueue(p, flags, (flags & XDTTS_RUN_NO_GRAPH) != 0, &mids);
         if (rc) return rc;
         CU(cudaEventRecord(p->ev[3], s));
         CU(cudaStreamSynchronize(s));
-        if (ms_iter && mids > 0) CU(cudaEventElapsedTime(ms_iter, p->ev[1], p->ev[2]));
-        if (n_iter_launches) *n_iter_launches = mids;
+        if ((flags & XDTTS_RUN_NO_GRAPH) && ms_iter && mids > 0) CU(cudaEventElapsedTime(ms_iter, p->ev[1], p->ev[2]));
+        if ((flags & XDTTS_RUN_NO_GRAPH) && n_iter_launches) *n_iter_launches = mids;
     } else {
-        const int gi = flags & 3;
+        const int gi = flags & 3;   // (PER_LAUNCH does not change what is captured: this branch is the per-launch path)
         if (!p->graphs[gi]) {
             cudaGraph_t g = nullptr;
             CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));

@@ -66,7 +66,8 @@ struct xdtts_gl_plan {
     float2* d_R = nullptr;
     short* d_pcm = nullptr;          // 16-bit PCM copy of d_out (allocated on first use)
     short* h_pcm = nullptr;
-    unsigned *d_flags = nullptr, *d_amax = nullptr;
+    unsigned *d_flags = nullptr, *d_amax = nullptr, *d_done = nullptr;
+    bool use_persistent = false;     // the run table fits the resident warps: one cooperative launch per vocode
     // pinned staging for pageable callers
     float *h_in = nullptr, *h_out = nullptr;
     size_t h_in_floats = 0;

@@ -188,6 +188,9 @@ struct GlParams {
     const float* turns_nyq;  // INIT: [frames]
     unsigned long long seed; // INIT: seed of the counter-based phase generator
     int utt_seed_base;       // INIT: global index of utterance 0 (so shards draw distinct phases)
+    float* ybuf[2];          // persistent kernel: the two waveform buffers (iteration i reads [(i-1)&1], writes [i&1])
+    unsigned* done;          // persistent kernel: [n_runs] number of iterations each run has completed
+    int n_iter;              // persistent kernel: iterations after the initial inverse transform
     float alpha;             // momentum / (1 + momentum)
     float inv_n;             // 1 / n_fft
     int pad_mode;
@@ -336,7 +339,19 @@ XD_HD bool frame_is_edge(int t, int T) { return (t < 2) || (t >= T - 2); }
 
 // quarter qi (one hop block, H samples) of frame t of the padded previous waveform -> q[2 NB]
 // element (n1 & 1) * NB + i  <->  sample 16 R3 n1 + 2 (lane + 32 i), n1 = 2 qi + (n1 & 1)
-template <int R3>
+// L2LOAD: read through L2 (ld.global.cg) -- required when the waveform was written by other SMs during
+// the same launch (persistent kernel), where an L1 line of the same buffer may be stale.
+template <typename T>
+XD_HD T ld_y(const T* p, bool l2) {
+#if defined(__CUDA_ARCH__)
+    return l2 ? __ldcg(p) : *p;
+#else
+    (void)l2;
+    return *p;
+#endif
+}
+
+template <int R3, bool L2LOAD = false>
 XD_HD void load_quarter(float2* q, int lane, const float* y, int T, int t, int qi, int pad_mode) {
     typedef Geo<R3> G;
     const int g = t - 2 + qi;                  // hop block of the trimmed signal
@@ -345,7 +360,7 @@ XD_HD void load_quarter(float2* q, int lane, const float* y, int T, int t, int q
         const float* yb = y + base + 2 * lane;
 #pragma unroll
         for (int e = 0; e < 2 * G::NB; e++)
-            q[e] = *reinterpret_cast<const float2*>(yb + 16 * R3 * (e / G::NB) + 64 * (e % G::NB));
+            q[e] = ld_y(reinterpret_cast<const float2*>(yb + 16 * R3 * (e / G::NB) + 64 * (e % G::NB)), L2LOAD);
     } else {
         const int len = G::H * (T - 1);
 #pragma unroll
@@ -353,11 +368,11 @@ XD_HD void load_quarter(float2* q, int lane, const float* y, int T, int t, int q
             const int j0 = base + 16 * R3 * (e / G::NB) + 64 * (e % G::NB) + 2 * lane, j1 = j0 + 1;
             float2 x;
             if (pad_mode == GL_PAD_REFLECT) {
-                x.x = y[reflect_index(j0, len)];
-                x.y = y[reflect_index(j1, len)];
+                x.x = ld_y(y + reflect_index(j0, len), L2LOAD);
+                x.y = ld_y(y + reflect_index(j1, len), L2LOAD);
             } else {
-                x.x = (j0 >= 0 && j0 < len) ? y[j0] : 0.f;
-                x.y = (j1 >= 0 && j1 < len) ? y[j1] : 0.f;
+                x.x = (j0 >= 0 && j0 < len) ? ld_y(y + j0, L2LOAD) : 0.f;
+                x.y = (j1 >= 0 && j1 < len) ? ld_y(y + j1, L2LOAD) : 0.f;
             }
             q[e] = x;
         }
@@ -368,7 +383,7 @@ XD_HD void load_quarter(float2* q, int lane, const float* y, int T, int t, int q
 // The frame's samples live in L.raw: a frame shares three of its four hop blocks with its
 // predecessor, so only the newest block comes from memory (first: the run's first frame, which
 // loads all four; have_pref: L.ynew already holds the newest block, fetched during the previous frame).
-template <int R3>
+template <int R3, bool L2LOAD = false>
 XD_HD void phase_f1(Lane<R3>& L, int lane, const float* y, int T, int t, int pad_mode, bool first, bool have_pref,
                     const float2* tab, float2* ex1) {
     typedef Geo<R3> G;
@@ -376,7 +391,7 @@ XD_HD void phase_f1(Lane<R3>& L, int lane, const float* y, int T, int t, int pad
 #pragma unroll
         for (int qi = 0; qi < 4; qi++) {
             float2 q[2 * G::NB];
-            load_quarter<R3>(q, lane, y, T, t, qi, pad_mode);
+            load_quarter<R3, L2LOAD>(q, lane, y, T, t, qi, pad_mode);
 #pragma unroll
             for (int e = 0; e < 2 * G::NB; e++) L.raw[(e % G::NB) * 8 + 2 * qi + e / G::NB] = q[e];
         }
@@ -390,7 +405,7 @@ XD_HD void phase_f1(Lane<R3>& L, int lane, const float* y, int T, int t, int pad
 #pragma unroll
             for (int e = 0; e < 2 * G::NB; e++) q[e] = L.ynew[e];
         } else {
-            load_quarter<R3>(q, lane, y, T, t, 3, pad_mode);
+            load_quarter<R3, L2LOAD>(q, lane, y, T, t, 3, pad_mode);
         }
 #pragma unroll
         for (int e = 0; e < 2 * G::NB; e++) L.raw[(e % G::NB) * 8 + 6 + e / G::NB] = q[e];
@@ -415,9 +430,9 @@ XD_HD void phase_f1(Lane<R3>& L, int lane, const float* y, int T, int t, int pad
 // Fetch the newest hop block of frame t+1 (inside the signal by construction: fast path) one frame
 // ahead.  Issued AFTER the warp sync that follows F1: the loads then share no scoreboard wait with
 // the window multiply of frame t, which consumes the block fetched a frame earlier.
-template <int R3>
+template <int R3, bool L2LOAD = false>
 XD_HD void prefetch_next_block(Lane<R3>& L, int lane, const float* y, int T, int t, int pad_mode) {
-    load_quarter<R3>(L.ynew, lane, y, T, t + 1, 3, pad_mode);
+    load_quarter<R3, L2LOAD>(L.ynew, lane, y, T, t + 1, 3, pad_mode);
 }
 
 // F2: pass 2 (radix 8 over n2) -> exchange 2.  Split into its read half and its write half so that

@@ -62,62 +62,72 @@ struct GlSmem {
     static constexpr size_t BYTES = sizeof(float2) * (size_t)(BAR_OFF + 1 + WARPS);
 };
 
-template <int R3, int MODE, bool STORE_R, bool TRACK_MAX>
-__global__ void __launch_bounds__(GlCfg<R3>::WARPS * 32, GlCfg<R3>::CTAS) gl_iter_kernel(const GlParams p) {
+// per-warp view of the CTA's shared memory
+template <int R3>
+struct WarpSmem {
+    float2 *tab, *ex1, *ex2, *r_stg;
+    float* s_stg;
+    unsigned long long *bar_tab, *bar;
+    __device__ __forceinline__ WarpSmem(float2* smem, int warp) {
+        typedef Geo<R3> G;
+        tab = smem;
+        unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + GlSmem<R3>::BAR_OFF);
+        ex1 = smem + G::TAB + warp * GlSmem<R3>::WARP;
+        ex2 = GlCfg<R3>::ALIAS ? ex1 : ex1 + G::EX1;
+        s_stg = reinterpret_cast<float*>(ex1 + GlSmem<R3>::EX);
+        r_stg = ex1 + GlSmem<R3>::EX + G::M / 2;
+        bar_tab = &bars[0];
+        bar = &bars[1 + warp];
+    }
+};
+
+// CTA prologue: barriers + the bulk copy of the constant tables (awaited by each warp before its first use)
+template <int R3>
+__device__ __forceinline__ void cta_prologue(float2* smem, const GlParams& p) {
     typedef Geo<R3> G;
     constexpr int GL_WARPS = GlCfg<R3>::WARPS;
-    extern __shared__ __align__(16) float2 smem[];
-    float2* tab = smem;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + GlSmem<R3>::BAR_OFF);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i <= GL_WARPS; i++) mbar_init(&bars[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (threadIdx.x == 0) {   // constant tables: one bulk copy per CTA, awaited by each warp before its first use
+    if (threadIdx.x == 0) {
         mbar_expect_tx(&bars[0], (unsigned)(G::TAB * sizeof(float2)));
-        bulk_g2s(tab, p.tables, (unsigned)(G::TAB * sizeof(float2)), &bars[0]);
+        bulk_g2s(smem, p.tables, (unsigned)(G::TAB * sizeof(float2)), &bars[0]);
     }
-    const int run_idx = blockIdx.x * GL_WARPS + warp;
-    if (run_idx >= p.n_runs) return;
-    float2* ex1 = smem + G::TAB + warp * GlSmem<R3>::WARP;
+}
+
+// One Griffin-Lim iteration over the frames of one run.  `phase` is the parity of the warp's staging
+// barrier (it flips once per frame and carries over between iterations in the persistent kernel).
+// COHERENT: the previous waveform was written by other SMs during this launch -> read it through L2.
+template <int R3, int MODE, bool STORE_R, bool TRACK_MAX, bool COHERENT>
+__device__ __forceinline__ void gl_run_frames(Lane<R3>& L, int lane, const GlParams& p, int run_idx, const GlRun& r, int T,
+                                              long foff, const WarpSmem<R3>& sm, unsigned& phase) {
+    typedef Geo<R3> G;
     constexpr bool ALIAS = GlCfg<R3>::ALIAS;
-    float2* ex2 = ALIAS ? ex1 : ex1 + G::EX1;
-    float* s_stg = reinterpret_cast<float*>(ex1 + GlSmem<R3>::EX);
-    float2* r_stg = ex1 + GlSmem<R3>::EX + G::M / 2;
-    unsigned long long* bar = &bars[1 + warp];
-
-    const GlRun r = p.runs[run_idx];
-    const int T = p.utt_T[r.utt];
-    const long foff = p.utt_foff[r.utt];
     const long yoff = foff * G::H;
-
-    Lane<R3> L;
-    lane_reset<R3>(L);
-    stage_issue<R3, MODE>(L, lane, p, foff + r.ta, s_stg, r_stg, bar);
-    stage_wait(&bars[0], 0);
-    lane_load_constants<R3>(L, lane, tab);
-
+    float2 *tab = sm.tab, *ex1 = sm.ex1, *ex2 = sm.ex2;
+    stage_issue<R3, MODE>(L, lane, p, foff + r.ta, sm.s_stg, sm.r_stg, sm.bar);
     bool pref = false;
     for (int t = r.ta; t < r.tb; t++) {
         const long frame = foff + t;
         if (MODE != GL_MODE_INIT) {
             const bool fetch_next = (t + 1 < r.tb) && (t + 2 <= T - 2);   // newest hop block of frame t+1 lies inside the signal
-            phase_f1<R3>(L, lane, p.y_in + yoff, T, t, p.pad_mode, t == r.ta, pref, tab, ex1);
+            phase_f1<R3, COHERENT>(L, lane, p.y_in + yoff, T, t, p.pad_mode, t == r.ta, pref, tab, ex1);
             pref = fetch_next;
             __syncwarp();
-            if (fetch_next) prefetch_next_block<R3>(L, lane, p.y_in + yoff, T, t, p.pad_mode);
+            if (fetch_next) prefetch_next_block<R3, COHERENT>(L, lane, p.y_in + yoff, T, t, p.pad_mode);
             phase_f2_load<R3>(L, lane, ex1);
             if (ALIAS) __syncwarp();
             phase_f2_store<R3>(L, lane, tab, ex2);
             __syncwarp();
         }
-        stage_wait(bar, (unsigned)(t - r.ta) & 1u);
-        phase_f3<R3, MODE, STORE_R>(L, lane, p, r.utt, T, t, frame, tab, ex2, s_stg, r_stg);
+        stage_wait(sm.bar, phase);
+        phase ^= 1u;
+        phase_f3<R3, MODE, STORE_R>(L, lane, p, r.utt, T, t, frame, tab, ex2, sm.s_stg, sm.r_stg);
         __syncwarp();   // every lane is done with the staged state (its values fed the stores above)
-        if (t + 1 < r.tb) stage_issue<R3, MODE>(L, lane, p, frame + 1, s_stg, r_stg, bar);
+        if (t + 1 < r.tb) stage_issue<R3, MODE>(L, lane, p, frame + 1, sm.s_stg, sm.r_stg, sm.bar);
         phase_f4_load<R3>(L, lane, tab, ex2);
         if (ALIAS) __syncwarp();
         phase_f4_store<R3>(L, lane, ex1);
@@ -139,9 +149,122 @@ __global__ void __launch_bounds__(GlCfg<R3>::WARPS * 32, GlCfg<R3>::CTAS) gl_ite
     }
 }
 
+template <int R3, int MODE, bool STORE_R, bool TRACK_MAX>
+__global__ void __launch_bounds__(GlCfg<R3>::WARPS * 32, GlCfg<R3>::CTAS) gl_iter_kernel(const GlParams p) {
+    extern __shared__ __align__(16) float2 smem[];
+    cta_prologue<R3>(smem, p);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int run_idx = blockIdx.x * GlCfg<R3>::WARPS + warp;
+    if (run_idx >= p.n_runs) return;
+    const WarpSmem<R3> sm(smem, warp);
+    const GlRun r = p.runs[run_idx];
+    const int T = p.utt_T[r.utt];
+    const long foff = p.utt_foff[r.utt];
+    Lane<R3> L;
+    lane_reset<R3>(L);
+    stage_wait(sm.bar_tab, 0);
+    lane_load_constants<R3>(L, lane, sm.tab);
+    unsigned phase = 0;
+    gl_run_frames<R3, MODE, STORE_R, TRACK_MAX, false>(L, lane, p, run_idx, r, T, foff, sm, phase);
+}
+
+// ------------------------------------------------------------------ persistent kernel
+// The whole vocode -- initial inverse transform + n_iter iterations -- in ONE cooperative launch:
+// every run keeps its warp, and a warp starts iteration i as soon as its two neighbouring runs (the
+// only ones whose hop blocks it reads) have published iteration i-1, instead of waiting for the whole
+// grid at a launch boundary.  The per-launch tail (SMs idling until the slowest warp is done) and the
+// per-launch prologue disappear; iterations of different runs overlap.  Neighbours never drift more than
+// one iteration apart, so two waveform buffers still suffice.  Needs every run resident at once: the host
+// uses it only when the run table fits the device's resident warps (cooperative launch checks it).
+__device__ __forceinline__ void wait_done(const unsigned* flag, unsigned want) {
+    unsigned v;
+    do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v < want) __nanosleep(64);
+    } while (v < want);
+}
+
+template <int R3>
+__global__ void __launch_bounds__(GlCfg<R3>::WARPS * 32, GlCfg<R3>::CTAS) gl_persist_kernel(const GlParams p0) {
+    extern __shared__ __align__(16) float2 smem[];
+    cta_prologue<R3>(smem, p0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int run_idx = blockIdx.x * GlCfg<R3>::WARPS + warp;
+    if (run_idx >= p0.n_runs) return;
+    const WarpSmem<R3> sm(smem, warp);
+    const GlRun r = p0.runs[run_idx];
+    const int T = p0.utt_T[r.utt];
+    const long foff = p0.utt_foff[r.utt];
+    const bool has_left = r.ta > 0, has_right = r.tb < T;   // neighbouring runs of the same utterance
+    Lane<R3> L;
+    stage_wait(sm.bar_tab, 0);
+    lane_load_constants<R3>(L, lane, sm.tab);
+    unsigned phase = 0;
+    GlParams p = p0;
+    for (int it = 0; it <= p0.n_iter; it++) {
+        p.y_in = p0.ybuf[(it + 1) & 1];
+        p.y_out = p0.ybuf[it & 1];
+        if (it > 0) {   // neighbours must have finished iteration it-1 (they also finished reading what this one overwrites)
+            if (lane == 0) {
+                if (has_left) wait_done(p0.done + run_idx - 1, (unsigned)it);
+                if (has_right) wait_done(p0.done + run_idx + 1, (unsigned)it);
+            }
+            __syncwarp();
+        }
+        lane_reset<R3>(L);
+        const bool last = it == p0.n_iter;
+        if (it == 0) {
+            if (last) gl_run_frames<R3, GL_MODE_INIT, false, true, true>(L, lane, p, run_idx, r, T, foff, sm, phase);
+            else gl_run_frames<R3, GL_MODE_INIT, false, false, true>(L, lane, p, run_idx, r, T, foff, sm, phase);
+        } else if (it == 1) {
+            if (last) gl_run_frames<R3, GL_MODE_FIRST, false, true, true>(L, lane, p, run_idx, r, T, foff, sm, phase);
+            else gl_run_frames<R3, GL_MODE_FIRST, true, false, true>(L, lane, p, run_idx, r, T, foff, sm, phase);
+        } else {
+            if (last) gl_run_frames<R3, GL_MODE_MID, false, true, true>(L, lane, p, run_idx, r, T, foff, sm, phase);
+            else gl_run_frames<R3, GL_MODE_MID, true, false, true>(L, lane, p, run_idx, r, T, foff, sm, phase);
+        }
+        // publish: this run's waveform blocks and rebuilt spectrum of iteration `it` are complete.  The
+        // spectrum rows are re-read by this warp's bulk copies (async proxy) in the next iteration.
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p0.done + run_idx), "r"((unsigned)(it + 1)) : "memory");
+    }
+}
+
 template <int R3>
 static size_t gl_smem_bytes() {
     return GlSmem<R3>::BYTES;
+}
+
+template <int R3>
+static cudaError_t persist_prepare() {
+    return cudaFuncSetAttribute(gl_persist_kernel<R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gl_smem_bytes<R3>());
+}
+
+template <int R3>
+static cudaError_t persist_launch(const GlParams& p, int sm_count, cudaStream_t s, bool* fits) {
+    constexpr int W = GlCfg<R3>::WARPS;
+    const int grid = (p.n_runs + W - 1) / W;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gl_persist_kernel<R3>, W * 32, gl_smem_bytes<R3>());
+    if (e != cudaSuccess) return e;
+    *fits = grid <= per_sm * sm_count;
+    if (!*fits) return cudaSuccess;
+    GlParams q = p;
+    void* args[1] = {&q};
+    return cudaLaunchCooperativeKernel((const void*)gl_persist_kernel<R3>, dim3(grid), dim3(W * 32), args, gl_smem_bytes<R3>(), s);
+}
+
+// the whole vocode in one cooperative launch; *fits == false (and nothing launched) when the run table
+// exceeds the resident warps of the device
+cudaError_t gl_launch_persistent(int n_fft, const GlParams& p, int sm_count, cudaStream_t s, bool* fits) {
+    switch (n_fft) {
+        case 512: return persist_launch<4>(p, sm_count, s, fits);
+        case 1024: return persist_launch<8>(p, sm_count, s, fits);
+        case 2048: return persist_launch<16>(p, sm_count, s, fits);
+    }
+    return cudaErrorInvalidValue;
 }
 
 template <int R3, int MODE, bool STORE_R, bool TRACK_MAX>
@@ -158,6 +281,7 @@ static cudaError_t prepare_r3() {
     if (e == cudaSuccess) e = prepare_one<R3, GL_MODE_FIRST, true, false>();
     if (e == cudaSuccess) e = prepare_one<R3, GL_MODE_MID, false, true>();
     if (e == cudaSuccess) e = prepare_one<R3, GL_MODE_MID, true, false>();
+    if (e == cudaSuccess) e = persist_prepare<R3>();
     return e;
 }
 

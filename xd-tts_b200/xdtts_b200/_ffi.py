@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libxdtts_b200.so")
 
 OK, ERR_BAD_ARG, ERR_SHAPE, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
-RUN_FROM_MAG, RUN_USE_PHASE, RUN_NO_GRAPH = 1, 2, 4
+RUN_FROM_MAG, RUN_USE_PHASE, RUN_NO_GRAPH, RUN_PER_LAUNCH = 1, 2, 4, 16
 
 _CODE_NAMES = {
     ERR_BAD_ARG: "BAD_ARG", ERR_SHAPE: "SHAPE", ERR_CUDA: "CUDA", ERR_OOM: "OOM", ERR_UNSUPPORTED: "UNSUPPORTED",
@@ -35,6 +35,7 @@ class GlOpts(ctypes.Structure):
         ("normalise", ctypes.c_int),
         ("run_frames", ctypes.c_int),
         ("seed", ctypes.c_ulonglong),
+        ("persistent", ctypes.c_int),
     ]
 
 
@@ -65,6 +66,7 @@ SIGNATURES = {
     "xdtts_gl_plan_run": (ctypes.c_int, [_vp, ctypes.c_int, _fp, _fp, _ip]),
     "xdtts_gl_plan_download": (ctypes.c_int, [_vp, _fpp]),
     "xdtts_gl_plan_peek": (ctypes.c_int, [_vp, ctypes.c_int, _fp, ctypes.c_longlong]),
+    "xdtts_gl_plan_is_persistent": (ctypes.c_int, [_vp]),
     "xdtts_gl_plan_info": (ctypes.c_int, [_vp, _ip]),
     "xdtts_postnet_create": (ctypes.c_int, [ctypes.c_int, _ip, ctypes.c_int, _fpp, _fpp, _fpp, _fpp, _fpp, _fpp, ctypes.c_float,
                                             ctypes.POINTER(PostnetOpts), ctypes.c_int, ctypes.POINTER(_vp)]),

@@ -57,13 +57,13 @@ class GriffinLim:
 
     @classmethod
     def new(cls, mel_basis, noverlap, power, iter, momentum, *, delog=DELOG_EXP, pad_mode=PAD_REFLECT,  # noqa: A002
-            normalise=NORM_PEAK, seed=0, run_frames=0, device=0):
+            normalise=NORM_PEAK, seed=0, run_frames=0, persistent=False, device=0):
         """GriffinLim::new(mel_basis, noverlap, power, iter, momentum) (src/tacotron2/mod.rs:456)."""
         lib = load_library()
         basis = np.ascontiguousarray(mel_basis, dtype=np.float32)
         if basis.ndim != 2:
             raise XdttsError(_ffi.ERR_SHAPE, "mel_basis must be 2-D [n_mels, K]")
-        opts = GlOpts(int(delog), int(pad_mode), int(normalise), int(run_frames), int(seed))
+        opts = GlOpts(int(delog), int(pad_mode), int(normalise), int(run_frames), int(seed), int(bool(persistent)))
         h = ctypes.c_void_p()
         check(lib.xdtts_gl_create(fptr(basis), basis.shape[0], basis.shape[1], int(noverlap), float(power), int(iter),
                                   float(momentum), ctypes.byref(opts), int(device), ctypes.byref(h)))
@@ -175,6 +175,13 @@ class GlPlan:
         a = (ctypes.c_int * 4)()
         check(load_library().xdtts_gl_plan_info(self._p, a))
         return dict(n_runs=a[0], run_frames=a[1], ctas=a[2], total_frames=a[3])
+
+    def is_persistent(self):
+        """True when run() vocodes the plan with the single cooperative launch (all runs resident at once)."""
+        rc = load_library().xdtts_gl_plan_is_persistent(self._p)
+        if rc < 0:
+            check(rc)
+        return bool(rc)
 
     def upload(self, kind, arrays):
         rows = self.voc.n_mels if kind == 0 else self.voc.k_bins
