@@ -9,8 +9,10 @@ One "step" = one pass of the path over one batch: mel -> linear lift (pseudo-inv
 
   value      whole-job frames/s with the mels already resident in HBM (device time, CUDA events
              around every step on the library's stream, max over ranks)
-  e2e        the same through the public call (GriffinLim.infer_batch -> xdtts_gl_infer_batch) with
-             pinned HOST buffers: H2D of the mels and D2H of the waveforms inside the timed region
+  e2e        the same from pinned HOST buffers through the public streaming call (xdtts_pipe_push, two
+             batches in flight): every step's H2D of the mels and D2H of the waveforms are inside the timed
+             region (the pipe is flushed before the clock stops) and overlap the neighbouring steps' kernels;
+             e2e.blocking_call is the one-batch-at-a-time call (xdtts_gl_infer_batch), copies exposed
   roofline   the steady-state iteration kernel: algorithmic bytes (20K+8H per frame)
              / its mean launch duration (events around the launches, kernel-by-kernel run) vs the
              measured HBM peak of MEASURED_PEAKS.json
@@ -359,8 +361,33 @@ def run_gpu(args):
     for _ in range(steps):
         e2e_step()
     barrier()
-    e2e_ms = (time.perf_counter() - t1) * 1e3
+    call_ms = (time.perf_counter() - t1) * 1e3
     peak_ok = all(abs(float(np.abs(a).max()) - 1.0) < 1e-5 for a, _ in pin_out)
+
+    # ---- end to end, streaming (the headline e2e): xdtts_pipe_push, two batches in flight, each with its own
+    # pinned host buffers; every step's H2D and D2H are inside the timed region and overlap the kernels of
+    # the neighbouring steps.  Same kernels, same results as the blocking call above (tests/test_gpu_postnet.py).
+    pin_in2 = [pinned_array(lib, (N_MELS, t)) for _ in range(b)]
+    for (a, _), m in zip(pin_in2, mels):
+        a[...] = m
+    pin_out2 = [pinned_array(lib, (out_len,)) for _ in range(b)]
+    sets = [(in_ptrs, out_ptrs), (_ffi.fptr_array([a for a, _ in pin_in2]), _ffi.fptr_array([a for a, _ in pin_out2]))]
+    for a, _ in pin_out + pin_out2:
+        a[...] = 0.0
+    pipe = ctypes.c_void_p()
+    _ffi.check(lib.xdtts_pipe_create(voc._h, post._h if with_postnet else None, t_arr, b, 2, ctypes.byref(pipe)))
+    for i in range(warmup):
+        _ffi.check(lib.xdtts_pipe_push(pipe, sets[i % 2][0], None, None, sets[i % 2][1]))
+    _ffi.check(lib.xdtts_pipe_flush(pipe))
+    barrier()
+    t1 = time.perf_counter()
+    for i in range(steps):
+        _ffi.check(lib.xdtts_pipe_push(pipe, sets[i % 2][0], None, None, sets[i % 2][1]))
+    _ffi.check(lib.xdtts_pipe_flush(pipe))
+    barrier()
+    e2e_ms = (time.perf_counter() - t1) * 1e3
+    lib.xdtts_pipe_destroy(pipe)
+    peak_ok = peak_ok and all(abs(float(np.abs(a).max()) - 1.0) < 1e-5 for a, _ in pin_out + pin_out2)
 
     # ---- the tensor-core leg (BASELINE.json configs[2]): postnet alone, device time by CUDA events
     pn_ms = None
@@ -371,8 +398,8 @@ def run_gpu(args):
         pn_ms = min((pplan.run(feed=plan) if with_postnet else pplan.run()) for _ in range(5))
 
     # ---- reduce over ranks: time = max, frames = sum
-    total_frames, total_launches, (dev_ms, wall_ms, e2e_ms, kern_ms) = shard.reduce_counters(
-        frames, launches, [dev_ms, wall_ms, e2e_ms, kern_ms], device="cuda")   # the single collective of the job
+    total_frames, total_launches, (dev_ms, wall_ms, e2e_ms, kern_ms, call_ms) = shard.reduce_counters(
+        frames, launches, [dev_ms, wall_ms, e2e_ms, kern_ms, call_ms], device="cuda")   # the single collective of the job
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -389,7 +416,11 @@ def run_gpu(args):
             "e2e": {"value": total_frames * steps / (e2e_ms * 1e-3), "unit": "frames/s",
                     "h2d_bytes_per_step": b * N_MELS * t * 4, "d2h_bytes_per_step": b * out_len * 4,
                     "ms_per_step": e2e_ms / steps,
-                    "api": ("xdtts_tail_infer_batch" if with_postnet else "xdtts_gl_infer_batch") + " (pinned host buffers)",
+                    "api": "xdtts_pipe_push%s, 2 batches in flight, pinned host buffers; flushed inside the timed region" % (
+                        " (postnet + vocoder)" if with_postnet else ""),
+                    "blocking_call": {"value": total_frames * steps / (call_ms * 1e-3), "ms_per_step": call_ms / steps,
+                                      "api": ("xdtts_tail_infer_batch" if with_postnet else "xdtts_gl_infer_batch") +
+                                             " (one batch at a time, pinned host buffers)"},
                     "peak_normalised_ok": peak_ok},
             "gpu_launches": total_launches,
             "roofline": {"bound": "hbm", "kernel": "gl_iter_kernel<MID> (one Griffin-Lim iteration)",
@@ -410,7 +441,7 @@ def run_gpu(args):
             v, cores, kind, sample, _ = cpu_arm(cfg, 1, 1)
             line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}
         print(json.dumps(line))
-    for _, p in pin_in + pin_out:
+    for _, p in pin_in + pin_out + pin_in2 + pin_out2:
         lib.xdtts_host_free(p)
     if dist is not None:
         dist.barrier()

@@ -170,6 +170,26 @@ int xdtts_tail_infer_batch(xdtts_postnet* pn, xdtts_gl* gl, const float* const* 
                            const float* const* init_phases_or_null, float* const* out_mels_or_null,
                            float* const* out_waves);
 
+/* ---- Streaming: the same tail for a sequence of batches of one shape, copies overlapped with kernels.
+ * XdTts::infer returns host samples per call (src/lib.rs:141-157) and the binary loops over chunks
+ * (src/lib.rs:83-104); a server doing the same batch after batch would leave the GPU idle during every
+ * PCIe copy.  A pipe owns `depth` (1..8; 2 is enough) device-resident slots with one stream each.
+ * xdtts_pipe_push enqueues H2D -> [postnet, when pn != null] -> lift -> Griffin-Lim -> D2H for one batch and
+ * returns without waiting; it blocks only when every slot is in flight (it then waits for the oldest).
+ * All host buffers of a batch -- inputs and outputs -- must stay valid and untouched until that batch has
+ * been collected: by xdtts_pipe_pop / xdtts_pipe_flush, or by the push that reuses its slot (`depth` pushes later).
+ * Pinned buffers (xdtts_host_alloc) make the copies asynchronous; pageable ones are staged (inputs then
+ * cost a wait for that slot's stream inside push).  Results are bit-identical to
+ * xdtts_gl_infer_batch / xdtts_tail_infer_batch on the same batch. */
+typedef struct xdtts_pipe xdtts_pipe;
+int xdtts_pipe_create(xdtts_gl* gl, xdtts_postnet* pn_or_null, const int* Ts, int B, int depth, xdtts_pipe** out);
+int xdtts_pipe_push(xdtts_pipe* q, const float* const* mels, const float* const* init_phases_or_null,
+                    float* const* out_mels_or_null, float* const* out_waves);
+int xdtts_pipe_pop(xdtts_pipe* q);      /* wait for the OLDEST batch in flight: 1 = collected, 0 = nothing in flight, < 0 error */
+int xdtts_pipe_flush(xdtts_pipe* q);    /* wait until every pushed batch is in its host buffers */
+int xdtts_pipe_pending(xdtts_pipe* q);  /* batches in flight (>= 0), or a negative error */
+void xdtts_pipe_destroy(xdtts_pipe* q); /* waits for batches in flight; destroy it before its gl / postnet handles */
+
 /* .npy I/O for [rows, cols] float32 arrays -- the format of the reference's spectrogram dump
  * (ndarray_npy::write_npy, src/lib.rs:125-139, --output-spectrogram src/bin/app.rs:12-14).
  * read: call with out == null to get the shape, then with a buffer of capacity >= rows*cols floats

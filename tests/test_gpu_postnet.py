@@ -145,6 +145,69 @@ def test_plan_feeds_vocoder_and_tail_call(taco, layers, built):
     assert np.array_equal(single, waves[0])
 
 
+def test_pipe_equals_blocking_calls_bitwise(taco, layers, built):
+    """xdtts_pipe (copies overlapped with the neighbouring batches' kernels) returns, batch for batch and in
+    push order, the bits of the blocking calls -- vocoder alone and postnet + vocoder, explicit and seeded phase."""
+    from xdtts_b200 import griffin_lim
+    from xdtts_b200._ffi import ERR_BAD_ARG, ERR_SHAPE, XdttsError
+
+    basis = o.create_mel_filter_bank(22050.0, 1024, 80, 0.0, 8000.0)
+    voc = griffin_lim.GriffinLim.new(basis, 768, 1.7, 6, 0.99, seed=3)
+    post = taco.Postnet.from_layers(layers, precision=0)
+    ts = [33, 90, 5]
+    batches = [[o.synth_mel(1000 + 10 * j + i, 80, t) for i, t in enumerate(ts)] for j in range(5)]
+    phases = [[o.phase_turns(j, i, 513, t) for i, t in enumerate(ts)] for j in range(5)]
+    # vocoder alone, depth 2, explicit phase for even batches and the seeded generator for odd ones
+    want = [voc.infer_batch(m, ph if j % 2 == 0 else None) for j, (m, ph) in enumerate(zip(batches, phases))]
+    pipe = voc.pipe(ts, depth=2)
+    got = []
+    for j, (m, ph) in enumerate(zip(batches, phases)):
+        r = pipe.push(m, ph if j % 2 == 0 else None)
+        assert (r is None) == (j < 2)
+        if r is not None:
+            got.append(r)
+    assert pipe.pending() == 2
+    got += pipe.flush()
+    assert pipe.pending() == 0 and pipe.pop() is None and len(got) == 5
+    for a, b in zip(got, want):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    pipe.close()
+    # the whole tail, depth 3, with the postnet mels returned
+    want = [taco.infer_tail_batch(post, voc, m, ph, return_mels=True) for m, ph in zip(batches, phases)]
+    pipe = voc.pipe(ts, depth=3, postnet=post, want_mels=True)
+    got = [r for r in (pipe.push(m, ph) for m, ph in zip(batches, phases)) if r is not None] + pipe.flush()
+    assert len(got) == 5
+    for (gw, gm), (ww, wm) in zip(got, want):
+        for x, y in zip(gw, ww):
+            assert np.array_equal(x, y)
+        for x, y in zip(gm, wm):
+            assert np.array_equal(x, y)
+    pipe.close()
+    # pageable host buffers straight through the C ABI (staged copies), depth 1
+    import ctypes
+
+    from xdtts_b200._ffi import check, fptr_array, load_library
+
+    lib = load_library()
+    q = ctypes.c_void_p()
+    t_arr = (ctypes.c_int * len(ts))(*ts)
+    check(lib.xdtts_pipe_create(voc._h, None, t_arr, len(ts), 1, ctypes.byref(q)))
+    outs = [np.zeros(256 * (t - 1), np.float32) for t in ts]
+    check(lib.xdtts_pipe_push(q, fptr_array(batches[0]), fptr_array(phases[0]), None, fptr_array(outs)))
+    check(lib.xdtts_pipe_flush(q))
+    for x, y in zip(outs, voc.infer_batch(batches[0], phases[0])):
+        assert np.array_equal(x, y)
+    assert lib.xdtts_pipe_push(q, fptr_array(batches[0]), None, fptr_array(outs), fptr_array(outs)) == ERR_BAD_ARG  # out_mels without postnet
+    lib.xdtts_pipe_destroy(q)
+    with pytest.raises(XdttsError) as e:
+        voc.pipe([33, 2], depth=2)          # T < 4
+    assert e.value.code == ERR_SHAPE
+    with pytest.raises(XdttsError) as e:
+        voc.pipe(ts, depth=0)
+    assert e.value.code == ERR_BAD_ARG
+
+
 def test_errors(taco, layers):
     from xdtts_b200._ffi import ERR_BAD_ARG, ERR_SHAPE, XdttsError
 

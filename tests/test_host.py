@@ -94,6 +94,22 @@ def test_argument_validation_without_gpu(lib):
     assert b"fmax" in lib.xdtts_last_error()
 
 
+def test_pipe_argument_validation_without_gpu(lib):
+    import ctypes
+
+    from xdtts_b200._ffi import ERR_BAD_ARG
+
+    q = ctypes.c_void_p()
+    ts = (ctypes.c_int * 2)(10, 12)
+    assert lib.xdtts_pipe_create(None, None, ts, 2, 2, ctypes.byref(q)) == ERR_BAD_ARG
+    assert not q.value
+    assert lib.xdtts_pipe_push(None, None, None, None, None) == ERR_BAD_ARG
+    assert lib.xdtts_pipe_pop(None) == ERR_BAD_ARG
+    assert lib.xdtts_pipe_flush(None) == ERR_BAD_ARG
+    assert lib.xdtts_pipe_pending(None) == ERR_BAD_ARG
+    lib.xdtts_pipe_destroy(None)    # no-op
+
+
 def test_no_cpu_fallback(lib):
     """Without a usable sm_100 device the product refuses to work instead of computing on the CPU."""
     import torch
@@ -110,7 +126,7 @@ def test_no_cpu_fallback(lib):
 
 
 # ---------------------------------------------------------------- lane program (CPU emulation)
-@pytest.mark.parametrize("n_fft,hop,t", [(1024, 256, 37), (2048, 512, 21), (512, 128, 30)])
+@pytest.mark.parametrize("n_fft,hop,t", [(1024, 256, 37), (2048, 512, 21), (512, 128, 30), (512, 128, 10)])
 def test_lane_program_matches_oracle(built, n_fft, hop, t):
     from emu import emu
 
@@ -119,7 +135,7 @@ def test_lane_program_matches_oracle(built, n_fft, hop, t):
     tu = o.phase_turns(9, 0, k, t)
     for it in (0, 1, 3):
         y64 = o.griffin_lim(s, tu, it, 0.99, n_fft, hop, dtype=np.float64)
-        for run_frames in (1000, 8, 4):     # one run; several runs; shortest legal runs
+        for run_frames in (1000, 8, 4):     # one run; several runs; shortest legal runs (5 frames: 4 is raised to 5)
             y, r, peak, n_runs = emu.gl_from_mag(s, tu, it, 0.99, run_frames)
             assert rel_rms(y, y64) < 5e-7, (it, run_frames)
             assert abs(peak - np.abs(y).max()) < 1e-6

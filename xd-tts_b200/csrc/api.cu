@@ -395,8 +395,9 @@ extern "C" int xdtts_gl_plan_info(const xdtts_gl_plan* p, int* info4) {
     return XDTTS_OK;
 }
 
-int xdtts::gl_plan_upload_locked(xdtts_gl_plan* p, int kind, const float* const* srcs) {
+int xdtts::gl_plan_upload_locked(xdtts_gl_plan* p, int kind, const float* const* srcs, cudaStream_t s) {
     xdtts_gl* h = p->h;
+    if (!s) s = h->stream;
     clear_stale_error(__func__);
     if (!srcs) return fail(XDTTS_ERR_BAD_ARG, "plan_upload: srcs is null");
     if (kind < 0 || kind > 2) return fail(XDTTS_ERR_BAD_ARG, "plan_upload: kind %d", kind);
@@ -423,11 +424,11 @@ int xdtts::gl_plan_upload_locked(xdtts_gl_plan* p, int kind, const float* const*
         }
         for (int b = 0; b < p->B; b++)
             memcpy(p->h_in + rows * (size_t)p->foff[b], srcs[b], rows * (size_t)p->Ts[b] * 4);
-        CU(cudaMemcpyAsync(*dst, p->h_in, need * 4, cudaMemcpyHostToDevice, h->stream));
-        CU(cudaStreamSynchronize(h->stream));   // the staging buffer is reused by the next upload
+        CU(cudaMemcpyAsync(*dst, p->h_in, need * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaStreamSynchronize(s));   // the staging buffer is reused by the next upload
     } else {
         for (int b = 0; b < p->B; b++)
-            CU(cudaMemcpyAsync(*dst + rows * (size_t)p->foff[b], srcs[b], rows * (size_t)p->Ts[b] * 4, cudaMemcpyHostToDevice, h->stream));
+            CU(cudaMemcpyAsync(*dst + rows * (size_t)p->foff[b], srcs[b], rows * (size_t)p->Ts[b] * 4, cudaMemcpyHostToDevice, s));
     }
     return XDTTS_OK;
 }
@@ -435,13 +436,12 @@ int xdtts::gl_plan_upload_locked(xdtts_gl_plan* p, int kind, const float* const*
 extern "C" int xdtts_gl_plan_upload(xdtts_gl_plan* p, int kind, const float* const* srcs) {
     if (!p) return fail(XDTTS_ERR_BAD_ARG, "plan_upload: plan is null");
     std::lock_guard<std::mutex> lk(p->h->mu);
-    return gl_plan_upload_locked(p, kind, srcs);
+    return gl_plan_upload_locked(p, kind, srcs, nullptr);
 }
 
 // enqueue the whole pass on the handle's stream; ev[1]/ev[2] bracket the steady-state launches when timed
-static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid) {
+static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid, cudaStream_t s) {
     xdtts_gl* h = p->h;
-    cudaStream_t s = h->stream;
     const int M = h->K - 1;
     const bool from_mag = flags & XDTTS_RUN_FROM_MAG, use_phase = flags & XDTTS_RUN_USE_PHASE;
     CU(cudaMemsetAsync(p->d_amax, 0, p->B * sizeof(unsigned), s));
@@ -506,6 +506,66 @@ static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid) {
     return XDTTS_OK;
 }
 
+// launch the plan's CUDA graph of the whole pass (captured on first use) on stream s, without waiting
+static int plan_launch_graph(xdtts_gl_plan* p, int flags, cudaStream_t s) {
+    xdtts_gl* h = p->h;
+    const int gi = flags & 3;   // (PER_LAUNCH does not change what is captured: this is the per-launch path)
+    if (!p->graphs[gi]) {
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        const unsigned long long before = g_launches.load();
+        int rc = plan_enqueue(p, flags, false, nullptr, s);
+        g_launches = before;   // captured, not launched
+        cudaError_t e = cudaStreamEndCapture(s, &g);
+        if (rc) {
+            if (g) cudaGraphDestroy(g);
+            return rc;
+        }
+        if (e != cudaSuccess) return fail(XDTTS_ERR_CUDA, "plan_run: graph capture: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&p->graphs[gi], g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(XDTTS_ERR_CUDA, "plan_run: graph instantiate: %s", cudaGetErrorString(e));
+    }
+    CU(cudaGraphLaunch(p->graphs[gi], s));
+    g_launches += (unsigned long long)(h->n_iter + 3 + ((flags & XDTTS_RUN_USE_PHASE) ? 1 : 0));
+    return XDTTS_OK;
+}
+
+// enqueue the pass on stream s and return without waiting (xdtts_pipe): CUDA graph, or the persistent kernel
+int xdtts::gl_plan_launch_async(xdtts_gl_plan* p, int flags, cudaStream_t s) {
+    clear_stale_error(__func__);
+    CU(cudaSetDevice(p->h->device));
+    if (p->use_persistent && !(flags & XDTTS_RUN_PER_LAUNCH)) return plan_enqueue(p, flags, false, nullptr, s);
+    return plan_launch_graph(p, flags, s);
+}
+
+// enqueue the device -> host copies of the result on stream s; pinned destinations receive the data
+// directly, pageable ones go through the plan's pinned buffer (*staged = true: call
+// gl_plan_download_finish after the stream has been synchronised)
+int xdtts::gl_plan_download_async(xdtts_gl_plan* p, float* const* outs, cudaStream_t s, bool* staged) {
+    xdtts_gl* h = p->h;
+    clear_stale_error(__func__);
+    if (!outs) return fail(XDTTS_ERR_BAD_ARG, "plan_download: outs is null");
+    for (int b = 0; b < p->B; b++)
+        if (!outs[b]) return fail(XDTTS_ERR_BAD_ARG, "plan_download: outs[%d] is null", b);
+    CU(cudaSetDevice(h->device));
+    bool all_pinned = true;
+    for (int b = 0; b < p->B; b++) all_pinned = all_pinned && is_pinned(outs[b]);
+    *staged = !all_pinned;
+    if (all_pinned) {
+        for (int b = 0; b < p->B; b++)
+            CU(cudaMemcpyAsync(outs[b], p->d_out + p->out_off[b], (size_t)h->hop * (p->Ts[b] - 1) * 4, cudaMemcpyDeviceToHost, s));
+    } else {
+        if (!p->h_out) CU(cudaHostAlloc((void**)&p->h_out, (size_t)p->out_total * 4, cudaHostAllocDefault));
+        CU(cudaMemcpyAsync(p->h_out, p->d_out, (size_t)p->out_total * 4, cudaMemcpyDeviceToHost, s));
+    }
+    return XDTTS_OK;
+}
+
+void xdtts::gl_plan_download_finish(xdtts_gl_plan* p, float* const* outs) {
+    for (int b = 0; b < p->B; b++) memcpy(outs[b], p->h_out + p->out_off[b], (size_t)p->h->hop * (p->Ts[b] - 1) * 4);
+}
+
 int xdtts::gl_plan_run_locked(xdtts_gl_plan* p, int flags, float* ms_total, float* ms_iter, int* n_iter_launches) {
     xdtts_gl* h = p->h;
     clear_stale_error(__func__);
@@ -520,33 +580,16 @@ int xdtts::gl_plan_run_locked(xdtts_gl_plan* p, int flags, float* ms_total, floa
     const bool persistent = p->use_persistent && !(flags & XDTTS_RUN_PER_LAUNCH);
     if ((flags & XDTTS_RUN_NO_GRAPH) || persistent) {   // the persistent path is 3-4 launches: no graph needed
         CU(cudaEventRecord(p->ev[0], s));
-        int rc = plan_enqueue(p, flags, (flags & XDTTS_RUN_NO_GRAPH) != 0, &mids);
+        int rc = plan_enqueue(p, flags, (flags & XDTTS_RUN_NO_GRAPH) != 0, &mids, s);
         if (rc) return rc;
         CU(cudaEventRecord(p->ev[3], s));
         CU(cudaStreamSynchronize(s));
         if ((flags & XDTTS_RUN_NO_GRAPH) && ms_iter && mids > 0) CU(cudaEventElapsedTime(ms_iter, p->ev[1], p->ev[2]));
         if ((flags & XDTTS_RUN_NO_GRAPH) && n_iter_launches) *n_iter_launches = mids;
     } else {
-        const int gi = flags & 3;   // (PER_LAUNCH does not change what is captured: this branch is the per-launch path)
-        if (!p->graphs[gi]) {
-            cudaGraph_t g = nullptr;
-            CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            const unsigned long long before = g_launches.load();
-            int rc = plan_enqueue(p, flags, false, nullptr);
-            g_launches = before;   // captured, not launched
-            cudaError_t e = cudaStreamEndCapture(s, &g);
-            if (rc) {
-                if (g) cudaGraphDestroy(g);
-                return rc;
-            }
-            if (e != cudaSuccess) return fail(XDTTS_ERR_CUDA, "plan_run: graph capture: %s", cudaGetErrorString(e));
-            e = cudaGraphInstantiate(&p->graphs[gi], g, 0);
-            cudaGraphDestroy(g);
-            if (e != cudaSuccess) return fail(XDTTS_ERR_CUDA, "plan_run: graph instantiate: %s", cudaGetErrorString(e));
-        }
         CU(cudaEventRecord(p->ev[0], s));
-        CU(cudaGraphLaunch(p->graphs[gi], s));
-        g_launches += (unsigned long long)(h->n_iter + 3 + ((flags & XDTTS_RUN_USE_PHASE) ? 1 : 0));
+        int rc = plan_launch_graph(p, flags, s);
+        if (rc) return rc;
         CU(cudaEventRecord(p->ev[3], s));
         CU(cudaStreamSynchronize(s));
     }
@@ -566,19 +609,11 @@ int xdtts::gl_plan_download_locked(xdtts_gl_plan* p, float* const* outs) {
     if (!outs) return fail(XDTTS_ERR_BAD_ARG, "plan_download: outs is null");
     for (int b = 0; b < p->B; b++)
         if (!outs[b]) return fail(XDTTS_ERR_BAD_ARG, "plan_download: outs[%d] is null", b);
-    CU(cudaSetDevice(h->device));
-    bool all_pinned = true;
-    for (int b = 0; b < p->B; b++) all_pinned = all_pinned && is_pinned(outs[b]);
-    if (all_pinned) {
-        for (int b = 0; b < p->B; b++)
-            CU(cudaMemcpyAsync(outs[b], p->d_out + p->out_off[b], (size_t)h->hop * (p->Ts[b] - 1) * 4, cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-    } else {
-        if (!p->h_out) CU(cudaHostAlloc((void**)&p->h_out, (size_t)p->out_total * 4, cudaHostAllocDefault));
-        CU(cudaMemcpyAsync(p->h_out, p->d_out, (size_t)p->out_total * 4, cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        for (int b = 0; b < p->B; b++) memcpy(outs[b], p->h_out + p->out_off[b], (size_t)h->hop * (p->Ts[b] - 1) * 4);
-    }
+    bool staged = false;
+    int rc = gl_plan_download_async(p, outs, h->stream, &staged);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    if (staged) gl_plan_download_finish(p, outs);
     return XDTTS_OK;
 }
 
@@ -673,11 +708,11 @@ static int batch_common(xdtts_gl* h, int kind, const float* const* ins, const in
         int rc = gl_cached_plan(h, Ts, B, &p);
         if (rc) return rc;
     }
-    int rc = gl_plan_upload_locked(p, kind, ins);
+    int rc = gl_plan_upload_locked(p, kind, ins, nullptr);
     if (rc) return rc;
     int flags = kind == 1 ? XDTTS_RUN_FROM_MAG : 0;
     if (phases) {
-        rc = gl_plan_upload_locked(p, 2, phases);
+        rc = gl_plan_upload_locked(p, 2, phases, nullptr);
         if (rc) return rc;
         flags |= XDTTS_RUN_USE_PHASE;
     }

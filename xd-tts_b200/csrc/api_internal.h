@@ -79,7 +79,10 @@ struct xdtts_gl_plan {
 namespace xdtts {
 // the *_locked functions expect h->mu to be held
 int gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out);
-int gl_plan_upload_locked(xdtts_gl_plan* p, int kind, const float* const* srcs);
+int gl_plan_upload_locked(xdtts_gl_plan* p, int kind, const float* const* srcs, cudaStream_t s);   // s == null: the handle's stream
+int gl_plan_launch_async(xdtts_gl_plan* p, int flags, cudaStream_t s);
+int gl_plan_download_async(xdtts_gl_plan* p, float* const* outs, cudaStream_t s, bool* staged);
+void gl_plan_download_finish(xdtts_gl_plan* p, float* const* outs);
 int gl_plan_run_locked(xdtts_gl_plan* p, int flags, float* ms_total, float* ms_iter, int* n_iter_launches);
 int gl_plan_download_locked(xdtts_gl_plan* p, float* const* outs);
 int gl_cached_plan(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out);

@@ -487,7 +487,7 @@ extern "C" int xdtts_tail_infer_batch(xdtts_postnet* pn, xdtts_gl* gl, const flo
     if (rc) return rc;
     int flags = 0;
     if (init_phases) {
-        rc = gl_plan_upload_locked(gp, 2, init_phases);
+        rc = gl_plan_upload_locked(gp, 2, init_phases, nullptr);
         if (rc) return rc;
         flags |= XDTTS_RUN_USE_PHASE;
     }
@@ -498,4 +498,196 @@ extern "C" int xdtts_tail_infer_batch(xdtts_postnet* pn, xdtts_gl* gl, const flo
         if (rc) return rc;
     }
     return gl_plan_download_locked(gp, out_waves);
+}
+
+// ------------------------------------------------------------------ streaming pipeline
+// XdTts::infer handles one utterance after another (src/lib.rs:83-104 loops over the chunks of the
+// input text) and every call ends with the samples on the host.  Served in batches, that pattern leaves
+// the GPU idle during each batch's PCIe copies.  A pipe owns `depth` device-resident slots of one batch
+// shape, each with its own stream: push() enqueues H2D -> [postnet] -> lift -> Griffin-Lim -> D2H of one
+// batch and returns; the copies of one batch then overlap the kernels of its neighbours.
+struct xdtts_pipe {
+    xdtts_gl* gl = nullptr;
+    xdtts_postnet* pn = nullptr;
+    int B = 0, depth = 0, head = 0;
+    std::vector<int> Ts;
+    struct Slot {
+        xdtts_gl_plan* gp = nullptr;
+        xdtts_postnet_plan* pp = nullptr;
+        cudaStream_t s = nullptr;
+        bool busy = false, staged_wave = false, staged_mel = false;
+        std::vector<float*> out_waves, out_mels;
+    };
+    std::vector<Slot> slots;
+    std::mutex mu;
+};
+
+// device -> host copy of "mel_outputs_postnet" on stream s without waiting (pinned: direct; pageable: staged)
+static int pn_download_async(xdtts_postnet_plan* p, const float* src, float* const* outs, cudaStream_t s, bool* staged) {
+    xdtts_postnet* h = p->h;
+    const size_t C0 = h->ch[0];
+    for (int b = 0; b < p->B; b++)
+        if (!outs[b]) return fail(XDTTS_ERR_BAD_ARG, "pipe_push: out_mels[%d] is null", b);
+    bool all_pinned = true;
+    for (int b = 0; b < p->B; b++) all_pinned = all_pinned && is_pinned(outs[b]);
+    *staged = !all_pinned;
+    if (all_pinned) {
+        for (int b = 0; b < p->B; b++)
+            CU(cudaMemcpyAsync(outs[b], src + C0 * (size_t)p->foff[b], C0 * (size_t)p->Ts[b] * 4, cudaMemcpyDeviceToHost, s));
+    } else {
+        if (!p->h_out) CU(cudaHostAlloc((void**)&p->h_out, C0 * (size_t)p->total_T * 4, cudaHostAllocDefault));
+        CU(cudaMemcpyAsync(p->h_out, src, C0 * (size_t)p->total_T * 4, cudaMemcpyDeviceToHost, s));
+    }
+    return XDTTS_OK;
+}
+
+// wait for the batch in `sl` and finish the staged copies of pageable destinations
+static int pipe_collect(xdtts_pipe* q, xdtts_pipe::Slot& sl) {
+    if (!sl.busy) return XDTTS_OK;
+    sl.busy = false;
+    CU(cudaSetDevice(q->gl->device));
+    CU(cudaStreamSynchronize(sl.s));
+    if (sl.staged_wave) gl_plan_download_finish(sl.gp, sl.out_waves.data());
+    if (sl.staged_mel) {
+        const size_t C0 = q->pn->ch[0];
+        for (int b = 0; b < q->B; b++)
+            memcpy(sl.out_mels[b], sl.pp->h_out + C0 * (size_t)sl.pp->foff[b], C0 * (size_t)sl.pp->Ts[b] * 4);
+    }
+    return XDTTS_OK;
+}
+
+extern "C" void xdtts_pipe_destroy(xdtts_pipe* q) {
+    if (!q) return;
+    cudaSetDevice(q->gl->device);
+    for (auto& sl : q->slots) {
+        if (sl.s) cudaStreamSynchronize(sl.s);
+        if (sl.gp) xdtts_gl_plan_destroy(sl.gp);
+        if (sl.pp) xdtts_postnet_plan_destroy(sl.pp);
+        if (sl.s) cudaStreamDestroy(sl.s);
+    }
+    cudaGetLastError();
+    delete q;
+}
+
+extern "C" int xdtts_pipe_create(xdtts_gl* gl, xdtts_postnet* pn, const int* Ts, int B, int depth, xdtts_pipe** out) {
+    if (!out) return fail(XDTTS_ERR_BAD_ARG, "pipe_create: out is null");
+    *out = nullptr;
+    if (!gl || !Ts) return fail(XDTTS_ERR_BAD_ARG, "pipe_create: null argument");
+    if (B < 1) return fail(XDTTS_ERR_BAD_ARG, "pipe_create: B = %d", B);
+    if (depth < 1 || depth > 8) return fail(XDTTS_ERR_BAD_ARG, "pipe_create: depth = %d, supported: 1..8", depth);
+    if (pn && pn->device != gl->device) return fail(XDTTS_ERR_BAD_ARG, "pipe_create: postnet on device %d, vocoder on %d", pn->device, gl->device);
+    if (pn && pn->ch[0] != gl->n_mels) return fail(XDTTS_ERR_SHAPE, "pipe_create: postnet has %d mel channels, vocoder %d", pn->ch[0], gl->n_mels);
+    xdtts_pipe* q = new (std::nothrow) xdtts_pipe();
+    if (!q) return fail(XDTTS_ERR_OOM, "pipe_create: out of host memory");
+    q->gl = gl; q->pn = pn; q->B = B; q->depth = depth; q->Ts.assign(Ts, Ts + B);
+    q->slots.resize(depth);
+    int rc = XDTTS_OK;
+    for (int i = 0; i < depth && rc == XDTTS_OK; i++) {
+        xdtts_pipe::Slot& sl = q->slots[i];
+        {
+            std::lock_guard<std::mutex> lk(gl->mu);
+            rc = gl_plan_build(gl, Ts, B, &sl.gp);      // also rejects T < 4
+        }
+        if (rc == XDTTS_OK && pn) {
+            std::lock_guard<std::mutex> lk(pn->mu);
+            rc = pn_plan_build(pn, Ts, B, &sl.pp);
+        }
+        if (rc == XDTTS_OK) {
+            float* arena = nullptr;
+            rc = gl_plan_mel_arena(sl.gp, &arena);
+        }
+        if (rc == XDTTS_OK && cudaStreamCreateWithFlags(&sl.s, cudaStreamNonBlocking) != cudaSuccess)
+            rc = fail(XDTTS_ERR_CUDA, "pipe_create: cudaStreamCreate failed");
+        sl.out_waves.resize(B);
+        sl.out_mels.resize(B);
+    }
+    if (rc != XDTTS_OK) {
+        xdtts_pipe_destroy(q);
+        return rc;
+    }
+    *out = q;
+    return XDTTS_OK;
+}
+
+extern "C" int xdtts_pipe_push(xdtts_pipe* q, const float* const* mels, const float* const* init_phases,
+                               float* const* out_mels, float* const* out_waves) {
+    if (!q) return fail(XDTTS_ERR_BAD_ARG, "pipe_push: pipe is null");
+    if (!mels || !out_waves) return fail(XDTTS_ERR_BAD_ARG, "pipe_push: null argument");
+    if (out_mels && !q->pn) return fail(XDTTS_ERR_BAD_ARG, "pipe_push: out_mels needs a pipe with a postnet");
+    for (int b = 0; b < q->B; b++)
+        if (!mels[b] || !out_waves[b] || (init_phases && !init_phases[b]))
+            return fail(XDTTS_ERR_BAD_ARG, "pipe_push: null buffer for utterance %d", b);
+    std::lock_guard<std::mutex> lk(q->mu);
+    xdtts_pipe::Slot& sl = q->slots[q->head];
+    int rc = pipe_collect(q, sl);      // the oldest batch in flight owns this slot: wait for it
+    if (rc) return rc;
+    CU(cudaSetDevice(q->gl->device));
+    clear_stale_error(__func__);
+    float* arena = nullptr;
+    rc = gl_plan_mel_arena(sl.gp, &arena);
+    if (rc) return rc;
+    int flags = 0;
+    if (q->pn) {
+        std::lock_guard<std::mutex> lk2(q->pn->mu);
+        rc = pn_plan_upload_locked(sl.pp, mels, sl.s);
+        if (rc == XDTTS_OK) rc = pn_enqueue(sl.pp, arena, sl.s);
+    } else {
+        std::lock_guard<std::mutex> lk2(q->gl->mu);
+        rc = gl_plan_upload_locked(sl.gp, 0, mels, sl.s);
+    }
+    if (rc) return rc;
+    {
+        std::lock_guard<std::mutex> lk2(q->gl->mu);
+        if (init_phases) {
+            rc = gl_plan_upload_locked(sl.gp, 2, init_phases, sl.s);
+            flags |= XDTTS_RUN_USE_PHASE;
+        }
+        if (rc == XDTTS_OK) rc = gl_plan_launch_async(sl.gp, flags, sl.s);
+        if (rc == XDTTS_OK) rc = gl_plan_download_async(sl.gp, out_waves, sl.s, &sl.staged_wave);
+    }
+    sl.staged_mel = false;
+    if (rc == XDTTS_OK && out_mels) rc = pn_download_async(sl.pp, arena, out_mels, sl.s, &sl.staged_mel);
+    if (rc) {
+        cudaStreamSynchronize(sl.s);   // leave nothing of a half-submitted batch in flight
+        cudaGetLastError();
+        return rc;
+    }
+    for (int b = 0; b < q->B; b++) {
+        sl.out_waves[b] = out_waves[b];
+        sl.out_mels[b] = out_mels ? out_mels[b] : nullptr;
+    }
+    sl.busy = true;
+    q->head = (q->head + 1) % q->depth;
+    return XDTTS_OK;
+}
+
+extern "C" int xdtts_pipe_flush(xdtts_pipe* q) {
+    if (!q) return fail(XDTTS_ERR_BAD_ARG, "pipe_flush: pipe is null");
+    std::lock_guard<std::mutex> lk(q->mu);
+    int rc = XDTTS_OK;
+    for (int i = 0; i < q->depth; i++) {   // oldest first
+        int r = pipe_collect(q, q->slots[(q->head + i) % q->depth]);
+        if (r && !rc) rc = r;
+    }
+    return rc;
+}
+
+extern "C" int xdtts_pipe_pop(xdtts_pipe* q) {
+    if (!q) return fail(XDTTS_ERR_BAD_ARG, "pipe_pop: pipe is null");
+    std::lock_guard<std::mutex> lk(q->mu);
+    for (int i = 0; i < q->depth; i++) {   // oldest first
+        xdtts_pipe::Slot& sl = q->slots[(q->head + i) % q->depth];
+        if (!sl.busy) continue;
+        int rc = pipe_collect(q, sl);
+        return rc ? rc : 1;
+    }
+    return 0;
+}
+
+extern "C" int xdtts_pipe_pending(xdtts_pipe* q) {
+    if (!q) return fail(XDTTS_ERR_BAD_ARG, "pipe_pending: pipe is null");
+    std::lock_guard<std::mutex> lk(q->mu);
+    int n = 0;
+    for (auto& sl : q->slots) n += sl.busy ? 1 : 0;
+    return n;
 }

@@ -85,6 +85,12 @@ SIGNATURES = {
     "xdtts_onnx_postnet_layer_info": (ctypes.c_int, [_vp, ctypes.c_int, _ip, _ip, _ip, _ip, _ip, _fp]),
     "xdtts_onnx_postnet_layer_copy": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _fp]),
     "xdtts_tail_infer_batch": (ctypes.c_int, [_vp, _vp, _fpp, _ip, ctypes.c_int, _fpp, _fpp, _fpp]),
+    "xdtts_pipe_create": (ctypes.c_int, [_vp, _vp, _ip, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]),
+    "xdtts_pipe_push": (ctypes.c_int, [_vp, _fpp, _fpp, _fpp, _fpp]),
+    "xdtts_pipe_pop": (ctypes.c_int, [_vp]),
+    "xdtts_pipe_flush": (ctypes.c_int, [_vp]),
+    "xdtts_pipe_pending": (ctypes.c_int, [_vp]),
+    "xdtts_pipe_destroy": (None, [_vp]),
     "xdtts_npy_write_f32": (ctypes.c_int, [ctypes.c_char_p, _fp, ctypes.c_int, ctypes.c_int]),
     "xdtts_npy_read_f32": (ctypes.c_int, [ctypes.c_char_p, _fp, ctypes.c_longlong, _ip, _ip]),
     "xdtts_host_alloc": (_vp, [ctypes.c_ulonglong]),

@@ -147,6 +147,10 @@ class GriffinLim:
     def plan(self, frame_counts):
         return GlPlan(self, frame_counts)
 
+    def pipe(self, frame_counts, depth=2, postnet=None, want_mels=False):
+        """Streaming vocoder for a sequence of batches of one shape (xdtts_pipe)."""
+        return Pipe(self, frame_counts, depth, postnet, want_mels)
+
 
 class GlPlan:
     """Device-resident batch (buffers + CUDA graph) for pipelines and benchmarking."""
@@ -218,3 +222,119 @@ class GlPlan:
         out = np.empty(shape, dtype=np.float32)
         check(load_library().xdtts_gl_plan_peek(self._p, what, fptr(out), out.size))
         return out
+
+
+def _pinned(shape, dtype=np.float32):
+    """numpy view of pinned host memory from xdtts_host_alloc -> (array, pointer to free)"""
+    lib = load_library()
+    n = int(np.prod(shape))
+    ptr = lib.xdtts_host_alloc(max(n, 1) * 4)
+    if not ptr:
+        raise MemoryError("xdtts_host_alloc(%d bytes)" % (n * 4))
+    buf = (ctypes.c_float * n).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape), ptr
+
+
+class Pipe:
+    """xdtts_pipe: `depth` batches of one shape in flight, PCIe copies overlapped with the kernels of the
+    neighbouring batches.  push() stages a batch in pinned host memory and enqueues it; results come back in
+    push order from pop() / flush() (and from push() itself when it has to free a slot first).
+
+    With `postnet` (a tacotron2.Postnet) the pipe runs the whole tail of XdTts::infer: decoder mels ->
+    postnet -> lift -> Griffin-Lim; want_mels also returns "mel_outputs_postnet".
+    """
+
+    def __init__(self, voc, frame_counts, depth=2, postnet=None, want_mels=False):
+        lib = load_library()
+        self.voc, self.postnet = voc, postnet
+        self.ts = [int(t) for t in frame_counts]
+        self.depth = int(depth)
+        self.want_mels = bool(want_mels)
+        if self.want_mels and postnet is None:
+            raise XdttsError(_ffi.ERR_BAD_ARG, "want_mels needs a postnet")
+        q = ctypes.c_void_p()
+        t_arr = (ctypes.c_int * len(self.ts))(*self.ts)
+        check(lib.xdtts_pipe_create(voc._h, None if postnet is None else postnet._h, t_arr, len(self.ts), self.depth,
+                                    ctypes.byref(q)))
+        self._q = q
+        self._ptrs = []
+        self._slots = []
+        for _ in range(self.depth):
+            sl = dict(mel=[self._pin((voc.n_mels, t)) for t in self.ts], phase=None,
+                      wave=[self._pin((voc.hop * (t - 1),)) for t in self.ts],
+                      omel=[self._pin((voc.n_mels, t)) for t in self.ts] if self.want_mels else None)
+            self._slots.append(sl)
+        self._head = 0
+        self._inflight = []   # slot indices, oldest first
+
+    def _pin(self, shape):
+        a, ptr = _pinned(shape)
+        self._ptrs.append(ptr)
+        return a
+
+    def close(self):
+        if getattr(self, "_q", None):
+            lib = load_library()
+            lib.xdtts_pipe_destroy(self._q)
+            self._q = None
+            for ptr in self._ptrs:
+                lib.xdtts_host_free(ptr)
+            self._ptrs = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _result(self, i):
+        sl = self._slots[i]
+        waves = [a.copy() for a in sl["wave"]]
+        return (waves, [a.copy() for a in sl["omel"]]) if self.want_mels else waves
+
+    def pop(self):
+        """Wait for the oldest batch in flight -> its waveforms (and mels), or None when the pipe is empty."""
+        rc = load_library().xdtts_pipe_pop(self._q)
+        if rc < 0:
+            check(rc)
+        if rc == 0:
+            return None
+        return self._result(self._inflight.pop(0))
+
+    def push(self, mels, init_phases=None):
+        """Enqueue one batch; returns the result of the oldest batch if a slot had to be freed, else None."""
+        lib = load_library()
+        done = self.pop() if len(self._inflight) == self.depth else None
+        sl = self._slots[self._head]
+        ins = [_as_f32_2d(a, self.voc.n_mels, "mel") for a in mels]
+        if [a.shape[1] for a in ins] != self.ts:
+            raise XdttsError(_ffi.ERR_SHAPE, "mels do not match the pipe's frame counts")
+        for dst, src in zip(sl["mel"], ins):
+            dst[...] = src
+        phs = None
+        if init_phases is not None:
+            phs = [_as_f32_2d(a, self.voc.k_bins, "init_phase") for a in init_phases]
+            if [a.shape[1] for a in phs] != self.ts:
+                raise XdttsError(_ffi.ERR_SHAPE, "init_phases do not match the pipe's frame counts")
+            if sl["phase"] is None:
+                sl["phase"] = [self._pin((self.voc.k_bins, t)) for t in self.ts]
+            for dst, src in zip(sl["phase"], phs):
+                dst[...] = src
+        check(lib.xdtts_pipe_push(self._q, fptr_array(sl["mel"]), None if phs is None else fptr_array(sl["phase"]),
+                                  fptr_array(sl["omel"]) if self.want_mels else None, fptr_array(sl["wave"])))
+        self._inflight.append(self._head)
+        self._head = (self._head + 1) % self.depth
+        return done
+
+    def flush(self):
+        """Wait for everything in flight -> list of results, oldest first."""
+        out = []
+        while self._inflight:
+            out.append(self.pop())
+        return out
+
+    def pending(self):
+        rc = load_library().xdtts_pipe_pending(self._q)
+        if rc < 0:
+            check(rc)
+        return rc
