@@ -170,6 +170,62 @@ int xdtts_tail_infer_batch(xdtts_postnet* pn, xdtts_gl* gl, const float* const* 
                            const float* const* init_phases_or_null, float* const* out_mels_or_null,
                            float* const* out_waves);
 
+/* ---- Tacotron2 decoder loop: replaces the `decoder` ort::Session and the per-frame loop around it in
+ * Tacotron2::run_decoder (src/tacotron2/mod.rs:272-342; session load :251-254; state DecoderState::new
+ * :204-238).  The graph is NVIDIA Tacotron2's Decoder.decode as exported by export_tacotron2_onnx.py
+ * (named at src/tacotron2/mod.rs:137-138): prenet -> attention LSTM -> location-sensitive attention ->
+ * decoder LSTM -> linear projection + gate, fp32.  The whole loop -- every step of up to 8 utterances in
+ * lockstep -- is ONE persistent cooperative kernel; nothing returns to the host between frames.
+ * Weights are passed in the PyTorch layouts of the checkpoint the reference's ONNX files were exported
+ * from (row-major float32; LSTM gate order i, f, g, o). */
+typedef struct xdtts_decoder_weights {
+    const float* prenet1;   /* [256, 80]    decoder.prenet.layers.0.linear_layer.weight */
+    const float* prenet2;   /* [256, 256]   decoder.prenet.layers.1.linear_layer.weight */
+    const float* att_w_ih;  /* [4096, 768]  decoder.attention_rnn.weight_ih, input = [prenet(256) | context(512)] */
+    const float* att_w_hh;  /* [4096, 1024] */
+    const float* att_b_ih;  /* [4096] */
+    const float* att_b_hh;  /* [4096] */
+    const float* query;     /* [128, 1024]  decoder.attention_layer.query_layer.linear_layer.weight */
+    const float* v;         /* [128]        decoder.attention_layer.v.linear_layer.weight */
+    const float* loc_conv;  /* [32, 2, 31]  ...location_layer.location_conv.conv.weight */
+    const float* loc_dense; /* [128, 32]    ...location_layer.location_dense.linear_layer.weight */
+    const float* dec_w_ih;  /* [4096, 1536] decoder.decoder_rnn.weight_ih, input = [attention_hidden(1024) | context(512)] */
+    const float* dec_w_hh;  /* [4096, 1024] */
+    const float* dec_b_ih;  /* [4096] */
+    const float* dec_b_hh;  /* [4096] */
+    const float* proj_w;    /* [80, 1536]   decoder.linear_projection, input = [decoder_hidden(1024) | context(512)] */
+    const float* proj_b;    /* [80] */
+    const float* gate_w;    /* [1536]       decoder.gate_layer */
+    const float* gate_b;    /* [1] */
+} xdtts_decoder_weights;
+
+typedef struct xdtts_decoder_opts {
+    float gate_threshold;    /* 0: 0.6, the reference's constant (src/tacotron2/mod.rs:279); stop when sigmoid(gate) > it */
+    int max_steps;           /* 0: 1000 (src/tacotron2/mod.rs:280) */
+    int prenet_dropout;      /* 0: on -- the exported prenet draws a Bernoulli(0.5) mask inside the graph at every step, so
+                                the reference's decoder is stochastic; here the mask is the counter-based generator
+                                splitmix64(seed, utterance, step * 512 + layer * 256 + unit) <= 0.5.  1: off (deterministic) */
+    unsigned long long seed; /* seed of the dropout stream */
+} xdtts_decoder_opts;
+
+typedef struct xdtts_decoder xdtts_decoder;
+int xdtts_decoder_create(const xdtts_decoder_weights* w, const xdtts_decoder_opts* opts_or_null, int device, xdtts_decoder** out);
+void xdtts_decoder_destroy(xdtts_decoder* h);
+int xdtts_decoder_max_steps(const xdtts_decoder* h);   /* frame capacity the output buffers must have */
+/* run_decoder for B utterances (the reference decodes one at a time).  memory[b]: [t_enc, 512],
+ * processed_memory[b]: [t_enc, 128] -- the encoder session's outputs without their batch axis, padded to a
+ * common t_enc <= 512 (the reference pads every chunk to 100, src/tacotron2/mod.rs:366-368); unpadded_len[b]
+ * in 1..t_enc is the mask boundary of DecoderState::new (:228-229).  out_mels[b] must hold 80 * max_steps
+ * floats and receives the spectrogram as [80, n_frames[b]] row-major (the transposed layout of :345, what the
+ * postnet consumes); the frame whose gate fires is kept (:312-324).  out_gates_or_null[b]: [n_frames[b]] gate
+ * logits (capacity max_steps); out_align_or_null[b]: [n_frames[b], t_enc] attention weights
+ * (capacity max_steps * t_enc). */
+int xdtts_decoder_infer_batch(xdtts_decoder* h, const float* const* memory, const float* const* processed_memory, int t_enc,
+                              const int* unpadded_len, int B, float* const* out_mels, int* n_frames,
+                              float* const* out_gates_or_null, float* const* out_align_or_null);
+/* device time (CUDA events around the persistent kernel launches) and steps executed by the last call */
+int xdtts_decoder_last_timing(const xdtts_decoder* h, float* ms, int* steps);
+
 /* ---- Streaming: the same tail for a sequence of batches of one shape, copies overlapped with kernels.
  * XdTts::infer returns host samples per call (src/lib.rs:141-157) and the binary loops over chunks
  * (src/lib.rs:83-104); a server doing the same batch after batch would leave the GPU idle during every

@@ -42,10 +42,76 @@ def torch_gl64(s_mag, turns, n_iter, momentum, n_fft, hop):
     return torch.istft(s * ang, n_fft, hop, window=w, center=True).numpy()
 
 
+def torch_decoder64(wt, memory, processed, unpadded_len, keeps, n_steps):
+    """The decoder step composed from torch modules (nn.LSTMCell, F.conv1d, F.linear, masked softmax) in
+    fp64: an implementation independent of oracle/decoder_oracle.py, teacher-free (feeds its own output)."""
+    import torch
+    import torch.nn.functional as F
+
+    W = {k: torch.from_numpy(np.asarray(v, np.float64)) for k, v in wt.items()}
+    mem = torch.from_numpy(memory.astype(np.float64))[None]
+    pm = torch.from_numpy(processed.astype(np.float64))[None]
+    t_enc = memory.shape[0]
+    att = torch.nn.LSTMCell(768, 1024).double()
+    dec = torch.nn.LSTMCell(1536, 1024).double()
+    with torch.no_grad():
+        for cell, pre in ((att, "att"), (dec, "dec")):
+            cell.weight_ih.copy_(W[pre + "_w_ih"]); cell.weight_hh.copy_(W[pre + "_w_hh"])
+            cell.bias_ih.copy_(W[pre + "_b_ih"]); cell.bias_hh.copy_(W[pre + "_b_hh"])
+        x = torch.zeros(1, 80, dtype=torch.float64)
+        ha, ca, hd, cd = (torch.zeros(1, 1024, dtype=torch.float64) for _ in range(4))
+        w = torch.zeros(1, t_enc, dtype=torch.float64)
+        wc = torch.zeros(1, t_enc, dtype=torch.float64)
+        ctx = torch.zeros(1, 512, dtype=torch.float64)
+        mask = torch.arange(t_enc)[None] >= unpadded_len
+        mels, gates, aligns = [], [], []
+        for i in range(n_steps):
+            h = x
+            for layer, name in enumerate(("prenet1", "prenet2")):
+                h = F.relu(F.linear(h, W[name])) * torch.from_numpy(keeps[i][layer].astype(np.float64))[None] * 2.0
+            ha, ca = att(torch.cat([h, ctx], 1), (ha, ca))
+            cat = torch.stack([w, wc], 1)                                       # [1, 2, t_enc]
+            loc = F.conv1d(cat, W["loc_conv"], padding=15).transpose(1, 2)       # [1, t_enc, 32]
+            pa = F.linear(loc, W["loc_dense"])
+            e = F.linear(torch.tanh(F.linear(ha, W["query"])[:, None] + pa + pm), W["v"][None]).squeeze(-1)
+            e = e.masked_fill(mask, -float("inf"))
+            w = F.softmax(e, dim=1)
+            ctx = torch.bmm(w[:, None], mem).squeeze(1)
+            wc = wc + w
+            hd, cd = dec(torch.cat([ha, ctx], 1), (hd, cd))
+            hc = torch.cat([hd, ctx], 1)
+            x = F.linear(hc, W["proj_w"], W["proj_b"])
+            g = F.linear(hc, W["gate_w"], W["gate_b"])
+            mels.append(x[0].numpy().copy()); gates.append(float(g[0, 0])); aligns.append(w[0].numpy().copy())
+    return np.stack(mels), np.array(gates), np.stack(aligns)
+
+
+def decoder_golden():
+    """tests/golden/decoder.npz: 16 free-running decoder steps, t_enc 24 (19 unpadded), seeded dropout."""
+    from oracle import decoder_oracle as d
+
+    wt = d.synth_weights(11)
+    memory, processed = d.synth_encoder_outputs(21, 24)
+    n = 16
+    keeps = [d.dropout_keep(5, 0, i) for i in range(n)]
+    mel_t, gate_t, align_t = torch_decoder64(wt, memory, processed, 19, keeps, n)
+    mel_o, gate_o, align_o = d.run_decoder(wt, memory, processed, 19, seed=5, utt=0, gate_threshold=2.0, max_steps=n,
+                                           return_aux=True)
+    np.savez_compressed(os.path.join(OUT, "decoder.npz"), memory=memory, processed=processed, unpadded_len=19, seed=5,
+                        weights_seed=11, mel_torch64=mel_t, gate_torch64=gate_t, align_torch64=align_t.astype(np.float32),
+                        mel_oracle64=mel_o, gate_oracle64=gate_o)
+    print("decoder.npz: oracle vs torch max abs diff mel %.2e gate %.2e align %.2e" % (
+        np.abs(mel_t - mel_o).max(), np.abs(gate_t - gate_o).max(), np.abs(align_t - align_o).max()))
+
+
 def main():
     import torch
     import torch.nn.functional as F
     import torchaudio
+
+    if "--decoder-only" in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        return decoder_golden()
 
     os.makedirs(OUT, exist_ok=True)
 
@@ -116,6 +182,7 @@ def main():
         mel=melp, out_torch32=(torch.from_numpy(melp) + x[0]).numpy(),
         out_oracle64=p.postnet(melp, layers, dtype=np.float64).astype(np.float32),
     )
+    decoder_golden()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

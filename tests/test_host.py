@@ -94,6 +94,40 @@ def test_argument_validation_without_gpu(lib):
     assert b"fmax" in lib.xdtts_last_error()
 
 
+def test_decoder_argument_validation_without_gpu(lib):
+    import ctypes
+
+    from oracle import decoder_oracle as d
+    from xdtts_b200 import tacotron2
+    from xdtts_b200._ffi import ERR_BAD_ARG, ERR_CUDA, ERR_SHAPE, XdttsError
+
+    h = ctypes.c_void_p()
+    assert lib.xdtts_decoder_create(None, None, 0, ctypes.byref(h)) == ERR_BAD_ARG
+    assert lib.xdtts_decoder_max_steps(None) == ERR_BAD_ARG
+    assert lib.xdtts_decoder_infer_batch(None, None, None, 10, None, 1, None, None, None, None) == ERR_BAD_ARG
+    lib.xdtts_decoder_destroy(None)
+    wt = d.synth_weights(11)
+    bad = dict(wt)
+    del bad["gate_b"]
+    with pytest.raises(XdttsError) as e:
+        tacotron2.Decoder.from_weights(bad)
+    assert e.value.code == ERR_BAD_ARG
+    bad = dict(wt)
+    bad["dec_w_ih"] = bad["dec_w_ih"][:, :1024]
+    with pytest.raises(XdttsError) as e:
+        tacotron2.Decoder.from_weights(bad)
+    assert e.value.code == ERR_SHAPE
+    with pytest.raises(XdttsError) as e:
+        tacotron2.Decoder.from_weights(wt, max_steps=-1)
+    assert e.value.code == ERR_BAD_ARG
+    import torch
+
+    if not torch.cuda.is_available():          # no CPU fallback: a valid request fails for want of a device
+        with pytest.raises(XdttsError) as e:
+            tacotron2.Decoder.from_weights(wt)
+        assert e.value.code == ERR_CUDA
+
+
 def test_pipe_argument_validation_without_gpu(lib):
     import ctypes
 

@@ -134,3 +134,34 @@ def test_pcm16_cast_semantics():
     y = np.array([0.0, 1.0, -1.0, 0.5, -0.5, 1.5, -1.5, 3.0517578e-05, -3.0517578e-05, np.nan, 0.99999, 2.0e-5], np.float32)
     want = np.array([0, 32767, -32767, 16383, -16383, 32767, -32768, 0, 0, 0, 32766, 0], np.int16)
     assert np.array_equal(o.pcm16(y), want)
+
+
+def test_decoder_oracle_matches_torch_fixture(golden_dir):
+    """oracle/decoder_oracle.py vs the decoder composed from torch modules (nn.LSTMCell, F.conv1d, masked
+    softmax) in fp64, 16 free-running steps with the seeded prenet dropout (oracle/make_golden.py)."""
+    import os
+
+    from oracle import decoder_oracle as d
+
+    g = np.load(os.path.join(golden_dir, "decoder.npz"))
+    wt = d.synth_weights(int(g["weights_seed"]))
+    mel, gate, align = d.run_decoder(wt, g["memory"], g["processed"], int(g["unpadded_len"]), seed=int(g["seed"]),
+                                     gate_threshold=2.0, max_steps=16, return_aux=True)
+    assert np.abs(mel - g["mel_torch64"]).max() < 1e-12
+    assert np.abs(gate - g["gate_torch64"]).max() < 1e-12
+    assert np.abs(align - g["align_torch64"]).max() < 1e-7          # stored as float32
+    # fp32 evaluation of the same graph stays within 1e-4 of fp64 over 16 steps (the device tolerance's scale)
+    mel32 = d.run_decoder(wt, g["memory"], g["processed"], int(g["unpadded_len"]), seed=int(g["seed"]), gate_threshold=2.0,
+                          max_steps=16, dtype=np.float32)
+    assert np.abs(mel32 - g["mel_torch64"]).max() < 1e-4
+    # stop rule: the frame that fires the gate is kept (src/tacotron2/mod.rs:312-324)
+    thr = 0.25
+    full, gates, _ = d.run_decoder(wt, g["memory"], g["processed"], 19, seed=3, gate_threshold=2.0, max_steps=40, return_aux=True)
+    fired = np.where(1 / (1 + np.exp(-gates)) > thr)[0]
+    cut = d.run_decoder(wt, g["memory"], g["processed"], 19, seed=3, gate_threshold=thr, max_steps=40)
+    assert cut.shape[0] == (fired[0] + 1 if len(fired) else 40)
+    assert np.array_equal(cut, full[:cut.shape[0]])
+    # dropout mask: Bernoulli(1/2), distinct per step / utterance, reproducible
+    k = np.stack([d.dropout_keep(1, 0, i) for i in range(50)])
+    assert 0.45 < k.mean() < 0.55 and not np.array_equal(k[0], k[1])
+    assert np.array_equal(d.dropout_keep(1, 0, 7), k[7]) and not np.array_equal(d.dropout_keep(1, 1, 7), k[7])

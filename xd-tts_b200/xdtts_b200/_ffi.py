@@ -28,6 +28,17 @@ class PostnetOpts(ctypes.Structure):
     _fields_ = [("precision", ctypes.c_int)]
 
 
+class DecoderWeights(ctypes.Structure):
+    _fields_ = [(n, ctypes.POINTER(ctypes.c_float)) for n in (
+        "prenet1", "prenet2", "att_w_ih", "att_w_hh", "att_b_ih", "att_b_hh", "query", "v", "loc_conv", "loc_dense",
+        "dec_w_ih", "dec_w_hh", "dec_b_ih", "dec_b_hh", "proj_w", "proj_b", "gate_w", "gate_b")]
+
+
+class DecoderOpts(ctypes.Structure):
+    _fields_ = [("gate_threshold", ctypes.c_float), ("max_steps", ctypes.c_int), ("prenet_dropout", ctypes.c_int),
+                ("seed", ctypes.c_ulonglong)]
+
+
 class GlOpts(ctypes.Structure):
     _fields_ = [
         ("delog", ctypes.c_int),
@@ -85,6 +96,12 @@ SIGNATURES = {
     "xdtts_onnx_postnet_layer_info": (ctypes.c_int, [_vp, ctypes.c_int, _ip, _ip, _ip, _ip, _ip, _fp]),
     "xdtts_onnx_postnet_layer_copy": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _fp]),
     "xdtts_tail_infer_batch": (ctypes.c_int, [_vp, _vp, _fpp, _ip, ctypes.c_int, _fpp, _fpp, _fpp]),
+    "xdtts_decoder_create": (ctypes.c_int, [ctypes.POINTER(DecoderWeights), ctypes.POINTER(DecoderOpts), ctypes.c_int,
+                                            ctypes.POINTER(_vp)]),
+    "xdtts_decoder_destroy": (None, [_vp]),
+    "xdtts_decoder_max_steps": (ctypes.c_int, [_vp]),
+    "xdtts_decoder_infer_batch": (ctypes.c_int, [_vp, _fpp, _fpp, ctypes.c_int, _ip, ctypes.c_int, _fpp, _ip, _fpp, _fpp]),
+    "xdtts_decoder_last_timing": (ctypes.c_int, [_vp, _fp, _ip]),
     "xdtts_pipe_create": (ctypes.c_int, [_vp, _vp, _ip, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]),
     "xdtts_pipe_push": (ctypes.c_int, [_vp, _fpp, _fpp, _fpp, _fpp]),
     "xdtts_pipe_pop": (ctypes.c_int, [_vp]),

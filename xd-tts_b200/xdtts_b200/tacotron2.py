@@ -19,7 +19,7 @@ import ctypes
 import numpy as np
 
 from . import _ffi
-from ._ffi import PostnetOpts, XdttsError, check, fptr, fptr_array, load_library
+from ._ffi import DecoderOpts, DecoderWeights, PostnetOpts, XdttsError, check, fptr, fptr_array, load_library
 
 PRECISION_BF16X3, PRECISION_BF16, PRECISION_FP32 = 0, 1, 2
 BN_EPS = 1e-5   # torch.nn.BatchNorm1d default, as exported to ONNX
@@ -121,6 +121,91 @@ class Postnet:
 
     def plan(self, frame_counts):
         return PostnetPlan(self, frame_counts)
+
+
+GATE_THRESHOLD, MAX_DECODER_STEPS = 0.6, 1000   # src/tacotron2/mod.rs:279-280
+_DECODER_SHAPES = dict(
+    prenet1=(256, 80), prenet2=(256, 256), att_w_ih=(4096, 768), att_w_hh=(4096, 1024), att_b_ih=(4096,), att_b_hh=(4096,),
+    query=(128, 1024), v=(128,), loc_conv=(32, 2, 31), loc_dense=(128, 32), dec_w_ih=(4096, 1536), dec_w_hh=(4096, 1024),
+    dec_b_ih=(4096,), dec_b_hh=(4096,), proj_w=(80, 1536), proj_b=(80,), gate_w=(1536,), gate_b=(1,))
+
+
+class Decoder:
+    """Device-side decoder loop: the `decoder` session of Tacotron2 plus the loop of `run_decoder`
+    (src/tacotron2/mod.rs:145,251-254,272-342).  One persistent kernel runs all steps; `run` / `run_batch`
+    take the encoder outputs and return the spectrogram `[80, T]` the postnet consumes (:345)."""
+
+    def __init__(self, handle, max_steps):
+        self._h = handle
+        self.max_steps = max_steps
+
+    @classmethod
+    def from_weights(cls, weights, *, gate_threshold=GATE_THRESHOLD, max_steps=MAX_DECODER_STEPS, prenet_dropout=True, seed=0,
+                     device=0):
+        """weights: dict of float32 arrays in the PyTorch layouts named in include/xdtts_b200.h
+        (xdtts_decoder_weights); gate_w may be [1, 1536]."""
+        lib = load_library()
+        keep, w = [], DecoderWeights()
+        for name, shape in _DECODER_SHAPES.items():
+            if name not in weights:
+                raise XdttsError(_ffi.ERR_BAD_ARG, "decoder weights: '%s' is missing" % name)
+            a = np.ascontiguousarray(weights[name], dtype=np.float32)
+            if a.size != int(np.prod(shape)):
+                raise XdttsError(_ffi.ERR_SHAPE, "decoder weights: '%s' must be %s, got %s" % (name, shape, a.shape))
+            keep.append(a)
+            setattr(w, name, fptr(a))
+        opts = DecoderOpts(float(gate_threshold), int(max_steps), 0 if prenet_dropout else 1, int(seed))
+        h = ctypes.c_void_p()
+        check(lib.xdtts_decoder_create(ctypes.byref(w), ctypes.byref(opts), int(device), ctypes.byref(h)))
+        return cls(h, lib.xdtts_decoder_max_steps(h))
+
+    def close(self):
+        if self._h:
+            load_library().xdtts_decoder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run_batch(self, memories, processed_memories, unpadded_lens, return_aux=False):
+        """run_decoder for B utterances: memories[b] [t_enc, 512], processed_memories[b] [t_enc, 128] (one common
+        t_enc), unpadded_lens[b] -> list of [80, T_b] float32 (+ gate logits [T_b], alignments [T_b, t_enc])."""
+        lib = load_library()
+        mem = [np.ascontiguousarray(a, dtype=np.float32) for a in memories]
+        pm = [np.ascontiguousarray(a, dtype=np.float32) for a in processed_memories]
+        n = len(mem)
+        if n == 0 or len(pm) != n or len(unpadded_lens) != n:
+            raise XdttsError(_ffi.ERR_BAD_ARG, "memories, processed_memories and unpadded_lens must have one entry per utterance")
+        t_enc = mem[0].shape[0]
+        for a, b in zip(mem, pm):
+            if a.ndim != 2 or a.shape != (t_enc, 512) or b.shape != (t_enc, 128):
+                raise XdttsError(_ffi.ERR_SHAPE, "memory must be [t_enc, 512] and processed_memory [t_enc, 128] with one common t_enc")
+        outs = [np.empty(80 * self.max_steps, dtype=np.float32) for _ in range(n)]
+        gates = [np.empty(self.max_steps, dtype=np.float32) for _ in range(n)] if return_aux else None
+        aligns = [np.empty(self.max_steps * t_enc, dtype=np.float32) for _ in range(n)] if return_aux else None
+        lens = (ctypes.c_int * n)(*[int(x) for x in unpadded_lens])
+        nf = (ctypes.c_int * n)()
+        check(lib.xdtts_decoder_infer_batch(self._h, fptr_array(mem), fptr_array(pm), t_enc, lens, n, fptr_array(outs), nf,
+                                            None if gates is None else fptr_array(gates),
+                                            None if aligns is None else fptr_array(aligns)))
+        mels = [o[:80 * nf[b]].reshape(80, nf[b]).copy() for b, o in enumerate(outs)]
+        if return_aux:
+            return (mels, [g[:nf[b]].copy() for b, g in enumerate(gates)],
+                    [a[:nf[b] * t_enc].reshape(nf[b], t_enc).copy() for b, a in enumerate(aligns)])
+        return mels
+
+    def run(self, memory, processed_memory, unpadded_len):
+        """Tacotron2::run_decoder up to the postnet (src/tacotron2/mod.rs:272-345): -> [80, T]."""
+        return self.run_batch([memory], [processed_memory], [unpadded_len])[0]
+
+    def last_timing(self):
+        """-> (device milliseconds of the decoder kernel, steps executed) of the last call"""
+        ms, steps = ctypes.c_float(), ctypes.c_int()
+        check(load_library().xdtts_decoder_last_timing(self._h, ctypes.byref(ms), ctypes.byref(steps)))
+        return ms.value, steps.value
 
 
 def write_npy(path, spectrogram):
