@@ -74,7 +74,8 @@ __device__ __forceinline__ void row_dot(const float* __restrict__ wrow, const fl
     }
 }
 
-// partial gate sums of this CTA's units over weight columns [col0, col0 + ncols): part[r][b], r = gate * 7 + unit
+// partial gate sums of this CTA's units over weight columns [col0, col0 + ncols) against the vectors that START at
+// zs (the caller offsets zs to the segment): part[r][b], r = gate * 7 + unit
 template <int NB>
 __device__ __forceinline__ void lstm_partial(const float* __restrict__ W, int ld, int col0, int ncols, const float* zs, int zld,
                                              int unit0, float* part, const float* __restrict__ bias_or_null) {
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
         for (int i = tid; i < nb * DC_ENC; i += DC_THREADS)
             zs[(i / DC_ENC) * ZLD + 2 * DC_RNN + i % DC_ENC] = __ldcg(p.ctx + i);
         __syncthreads();
-        lstm_partial<NB>(p.Wd, DC_ZD, 2 * DC_RNN, DC_ENC, zs, ZLD, unit0, part_d, nullptr);
+        lstm_partial<NB>(p.Wd, DC_ZD, 2 * DC_RNN, DC_ENC, zs + 2 * DC_RNN, ZLD, unit0, part_d, nullptr);
         __syncthreads();
         lstm_cell<NB>(part_d, cst_d, unit0, nb, p.h_d + (size_t)nxt * nb * DC_RNN);
         grid_barrier(p.barrier, epoch, G);
