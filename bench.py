@@ -83,6 +83,72 @@ def synth_postnet_layers(seed=7, channels=(80, 512, 512, 512, 512, 80), ksize=5)
     return layers
 
 
+DEC_T_ENC, DEC_UNPADDED, DEC_STEPS = 100, 77, 1000   # the reference's fixed 100-position chunk, 1000-step cap (src/tacotron2/mod.rs:280,366)
+# weights one decoder step reads: prenet 80x256 + 256x256, attention LSTM 4096x1792, query 128x1024, decoder LSTM
+# 4096x2560, projection + gate 81x1536 (fp32)
+DEC_WEIGHT_BYTES = 4 * (80 * 256 + 256 * 256 + 4096 * 1792 + 128 * 1024 + 4096 * 2560 + 81 * 1536)
+
+
+def synth_decoder_weights(seed=11, gain=2.0):
+    """Seeded random Tacotron2 decoder in PyTorch layouts (the LFS weights of the reference are absent)."""
+    rng = np.random.default_rng(seed)
+
+    def mat(rows, cols, g=gain):
+        return (g * rng.standard_normal((rows, cols)) / np.sqrt(cols)).astype(np.float32)
+
+    def vec(n, s=0.1):
+        return (s * rng.standard_normal(n)).astype(np.float32)
+
+    return dict(
+        prenet1=mat(256, 80), prenet2=mat(256, 256), att_w_ih=mat(4096, 768), att_w_hh=mat(4096, 1024), att_b_ih=vec(4096),
+        att_b_hh=vec(4096), query=mat(128, 1024), v=mat(1, 128, 2.0)[0],
+        loc_conv=(rng.standard_normal((32, 2, 31)) / np.sqrt(62)).astype(np.float32), loc_dense=mat(128, 32, 1.0),
+        dec_w_ih=mat(4096, 1536), dec_w_hh=mat(4096, 1024), dec_b_ih=vec(4096), dec_b_hh=vec(4096), proj_w=mat(80, 1536),
+        proj_b=vec(80), gate_w=mat(1, 1536, 6.0), gate_b=np.array([-2.0], np.float32))
+
+
+def synth_encoder_outputs(seed, t_enc):
+    rng = np.random.default_rng(seed)
+    return (0.5 * rng.standard_normal((t_enc, 512))).astype(np.float32), (0.5 * rng.standard_normal((t_enc, 128))).astype(np.float32)
+
+
+def decoder_leg(device, with_cpu):
+    """The decoder loop: 1000 steps of the Tacotron2 decoder in one persistent kernel, for one
+    utterance (the reference's shape) and for 8 in lockstep.  Device time = CUDA events around the launch."""
+    from xdtts_b200 import tacotron2
+
+    wt = synth_decoder_weights()
+    dec = tacotron2.Decoder.from_weights(wt, gate_threshold=0.999999, max_steps=DEC_STEPS, seed=1, device=device)
+    out = {"bound": "hbm", "kernel": "dec_persist_kernel (one cooperative launch = %d decoder steps, 7 grid barriers per step)" % DEC_STEPS,
+           "workload": "Tacotron2 decoder loop, t_enc=%d (%d unpadded), %d steps, fp32, synthetic weights" % (DEC_T_ENC, DEC_UNPADDED, DEC_STEPS),
+           "algorithmic_bytes_per_step": DEC_WEIGHT_BYTES}
+    for nb in (1, 8):
+        enc = [synth_encoder_outputs(100 + i, DEC_T_ENC) for i in range(nb)]
+        best = None
+        for _ in range(4):
+            mels = dec.run_batch([m for m, _ in enc], [p for _, p in enc], [DEC_UNPADDED] * nb)
+            ms, steps = dec.last_timing()
+            best = ms if best is None or ms < best else best
+        assert steps == DEC_STEPS and all(m.shape == (80, DEC_STEPS) and np.isfinite(m).all() for m in mels)
+        out["b%d" % nb] = {"ms": best, "us_per_step": best * 1e3 / DEC_STEPS, "frames_per_s": nb * DEC_STEPS / (best * 1e-3)}
+    peak, src = measured_peak()
+    out["achieved"] = DEC_WEIGHT_BYTES / (out["b1"]["us_per_step"] * 1e-6) / 1e9
+    out.update({"peak": peak, "unit": "GB/s", "frac": out["achieved"] / peak, "peak_source": src,
+                "note": "weights (72.7 MB) are re-read every step; achieved above the HBM peak would mean they are served from the 126 MB L2"})
+    if with_cpu:
+        from oracle import decoder_oracle as d   # CPU baseline leg only
+
+        mem, pm = synth_encoder_outputs(100, DEC_T_ENC)
+        n = 40
+        t0 = time.perf_counter()
+        d.run_decoder(wt, mem, pm, DEC_UNPADDED, seed=1, gate_threshold=2.0, max_steps=n, dtype=np.float32)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": "%d steps of the numpy/BLAS fp32 oracle (one utterance)" % n}
+    dec.close()
+    return out
+
+
 def synth_mel(seed, n_mels, n_frames):
     """ln-mel in U(-8, 0), the range Tacotron2 emits: the benchmark's synthetic input."""
     return np.random.default_rng(seed).uniform(-8.0, 0.0, (n_mels, n_frames)).astype(np.float32)
@@ -397,6 +463,9 @@ def run_gpu(args):
                 pplan.run()
         pn_ms = min((pplan.run(feed=plan) if with_postnet else pplan.run()) for _ in range(5))
 
+    # ---- next row N1: the decoder loop that produces the mels this path consumes
+    dec_line = decoder_leg(local_rank, not args.no_cpu) if (world == 1 and cfg == "cfg2" and not args.no_decoder) else None
+
     # ---- reduce over ranks: time = max, frames = sum
     total_frames, total_launches, (dev_ms, wall_ms, e2e_ms, kern_ms, call_ms) = shard.reduce_counters(
         frames, launches, [dev_ms, wall_ms, e2e_ms, kern_ms, call_ms], device="cuda")   # the single collective of the job
@@ -437,6 +506,8 @@ def run_gpu(args):
                                "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak, "frac_executed": 3 * tf / tpeak,
                                "peak_source": tsrc, "algorithmic_flop_per_frame": POSTNET_FLOP_PER_FRAME,
                                "in_timed_step": with_postnet}
+        if dec_line is not None:
+            line["decoder"] = dec_line
         if world == 1 and not args.no_cpu:
             v, cores, kind, sample, _ = cpu_arm(cfg, 1, 1)
             line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}
@@ -456,6 +527,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-decoder", action="store_true", help="skip the decoder-loop leg")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 10:

@@ -12,6 +12,9 @@ for cfg in cfg2 cfg3 cfg5; do
 import json
 try:
     d = json.load(open("$out/bench_$cfg.json"))
+    if "decoder" in d:
+        q = d["decoder"]
+        print("decoder b1 %.1f us/step (%.0f GB/s, frac %.2f)  b8 %.1f us/step  %.0f / %.0f frames/s" % (q["b1"]["us_per_step"], q["achieved"], q["frac"], q["b8"]["us_per_step"], q["b1"]["frames_per_s"], q["b8"]["frames_per_s"]))
     print("$cfg value %.3fM  e2e %.3fM (blocking %.3fM)  kernel %.2f us frac %.3f" % (d["value"] / 1e6, d["e2e"]["value"] / 1e6,
           d["e2e"].get("blocking_call", {}).get("value", 0) / 1e6, d["roofline"]["kernel_ms"] * 1e3, d["roofline"]["frac"]))
 except Exception as e:
