@@ -11,14 +11,18 @@
 // every SM at once, (2) keeping all state on chip or in L2 between steps, (3) as few grid-wide barriers as
 // the data dependences allow, with the weight streaming placed so that it overlaps the small serial stages:
 //
-//   stage P   prenet layer 1 (every CTA, redundantly) + layer 2 rows (one per CTA)               | barrier
-//   stage A2  attention LSTM: the 256 prenet columns + cell update                               | barrier
-//   stage Q   query rows (one per CTA)  +  decoder LSTM over its [h_att | h_dec] columns (D1)     | barrier
-//   stage E   attention energies, one warp per encoder position                                  | barrier
-//   stage C   softmax (every CTA, redundantly) + context chunks (one warp per 32 dims)            | barrier
-//   stage D2  decoder LSTM: the 512 context columns + cell update                                | barrier
-//   stage R   projection + gate rows (one per CTA)  +  attention LSTM of the NEXT step over its
-//             [ctx | h_att] columns (A1)                                                        | barrier
+//   stage     on the critical path (published before the barrier)            streamed behind the barrier
+//   P   prenet layer 1 (every CTA, redundantly) + layer 2 rows (one per CTA)    att. LSTM, h_att columns (2nd half)
+//   A2  attention LSTM: the 256 prenet columns + cell update                    dec. LSTM, h_dec columns (2nd half)
+//   Q   query rows (one per CTA)                                                dec. LSTM, h_att columns [0, 384)
+//   E   attention energies, one warp per encoder position                       dec. LSTM, h_att columns [384, 768)
+//   C   softmax (every CTA, redundantly) + context chunks (a warp per 32 dims)  dec. LSTM, h_att columns [768, 1024)
+//   D2  decoder LSTM: the 512 context columns + cell update                     NEXT step's att. LSTM, ctx columns
+//   R   projection + gate rows (one per CTA)                                    NEXT step: att. LSTM h_att (1st half),
+//                                                                               dec. LSTM h_dec (1st half)
+// Every barrier is split-phase: a stage publishes its small result, arrives, streams LSTM weight columns whose
+// input vectors are already known (82% of the bytes of a step) and only then waits, so the barrier latency and
+// the serial stages overlap the weight traffic instead of adding to it.
 //
 // CTA c owns hidden units [7c, 7c+7) of both LSTMs: their four gate rows, the partial gate sums (which live
 // in shared memory across barriers) and the cell state never leave the SM.  A warp computes one weight row
@@ -33,20 +37,6 @@
 
 namespace xdtts {
 
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch, unsigned n_ctas) {
-    __syncthreads();
-    epoch += n_ctas;
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
-        unsigned v;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-        } while (v < epoch);
-    }
-    __syncthreads();
-}
-
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // dot products of `ncols` consecutive weights (a multiple of 128) with NB vectors in shared memory
@@ -57,7 +47,7 @@ __device__ __forceinline__ void row_dot(const float* __restrict__ wrow, const fl
     float a[NB];
 #pragma unroll
     for (int b = 0; b < NB; b++) a[b] = 0.f;
-#pragma unroll 4
+#pragma unroll 8
     for (int c = lane * 4; c < ncols; c += 128) {
         const float4 w = __ldg(reinterpret_cast<const float4*>(wrow + c));
 #pragma unroll
@@ -74,23 +64,55 @@ __device__ __forceinline__ void row_dot(const float* __restrict__ wrow, const fl
     }
 }
 
-// partial gate sums of this CTA's units over weight columns [col0, col0 + ncols) against the vectors that START at
-// zs (the caller offsets zs to the segment): part[r][b], r = gate * 7 + unit
-template <int NB>
-__device__ __forceinline__ void lstm_partial(const float* __restrict__ W, int ld, int col0, int ncols, const float* zs, int zld,
-                                             int unit0, float* part, const float* __restrict__ bias_or_null) {
+// partial gate sums of this CTA's units over weight columns [col0, col0 + 128 NC4) against the vectors that START
+// at zs (the caller offsets zs to the segment): part[r][b], r = gate * 7 + unit.  A warp owns rows r = warp and
+// warp + 16 and issues the loads of BOTH before it touches either (these products are latency-bound: a slice is
+// 2-6 float4 per lane and row, so everything that can be in flight must be).
+template <int NB, int NC4>
+__device__ __forceinline__ void lstm_partial(const float* __restrict__ W, int ld, int col0, const float* zs, int zld, int unit0,
+                                             float* part, const float* __restrict__ bias_or_null) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int r = warp; r < 4 * DC_UNITS; r += DC_THREADS / 32) {
-        const int unit = unit0 + r % DC_UNITS;
-        if (unit >= DC_RNN) continue;
-        const int row = (r / DC_UNITS) * DC_RNN + unit;
-        float acc[NB];
+    constexpr int WARPS = DC_THREADS / 32;
+    // rows past the end (last CTAs, second row of warps 12..15) are clamped to a valid row and their sums dropped
+    const int r0 = warp, r1 = warp + WARPS < 4 * DC_UNITS ? warp + WARPS : 4 * DC_UNITS - 1;
+    const int u0 = min(unit0 + r0 % DC_UNITS, DC_RNN - 1), u1 = min(unit0 + r1 % DC_UNITS, DC_RNN - 1);
+    const int row0 = (r0 / DC_UNITS) * DC_RNN + u0, row1 = (r1 / DC_UNITS) * DC_RNN + u1;
+    const bool ok0 = unit0 + r0 % DC_UNITS < DC_RNN, ok1 = warp + WARPS < 4 * DC_UNITS && unit0 + r1 % DC_UNITS < DC_RNN;
+    const float* wr0 = W + (size_t)row0 * ld + col0 + lane * 4;
+    const float* wr1 = W + (size_t)row1 * ld + col0 + lane * 4;
+    float4 w0[NC4], w1[NC4];
 #pragma unroll
-        for (int b = 0; b < NB; b++) acc[b] = 0.f;
-        row_dot<NB>(W + (size_t)row * ld + col0, zs, zld, ncols, acc);
-        if (lane == 0) {
+    for (int c = 0; c < NC4; c++) w0[c] = __ldg(reinterpret_cast<const float4*>(wr0 + 128 * c));
 #pragma unroll
-            for (int b = 0; b < NB; b++) part[r * NB + b] = (bias_or_null ? bias_or_null[row] : part[r * NB + b]) + acc[b];
+    for (int c = 0; c < NC4; c++) w1[c] = __ldg(reinterpret_cast<const float4*>(wr1 + 128 * c));
+    float a0[NB], a1[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) a0[b] = a1[b] = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC4; c++) {
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            const float4 z = *reinterpret_cast<const float4*>(zs + b * zld + lane * 4 + 128 * c);
+            a0[b] = fmaf(w0[c].x, z.x, fmaf(w0[c].y, z.y, fmaf(w0[c].z, z.z, fmaf(w0[c].w, z.w, a0[b]))));
+            a1[b] = fmaf(w1[c].x, z.x, fmaf(w1[c].y, z.y, fmaf(w1[c].z, z.z, fmaf(w1[c].w, z.w, a1[b]))));
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            a0[b] += __shfl_xor_sync(0xffffffffu, a0[b], o);
+            a1[b] += __shfl_xor_sync(0xffffffffu, a1[b], o);
+        }
+    }
+    if (lane == 0) {
+        if (ok0) {
+#pragma unroll
+            for (int b = 0; b < NB; b++) part[r0 * NB + b] = (bias_or_null ? bias_or_null[row0] : part[r0 * NB + b]) + a0[b];
+        }
+        if (ok1) {
+#pragma unroll
+            for (int b = 0; b < NB; b++) part[r1 * NB + b] = (bias_or_null ? bias_or_null[row1] : part[r1 * NB + b]) + a1[b];
         }
     }
 }
@@ -120,10 +142,13 @@ __device__ __forceinline__ float keep_scale(const DecParams& p, int b, int step,
 template <int NB>
 struct DecSmem {
     static constexpr int a4(int x) { return (x + 3) & ~3; }  // regions start on 16-byte boundaries (float4 reads)
-    static constexpr int ZLD = DC_ZD;
-    static constexpr int Z = 0;                                    // [NB][2560] input vectors of the current stage
-    static constexpr int X1 = Z + NB * ZLD;                        // [NB][256] prenet layer 1 output
-    static constexpr int WEFF = X1 + NB * DC_PRE;                  // [128][63]
+    static constexpr int ZA_LD = DC_ENC + DC_RNN;                  // [ctx | h_att]: attention-LSTM columns streamed ahead
+    static constexpr int ZD_LD = 2 * DC_RNN;                       // [h_att | h_dec]: decoder-LSTM columns streamed ahead
+    static constexpr int ZA = 0;
+    static constexpr int ZD = ZA + NB * ZA_LD;
+    static constexpr int X1 = ZD + NB * ZD_LD;                     // [NB][256] prenet layer 1 output
+    static constexpr int X2 = X1 + NB * DC_PRE;                    // [NB][256] prenet output (copy of the global one)
+    static constexpr int WEFF = X2 + NB * DC_PRE;                  // [128][63]
     static constexpr int PART_A = a4(WEFF + DC_ATT * DC_WEFF_LD);  // [28][NB] attention-LSTM gate sums
     static constexpr int PART_D = a4(PART_A + 4 * DC_UNITS * NB);
     static constexpr int CST_A = a4(PART_D + 4 * DC_UNITS * NB);   // [7][NB] cell states
@@ -134,17 +159,40 @@ struct DecSmem {
     static size_t bytes(int t_enc) { return sizeof(float) * (size_t)(DYN + NB * t_enc + NB * 2 * (t_enc + 30) + 8); }
 };
 
+// Split-phase grid barrier.  A stage publishes its results, ARRIVES, then streams LSTM weight columns whose
+// inputs were already known, and only then WAITS: the barrier's latency (two L2 round trips) is hidden
+// behind useful memory traffic instead of being paid seven times per step.
+__device__ __forceinline__ void bar_arrive(unsigned* counter) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    }
+}
+__device__ __forceinline__ void bar_wait(unsigned* counter, unsigned& epoch, unsigned n_ctas) {
+    epoch += n_ctas;
+    if (threadIdx.x == 0) {
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < epoch);
+    }
+    __syncthreads();
+}
+
 template <int NB>
 __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecParams p) {
     extern __shared__ __align__(16) float sm[];
     typedef DecSmem<NB> S;
-    constexpr int ZLD = S::ZLD;
-    float* zs = sm + S::Z;
+    constexpr int ZA_LD = S::ZA_LD, ZD_LD = S::ZD_LD;
+    float* zA = sm + S::ZA;          // [NB][ctx(512) | h_att(1024)]
+    float* zD = sm + S::ZD;          // [NB][h_att(1024) | h_dec(1024)]
+    float* x1 = sm + S::X1;
+    float* x2s = sm + S::X2;
     float* part_a = sm + S::PART_A;
     float* part_d = sm + S::PART_D;
     float* cst_a = sm + S::CST_A;
     float* cst_d = sm + S::CST_D;
-    float* x1 = sm + S::X1;
     float* xin = sm + S::XIN;
     float* vs = sm + S::VS;
     float* weff = sm + S::WEFF;
@@ -155,7 +203,8 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = gridDim.x, cta = blockIdx.x, nb = p.nb;
     const int unit0 = cta * DC_UNITS;
-    constexpr int LIGHT_WARP = DC_THREADS / 32 - 1;   // has one LSTM row where most warps have two
+    constexpr int WARPS = DC_THREADS / 32;
+    constexpr int LIGHT_WARP = WARPS - 1;      // has one LSTM row where most warps have two
     unsigned epoch = 0;
 
     // ---- prologue: constants and the all-zero DecoderState (src/tacotron2/mod.rs:212-236)
@@ -163,11 +212,13 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
         weff[(i / (2 * DC_LOCK)) * DC_WEFF_LD + i % (2 * DC_LOCK)] = p.Weff[i];
     for (int i = tid; i < DC_ATT; i += DC_THREADS) vs[i] = p.v[i];
     for (int i = tid; i < NB * 2 * wld; i += DC_THREADS) wpad[i] = 0.f;
-    for (int i = tid; i < NB * ZLD; i += DC_THREADS) zs[i] = 0.f;
+    for (int i = tid; i < NB * (ZA_LD + ZD_LD); i += DC_THREADS) zA[i] = 0.f;   // zA and zD are adjacent
     for (int i = tid; i < DC_UNITS * NB; i += DC_THREADS) { cst_a[i] = 0.f; cst_d[i] = 0.f; }
-    for (int i = tid; i < 4 * DC_UNITS * NB; i += DC_THREADS) {   // A1 of step 0: ctx = h_att = 0 -> bias only
+    for (int i = tid; i < 4 * DC_UNITS * NB; i += DC_THREADS) {   // zero state: the streamed-ahead columns give the bias
         const int r = i / NB, unit = unit0 + r % DC_UNITS;
-        part_a[i] = unit < DC_RNN ? p.ba[(r / DC_UNITS) * DC_RNN + unit] : 0.f;
+        const int row = (r / DC_UNITS) * DC_RNN + unit;
+        part_a[i] = unit < DC_RNN ? p.ba[row] : 0.f;
+        part_d[i] = unit < DC_RNN ? p.bd[row] : 0.f;
     }
     bool done[NB];
 #pragma unroll
@@ -177,27 +228,38 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
     int step = 0;
     for (; step < p.max_steps; step++) {
         const int cur = step & 1, nxt = cur ^ 1;
-        // ================= stage P: prenet
+        // ================= stage P: prenet of this step  ||  attention LSTM, second half of its h_att columns
         for (int i = tid; i < nb * DC_MEL; i += DC_THREADS) {
             const int b = i / DC_MEL, k = i % DC_MEL;
             xin[b * DC_MEL + k] = step ? __ldcg(p.mel_out + ((size_t)b * p.max_steps + (step - 1)) * DC_MEL + k) : 0.f;
         }
         __syncthreads();
-        if (tid < DC_PRE) {
+        {   // layer 1: thread = (output row, half of the 80 inputs); the 40 weight loads of a thread are all in flight
+            const int r = tid & (DC_PRE - 1), half = tid >> 8;
+            float wv[DC_MEL / 2];
+#pragma unroll
+            for (int k = 0; k < DC_MEL / 2; k++) wv[k] = __ldg(p.p1T + (half * (DC_MEL / 2) + k) * DC_PRE + r);
             float acc[NB];
 #pragma unroll
             for (int b = 0; b < NB; b++) acc[b] = 0.f;
-            for (int k = 0; k < DC_MEL; k++) {
-                const float w = __ldg(p.p1T + k * DC_PRE + tid);
 #pragma unroll
-                for (int b = 0; b < NB; b++) acc[b] = fmaf(w, xin[b * DC_MEL + k], acc[b]);
+            for (int k = 0; k < DC_MEL / 2; k++) {
+#pragma unroll
+                for (int b = 0; b < NB; b++) acc[b] = fmaf(wv[k], xin[b * DC_MEL + half * (DC_MEL / 2) + k], acc[b]);
             }
+            if (half) {
 #pragma unroll
-            for (int b = 0; b < NB; b++)
-                if (b < nb) x1[b * DC_PRE + tid] = fmaxf(acc[b], 0.f) * keep_scale(p, b, step, 0, tid);
+                for (int b = 0; b < NB; b++) x2s[b * DC_PRE + r] = acc[b];   // x2s is free until stage A2
+            }
+            __syncthreads();
+            if (!half) {
+#pragma unroll
+                for (int b = 0; b < NB; b++)
+                    if (b < nb) x1[b * DC_PRE + r] = fmaxf(acc[b] + x2s[b * DC_PRE + r], 0.f) * keep_scale(p, b, step, 0, r);
+            }
         }
         __syncthreads();
-        for (int r = cta + G * warp; r < DC_PRE; r += G * (DC_THREADS / 32)) {
+        for (int r = cta + G * warp; r < DC_PRE; r += G * WARPS) {
             float acc[NB];
 #pragma unroll
             for (int b = 0; b < NB; b++) acc[b] = 0.f;
@@ -208,39 +270,41 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
                     if (b < nb) p.x2[b * DC_PRE + r] = fmaxf(acc[b], 0.f) * keep_scale(p, b, step, 1, r);
             }
         }
-        grid_barrier(p.barrier, epoch, G);
+        bar_arrive(p.barrier);
+        if (step) lstm_partial<NB, 4>(p.Wa, DC_ZA, DC_ENC + DC_RNN / 2, zA + DC_ENC + DC_RNN / 2, ZA_LD, unit0, part_a, nullptr);
+        bar_wait(p.barrier, epoch, G);
 
-        // ================= stage A2: attention LSTM, prenet columns + cell update
-        for (int i = tid; i < nb * DC_PRE; i += DC_THREADS) zs[(i / DC_PRE) * ZLD + i % DC_PRE] = __ldcg(p.x2 + i);
+        // ================= stage A2: attention LSTM, prenet columns + cell update  ||  decoder LSTM, second half of h_dec columns
+        for (int i = tid; i < nb * DC_PRE; i += DC_THREADS) x2s[i] = __ldcg(p.x2 + i);
         __syncthreads();
-        lstm_partial<NB>(p.Wa, DC_ZA, DC_ENC + DC_RNN, DC_PRE, zs, ZLD, unit0, part_a, nullptr);
+        lstm_partial<NB, 2>(p.Wa, DC_ZA, DC_ENC + DC_RNN, x2s, DC_PRE, unit0, part_a, nullptr);
         __syncthreads();
         lstm_cell<NB>(part_a, cst_a, unit0, nb, p.h_a + (size_t)nxt * nb * DC_RNN);
-        grid_barrier(p.barrier, epoch, G);
+        bar_arrive(p.barrier);
+        if (step) lstm_partial<NB, 4>(p.Wd, DC_ZD, DC_RNN + DC_RNN / 2, zD + DC_RNN + DC_RNN / 2, ZD_LD, unit0, part_d, nullptr);
+        bar_wait(p.barrier, epoch, G);
 
-        // ================= stage Q: query rows + decoder LSTM over [h_att | h_dec]
-        for (int i = tid; i < nb * DC_RNN; i += DC_THREADS) {
-            const int b = i / DC_RNN, k = i % DC_RNN;
-            zs[b * ZLD + k] = __ldcg(p.h_a + (size_t)nxt * nb * DC_RNN + i);
-            zs[b * ZLD + DC_RNN + k] = __ldcg(p.h_d + (size_t)cur * nb * DC_RNN + i);
-        }
+        // ================= stage Q: query rows  ||  decoder LSTM, h_att columns [0, 384)
+        for (int i = tid; i < nb * DC_RNN; i += DC_THREADS)
+            zD[(i / DC_RNN) * ZD_LD + i % DC_RNN] = __ldcg(p.h_a + (size_t)nxt * nb * DC_RNN + i);
         __syncthreads();
         if (warp == LIGHT_WARP && cta < DC_ATT) {
             float acc[NB];
 #pragma unroll
             for (int b = 0; b < NB; b++) acc[b] = 0.f;
-            row_dot<NB>(p.Wq + (size_t)cta * DC_RNN, zs, ZLD, DC_RNN, acc);
+            row_dot<NB>(p.Wq + (size_t)cta * DC_RNN, zD, ZD_LD, DC_RNN, acc);
             if (lane == 0) {
 #pragma unroll
                 for (int b = 0; b < NB; b++)
                     if (b < nb) p.pq[b * DC_ATT + cta] = acc[b];
             }
         }
-        lstm_partial<NB>(p.Wd, DC_ZD, 0, 2 * DC_RNN, zs, ZLD, unit0, part_d, p.bd);
-        grid_barrier(p.barrier, epoch, G);
+        bar_arrive(p.barrier);
+        lstm_partial<NB, 3>(p.Wd, DC_ZD, 0, zD, ZD_LD, unit0, part_d, nullptr);
+        bar_wait(p.barrier, epoch, G);
 
-        // ================= stage E: energies e[b][t] = v . tanh(pq + Weff * [w; w_cum](t-15..t+15) + pm[t])
-        for (int item = cta * (DC_THREADS / 32) + warp; item < nb * t_enc; item += G * (DC_THREADS / 32)) {
+        // ================= stage E: energies e[b][t] = v . tanh(pq + Weff * [w; w_cum](t-15..t+15) + pm[t])  ||  h_att columns [384, 768)
+        for (int item = cta + G * warp; item < nb * t_enc; item += G * WARPS) {
             const int b = item / t_enc, t = item % t_enc;
             if (t >= p.t_len[b]) continue;
             const float* w0 = wpad + (b * 2 + 0) * wld + t;   // padded by 15 on both sides: index t <-> position t - 15
@@ -263,9 +327,11 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
             for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (lane == 0) p.e[b * t_enc + t] = s;
         }
-        grid_barrier(p.barrier, epoch, G);
+        bar_arrive(p.barrier);
+        lstm_partial<NB, 3>(p.Wd, DC_ZD, 384, zD + 384, ZD_LD, unit0, part_d, nullptr);
+        bar_wait(p.barrier, epoch, G);
 
-        // ================= stage C: softmax (every CTA keeps w / w_cum itself) + context chunks
+        // ================= stage C: softmax (every CTA keeps w / w_cum itself) + context chunks  ||  h_att columns [768, 1024)
         if (warp < nb) {
             const int b = warp, tl = p.t_len[b];
             float ev[DC_MAX_TENC / 32];
@@ -299,40 +365,55 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
             }
         }
         __syncthreads();
-        for (int item = cta + G * warp; item < nb * (DC_ENC / 32); item += G * (DC_THREADS / 32)) {
-            const int b = item / (DC_ENC / 32), d = (item % (DC_ENC / 32)) * 32 + lane, tl = p.t_len[b];
-            const float* mp = p.memory + (size_t)b * t_enc * DC_ENC + d;
-            float acc = 0.f;
-            for (int t = 0; t < tl; t++) acc = fmaf(wnew[b * t_enc + t], __ldg(mp + (size_t)t * DC_ENC), acc);
-            p.ctx[b * DC_ENC + d] = acc;   // read by every CTA after the barrier
+        {   // context: a CTA owns 32 dims of one utterance (lane = dim); its 16 warps split the encoder positions
+            // (t = warp, warp + 16, ...: independent loads, all in flight), then the 16 partial sums are added in warp
+            // order -- the same summation order whatever the batch, so a batch returns the bits of single calls
+            float* scratch = x1;   // [WARPS][32], free in this stage
+            for (int item = cta; item < nb * (DC_ENC / 32); item += G) {
+                const int b = item / (DC_ENC / 32), d0 = (item % (DC_ENC / 32)) * 32, tl = p.t_len[b];
+                const float* mp = p.memory + (size_t)b * t_enc * DC_ENC + d0 + lane;
+                float acc = 0.f;
+#pragma unroll 8
+                for (int t = warp; t < tl; t += WARPS) acc = fmaf(wnew[b * t_enc + t], __ldg(mp + (size_t)t * DC_ENC), acc);
+                scratch[warp * 32 + lane] = acc;
+                __syncthreads();
+                if (tid < 32) {
+                    float sum = 0.f;
+#pragma unroll
+                    for (int w = 0; w < WARPS; w++) sum += scratch[w * 32 + tid];
+                    p.ctx[b * DC_ENC + d0 + tid] = sum;   // read by every CTA after the barrier
+                }
+                __syncthreads();
+            }
         }
-        grid_barrier(p.barrier, epoch, G);
+        bar_arrive(p.barrier);
+        lstm_partial<NB, 2>(p.Wd, DC_ZD, 768, zD + 768, ZD_LD, unit0, part_d, nullptr);
+        bar_wait(p.barrier, epoch, G);
 
-        // ================= stage D2: decoder LSTM, context columns + cell update
-        for (int i = tid; i < nb * DC_ENC; i += DC_THREADS)
-            zs[(i / DC_ENC) * ZLD + 2 * DC_RNN + i % DC_ENC] = __ldcg(p.ctx + i);
+        // ================= stage D2: decoder LSTM, context columns + cell update  ||  attention LSTM of the NEXT step, context columns
+        for (int i = tid; i < nb * DC_ENC; i += DC_THREADS) zA[(i / DC_ENC) * ZA_LD + i % DC_ENC] = __ldcg(p.ctx + i);
+        for (int i = tid; i < nb * DC_RNN; i += DC_THREADS)
+            zA[(i / DC_RNN) * ZA_LD + DC_ENC + i % DC_RNN] = zD[(i / DC_RNN) * ZD_LD + i % DC_RNN];   // h_att of this step
         __syncthreads();
-        lstm_partial<NB>(p.Wd, DC_ZD, 2 * DC_RNN, DC_ENC, zs + 2 * DC_RNN, ZLD, unit0, part_d, nullptr);
+        lstm_partial<NB, 4>(p.Wd, DC_ZD, 2 * DC_RNN, zA, ZA_LD, unit0, part_d, nullptr);
         __syncthreads();
         lstm_cell<NB>(part_d, cst_d, unit0, nb, p.h_d + (size_t)nxt * nb * DC_RNN);
-        grid_barrier(p.barrier, epoch, G);
+        bar_arrive(p.barrier);
+        lstm_partial<NB, 4>(p.Wa, DC_ZA, 0, zA, ZA_LD, unit0, part_a, p.ba);
+        bar_wait(p.barrier, epoch, G);
 
-        // ================= stage R: projection + gate rows, and A1 of the next step
-        // zs: [0, 512) ctx | [512, 1536) h_att (new) | [1536, 2560) h_dec (new)
-        for (int i = tid; i < nb * DC_ENC; i += DC_THREADS) zs[(i / DC_ENC) * ZLD + i % DC_ENC] = __ldcg(p.ctx + i);
-        for (int i = tid; i < nb * DC_RNN; i += DC_THREADS) {
-            const int b = i / DC_RNN, k = i % DC_RNN;
-            zs[b * ZLD + DC_ENC + k] = __ldcg(p.h_a + (size_t)nxt * nb * DC_RNN + i);
-            zs[b * ZLD + DC_ENC + DC_RNN + k] = __ldcg(p.h_d + (size_t)nxt * nb * DC_RNN + i);
-        }
+        // ================= stage R: projection + gate rows  ||  next step: attention LSTM h_att columns (first half),
+        //                   decoder LSTM h_dec columns (first half)
+        for (int i = tid; i < nb * DC_RNN; i += DC_THREADS)
+            zD[(i / DC_RNN) * ZD_LD + DC_RNN + i % DC_RNN] = __ldcg(p.h_d + (size_t)nxt * nb * DC_RNN + i);
         __syncthreads();
         if (warp == LIGHT_WARP && cta <= DC_MEL) {
             float acc[NB];
 #pragma unroll
             for (int b = 0; b < NB; b++) acc[b] = 0.f;
             const float* wrow = p.Wp + (size_t)cta * DC_ZP;              // columns [ctx | h_dec]
-            row_dot<NB>(wrow, zs, ZLD, DC_ENC, acc);
-            row_dot<NB>(wrow + DC_ENC, zs + DC_ENC + DC_RNN, ZLD, DC_RNN, acc);
+            row_dot<NB>(wrow, zA, ZA_LD, DC_ENC, acc);
+            row_dot<NB>(wrow + DC_ENC, zD + DC_RNN, ZD_LD, DC_RNN, acc);
             if (lane == 0) {
                 const float bias = p.bp[cta];
 #pragma unroll
@@ -343,8 +424,10 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
                 }
             }
         }
-        lstm_partial<NB>(p.Wa, DC_ZA, 0, DC_ENC + DC_RNN, zs, ZLD, unit0, part_a, p.ba);
-        grid_barrier(p.barrier, epoch, G);
+        bar_arrive(p.barrier);
+        lstm_partial<NB, 4>(p.Wa, DC_ZA, DC_ENC, zA + DC_ENC, ZA_LD, unit0, part_a, nullptr);
+        lstm_partial<NB, 4>(p.Wd, DC_ZD, DC_RNN, zD + DC_RNN, ZD_LD, unit0, part_d, p.bd);
+        bar_wait(p.barrier, epoch, G);
 
         // ================= stop rule (src/tacotron2/mod.rs:319-324): every CTA takes the same decision
         bool all = true;
