@@ -32,4 +32,15 @@ for n_fft, ts in ((1024, [37, 4, 150]), (2048, [21, 9]), (512, [30])):
         post = tacotron2.Postnet.from_layers(layers)
         w = tacotron2.infer_tail_batch(post, voc, mels)
         assert all(np.isfinite(x).all() for x in w)
+        pipe = voc.pipe(ts, depth=2, postnet=post)
+        got = [r for r in (pipe.push(mels) for _ in range(3)) if r is not None] + pipe.flush()
+        assert len(got) == 3 and all(np.array_equal(a, b) for a, b in zip(got[0], w))
+        pipe.close()
+# decoder loop: batch of 3 (template NB = 4), 6 steps, spin barriers under the sanitizer are slow but finite
+from oracle import decoder_oracle as d  # noqa: E402
+
+dec = tacotron2.Decoder.from_weights(d.synth_weights(11), gate_threshold=0.999999, max_steps=6, seed=1)
+enc = [d.synth_encoder_outputs(40 + i, 20) for i in range(3)]
+out = dec.run_batch([m for m, _ in enc], [p for _, p in enc], [20, 17, 11])
+assert all(x.shape == (80, 6) and np.isfinite(x).all() for x in out)
 print("sanitize target ok")

@@ -20,5 +20,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:gl_i
     python tools/prof_target.py cfg5 1 > $out/prof_cfg5.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:pn_conv_tc -s 1 -c 2 -f -o $out/prof_postnet_cfg3 \
     python tools/prof_postnet.py 1 0 > $out/prof_postnet.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:dec_persist -c 1 -f -o $out/prof_decoder_b1 \
+    python tools/prof_decoder.py 1 300 > $out/prof_decoder.log 2>&1
 timeout 900 compute-sanitizer --tool memcheck python tests/gpu_tools/sanitize_target.py > $out/sanitizer_memcheck.log 2>&1; tail -3 $out/sanitizer_memcheck.log
 ls -la $out
