@@ -41,6 +41,13 @@ typedef struct xdtts_gl_opts {
     unsigned long long seed; /* seed of the random initial phase used when the caller passes none */
     int persistent;          /* 0: one launch per iteration, CUDA graph (default; fastest at full occupancy)
                                 1: whole vocode in one cooperative launch when the batch fits one resident wave */
+    int lift;                /* mel -> linear magnitude.  0: S = max(0, pinv(basis) . delog(mel)) ^ power (default)
+                                1: non-negative least squares as librosa's mel_to_stft does it (util.nnls: start from the
+                                   clipped least-squares solution, minimise |basis . x - delog(mel)|^2 over x >= 0), solved
+                                   per frame by accelerated projected gradient on the device; S = x ^ power */
+    int nnls_iters;          /* lift = 1: iteration cap per frame (0: 300); a frame stops early once its projected gradient
+                                falls below 3e-6 (librosa passes pgtol = 1e-5 to L-BFGS-B; 3e-6 here reaches that
+                                solver's objective, tests/test_oracle.py) */
 } xdtts_gl_opts;
 
 typedef struct xdtts_gl xdtts_gl;           /* replaces griffin_lim::GriffinLim */

@@ -120,6 +120,40 @@ def lift_nnls(mel, mel_basis, power=1.7, delog_mode=DELOG_EXP, maxiter=15000):
     return np.power(x.reshape(shape), power)
 
 
+def lift_nnls_fista(mel, mel_basis, power=1.7, delog_mode=DELOG_EXP, max_iter=300, pgtol=3e-6, dtype=np.float64):
+    """The device's NNLS lift (xdtts_gl_opts.lift = 1), restated: librosa's `nnls` problem -- minimise
+    0.5 |A x - b|^2 over x >= 0 from x0 = clip(pinv(A) b) -- solved per frame by accelerated projected
+    gradient (FISTA, step 1/L, L = 1.001 sigma_max(A)^2, gradient restart), at most max_iter iterations, a
+    frame stops once its projected-gradient step is below pgtol / L.  Returns (x ** power, iterations used)."""
+    a = np.asarray(mel_basis, dtype=dtype)
+    b = delog(mel, delog_mode, np.float32).astype(dtype)
+    big_l = dtype(np.linalg.norm(np.asarray(mel_basis, np.float64), 2) ** 2 * 1.001)
+    x = np.maximum(pinv_basis(mel_basis).astype(dtype) @ b, 0)
+    y = x.copy()
+    n = x.shape[1]
+    tk = np.ones(n, dtype)
+    active = np.ones(n, bool)
+    used = np.zeros(n, int)
+    for _ in range(max_iter):
+        if not active.any():
+            break
+        idx = np.where(active)[0]
+        ya, xa = y[:, idx], x[:, idx]
+        g = a.T @ (a @ ya - b[:, idx])
+        xn = np.maximum(ya - g / big_l, 0)
+        dot = (g * (xn - xa)).sum(0)
+        step = np.abs(xn - ya).max(0)
+        restart = dot > 0
+        tn = (1 + np.sqrt(1 + 4 * tk[idx] ** 2)) / 2
+        beta = np.where(restart, 0, (tk[idx] - 1) / tn)
+        tk[idx] = np.where(restart, 1, tn)
+        y[:, idx] = xn + beta * (xn - xa)
+        x[:, idx] = xn
+        used[idx] += 1
+        active[idx[step < pgtol / big_l]] = False
+    return np.power(x, dtype(power)).astype(dtype), used
+
+
 # ----------------------------------------------------------------------------
 # STFT / ISTFT -- librosa 0.9.2 semantics (SURVEY.md appendix B)
 # ----------------------------------------------------------------------------

@@ -318,3 +318,47 @@ def test_persistent_kernel_equals_per_iteration_launches_bitwise(gl):
         plan.run(_ffi.RUN_USE_PHASE)               # and again: flags / counters are reusable
         for x, y in zip(plan.download(), a):
             assert np.array_equal(x, y)
+
+
+def test_nnls_lift_matches_oracle(gl):
+    """xdtts_gl_opts.lift = 1 (librosa's mel_to_stft problem, accelerated projected gradient per frame) against the
+    numpy restatement of the same recurrence, fp32 device vs fp64 oracle.  The recurrence has kinks (max(0, .),
+    restarts), so bins that are weakly determined by the mel may drift; what is compared tightly is what the mel
+    does determine -- the filterbank image basis . x -- and the objective."""
+    basis = basis_for(1024)
+    a = basis.astype(np.float64)
+    ts = [37, 5, 64]
+    mels = [o.synth_mel(50 + i, 80, t) for i, t in enumerate(ts)]
+    mels[2] = np.log(np.maximum(a @ o.synth_speech_like_mag(9, 1024, 256, 64).astype(np.float64), 1e-5)).astype(np.float32)
+    voc = gl.GriffinLim.new(basis, 768, 1.0, 0, 0.99, lift=gl.LIFT_NNLS, nnls_iters=150)
+    plan = voc.plan(ts)
+    plan.upload(0, mels)
+    plan.run(0)
+    s = plan.peek(0)
+    s_nyq = plan.peek(1)
+    off = 0
+    for mel, t in zip(mels, ts):
+        x_gpu = np.concatenate([s[off:off + t].T, s_nyq[None, off:off + t]]).astype(np.float64)     # [K, t]
+        off += t
+        x_ref, _ = o.lift_nnls_fista(mel, basis, power=1.0, max_iter=150)
+        x0 = o.lift_pinv_clamp(mel, basis, power=1.0, dtype=np.float64)
+        b = np.exp(mel.astype(np.float32)).astype(np.float64)
+        f = lambda x: 0.5 * ((a @ x - b) ** 2).sum(0)   # noqa: E731
+        assert (x_gpu >= 0).all() and np.isfinite(x_gpu).all()
+        assert np.all(f(x_gpu) <= f(x_ref) * 1.01 + 1e-9 * (b ** 2).sum(0))
+        assert np.all(f(x_gpu) <= f(x0) * (1 + 1e-5) + 1e-12)
+        img_err = np.abs(a @ x_gpu - a @ x_ref).max() / np.abs(a @ x_ref).max()
+        assert img_err < 2e-4, img_err
+        assert np.linalg.norm(x_gpu - x_ref) / np.linalg.norm(x_ref) < 2e-2
+    # the exponent is applied after the solve; end to end the vocoder accepts the option
+    voc17 = gl.GriffinLim.new(basis, 768, 1.7, 4, 0.99, lift=gl.LIFT_NNLS, nnls_iters=150)
+    phs = [o.phase_turns(3, i, 513, t) for i, t in enumerate(ts)]
+    ys = voc17.infer_batch(mels, phs)
+    for y, mel, ph in zip(ys, mels, phs):
+        x_ref, _ = o.lift_nnls_fista(mel, basis, power=1.7, max_iter=150)
+        ref = o.peak_normalise(o.griffin_lim(x_ref.astype(np.float32), ph, 4, 0.99, 1024, 256, dtype=np.float64))
+        assert float(np.sqrt(np.mean((y - ref) ** 2))) < 2e-3
+    # lift = 0 is unchanged by the new option
+    voc0 = gl.GriffinLim.new(basis, 768, 1.7, 4, 0.99)
+    y0 = voc0.infer_batch(mels, phs)
+    assert not np.array_equal(y0[0], ys[0])

@@ -165,3 +165,20 @@ def test_decoder_oracle_matches_torch_fixture(golden_dir):
     k = np.stack([d.dropout_keep(1, 0, i) for i in range(50)])
     assert 0.45 < k.mean() < 0.55 and not np.array_equal(k[0], k[1])
     assert np.array_equal(d.dropout_keep(1, 0, 7), k[7]) and not np.array_equal(d.dropout_keep(1, 1, 7), k[7])
+
+
+def test_nnls_fista_lift_solves_librosas_problem():
+    """The restated device algorithm (FISTA with restart) reaches the objective of librosa's own solver
+    (lstsq start -> clip -> L-BFGS-B, oracle lift_nnls) on the same non-negative least-squares problem; the
+    minimiser itself is not unique (80 equations, 513 unknowns), so the comparison is on the mel residual."""
+    basis = o.create_mel_filter_bank(22050.0, 1024, 80, 0.0, 8000.0)
+    a = basis.astype(np.float64)
+    for mel in (o.synth_mel(1234, 80, 6), np.log(np.maximum(a @ o.synth_speech_like_mag(5, 1024, 256, 6).astype(np.float64), 1e-5)).astype(np.float32)):
+        b = np.exp(mel.astype(np.float32)).astype(np.float64)
+        x_f, used = o.lift_nnls_fista(mel, basis, power=1.0, max_iter=400)
+        x_l = o.lift_nnls(mel, basis, power=1.0)
+        x_p = o.lift_pinv_clamp(mel, basis, power=1.0, dtype=np.float64)
+        f = lambda x: 0.5 * ((a @ x - b) ** 2).sum(0)   # noqa: E731
+        assert (x_f >= 0).all() and used.max() <= 400
+        assert np.all(f(x_f) <= f(x_l) * 1.005 + 1e-8 * (b ** 2).sum(0))   # as good as L-BFGS-B at librosa's tolerances
+        assert np.all(f(x_f) <= f(x_p) + 1e-15)                 # and never worse than the clipped pseudo-inverse start

@@ -22,6 +22,8 @@
 namespace xdtts {
 cudaError_t gl_launch_lift(const float*, const float*, const int*, const int*, int, int, int, int, float, int, float*,
                            float*, cudaStream_t);
+cudaError_t gl_launch_nnls(const float*, const int*, const float*, const int*, const float*, const int*, const int*, int, int, int,
+                           int, float, int, float, int, float, float*, float*, cudaStream_t);
 cudaError_t gl_launch_to_frame_major(const float*, const int*, const int*, int, int, int, float*, float*, cudaStream_t);
 cudaError_t gl_launch_finish(const float*, const int*, const int*, const long long*, const unsigned*, int, int, int, int,
                              float*, cudaStream_t);
@@ -203,7 +205,8 @@ extern "C" int xdtts_gl_create(const float* mel_basis, int n_mels, int K, int no
     for (size_t i = 0; i < (size_t)n_mels * K; i++)
         if (!std::isfinite(mel_basis[i])) return fail(XDTTS_ERR_BAD_ARG, "gl_create: mel_basis has a non-finite entry");
     if (opts && (opts->delog < 0 || opts->delog > 2 || opts->pad_mode < 0 || opts->pad_mode > 1 || opts->normalise < 0 ||
-                 opts->normalise > 1 || opts->run_frames < 0 || opts->persistent < 0 || opts->persistent > 1))
+                 opts->normalise > 1 || opts->run_frames < 0 || opts->persistent < 0 || opts->persistent > 1 || opts->lift < 0 ||
+                 opts->lift > 1 || opts->nnls_iters < 0))
         return fail(XDTTS_ERR_BAD_ARG, "gl_create: option out of range");
 
     int n_dev = 0;
@@ -233,12 +236,59 @@ extern "C" int xdtts_gl_create(const float* mel_basis, int n_mels, int K, int no
             h->pinv[(size_t)k * n_mels + m] = v;
             pT[(size_t)m * K + k] = v;
         }
+    // sparse forms of the basis + its largest singular value squared (power iteration on A A^T, fp64) for the NNLS lift
+    std::vector<int> csr(n_mels + 1, 0), csc(K + 1, 0);
+    std::vector<float> csr_val, csc_val;
+    for (int m = 0; m < n_mels; m++) {
+        for (int k = 0; k < K; k++)
+            if (mel_basis[(size_t)m * K + k] != 0.f) { csr.push_back(k); csr_val.push_back(mel_basis[(size_t)m * K + k]); }
+        csr[m + 1] = (int)csr_val.size();
+    }
+    for (int k = 0; k < K; k++) {
+        for (int m = 0; m < n_mels; m++)
+            if (mel_basis[(size_t)m * K + k] != 0.f) { csc.push_back(m); csc_val.push_back(mel_basis[(size_t)m * K + k]); }
+        csc[k + 1] = (int)csc_val.size();
+    }
+    {   // row_ptr / col_ptr were reserved at the front; the indices follow them
+        std::vector<int> rp(csr.begin(), csr.begin() + n_mels + 1), ri(csr.begin() + n_mels + 1, csr.end());
+        std::vector<double> v(n_mels, 1.0), w(K), v2(n_mels);
+        double lam = 0.0;
+        for (int it = 0; it < 300; it++) {
+            for (int k = 0; k < K; k++) w[k] = 0.0;
+            for (int m = 0; m < n_mels; m++)
+                for (int p = rp[m]; p < rp[m + 1]; p++) w[ri[p]] += (double)csr_val[p] * v[m];
+            double nrm = 0.0;
+            for (int m = 0; m < n_mels; m++) {
+                double a = 0.0;
+                for (int p = rp[m]; p < rp[m + 1]; p++) a += (double)csr_val[p] * w[ri[p]];
+                v2[m] = a;
+                nrm += a * a;
+            }
+            nrm = std::sqrt(nrm);
+            if (!(nrm > 0.0)) break;
+            lam = nrm;
+            for (int m = 0; m < n_mels; m++) v[m] = v2[m] / nrm;
+        }
+        h->lipschitz = (float)(lam * 1.001);   // small margin above the estimate keeps the step a descent step
+    }
+    if (h->opts.lift == 1 && !(h->lipschitz > 0.f)) {
+        delete h;
+        return fail(XDTTS_ERR_BAD_ARG, "gl_create: the NNLS lift needs a non-zero mel basis");
+    }
     std::vector<float2> tab = n_fft == 512 ? build_tables<4>() : (n_fft == 1024 ? build_tables<8>() : build_tables<16>());
     std::vector<float> edge = build_edge_scale(n_fft);
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = cudaMalloc(&h->d_pinvT, pT.size() * 4);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_tables, tab.size() * sizeof(float2));
     if (e == cudaSuccess) e = cudaMalloc(&h->d_edge, edge.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_csr, csr.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_csc, csc.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_csr_val, (csr_val.size() + 1) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_csc_val, (csc_val.size() + 1) * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_csr, csr.data(), csr.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_csc, csc.data(), csc.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !csr_val.empty()) e = cudaMemcpy(h->d_csr_val, csr_val.data(), csr_val.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !csc_val.empty()) e = cudaMemcpy(h->d_csc_val, csc_val.data(), csc_val.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_pinvT, pT.data(), pT.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_tables, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_edge, edge.data(), edge.size() * 4, cudaMemcpyHostToDevice);
@@ -259,6 +309,7 @@ extern "C" void xdtts_gl_destroy(xdtts_gl* h) {
     cudaFree(h->d_pinvT);
     cudaFree(h->d_tables);
     cudaFree(h->d_edge);
+    cudaFree(h->d_csr); cudaFree(h->d_csc); cudaFree(h->d_csr_val); cudaFree(h->d_csc_val);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -448,7 +499,14 @@ static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid, cud
     if (from_mag) {
         CU(gl_launch_to_frame_major(p->d_in_mag, p->d_T, p->d_foff, p->B, p->max_T, h->K, p->d_S, p->d_S_nyq, s));
     } else {
-        CU(gl_launch_lift(p->d_mel, h->d_pinvT, p->d_T, p->d_foff, p->B, p->max_T, h->n_mels, h->K, h->power, h->opts.delog, p->d_S, p->d_S_nyq, s));
+        const bool nnls = h->opts.lift == 1;
+        CU(gl_launch_lift(p->d_mel, h->d_pinvT, p->d_T, p->d_foff, p->B, p->max_T, h->n_mels, h->K, nnls ? 1.0f : h->power, h->opts.delog, p->d_S, p->d_S_nyq, s));
+        if (nnls) {   // refine the clipped least-squares start in place, then apply the exponent
+            CU(gl_launch_nnls(p->d_mel, h->d_csr, h->d_csr_val, h->d_csc, h->d_csc_val, p->d_T, p->d_foff, p->B, p->max_T, h->n_mels,
+                              h->K, h->power, h->opts.delog, h->lipschitz, h->opts.nnls_iters > 0 ? h->opts.nnls_iters : 300, 3e-6f,
+                              p->d_S, p->d_S_nyq, s));
+            g_launches++;
+        }
     }
     g_launches++;
     if (use_phase) {

@@ -45,6 +45,9 @@ struct xdtts_gl {
     float* d_pinvT = nullptr;       // [n_mels][K]
     float2* d_tables = nullptr;
     float* d_edge = nullptr;
+    int *d_csr = nullptr, *d_csc = nullptr;        // sparse forms of the mel basis for the NNLS lift (rows / columns)
+    float *d_csr_val = nullptr, *d_csc_val = nullptr;
+    float lipschitz = 0.f;                          // sigma_max(basis)^2
     cudaStream_t stream = nullptr;
     std::mutex mu;
     std::vector<xdtts_gl_plan*> cache;   // plans owned by the batch entry points

@@ -78,6 +78,132 @@ cudaError_t gl_launch_lift(const float* mel_arena, const float* pinvT, const int
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- NNLS lift
+// The crate behind griffin_lim::GriffinLim::infer ports librosa, whose mel -> linear step is
+// `nnls(mel_basis, mel)`: start from the clipped least-squares solution and minimise
+// 0.5 |A x - b|^2 over x >= 0 (librosa.util.nnls).  librosa hands that to L-BFGS-B; the
+// minimiser is not unique (80 equations, 513 unknowns), so there is no trajectory to be bit-faithful to -- what is
+// defined is the optimisation problem and its starting point.  Here every frame is solved by accelerated
+// projected gradient (FISTA, step 1/L with L = sigma_max(A)^2, gradient-based adaptive restart), a fixed,
+// deterministic recurrence: one warp per frame, x and the extrapolated point y in registers (bin k = lane + 32 j),
+// the mel residual in shared memory.  A is used in both sparse forms (rows for A y, columns for A^T r): a mel
+// filterbank has <= 2 non-zeros per column, so an iteration costs ~1.5 k multiply-adds instead of 82 k.
+// In: S / S_nyq hold x0 = max(0, pinv(A) b) (gl_lift_kernel with power 1).  Out: S = x^power, in place.
+struct NnlsMat {
+    const int* row_ptr;    // [n_mels + 1]
+    const int* row_col;    // [nnz] bin of each non-zero, row by row
+    const float* row_val;
+    const int* col_ptr;    // [K + 1]
+    const int* col_row;    // [nnz] mel row of each non-zero, column by column
+    const float* col_val;
+};
+
+template <int KJ>
+__global__ void __launch_bounds__(128) gl_nnls_kernel(const float* __restrict__ mel_arena, NnlsMat A, const int* __restrict__ utt_T,
+                                                      const int* __restrict__ utt_foff, int n_mels, int K, float power, int delog,
+                                                      float inv_L, int max_iter, float pgtol_over_L, float* __restrict__ S,
+                                                      float* __restrict__ S_nyq) {
+    extern __shared__ __align__(16) float nn_sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int u = blockIdx.y, T = utt_T[u], t = blockIdx.x * 4 + warp;
+    const int M = K - 1, kpad = 32 * KJ;
+    if (t >= T) return;
+    const long foff = utt_foff[u];
+    float* ys = nn_sm + warp * (kpad + 2 * LIFT_MAX_MELS);   // [kpad] extrapolated point
+    float* rs = ys + kpad;                                   // [n_mels] residual A y - b
+    float* bs = rs + LIFT_MAX_MELS;                          // [n_mels] de-logged mel frame
+    const float* mel = mel_arena + foff * n_mels;
+    for (int m = lane; m < n_mels; m += 32) {
+        const float v = mel[(long)m * T + t];
+        bs[m] = delog == 0 ? expf(v) : (delog == 1 ? powf(10.f, v) : v);
+    }
+    float x[KJ], y[KJ];
+    const long frame = foff + t;
+#pragma unroll
+    for (int j = 0; j < KJ; j++) {
+        const int k = lane + 32 * j;
+        x[j] = k < M ? S[frame * M + k] : (k == M ? S_nyq[frame] : 0.f);
+        y[j] = x[j];
+    }
+    float tk = 1.f;
+    for (int it = 0; it < max_iter; it++) {
+#pragma unroll
+        for (int j = 0; j < KJ; j++) ys[lane + 32 * j] = y[j];
+        __syncwarp();
+        for (int m = lane; m < n_mels; m += 32) {
+            float acc = -bs[m];
+            const int p1 = A.row_ptr[m + 1];
+            for (int p = A.row_ptr[m]; p < p1; p++) acc = fmaf(__ldg(A.row_val + p), ys[__ldg(A.row_col + p)], acc);
+            rs[m] = acc;
+        }
+        __syncwarp();
+        float dot = 0.f, step = 0.f;
+#pragma unroll
+        for (int j = 0; j < KJ; j++) {
+            const int k = lane + 32 * j;
+            if (k < K) {
+                float g = 0.f;
+                const int p1 = A.col_ptr[k + 1];
+                for (int p = A.col_ptr[k]; p < p1; p++) g = fmaf(__ldg(A.col_val + p), rs[__ldg(A.col_row + p)], g);
+                const float xn = fmaxf(y[j] - g * inv_L, 0.f);
+                dot = fmaf(g, xn - x[j], dot);
+                step = fmaxf(step, fabsf(xn - y[j]));
+                y[j] = xn;   // x[j] keeps the previous iterate until the momentum is known
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            step = fmaxf(step, __shfl_xor_sync(0xffffffffu, step, o));
+        }
+        // gradient restart (O'Donoghue & Candes): drop the momentum when it points uphill
+        float beta = 0.f;
+        if (dot > 0.f) {
+            tk = 1.f;
+        } else {
+            const float tn = 0.5f * (1.f + sqrtf(1.f + 4.f * tk * tk));
+            beta = (tk - 1.f) / tn;
+            tk = tn;
+        }
+#pragma unroll
+        for (int j = 0; j < KJ; j++) {
+            const float xn = y[j];
+            y[j] = fmaf(beta, xn - x[j], xn);
+            x[j] = xn;
+        }
+        __syncwarp();
+        if (step < pgtol_over_L) break;   // projected-gradient step below pgtol / L (warp-uniform)
+    }
+#pragma unroll
+    for (int j = 0; j < KJ; j++) {
+        const int k = lane + 32 * j;
+        const float v = x[j] > 0.f ? (power == 1.0f ? x[j] : powf(x[j], power)) : 0.f;
+        if (k < M) S[frame * M + k] = v;
+        else if (k == M) S_nyq[frame] = v;
+    }
+}
+
+cudaError_t gl_launch_nnls(const float* mel_arena, const int* csr, const float* csr_val, const int* csc, const float* csc_val,
+                           const int* utt_T, const int* utt_foff, int n_utt, int max_T, int n_mels, int K, float power, int delog,
+                           float L, int max_iter, float pgtol, float* S, float* S_nyq, cudaStream_t s) {
+    if (n_mels > LIFT_MAX_MELS) return cudaErrorInvalidValue;
+    NnlsMat A;
+    A.row_ptr = csr; A.row_col = csr + n_mels + 1; A.row_val = csr_val;
+    A.col_ptr = csc; A.col_row = csc + K + 1; A.col_val = csc_val;
+    dim3 grid((max_T + 3) / 4, n_utt);
+    const int kj = (K + 31) / 32;
+    const float inv_L = 1.0f / L, tol = pgtol / L;
+#define XD_NNLS_LAUNCH(KJ_)                                                                                                   \
+    gl_nnls_kernel<KJ_><<<grid, 128, 4 * (size_t)(32 * KJ_ + 2 * LIFT_MAX_MELS) * sizeof(float), s>>>(                          \
+        mel_arena, A, utt_T, utt_foff, n_mels, K, power, delog, inv_L, max_iter, tol, S, S_nyq)
+    if (kj <= 9) XD_NNLS_LAUNCH(9);
+    else if (kj <= 17) XD_NNLS_LAUNCH(17);
+    else if (kj <= 33) XD_NNLS_LAUNCH(33);
+    else return cudaErrorInvalidValue;
+#undef XD_NNLS_LAUNCH
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------- [K,T] -> frame-major
 // src arena: utterance u is a row-major [K][T_u] block at float offset foff[u]*K.
 __global__ void __launch_bounds__(256) gl_to_frame_major_kernel(const float* __restrict__ src_arena,

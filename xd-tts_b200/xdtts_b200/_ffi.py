@@ -47,6 +47,8 @@ class GlOpts(ctypes.Structure):
         ("run_frames", ctypes.c_int),
         ("seed", ctypes.c_ulonglong),
         ("persistent", ctypes.c_int),
+        ("lift", ctypes.c_int),
+        ("nnls_iters", ctypes.c_int),
     ]
 
 

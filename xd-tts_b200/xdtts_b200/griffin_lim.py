@@ -20,6 +20,7 @@ from ._ffi import GlOpts, XdttsError, check, fptr, fptr_array, load_library, spt
 DELOG_EXP, DELOG_POW10, DELOG_NONE = 0, 1, 2
 PAD_REFLECT, PAD_CONSTANT = 0, 1
 NORM_PEAK, NORM_NONE = 0, 1
+LIFT_PINV, LIFT_NNLS = 0, 1
 
 
 class mel:  # noqa: N801  (module-like namespace, as in griffin_lim::mel)
@@ -57,13 +58,14 @@ class GriffinLim:
 
     @classmethod
     def new(cls, mel_basis, noverlap, power, iter, momentum, *, delog=DELOG_EXP, pad_mode=PAD_REFLECT,  # noqa: A002
-            normalise=NORM_PEAK, seed=0, run_frames=0, persistent=False, device=0):
+            normalise=NORM_PEAK, seed=0, run_frames=0, persistent=False, lift=LIFT_PINV, nnls_iters=0, device=0):
         """GriffinLim::new(mel_basis, noverlap, power, iter, momentum) (src/tacotron2/mod.rs:456)."""
         lib = load_library()
         basis = np.ascontiguousarray(mel_basis, dtype=np.float32)
         if basis.ndim != 2:
             raise XdttsError(_ffi.ERR_SHAPE, "mel_basis must be 2-D [n_mels, K]")
-        opts = GlOpts(int(delog), int(pad_mode), int(normalise), int(run_frames), int(seed), int(bool(persistent)))
+        opts = GlOpts(int(delog), int(pad_mode), int(normalise), int(run_frames), int(seed), int(bool(persistent)), int(lift),
+                      int(nnls_iters))
         h = ctypes.c_void_p()
         check(lib.xdtts_gl_create(fptr(basis), basis.shape[0], basis.shape[1], int(noverlap), float(power), int(iter),
                                   float(momentum), ctypes.byref(opts), int(device), ctypes.byref(h)))
