@@ -316,7 +316,7 @@ def run_reference(args):
         "gpu_launches": 0,
         "note": "reference Rust crate (griffin-lim 0.2.0) cannot be built here (no cargo, not vendored): CPU arm is the oracle's C/OpenMP port",
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------- GPU arm
@@ -334,8 +334,6 @@ def run_gpu(args):
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line (NCCL prints its banner there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import __graft_entry__ as g
@@ -511,7 +509,7 @@ def run_gpu(args):
         if world == 1 and not args.no_cpu:
             v, cores, kind, sample, _ = cpu_arm(cfg, 1, 1)
             line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}
-        print(json.dumps(line))
+        emit(line)
     for _, p in pin_in + pin_out + pin_in2 + pin_out2:
         lib.xdtts_host_free(p)
     if dist is not None:
@@ -519,7 +517,30 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner, torchrun
+    notices), so file descriptor 1 is pointed at stderr for the whole run and the line goes to the original."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
