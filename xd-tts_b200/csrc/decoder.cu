@@ -64,57 +64,75 @@ __device__ __forceinline__ void row_dot(const float* __restrict__ wrow, const fl
     }
 }
 
-// partial gate sums of this CTA's units over weight columns [col0, col0 + 128 NC4) against the vectors that START
-// at zs (the caller offsets zs to the segment): part[r][b], r = gate * 7 + unit.  A warp owns rows r = warp and
-// warp + 16 and issues the loads of BOTH before it touches either (these products are latency-bound: a slice is
-// 2-6 float4 per lane and row, so everything that can be in flight must be).
+// The gate sums of a warp's two rows (r = warp and warp + 16; r = gate * 7 + unit), accumulated PER LANE across the
+// column slices of a step and reduced over the warp only once, when the row is complete (lstm_finish): a slice
+// costs loads and FMAs, no shuffles.  The registers live across the grid barriers of the persistent kernel.
+template <int NB>
+struct GateAcc {
+    float a0[NB], a1[NB];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int b = 0; b < NB; b++) a0[b] = a1[b] = 0.f;
+    }
+};
+
+// adds weight columns [col0, col0 + 128 NC4) times the vectors that START at zs (the caller offsets zs to the
+// segment).  The loads of BOTH rows are issued before either is used (these products are latency-bound: a slice is
+// 2-4 float4 per lane and row, so everything that can be in flight must be).  Rows past the end (last CTAs, second
+// row of warps 12..15) are clamped to a valid row and dropped in lstm_finish.
 template <int NB, int NC4>
-__device__ __forceinline__ void lstm_partial(const float* __restrict__ W, int ld, int col0, const float* zs, int zld, int unit0,
-                                             float* part, const float* __restrict__ bias_or_null) {
+__device__ __forceinline__ void lstm_partial(GateAcc<NB>& acc, const float* __restrict__ W, int ld, int col0, const float* zs,
+                                             int zld, int unit0) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int WARPS = DC_THREADS / 32;
-    // rows past the end (last CTAs, second row of warps 12..15) are clamped to a valid row and their sums dropped
     const int r0 = warp, r1 = warp + WARPS < 4 * DC_UNITS ? warp + WARPS : 4 * DC_UNITS - 1;
     const int u0 = min(unit0 + r0 % DC_UNITS, DC_RNN - 1), u1 = min(unit0 + r1 % DC_UNITS, DC_RNN - 1);
-    const int row0 = (r0 / DC_UNITS) * DC_RNN + u0, row1 = (r1 / DC_UNITS) * DC_RNN + u1;
-    const bool ok0 = unit0 + r0 % DC_UNITS < DC_RNN, ok1 = warp + WARPS < 4 * DC_UNITS && unit0 + r1 % DC_UNITS < DC_RNN;
-    const float* wr0 = W + (size_t)row0 * ld + col0 + lane * 4;
-    const float* wr1 = W + (size_t)row1 * ld + col0 + lane * 4;
+    const float* wr0 = W + (size_t)((r0 / DC_UNITS) * DC_RNN + u0) * ld + col0 + lane * 4;
+    const float* wr1 = W + (size_t)((r1 / DC_UNITS) * DC_RNN + u1) * ld + col0 + lane * 4;
     float4 w0[NC4], w1[NC4];
 #pragma unroll
     for (int c = 0; c < NC4; c++) w0[c] = __ldg(reinterpret_cast<const float4*>(wr0 + 128 * c));
 #pragma unroll
     for (int c = 0; c < NC4; c++) w1[c] = __ldg(reinterpret_cast<const float4*>(wr1 + 128 * c));
-    float a0[NB], a1[NB];
-#pragma unroll
-    for (int b = 0; b < NB; b++) a0[b] = a1[b] = 0.f;
 #pragma unroll
     for (int c = 0; c < NC4; c++) {
 #pragma unroll
         for (int b = 0; b < NB; b++) {
             const float4 z = *reinterpret_cast<const float4*>(zs + b * zld + lane * 4 + 128 * c);
-            a0[b] = fmaf(w0[c].x, z.x, fmaf(w0[c].y, z.y, fmaf(w0[c].z, z.z, fmaf(w0[c].w, z.w, a0[b]))));
-            a1[b] = fmaf(w1[c].x, z.x, fmaf(w1[c].y, z.y, fmaf(w1[c].z, z.z, fmaf(w1[c].w, z.w, a1[b]))));
+            acc.a0[b] = fmaf(w0[c].x, z.x, fmaf(w0[c].y, z.y, fmaf(w0[c].z, z.z, fmaf(w0[c].w, z.w, acc.a0[b]))));
+            acc.a1[b] = fmaf(w1[c].x, z.x, fmaf(w1[c].y, z.y, fmaf(w1[c].z, z.z, fmaf(w1[c].w, z.w, acc.a1[b]))));
         }
     }
+}
+
+// rows complete: reduce over the warp, add the bias, hand the gate sums to the cell update through shared memory
+template <int NB>
+__device__ __forceinline__ void lstm_finish(GateAcc<NB>& acc, int unit0, float* part, const float* __restrict__ bias) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int WARPS = DC_THREADS / 32;
+    const int r0 = warp, r1 = warp + WARPS < 4 * DC_UNITS ? warp + WARPS : 4 * DC_UNITS - 1;
+    const bool ok0 = unit0 + r0 % DC_UNITS < DC_RNN, ok1 = warp + WARPS < 4 * DC_UNITS && unit0 + r1 % DC_UNITS < DC_RNN;
 #pragma unroll
     for (int b = 0; b < NB; b++) {
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
-            a0[b] += __shfl_xor_sync(0xffffffffu, a0[b], o);
-            a1[b] += __shfl_xor_sync(0xffffffffu, a1[b], o);
+            acc.a0[b] += __shfl_xor_sync(0xffffffffu, acc.a0[b], o);
+            acc.a1[b] += __shfl_xor_sync(0xffffffffu, acc.a1[b], o);
         }
     }
     if (lane == 0) {
         if (ok0) {
+            const float bv = bias[(r0 / DC_UNITS) * DC_RNN + unit0 + r0 % DC_UNITS];
 #pragma unroll
-            for (int b = 0; b < NB; b++) part[r0 * NB + b] = (bias_or_null ? bias_or_null[row0] : part[r0 * NB + b]) + a0[b];
+            for (int b = 0; b < NB; b++) part[r0 * NB + b] = bv + acc.a0[b];
         }
         if (ok1) {
+            const float bv = bias[(r1 / DC_UNITS) * DC_RNN + unit0 + r1 % DC_UNITS];
 #pragma unroll
-            for (int b = 0; b < NB; b++) part[r1 * NB + b] = (bias_or_null ? bias_or_null[row1] : part[r1 * NB + b]) + a1[b];
+            for (int b = 0; b < NB; b++) part[r1 * NB + b] = bv + acc.a1[b];
         }
     }
+    acc.clear();
 }
 
 // LSTM cell update of this CTA's units from the finished gate sums; h goes to global memory
@@ -215,12 +233,9 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
     for (int i = tid; i < NB * 2 * wld; i += DC_THREADS) wpad[i] = 0.f;
     for (int i = tid; i < NB * (ZA_LD + ZD_LD); i += DC_THREADS) zA[i] = 0.f;   // zA and zD are adjacent
     for (int i = tid; i < DC_UNITS * NB; i += DC_THREADS) { cst_a[i] = 0.f; cst_d[i] = 0.f; }
-    for (int i = tid; i < 4 * DC_UNITS * NB; i += DC_THREADS) {   // zero state: the streamed-ahead columns give the bias
-        const int r = i / NB, unit = unit0 + r % DC_UNITS;
-        const int row = (r / DC_UNITS) * DC_RNN + unit;
-        part_a[i] = unit < DC_RNN ? p.ba[row] : 0.f;
-        part_d[i] = unit < DC_RNN ? p.bd[row] : 0.f;
-    }
+    GateAcc<NB> acc_a, acc_d;   // zero state: the columns streamed ahead of step 0 contribute nothing
+    acc_a.clear();
+    acc_d.clear();
     bool done[NB];
 #pragma unroll
     for (int b = 0; b < NB; b++) done[b] = b >= nb;
@@ -272,17 +287,18 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
             }
         }
         bar_arrive(p.barrier);
-        if (step) lstm_partial<NB, 4>(p.Wa, DC_ZA, DC_ENC + DC_RNN / 2, zA + DC_ENC + DC_RNN / 2, ZA_LD, unit0, part_a, nullptr);
+        if (step) lstm_partial<NB, 4>(acc_a, p.Wa, DC_ZA, DC_ENC + DC_RNN / 2, zA + DC_ENC + DC_RNN / 2, ZA_LD, unit0);
         bar_wait(p.barrier, epoch, G);
 
         // ================= stage A2: attention LSTM, prenet columns + cell update  ||  decoder LSTM, second half of h_dec columns
         for (int i = tid; i < nb * DC_PRE; i += DC_THREADS) x2s[i] = __ldcg(p.x2 + i);
         __syncthreads();
-        lstm_partial<NB, 2>(p.Wa, DC_ZA, DC_ENC + DC_RNN, x2s, DC_PRE, unit0, part_a, nullptr);
+        lstm_partial<NB, 2>(acc_a, p.Wa, DC_ZA, DC_ENC + DC_RNN, x2s, DC_PRE, unit0);
+        lstm_finish<NB>(acc_a, unit0, part_a, p.ba);
         __syncthreads();
         lstm_cell<NB>(part_a, cst_a, unit0, nb, p.h_a + (size_t)nxt * nb * DC_RNN);
         bar_arrive(p.barrier);
-        if (step) lstm_partial<NB, 4>(p.Wd, DC_ZD, DC_RNN + DC_RNN / 2, zD + DC_RNN + DC_RNN / 2, ZD_LD, unit0, part_d, nullptr);
+        if (step) lstm_partial<NB, 4>(acc_d, p.Wd, DC_ZD, DC_RNN + DC_RNN / 2, zD + DC_RNN + DC_RNN / 2, ZD_LD, unit0);
         bar_wait(p.barrier, epoch, G);
 
         // ================= stage Q: query rows  ||  decoder LSTM, h_att columns [0, 384)
@@ -301,7 +317,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
             }
         }
         bar_arrive(p.barrier);
-        lstm_partial<NB, 3>(p.Wd, DC_ZD, 0, zD, ZD_LD, unit0, part_d, nullptr);
+        lstm_partial<NB, 3>(acc_d, p.Wd, DC_ZD, 0, zD, ZD_LD, unit0);
         bar_wait(p.barrier, epoch, G);
 
         // ================= stage E: energies e[b][t] = v . tanh(pq + Weff * [w; w_cum](t-15..t+15) + pm[t])  ||  h_att columns [384, 768)
@@ -329,7 +345,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
             if (lane == 0) p.e[b * t_enc + t] = s;
         }
         bar_arrive(p.barrier);
-        lstm_partial<NB, 3>(p.Wd, DC_ZD, 384, zD + 384, ZD_LD, unit0, part_d, nullptr);
+        lstm_partial<NB, 3>(acc_d, p.Wd, DC_ZD, 384, zD + 384, ZD_LD, unit0);
         bar_wait(p.barrier, epoch, G);
 
         // ================= stage C: softmax (every CTA keeps w / w_cum itself) + context chunks  ||  h_att columns [768, 1024)
@@ -388,7 +404,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
             }
         }
         bar_arrive(p.barrier);
-        lstm_partial<NB, 2>(p.Wd, DC_ZD, 768, zD + 768, ZD_LD, unit0, part_d, nullptr);
+        lstm_partial<NB, 2>(acc_d, p.Wd, DC_ZD, 768, zD + 768, ZD_LD, unit0);
         bar_wait(p.barrier, epoch, G);
 
         // ================= stage D2: decoder LSTM, context columns + cell update  ||  attention LSTM of the NEXT step, context columns
@@ -396,11 +412,12 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
         for (int i = tid; i < nb * DC_RNN; i += DC_THREADS)
             zA[(i / DC_RNN) * ZA_LD + DC_ENC + i % DC_RNN] = zD[(i / DC_RNN) * ZD_LD + i % DC_RNN];   // h_att of this step
         __syncthreads();
-        lstm_partial<NB, 4>(p.Wd, DC_ZD, 2 * DC_RNN, zA, ZA_LD, unit0, part_d, nullptr);
+        lstm_partial<NB, 4>(acc_d, p.Wd, DC_ZD, 2 * DC_RNN, zA, ZA_LD, unit0);
+        lstm_finish<NB>(acc_d, unit0, part_d, p.bd);
         __syncthreads();
         lstm_cell<NB>(part_d, cst_d, unit0, nb, p.h_d + (size_t)nxt * nb * DC_RNN);
         bar_arrive(p.barrier);
-        lstm_partial<NB, 4>(p.Wa, DC_ZA, 0, zA, ZA_LD, unit0, part_a, p.ba);
+        lstm_partial<NB, 4>(acc_a, p.Wa, DC_ZA, 0, zA, ZA_LD, unit0);
         bar_wait(p.barrier, epoch, G);
 
         // ================= stage R: projection + gate rows  ||  next step: attention LSTM h_att columns (first half),
@@ -426,8 +443,8 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
             }
         }
         bar_arrive(p.barrier);
-        lstm_partial<NB, 4>(p.Wa, DC_ZA, DC_ENC, zA + DC_ENC, ZA_LD, unit0, part_a, nullptr);
-        lstm_partial<NB, 4>(p.Wd, DC_ZD, DC_RNN, zD + DC_RNN, ZD_LD, unit0, part_d, p.bd);
+        lstm_partial<NB, 4>(acc_a, p.Wa, DC_ZA, DC_ENC, zA + DC_ENC, ZA_LD, unit0);
+        lstm_partial<NB, 4>(acc_d, p.Wd, DC_ZD, DC_RNN, zD + DC_RNN, ZD_LD, unit0);
         bar_wait(p.barrier, epoch, G);
 
         // ================= stop rule (src/tacotron2/mod.rs:319-324): every CTA takes the same decision
