@@ -321,40 +321,125 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
         bar_wait(p.barrier, epoch, G);
 
         // ================= stage E: energies e[b][t] = v . tanh(pq + Weff * [w; w_cum](t-15..t+15) + pm[t])  ||  h_att columns [384, 768)
-        for (int item = cta + G * warp; item < nb * t_enc; item += G * WARPS) {
-            const int b = item / t_enc, t = item % t_enc;
-            if (t >= p.t_len[b]) continue;
-            const float* w0 = wpad + (b * 2 + 0) * wld + t;   // padded by 15 on both sides: index t <-> position t - 15
-            const float* w1 = wpad + (b * 2 + 1) * wld + t;
-            float s = 0.f;
-#pragma unroll
-            for (int j = 0; j < DC_ATT / 32; j++) {
-                const int a = lane + 32 * j;
-                const float* f = weff + a * DC_WEFF_LD;
+        if (nb * t_enc <= G) {
+            // at most one encoder position per CTA (the reference's shape: one utterance, 100 positions): the whole
+            // CTA computes it -- thread = (attention dim, quarter of the 62 taps) -- instead of one warp grinding
+            // through 250 dependent FMAs.  Same partial sums, same order of additions as the warp path below.
+            const int b = cta / t_enc, t = cta % t_enc;
+            const bool have = cta < nb * t_enc && t < p.t_len[b < nb ? b : 0];   // CTA-uniform
+            float* scratch = x1;   // [4][128] partial sums, then [128] tanh values (x1 and x2s are adjacent and free here)
+            if (have) {
+                const int a = tid & (DC_ATT - 1), g = tid >> 7;            // g: 0/1 even/odd taps of w, 2/3 of w_cum
+                const float* f = weff + a * DC_WEFF_LD + (g >> 1) * DC_LOCK;
+                const float* wv = wpad + (b * 2 + (g >> 1)) * wld + t;
                 float pa = 0.f;
 #pragma unroll
-                for (int k = 0; k < DC_LOCK; k++) pa = fmaf(f[k], w0[k], pa);
-#pragma unroll
-                for (int k = 0; k < DC_LOCK; k++) pa = fmaf(f[DC_LOCK + k], w1[k], pa);
-                const float q = __ldcg(p.pq + b * DC_ATT + a);
-                const float m = __ldg(p.pm + ((size_t)b * t_enc + t) * DC_ATT + a);
-                s = fmaf(vs[a], tanhf(q + pa + m), s);
+                for (int k = 0; k < DC_LOCK; k += 2)
+                    if (k + (g & 1) < DC_LOCK) pa = fmaf(f[k + (g & 1)], wv[k + (g & 1)], pa);
+                scratch[g * DC_ATT + a] = pa;
             }
+            float q = 0.f, m = 0.f;
+            if (have && tid < DC_ATT) {
+                q = __ldcg(p.pq + b * DC_ATT + tid);
+                m = __ldg(p.pm + ((size_t)b * t_enc + t) * DC_ATT + tid);
+            }
+            __syncthreads();
+            float th = 0.f;
+            if (have && tid < DC_ATT)
+                th = tanhf(q + ((scratch[tid] + scratch[DC_ATT + tid]) + (scratch[2 * DC_ATT + tid] + scratch[3 * DC_ATT + tid])) + m);
+            __syncthreads();
+            if (have && tid < DC_ATT) scratch[tid] = th;
+            __syncthreads();
+            if (have && warp == 0) {
+                float s = 0.f;
 #pragma unroll
-            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) p.e[b * t_enc + t] = s;
+                for (int j = 0; j < DC_ATT / 32; j++) s = fmaf(vs[lane + 32 * j], scratch[lane + 32 * j], s);
+#pragma unroll
+                for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0) p.e[b * t_enc + t] = s;
+            }
+        } else {
+            for (int item = cta + G * warp; item < nb * t_enc; item += G * WARPS) {
+                const int b = item / t_enc, t = item % t_enc;
+                if (t >= p.t_len[b]) continue;
+                const float* w0 = wpad + (b * 2 + 0) * wld + t;   // padded by 15 on both sides: index t <-> position t - 15
+                const float* w1 = wpad + (b * 2 + 1) * wld + t;
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < DC_ATT / 32; j++) {
+                    const int a = lane + 32 * j;
+                    const float* f = weff + a * DC_WEFF_LD;
+                    // four independent partial sums: a single chain of 62 dependent FMAs is pure latency for the one warp
+                    // that owns this encoder position
+                    float pa0 = 0.f, pa1 = 0.f, pa2 = 0.f, pa3 = 0.f;
+#pragma unroll
+                    for (int k = 0; k < DC_LOCK; k += 2) {
+                        pa0 = fmaf(f[k], w0[k], pa0);
+                        pa2 = fmaf(f[DC_LOCK + k], w1[k], pa2);
+                        if (k + 1 < DC_LOCK) {
+                            pa1 = fmaf(f[k + 1], w0[k + 1], pa1);
+                            pa3 = fmaf(f[DC_LOCK + k + 1], w1[k + 1], pa3);
+                        }
+                    }
+                    const float pa = (pa0 + pa1) + (pa2 + pa3);
+                    const float q = __ldcg(p.pq + b * DC_ATT + a);
+                    const float m = __ldg(p.pm + ((size_t)b * t_enc + t) * DC_ATT + a);
+                    s = fmaf(vs[a], tanhf(q + pa + m), s);
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0) p.e[b * t_enc + t] = s;
+            }
         }
         bar_arrive(p.barrier);
         lstm_partial<NB, 3>(acc_d, p.Wd, DC_ZD, 384, zD + 384, ZD_LD, unit0);
         bar_wait(p.barrier, epoch, G);
 
         // ================= stage C: softmax (every CTA keeps w / w_cum itself) + context chunks  ||  h_att columns [768, 1024)
-        if (warp < nb) {
+        if (NB <= 2) {
+            // one or two utterances: thread = encoder position, so the exponentials are one instruction deep instead
+            // of a loop in a single warp.  Same sums in the same order as the warp path below (maximum is exact;
+            // the sum is taken per lane over t = lane + 32 j, then by the same butterfly).
+            float* red = x1;   // [17] scratch, free in this stage
+            const int nj = (t_enc + 31) / 32;
+            for (int b = 0; b < nb; b++) {
+                const int tl = p.t_len[b];
+                const float ev = tid < tl ? __ldcg(p.e + b * t_enc + tid) : -INFINITY;
+                float m = ev;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                if (lane == 0) red[warp] = m;
+                __syncthreads();
+                m = red[0];
+#pragma unroll
+                for (int w = 1; w < WARPS; w++) m = fmaxf(m, red[w]);
+                const float ex = tid < tl ? expf(ev - m) : 0.f;
+                if (tid < t_enc) wnew[b * t_enc + tid] = ex;
+                __syncthreads();
+                if (warp == 0) {
+                    float sum = 0.f;
+                    for (int j = 0; j < nj; j++) sum += (lane + 32 * j) < t_enc ? wnew[b * t_enc + lane + 32 * j] : 0.f;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                    if (lane == 0) red[WARPS] = sum;
+                }
+                __syncthreads();
+                if (tid < t_enc) {
+                    const float w = ex / red[WARPS];
+                    wnew[b * t_enc + tid] = w;
+                    wpad[(b * 2 + 0) * wld + DC_LOCK / 2 + tid] = w;
+                    wpad[(b * 2 + 1) * wld + DC_LOCK / 2 + tid] += w;
+                    if (p.align_out && cta == 0) p.align_out[((size_t)b * p.max_steps + step) * t_enc + tid] = w;
+                }
+            }
+        } else         if (warp < nb) {
             const int b = warp, tl = p.t_len[b];
             float ev[DC_MAX_TENC / 32];
             float m = -INFINITY;
+            const int nj = (t_enc + 31) / 32;   // the loops below are unrolled to 16 but stop at the encoder length
 #pragma unroll
             for (int j = 0; j < DC_MAX_TENC / 32; j++) {
+                if (j >= nj) break;
                 const int t = lane + 32 * j;
                 ev[j] = t < tl ? __ldcg(p.e + b * t_enc + t) : -INFINITY;
                 m = fmaxf(m, ev[j]);
@@ -364,6 +449,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
             float sum = 0.f;
 #pragma unroll
             for (int j = 0; j < DC_MAX_TENC / 32; j++) {
+                if (j >= nj) break;
                 ev[j] = (lane + 32 * j) < tl ? expf(ev[j] - m) : 0.f;
                 sum += ev[j];
             }
@@ -371,6 +457,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
             for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
 #pragma unroll
             for (int j = 0; j < DC_MAX_TENC / 32; j++) {
+                if (j >= nj) break;
                 const int t = lane + 32 * j;
                 if (t < t_enc) {
                     const float w = ev[j] / sum;
