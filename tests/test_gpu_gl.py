@@ -358,6 +358,18 @@ def test_nnls_lift_matches_oracle(gl):
         x_ref, _ = o.lift_nnls_fista(mel, basis, power=1.7, max_iter=150)
         ref = o.peak_normalise(o.griffin_lim(x_ref.astype(np.float32), ph, 4, 0.99, 1024, 256, dtype=np.float64))
         assert float(np.sqrt(np.mean((y - ref) ** 2))) < 2e-3
+    # the banded fast form (what a filterbank gets) and the generic sparse form are the same recurrence
+    import os
+
+    os.environ["XDTTS_NNLS_GENERIC"] = "1"
+    try:
+        plan_g = voc.plan(ts)
+        plan_g.upload(0, mels)
+        plan_g.run(0)
+        s_gen = plan_g.peek(0)
+    finally:
+        del os.environ["XDTTS_NNLS_GENERIC"]
+    assert np.abs(s_gen - s).max() <= 1e-4 * np.abs(s).max()
     # lift = 0 is unchanged by the new option
     voc0 = gl.GriffinLim.new(basis, 768, 1.7, 4, 0.99)
     y0 = voc0.infer_batch(mels, phs)

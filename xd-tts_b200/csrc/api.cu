@@ -24,6 +24,8 @@ cudaError_t gl_launch_lift(const float*, const float*, const int*, const int*, i
                            float*, cudaStream_t);
 cudaError_t gl_launch_nnls(const float*, const int*, const float*, const int*, const float*, const int*, const int*, int, int, int,
                            int, float, int, float, int, float, float*, float*, cudaStream_t);
+cudaError_t gl_launch_nnls_band(const float*, const int*, const float*, int, const int*, const float*, int, const int*, const int*, int,
+                                int, int, int, float, int, float, int, float, float*, float*, cudaStream_t);
 cudaError_t gl_launch_to_frame_major(const float*, const int*, const int*, int, int, int, float*, float*, cudaStream_t);
 cudaError_t gl_launch_finish(const float*, const int*, const int*, const long long*, const unsigned*, int, int, int, int,
                              float*, cudaStream_t);
@@ -271,6 +273,38 @@ extern "C" int xdtts_gl_create(const float* mel_basis, int n_mels, int K, int no
         }
         h->lipschitz = (float)(lam * 1.001);   // small margin above the estimate keeps the step a descent step
     }
+    // banded form (a mel filterbank: each row one short run of bins, each column <= 4 filters)
+    std::vector<int> band_lo(n_mels, 0), ell_row;
+    std::vector<float> bandT, ell_val;
+    {
+        int rw = 0, cw = 0;
+        bool banded = true;
+        for (int m = 0; m < n_mels; m++) {
+            int lo = -1, hi = -1;
+            for (int k = 0; k < K; k++)
+                if (mel_basis[(size_t)m * K + k] != 0.f) { if (lo < 0) lo = k; hi = k; }
+            band_lo[m] = lo < 0 ? 0 : lo;
+            rw = std::max(rw, lo < 0 ? 0 : hi - lo + 1);
+        }
+        for (int k = 0; k < K; k++) cw = std::max(cw, csc[k + 1] - csc[k]);
+        rw = (std::max(rw, 1) + 3) & ~3;
+        banded = rw <= 64 && cw >= 1 && cw <= 4;
+        if (banded) {
+            cw = cw <= 2 ? 2 : 4;
+            bandT.assign((size_t)rw * n_mels, 0.f);
+            for (int m = 0; m < n_mels; m++)
+                for (int i = 0; i < rw && band_lo[m] + i < K; i++) bandT[(size_t)i * n_mels + m] = mel_basis[(size_t)m * K + band_lo[m] + i];
+            ell_row.assign((size_t)cw * K, 0);
+            ell_val.assign((size_t)cw * K, 0.f);
+            for (int k = 0; k < K; k++)
+                for (int p = csc[k], c = 0; p < csc[k + 1]; p++, c++) {
+                    ell_row[(size_t)c * K + k] = csc[K + 1 + p];
+                    ell_val[(size_t)c * K + k] = csc_val[p];
+                }
+            h->band_rw = rw;
+            h->band_cw = cw;
+        }
+    }
     if (h->opts.lift == 1 && !(h->lipschitz > 0.f)) {
         delete h;
         return fail(XDTTS_ERR_BAD_ARG, "gl_create: the NNLS lift needs a non-zero mel basis");
@@ -289,6 +323,16 @@ extern "C" int xdtts_gl_create(const float* mel_basis, int n_mels, int K, int no
     if (e == cudaSuccess) e = cudaMemcpy(h->d_csc, csc.data(), csc.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && !csr_val.empty()) e = cudaMemcpy(h->d_csr_val, csr_val.data(), csr_val.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && !csc_val.empty()) e = cudaMemcpy(h->d_csc_val, csc_val.data(), csc_val.size() * 4, cudaMemcpyHostToDevice);
+    if (h->band_rw > 0) {
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_band_lo, band_lo.size() * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_bandT, bandT.size() * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_ell_row, ell_row.size() * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_ell_val, ell_val.size() * 4);
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_band_lo, band_lo.data(), band_lo.size() * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_bandT, bandT.data(), bandT.size() * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_ell_row, ell_row.data(), ell_row.size() * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_ell_val, ell_val.data(), ell_val.size() * 4, cudaMemcpyHostToDevice);
+    }
     if (e == cudaSuccess) e = cudaMemcpy(h->d_pinvT, pT.data(), pT.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_tables, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_edge, edge.data(), edge.size() * 4, cudaMemcpyHostToDevice);
@@ -310,6 +354,7 @@ extern "C" void xdtts_gl_destroy(xdtts_gl* h) {
     cudaFree(h->d_tables);
     cudaFree(h->d_edge);
     cudaFree(h->d_csr); cudaFree(h->d_csc); cudaFree(h->d_csr_val); cudaFree(h->d_csc_val);
+    cudaFree(h->d_band_lo); cudaFree(h->d_bandT); cudaFree(h->d_ell_row); cudaFree(h->d_ell_val);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -502,9 +547,14 @@ static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid, cud
         const bool nnls = h->opts.lift == 1;
         CU(gl_launch_lift(p->d_mel, h->d_pinvT, p->d_T, p->d_foff, p->B, p->max_T, h->n_mels, h->K, nnls ? 1.0f : h->power, h->opts.delog, p->d_S, p->d_S_nyq, s));
         if (nnls) {   // refine the clipped least-squares start in place, then apply the exponent
-            CU(gl_launch_nnls(p->d_mel, h->d_csr, h->d_csr_val, h->d_csc, h->d_csc_val, p->d_T, p->d_foff, p->B, p->max_T, h->n_mels,
-                              h->K, h->power, h->opts.delog, h->lipschitz, h->opts.nnls_iters > 0 ? h->opts.nnls_iters : 300, 3e-6f,
-                              p->d_S, p->d_S_nyq, s));
+            const int iters = h->opts.nnls_iters > 0 ? h->opts.nnls_iters : 300;
+            if (h->band_rw > 0 && !getenv("XDTTS_NNLS_GENERIC"))
+                CU(gl_launch_nnls_band(p->d_mel, h->d_band_lo, h->d_bandT, h->band_rw, h->d_ell_row, h->d_ell_val, h->band_cw, p->d_T,
+                                       p->d_foff, p->B, p->max_T, h->n_mels, h->K, h->power, h->opts.delog, h->lipschitz, iters, 3e-6f,
+                                       p->d_S, p->d_S_nyq, s));
+            else
+                CU(gl_launch_nnls(p->d_mel, h->d_csr, h->d_csr_val, h->d_csc, h->d_csc_val, p->d_T, p->d_foff, p->B, p->max_T, h->n_mels,
+                                  h->K, h->power, h->opts.delog, h->lipschitz, iters, 3e-6f, p->d_S, p->d_S_nyq, s));
             g_launches++;
         }
     }

@@ -47,6 +47,11 @@ struct xdtts_gl {
     float* d_edge = nullptr;
     int *d_csr = nullptr, *d_csc = nullptr;        // sparse forms of the mel basis for the NNLS lift (rows / columns)
     float *d_csr_val = nullptr, *d_csc_val = nullptr;
+    int band_rw = 0, band_cw = 0;                   // > 0: the basis is banded (a filterbank): fast form of the NNLS lift
+    int* d_band_lo = nullptr;
+    float* d_bandT = nullptr;
+    int* d_ell_row = nullptr;
+    float* d_ell_val = nullptr;
     float lipschitz = 0.f;                          // sigma_max(basis)^2
     cudaStream_t stream = nullptr;
     std::mutex mu;

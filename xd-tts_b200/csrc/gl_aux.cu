@@ -183,6 +183,141 @@ __global__ void __launch_bounds__(128) gl_nnls_kernel(const float* __restrict__ 
     }
 }
 
+// Banded form of the same solver, used when every row of the basis is a short run of consecutive bins and every
+// column has at most 4 non-zeros -- i.e. for a mel filterbank (triangles: rows of <= 27 bins at n_fft 1024, columns
+// of <= 2 filters).  Rows are stored as dense bands, transposed ([i][m]: lanes read consecutive addresses), columns
+// in ELL form ([c][k]); both loops have fixed trip counts, so the loads are independent of each other and the
+// multiply-adds run as four interleaved chains instead of one pointer-chasing loop per row (measured on B200:
+// 15.7 -> 11.6 ms for 32 x 1000 worst-case frames at n_fft 1024, 104 -> 50 ms for 8 x 8000 at n_fft 2048).
+struct NnlsBand {
+    const int* row_lo;      // [n_mels] first bin of the row's band
+    const float* bandT;     // [rw][n_mels] A[m][row_lo[m] + i], zero past the band
+    const int* col_row;     // [CW][K] mel row of the c-th non-zero of column k (0 when absent)
+    const float* col_val;   // [CW][K] its value (0 when absent)
+    int rw;                 // band width, a multiple of 4
+};
+
+template <int KJ, int CW>
+__global__ void __launch_bounds__(128) gl_nnls_band_kernel(const float* __restrict__ mel_arena, NnlsBand A, const int* __restrict__ utt_T,
+                                                           const int* __restrict__ utt_foff, int n_mels, int K, float power, int delog,
+                                                           float inv_L, int max_iter, float pgtol_over_L, float* __restrict__ S,
+                                                           float* __restrict__ S_nyq) {
+    extern __shared__ __align__(16) float nn_sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int u = blockIdx.y, T = utt_T[u], t = blockIdx.x * 4 + warp;
+    if (t >= T) return;
+    const long foff = utt_foff[u];
+    const int M = K - 1;
+    constexpr int YS = 32 * KJ + 64;                         // the extrapolated point, zero padded past K for the bands
+    float* ys = nn_sm + warp * (YS + 2 * LIFT_MAX_MELS);
+    float* rs = ys + YS;
+    float* bs = rs + LIFT_MAX_MELS;
+    const float* mel = mel_arena + foff * n_mels;
+    for (int m = lane; m < n_mels; m += 32) {
+        const float v = mel[(long)m * T + t];
+        bs[m] = delog == 0 ? expf(v) : (delog == 1 ? powf(10.f, v) : v);
+    }
+    ys[32 * KJ + lane] = 0.f;
+    ys[32 * KJ + 32 + lane] = 0.f;
+    float x[KJ], y[KJ];
+    const long frame = foff + t;
+#pragma unroll
+    for (int j = 0; j < KJ; j++) {
+        const int k = lane + 32 * j;
+        x[j] = k < M ? S[frame * M + k] : (k == M ? S_nyq[frame] : 0.f);
+        y[j] = x[j];
+    }
+    float tk = 1.f;
+    for (int it = 0; it < max_iter; it++) {
+#pragma unroll
+        for (int j = 0; j < KJ; j++) ys[lane + 32 * j] = y[j];
+        __syncwarp();
+        for (int m = lane; m < n_mels; m += 32) {
+            const float* yb = ys + __ldg(A.row_lo + m);
+            const float* ab = A.bandT + m;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            for (int i = 0; i < A.rw; i += 4) {
+                a0 = fmaf(__ldg(ab + (size_t)(i + 0) * n_mels), yb[i + 0], a0);
+                a1 = fmaf(__ldg(ab + (size_t)(i + 1) * n_mels), yb[i + 1], a1);
+                a2 = fmaf(__ldg(ab + (size_t)(i + 2) * n_mels), yb[i + 2], a2);
+                a3 = fmaf(__ldg(ab + (size_t)(i + 3) * n_mels), yb[i + 3], a3);
+            }
+            rs[m] = ((a0 + a1) + (a2 + a3)) - bs[m];
+        }
+        __syncwarp();
+        float dot = 0.f, step = 0.f;
+#pragma unroll
+        for (int j = 0; j < KJ; j++) {
+            const int k = lane + 32 * j;
+            if (k < K) {
+                float g = 0.f;
+#pragma unroll
+                for (int c = 0; c < CW; c++) g = fmaf(__ldg(A.col_val + (size_t)c * K + k), rs[__ldg(A.col_row + (size_t)c * K + k)], g);
+                const float xn = fmaxf(y[j] - g * inv_L, 0.f);
+                dot = fmaf(g, xn - x[j], dot);
+                step = fmaxf(step, fabsf(xn - y[j]));
+                y[j] = xn;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            step = fmaxf(step, __shfl_xor_sync(0xffffffffu, step, o));
+        }
+        float beta = 0.f;
+        if (dot > 0.f) {
+            tk = 1.f;
+        } else {
+            const float tn = 0.5f * (1.f + sqrtf(1.f + 4.f * tk * tk));
+            beta = (tk - 1.f) / tn;
+            tk = tn;
+        }
+#pragma unroll
+        for (int j = 0; j < KJ; j++) {
+            const float xn = y[j];
+            y[j] = fmaf(beta, xn - x[j], xn);
+            x[j] = xn;
+        }
+        __syncwarp();
+        if (step < pgtol_over_L) break;
+    }
+#pragma unroll
+    for (int j = 0; j < KJ; j++) {
+        const int k = lane + 32 * j;
+        const float v = x[j] > 0.f ? (power == 1.0f ? x[j] : powf(x[j], power)) : 0.f;
+        if (k < M) S[frame * M + k] = v;
+        else if (k == M) S_nyq[frame] = v;
+    }
+}
+
+// band: [n_mels] row_lo | then nothing else (ints); band_val: [rw][n_mels]; colrow: [cw][K]; colval: [cw][K]
+cudaError_t gl_launch_nnls_band(const float* mel_arena, const int* row_lo, const float* bandT, int rw, const int* col_row,
+                                const float* col_val, int cw, const int* utt_T, const int* utt_foff, int n_utt, int max_T, int n_mels,
+                                int K, float power, int delog, float L, int max_iter, float pgtol, float* S, float* S_nyq,
+                                cudaStream_t s) {
+    if (n_mels > LIFT_MAX_MELS || cw < 1 || cw > 4 || rw < 4 || rw > 64 || (rw & 3)) return cudaErrorInvalidValue;
+    NnlsBand A;
+    A.row_lo = row_lo; A.bandT = bandT; A.col_row = col_row; A.col_val = col_val; A.rw = rw;
+    dim3 grid((max_T + 3) / 4, n_utt);
+    const int kj = (K + 31) / 32;
+    const float inv_L = 1.0f / L, tol = pgtol / L;
+#define XD_BAND_LAUNCH(KJ_, CW_)                                                                                                  \
+    gl_nnls_band_kernel<KJ_, CW_><<<grid, 128, 4 * (size_t)(32 * KJ_ + 64 + 2 * LIFT_MAX_MELS) * sizeof(float), s>>>(             \
+        mel_arena, A, utt_T, utt_foff, n_mels, K, power, delog, inv_L, max_iter, tol, S, S_nyq)
+#define XD_BAND_CW(KJ_)                                                                                                           \
+    do {                                                                                                                          \
+        if (cw <= 2) XD_BAND_LAUNCH(KJ_, 2);                                                                                      \
+        else XD_BAND_LAUNCH(KJ_, 4);                                                                                              \
+    } while (0)
+    if (kj <= 9) XD_BAND_CW(9);
+    else if (kj <= 17) XD_BAND_CW(17);
+    else if (kj <= 33) XD_BAND_CW(33);
+    else return cudaErrorInvalidValue;
+#undef XD_BAND_CW
+#undef XD_BAND_LAUNCH
+    return cudaGetLastError();
+}
+
 cudaError_t gl_launch_nnls(const float* mel_arena, const int* csr, const float* csr_val, const int* csc, const float* csc_val,
                            const int* utt_T, const int* utt_foff, int n_utt, int max_T, int n_mels, int K, float power, int delog,
                            float L, int max_iter, float pgtol, float* S, float* S_nyq, cudaStream_t s) {
