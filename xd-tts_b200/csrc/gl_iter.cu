@@ -30,11 +30,21 @@ namespace xdtts {
 #define XDTTS_GL16_CTAS 2
 #define XDTTS_GL16_ALIAS 1
 #endif
+#ifndef XDTTS_GL16_LATE
+#define XDTTS_GL16_LATE 1
+#endif
+#ifndef XDTTS_GL8_LATE
+#define XDTTS_GL8_LATE 0
+#endif
 template <int R3>
 struct GlCfg {
     static constexpr int WARPS = (R3 == 16) ? XDTTS_GL16_WARPS : XDTTS_GL8_WARPS;
     static constexpr int CTAS = (R3 == 16) ? XDTTS_GL16_CTAS : XDTTS_GL8_CTAS;
     static constexpr bool ALIAS = (R3 == 16) ? XDTTS_GL16_ALIAS : XDTTS_GL8_ALIAS;   // exchange 1 and 2 share storage
+    // when the next frame's newest hop block is requested: right after F1 (live through the whole frame), or before
+    // the last inverse pass (live through a fifth of it: still several DRAM latencies, and out of the way of the
+    // register peak in the middle passes)
+    static constexpr int LATE_PREFETCH = (R3 == 16) ? XDTTS_GL16_LATE : XDTTS_GL8_LATE;   // 0: after F1, 2: after F3, 1: after F4
 };
 
 template <int R3, bool TRACK_MAX>
@@ -117,7 +127,7 @@ __device__ __forceinline__ void gl_run_frames(Lane<R3>& L, int lane, const GlPar
             phase_f1<R3, COHERENT>(L, lane, p.y_in + yoff, T, t, p.pad_mode, t == r.ta, pref, tab, ex1);
             pref = fetch_next;
             __syncwarp();
-            if (fetch_next) prefetch_next_block<R3, COHERENT>(L, lane, p.y_in + yoff, T, t, p.pad_mode);
+            if (!GlCfg<R3>::LATE_PREFETCH && fetch_next) prefetch_next_block<R3, COHERENT>(L, lane, p.y_in + yoff, T, t, p.pad_mode);
             phase_f2_load<R3>(L, lane, ex1);
             if (ALIAS) __syncwarp();
             phase_f2_store<R3>(L, lane, tab, ex2);
@@ -128,10 +138,12 @@ __device__ __forceinline__ void gl_run_frames(Lane<R3>& L, int lane, const GlPar
         phase_f3<R3, MODE, STORE_R>(L, lane, p, r.utt, T, t, frame, tab, ex2, sm.s_stg, sm.r_stg);
         __syncwarp();   // every lane is done with the staged state (its values fed the stores above)
         if (t + 1 < r.tb) stage_issue<R3, MODE>(L, lane, p, frame + 1, sm.s_stg, sm.r_stg, sm.bar);
+        if (MODE != GL_MODE_INIT && GlCfg<R3>::LATE_PREFETCH == 2 && pref) prefetch_next_block<R3, COHERENT>(L, lane, p.y_in + yoff, T, t, p.pad_mode);
         phase_f4_load<R3>(L, lane, tab, ex2);
         if (ALIAS) __syncwarp();
         phase_f4_store<R3>(L, lane, ex1);
         __syncwarp();
+        if (MODE != GL_MODE_INIT && GlCfg<R3>::LATE_PREFETCH == 1 && pref) prefetch_next_block<R3, COHERENT>(L, lane, p.y_in + yoff, T, t, p.pad_mode);
         phase_f5<R3>(L, lane, tab, ex1);
         float2 out[2 * G::NB];
         ola_shift<R3>(L, out);
