@@ -84,6 +84,35 @@ def test_reference_shapes_t_enc_100(taco, weights):
     assert np.abs(mel.T - ref).max() < 3e-4
 
 
+def test_synthesize_encoder_outputs_to_waveform(taco, weights):
+    """decoder loop -> postnet -> lift -> Griffin-Lim on the device == the same chain of oracles, per utterance
+    (different stop frames -> ragged tail batch)."""
+    from oracle import gl_oracle as o
+    from oracle import postnet_oracle as po
+    from xdtts_b200 import griffin_lim
+
+    layers = po.synth_weights(seed=7)
+    basis = o.create_mel_filter_bank(22050.0, 1024, 80, 0.0, 8000.0)
+    voc = griffin_lim.GriffinLim.new(basis, 768, 1.7, 6, 0.99, seed=5)
+    post = taco.Postnet.from_layers(layers)
+    dec = taco.Decoder.from_weights(weights, gate_threshold=0.25, max_steps=40, prenet_dropout=False)
+    enc = [d.synth_encoder_outputs(31 + i, 40) for i in (1, 2, 3)]
+    lens = [37, 34, 31]
+    waves, mels = taco.synthesize_batch(dec, post, voc, [m for m, _ in enc], [p for _, p in enc], lens, return_mels=True)
+    frames = set()
+    for b, ((mem, pm), u) in enumerate(zip(enc, lens)):
+        dmel = d.run_decoder(weights, mem, pm, u, dropout=False, gate_threshold=0.25, max_steps=40).T      # [80, T]
+        pmel = po.postnet(dmel.astype(np.float32), layers, dtype=np.float64).astype(np.float32)
+        assert mels[b].shape == pmel.shape
+        assert np.abs(mels[b] - pmel).max() < 2e-3
+        t = pmel.shape[1]
+        frames.add(t)
+        assert waves[b].shape == (256 * (t - 1),) and np.isfinite(waves[b]).all()
+        ref = o.infer(mels[b], basis, 768, 1.7, 6, 0.99, o.phase_turns(5, b, 513, t), dtype=np.float64)
+        assert float(np.sqrt(np.mean((waves[b] - ref) ** 2))) < 1e-4
+    assert len(frames) > 1
+
+
 def test_errors(taco, weights):
     from xdtts_b200._ffi import ERR_BAD_ARG, ERR_SHAPE, XdttsError
 

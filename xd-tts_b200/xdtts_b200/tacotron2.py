@@ -320,3 +320,15 @@ def infer_tail_batch(post, vocoder, mels, init_phases=None, return_mels=False):
 
 def infer_tail(post, vocoder, mel, init_phase=None):
     return infer_tail_batch(post, vocoder, [mel], None if init_phase is None else [init_phase])[0]
+
+
+def synthesize_batch(decoder, post, vocoder, memories, processed_memories, unpadded_lens, init_phases=None, return_mels=False):
+    """Everything `XdTts::infer` does after the encoder session, for B utterances (src/lib.rs:123 `model.infer`
+    = decoder loop + postnet, src/tacotron2/mod.rs:272-357, then :141 `vocoder.infer`): encoder outputs ->
+    decoder loop -> postnet -> mel-to-linear lift -> Griffin-Lim -> float32 samples.  The frame counts come out of
+    the decoder's stop rule, so the tail runs as one batch of ragged lengths."""
+    mels = decoder.run_batch(memories, processed_memories, unpadded_lens)
+    short = [i for i, m in enumerate(mels) if m.shape[1] < 4]
+    if short:
+        raise XdttsError(_ffi.ERR_SHAPE, "utterances %s stopped after fewer than 4 frames: too short to vocode" % short)
+    return infer_tail_batch(post, vocoder, mels, init_phases, return_mels=return_mels)
