@@ -374,3 +374,45 @@ def test_nnls_lift_matches_oracle(gl):
     voc0 = gl.GriffinLim.new(basis, 768, 1.7, 4, 0.99)
     y0 = voc0.infer_batch(mels, phs)
     assert not np.array_equal(y0[0], ys[0])
+
+
+def test_handles_are_thread_safe(gl):
+    """Calls on one handle are serialised internally, handles are independent (the shim declares Send + Sync):
+    four threads hammer one shared vocoder and one private vocoder each; every result equals the serial one."""
+    import threading
+
+    basis = basis_for(1024)
+    shared = make(gl, 1024, 5, seed=3)
+    ts = [21, 64, 9]
+    mels = [o.synth_mel(900 + i, 80, t) for i, t in enumerate(ts)]
+    want = shared.infer_batch(mels)
+    errors = []
+
+    def worker(k):
+        try:
+            own = gl.GriffinLim.new(basis, 768, 1.7, 5, 0.99, seed=3)
+            pipe = shared.pipe(ts, depth=2) if k % 2 == 0 else None
+            for _ in range(6):
+                for got in (shared.infer_batch(mels), own.infer_batch(mels)):
+                    for a, b in zip(got, want):
+                        if not np.array_equal(a, b):
+                            errors.append("thread %d: result differs" % k)
+                if pipe is not None:
+                    pipe.push(mels)
+                    pipe.push(mels)
+                    for got in pipe.flush():
+                        for a, b in zip(got, want):
+                            if not np.array_equal(a, b):
+                                errors.append("thread %d: pipe result differs" % k)
+            if pipe is not None:
+                pipe.close()
+            own.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append("thread %d: %r" % (k, e))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
