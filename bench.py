@@ -14,8 +14,9 @@ One "step" = one pass of the path over one batch: mel -> linear lift (pseudo-inv
              region (the pipe is flushed before the clock stops) and overlap the neighbouring steps' kernels;
              e2e.blocking_call is the one-batch-at-a-time call (xdtts_gl_infer_batch), copies exposed
   roofline   the steady-state iteration kernel: algorithmic bytes (20K+8H per frame)
-             / its mean launch duration (events around the launches, kernel-by-kernel run) vs the
-             measured HBM peak of MEASURED_PEAKS.json
+             / its mean launch duration inside the plan's CUDA graph (events around the graph of the full
+             pass minus the graph of a half-length pass, per extra launch) vs the measured HBM peak of
+             MEASURED_PEAKS.json; kernel_ms_stream_launches is the same kernel launched one by one
   cpu_baseline  the oracle's C/OpenMP port of the same step on this host's cores, bounded sample
 
 --impl reference times that CPU port (the reference's Rust crate cannot be built here:
@@ -394,13 +395,32 @@ def run_gpu(args):
     launches = lib.xdtts_kernel_launches() - launches0
     clocks = sampler.stop()
 
-    # ---- steady-state kernel duration, live, kernel-by-kernel run with events around the launches
+    # ---- steady-state duration of the iteration kernel, live, two ways:
+    #  (1) as launched in the timed region -- inside the plan's CUDA graph: CUDA events around the graph of the full pass
+    #      and around the graph of a pass with half the iterations (same batch, same kernels); the difference divided by
+    #      the extra launches is the average duration of one steady-state launch where the product runs it;
+    #  (2) kernel-by-kernel stream launches with events around the n_iter - 2 steady-state launches (adds the
+    #      stream's launch-to-launch gap to every kernel: an upper bound, kept as kernel_ms_stream_launches).
     iter_ms, iter_n = 0.0, 0
     for _ in range(max(2, min(steps, 5))):
         _, mi, n = plan.run(_ffi.RUN_NO_GRAPH)
         iter_ms += mi
         iter_n += n
-    kern_ms = iter_ms / max(iter_n, 1)
+    kern_stream_ms = iter_ms / max(iter_n, 1)
+    it_half = it // 2
+    voc_half = griffin_lim.GriffinLim.new(basis, n_fft - hop, POWER, it_half, MOMENTUM, seed=shard.rank_seed(0, rank), device=local_rank)
+    plan_half = voc_half.plan([t] * b)
+    plan_half.upload(0, mels)
+    if with_postnet:
+        plan.upload(0, mels)      # any mel will do for the timing: the arithmetic does not depend on the values
+    for _ in range(2):
+        plan_half.run(0)
+        plan.run(0)
+    t_full = min(plan.run(0)[0] for _ in range(5))
+    t_half = min(plan_half.run(0)[0] for _ in range(5))
+    kern_ms = (t_full - t_half) / (it - it_half)
+    plan_half.close()
+    voc_half.close()
 
     # ---- end to end through the public call, pinned host buffers
     pin_in = [pinned_array(lib, (N_MELS, t)) for _ in range(b)]
@@ -465,8 +485,8 @@ def run_gpu(args):
     dec_line = decoder_leg(local_rank, not args.no_cpu) if (world == 1 and cfg == "cfg2" and not args.no_decoder) else None
 
     # ---- reduce over ranks: time = max, frames = sum
-    total_frames, total_launches, (dev_ms, wall_ms, e2e_ms, kern_ms, call_ms) = shard.reduce_counters(
-        frames, launches, [dev_ms, wall_ms, e2e_ms, kern_ms, call_ms], device="cuda")   # the single collective of the job
+    total_frames, total_launches, (dev_ms, wall_ms, e2e_ms, kern_ms, call_ms, kern_stream_ms) = shard.reduce_counters(
+        frames, launches, [dev_ms, wall_ms, e2e_ms, kern_ms, call_ms, kern_stream_ms], device="cuda")   # the single collective of the job
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -493,6 +513,8 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "kernel": "gl_iter_kernel<MID> (one Griffin-Lim iteration)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(cfg), "peak_source": peak_src, "kernel_ms": kern_ms,
+                         "kernel_ms_how": "(CUDA-graph pass with %d iterations - pass with %d) / %d, CUDA events on the library's stream" % (it, it_half, it - it_half),
+                         "kernel_ms_stream_launches": kern_stream_ms,
                          "algorithmic_bytes_per_launch": alg_bytes},
             "clocks": clocks,
         }
