@@ -22,5 +22,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:pn_c
     python tools/prof_postnet.py 1 0 > $out/prof_postnet.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:dec_persist -c 1 -f -o $out/prof_decoder_b1 \
     python tools/prof_decoder.py 1 300 > $out/prof_decoder.log 2>&1
-timeout 900 compute-sanitizer --tool memcheck python tests/gpu_tools/sanitize_target.py > $out/sanitizer_memcheck.log 2>&1; tail -3 $out/sanitizer_memcheck.log
+for tool in memcheck racecheck synccheck; do
+  timeout 900 compute-sanitizer --tool $tool python tests/gpu_tools/sanitize_target.py > $out/sanitizer_$tool.log 2>&1; tail -2 $out/sanitizer_$tool.log
+done
 ls -la $out

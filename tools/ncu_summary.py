@@ -135,6 +135,10 @@ def main():
             shutil.copy(p, os.path.join(dst, "%s_%s" % (tag, f)))
         elif f.endswith(".json") or f in ("pytest_gpu.log", "smoke.log", "gpu.txt"):
             shutil.copy(p, os.path.join(dst, "%s_%s" % (tag, f)))
+        elif f.startswith("sanitizer_") and f.endswith(".log"):     # keep the verdict lines, not the whole log
+            lines = [ln for ln in open(p, errors="replace").read().splitlines() if "SUMMARY" in ln or "sanitize target" in ln]
+            with open(os.path.join(dst, "%s_%s" % (tag, f)), "w") as out:
+                out.write("\n".join(lines) + "\n")
     json.dump(traffic, open(tpath, "w"), indent=1)
     print("profiles/ updated from", src)
 

@@ -148,8 +148,11 @@ __device__ __forceinline__ void gl_run_frames(Lane<R3>& L, int lane, const GlPar
         float2 out[2 * G::NB];
         ola_shift<R3>(L, out);
         if (emit_block<R3, TRACK_MAX>(L, lane, p, run_idx, r, yoff, t, out)) arrive<R3, TRACK_MAX>(L, lane, p, run_idx - 1);
-        // the next frame's first shared-memory writes (F1 -> ex1, or F3 -> ex2 in INIT mode) go to the
-        // addresses this same lane read last, so no barrier is needed here
+        // the next frame's first shared-memory writes (F1 -> ex1) go to the addresses this same lane read last in F5,
+        // so no barrier is needed here -- except in INIT mode with aliased exchange buffers, where the next frame
+        // starts with F3's writes to ex2 (= ex1) in a different index mapping than F5's reads (compute-sanitizer
+        // racecheck flagged exactly this pair)
+        if (ALIAS && MODE == GL_MODE_INIT) __syncwarp();
     }
     if (emit_tail<R3, TRACK_MAX>(L, lane, p, run_idx, r, yoff, T)) arrive<R3, TRACK_MAX>(L, lane, p, run_idx);
 
