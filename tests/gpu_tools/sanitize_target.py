@@ -43,4 +43,9 @@ dec = tacotron2.Decoder.from_weights(d.synth_weights(11), gate_threshold=0.99999
 enc = [d.synth_encoder_outputs(40 + i, 20) for i in range(3)]
 out = dec.run_batch([m for m, _ in enc], [p for _, p in enc], [20, 17, 11])
 assert all(x.shape == (80, 6) and np.isfinite(x).all() for x in out)
+one = dec.run(enc[0][0], enc[0][1], 20)                    # batch 1: the whole-CTA energies / softmax forms
+assert np.array_equal(one, out[0])
+enc8 = [d.synth_encoder_outputs(60 + i, 20) for i in range(8)]
+out8 = dec.run_batch([m for m, _ in enc8], [p for _, p in enc8], [20 - i for i in range(8)])   # template NB = 8
+assert all(x.shape == (80, 6) and np.isfinite(x).all() for x in out8)
 print("sanitize target ok")
