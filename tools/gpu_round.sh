@@ -7,7 +7,7 @@ mkdir -p $out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $out/gpu.txt 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q > $out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $out/pytest_gpu.log
 tail -3 $out/pytest_gpu.log
-timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' > $out/smoke.log 2>&1; tail -1 $out/smoke.log
+timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' > $out/smoke.log 2>&1; tail -2 $out/smoke.log
 timeout 600 python bench.py --steps 10 --warmup 3 > $out/bench_cfg2.json 2> $out/bench_cfg2.err; cat $out/bench_cfg2.json
 timeout 600 python bench.py --config cfg3 --steps 10 --warmup 3 > $out/bench_cfg3.json 2> $out/bench_cfg3.err; cat $out/bench_cfg3.json
 timeout 600 python bench.py --config cfg5 --steps 5 --warmup 3 --no-cpu > $out/bench_cfg5.json 2> $out/bench_cfg5.err; cat $out/bench_cfg5.json
@@ -22,7 +22,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:pn_c
     python tools/prof_postnet.py 1 0 > $out/prof_postnet.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:dec_persist -c 1 -f -o $out/prof_decoder_b1 \
     python tools/prof_decoder.py 1 300 > $out/prof_decoder.log 2>&1
-for tool in memcheck racecheck synccheck; do
+for tool in memcheck racecheck synccheck initcheck; do
   timeout 900 compute-sanitizer --tool $tool python tests/gpu_tools/sanitize_target.py > $out/sanitizer_$tool.log 2>&1; tail -2 $out/sanitizer_$tool.log
 done
 ls -la $out
