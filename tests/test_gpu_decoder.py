@@ -113,6 +113,23 @@ def test_synthesize_encoder_outputs_to_waveform(taco, weights):
     assert len(frames) > 1
 
 
+def test_longest_encoder_and_full_group(taco, weights):
+    """The largest shapes one launch takes: 8 utterances in lockstep, 512 encoder positions (shared memory at its
+    maximum), ragged unpadded lengths including 1."""
+    enc = [d.synth_encoder_outputs(200 + i, 512) for i in range(8)]
+    lens = [512, 400, 257, 256, 33, 32, 2, 1]
+    dec = taco.Decoder.from_weights(weights, gate_threshold=0.999999, max_steps=3, seed=8)
+    mels, gates, aligns = dec.run_batch([m for m, _ in enc], [p for _, p in enc], lens, return_aux=True)
+    for b in (0, 2, 4, 6, 7):
+        ref, _, ref_al = d.run_decoder(weights, enc[b][0], enc[b][1], lens[b], seed=8, utt=b, gate_threshold=2.0, max_steps=3,
+                                       return_aux=True)
+        assert np.abs(mels[b].T - ref).max() < 2e-4, b
+        assert np.abs(aligns[b] - ref_al).max() < 1e-5, b
+        assert np.all(aligns[b][:, lens[b]:] == 0)
+    with pytest.raises(Exception):
+        dec.run(np.zeros((513, 512), np.float32), np.zeros((513, 128), np.float32), 10)      # t_enc > 512
+
+
 def test_errors(taco, weights):
     from xdtts_b200._ffi import ERR_BAD_ARG, ERR_SHAPE, XdttsError
 
