@@ -12,7 +12,7 @@
 namespace xdtts {
 
 // ---------------------------------------------------------------- lift
-// grid (ceil(K/128), ceil(maxT/16), n_utt); thread <-> bin k, 16 frames per block.
+// grid (1, ceil(maxT/16), n_utt); thread <-> bins k, k + 128, ...; 16 frames per block.
 // Accumulates in fp64: the pseudo-inverse has 36% negative entries, an fp32 sum
 // loses ~1e-3 relative to cancellation.  The de-logged mel tile is converted to fp64 once, in shared
 // memory, so the inner loop is one coalesced load of the pseudo-inverse column and 16 DFMAs fed by
@@ -41,38 +41,40 @@ __global__ void __launch_bounds__(128) gl_lift_kernel(const float* __restrict__ 
         e[i] = (double)v;
     }
     __syncthreads();
-    const int k = blockIdx.x * 128 + threadIdx.x;
-    if (k >= K) return;
-    double acc[LIFT_TT];
-#pragma unroll
-    for (int tt = 0; tt < LIFT_TT; tt++) acc[tt] = 0.0;
-    const float* col = pinvT + k;
-#pragma unroll 4
-    for (int m = 0; m < n_mels; m++) {
-        const double a = (double)col[(long)m * K];
-        const double2* er = reinterpret_cast<const double2*>(e + m * LIFT_TT);
-#pragma unroll
-        for (int q = 0; q < LIFT_TT / 2; q++) {
-            const double2 x = er[q];
-            acc[2 * q + 0] = fma(a, x.x, acc[2 * q + 0]);
-            acc[2 * q + 1] = fma(a, x.y, acc[2 * q + 1]);
-        }
-    }
+    // the de-logged tile is staged once and reused for every block of 128 bins (staging it costs about as much
+    // as one block's multiply-adds)
     const int M = K - 1;
+    for (int k = threadIdx.x; k < K; k += 128) {
+        double acc[LIFT_TT];
 #pragma unroll
-    for (int tt = 0; tt < LIFT_TT; tt++) {
-        if (t0 + tt >= T) break;
-        float s = (float)acc[tt];
-        s = s > 0.f ? (power == 1.0f ? s : powf(s, power)) : 0.f;
-        if (k < M) S[(foff + t0 + tt) * M + k] = s;
-        else S_nyq[foff + t0 + tt] = s;
+        for (int tt = 0; tt < LIFT_TT; tt++) acc[tt] = 0.0;
+        const float* col = pinvT + k;
+#pragma unroll 4
+        for (int m = 0; m < n_mels; m++) {
+            const double a = (double)col[(long)m * K];
+            const double2* er = reinterpret_cast<const double2*>(e + m * LIFT_TT);
+#pragma unroll
+            for (int q = 0; q < LIFT_TT / 2; q++) {
+                const double2 x = er[q];
+                acc[2 * q + 0] = fma(a, x.x, acc[2 * q + 0]);
+                acc[2 * q + 1] = fma(a, x.y, acc[2 * q + 1]);
+            }
+        }
+#pragma unroll
+        for (int tt = 0; tt < LIFT_TT; tt++) {
+            if (t0 + tt >= T) break;
+            float s = (float)acc[tt];
+            s = s > 0.f ? (power == 1.0f ? s : powf(s, power)) : 0.f;
+            if (k < M) S[(foff + t0 + tt) * M + k] = s;
+            else S_nyq[foff + t0 + tt] = s;
+        }
     }
 }
 
 cudaError_t gl_launch_lift(const float* mel_arena, const float* pinvT, const int* utt_T, const int* utt_foff, int n_utt,
                            int max_T, int n_mels, int K, float power, int delog, float* S, float* S_nyq, cudaStream_t s) {
     if (n_mels > LIFT_MAX_MELS) return cudaErrorInvalidValue;
-    dim3 grid((K + 127) / 128, (max_T + LIFT_TT - 1) / LIFT_TT, n_utt);
+    dim3 grid(1, (max_T + LIFT_TT - 1) / LIFT_TT, n_utt);
     gl_lift_kernel<<<grid, 128, (size_t)n_mels * LIFT_TT * sizeof(double), s>>>(mel_arena, pinvT, utt_T, utt_foff, n_mels, K, power,
                                                                                delog, S, S_nyq);
     return cudaGetLastError();
