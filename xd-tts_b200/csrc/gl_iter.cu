@@ -32,7 +32,7 @@ namespace xdtts {
 #define XDTTS_GL16_ALIAS 1
 #endif
 #ifndef XDTTS_GL16_LATE
-#define XDTTS_GL16_LATE 1
+#define XDTTS_GL16_LATE 2
 #endif
 #ifndef XDTTS_GL8_LATE
 #define XDTTS_GL8_LATE 0
