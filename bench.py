@@ -235,6 +235,27 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.samples), "how": "NVML, 5 ms period, timed region only"}
 
 
+def bind_to_gpu_numa_node(index):
+    """One process per GPU: run on the CPUs next to this GPU so that the pinned host buffers (first touch) sit on its
+    NUMA node and the PCIe copies do not cross the socket interconnect.  Best effort."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1 and 64 * w + b < n_cpu}
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return sorted(allowed)
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def pinned_array(lib, shape):
     n = int(np.prod(shape))
     ptr = lib.xdtts_host_alloc(n * 4)
@@ -332,6 +353,7 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        bind_to_gpu_numa_node(local_rank)
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
