@@ -6,8 +6,8 @@
 // One step of the exported graph (NVIDIA Tacotron2 Decoder.decode, oracle/decoder_oracle.py):
 //   prenet (2 x linear+relu+dropout) -> attention LSTM -> location-sensitive attention -> decoder LSTM
 //   -> linear projection (mel frame) + gate.
-// At batch 1 this is a chain of matrix-vector products: 18.4 M weights = 73.5 MB fp32 are read once per
-// step and everything else is latency, so the design is about (1) streaming the two LSTM matrices with
+// At batch 1 this is a chain of matrix-vector products: 18.2 M weights = 72.7 MB fp32 are read once per
+// step (they stay in the 126 MB L2) and everything else is latency, so the design is about (1) streaming the two LSTM matrices with
 // every SM at once, (2) keeping all state on chip or in L2 between steps, (3) as few grid-wide barriers as
 // the data dependences allow, with the weight streaming placed so that it overlaps the small serial stages:
 //
@@ -15,8 +15,8 @@
 //   P   prenet layer 1 (every CTA, redundantly) + layer 2 rows (one per CTA)    att. LSTM, h_att columns (2nd half)
 //   A2  attention LSTM: the 256 prenet columns + cell update                    dec. LSTM, h_dec columns (2nd half)
 //   Q   query rows (one per CTA)                                                dec. LSTM, h_att columns [0, 384)
-//   E   attention energies, one warp per encoder position                       dec. LSTM, h_att columns [384, 768)
-//   C   softmax (every CTA, redundantly) + context chunks (a warp per 32 dims)  dec. LSTM, h_att columns [768, 1024)
+//   E   attention energies, one encoder position per CTA (or per warp)          dec. LSTM, h_att columns [384, 768)
+//   C   softmax (every CTA, redundantly) + context chunks (32 dims per CTA)     dec. LSTM, h_att columns [768, 1024)
 //   D2  decoder LSTM: the 512 context columns + cell update                     NEXT step's att. LSTM, ctx columns
 //   R   projection + gate rows (one per CTA)                                    NEXT step: att. LSTM h_att (1st half),
 //                                                                               dec. LSTM h_dec (1st half)
@@ -24,10 +24,12 @@
 // input vectors are already known (82% of the bytes of a step) and only then waits, so the barrier latency and
 // the serial stages overlap the weight traffic instead of adding to it.
 //
-// CTA c owns hidden units [7c, 7c+7) of both LSTMs: their four gate rows, the partial gate sums (which live
-// in shared memory across barriers) and the cell state never leave the SM.  A warp computes one weight row
-// at a time against up to 8 utterances' input vectors held in shared memory (float4 loads, shuffle
-// reduction), so the weights are read once per step however many utterances decode in lockstep.
+// CTA c owns hidden units [7c, 7c+7) of both LSTMs: their four gate rows, the partial gate sums (per lane, in
+// registers, across slices and barriers) and the cell state never leave the SM.  A warp computes two weight rows
+// at a time against up to 8 utterances' input vectors held in shared memory (float4 loads, all loads of a slice in
+// flight; one shuffle reduction per row and step), so the weights are read once per step however many utterances
+// decode in lockstep.  Measured (B200): 20 us per step at batch 1, of which 8.6 us are the seven barriers and 0.9 us
+// the weight traffic; the rest is dependent instruction chains in the serial stages.
 // Attention weights / cumulative weights are kept by every CTA in shared memory (same instructions, same
 // bits), hence never travel.  All cross-CTA state is read through L2 (ld.global.cg).
 #include <cuda_runtime.h>
