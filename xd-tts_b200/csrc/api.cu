@@ -417,10 +417,25 @@ int xdtts::gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out)
         const long long resident = (long long)h->sm_count * gl_resident_warps_per_sm(h->n_fft);
         const long long target = total <= resident * 64 ? resident : (total + 63) / 64;
         std::vector<int> counts(B);
+        long long used = 0;
         for (int b = 0; b < B; b++) {
             long long n = (long long)Ts[b] * target / total;   // floor: the sum never exceeds the target
             if (n > Ts[b] / 4) n = Ts[b] / 4;                   // a hop block may be shared by at most two runs
             counts[b] = n < 1 ? 1 : (int)n;
+            used += counts[b];
+        }
+        // hand the slots the floors left over to the utterances with the longest runs (largest frames per run first,
+        // ties by index: deterministic), so that a resident wave is filled exactly
+        if (total <= resident * 64) {
+            for (long long left = target - used; left > 0; left--) {
+                int best = -1;
+                for (int b = 0; b < B; b++) {
+                    if (counts[b] + 1 > Ts[b] / 4) continue;
+                    if (best < 0 || (long long)Ts[b] * counts[best] > (long long)Ts[best] * counts[b]) best = b;
+                }
+                if (best < 0) break;
+                counts[best]++;
+            }
         }
         build_runs_counts(Ts, B, counts.data(), &p->runs, &p->foff);
         rf = 0;
