@@ -595,8 +595,6 @@ def main():
     ap.add_argument("--no-decoder", action="store_true", help="skip the decoder-loop leg")
     args = ap.parse_args()
     if args.impl == "reference":
-        if args.steps == 10:
-            args.steps = 3
         run_reference(args)
     else:
         run_gpu(args)
