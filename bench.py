@@ -551,7 +551,7 @@ def run_gpu(args):
         if dec_line is not None:
             line["decoder"] = dec_line
         if world == 1 and not args.no_cpu:
-            v, cores, kind, sample, _ = cpu_arm(cfg, 1, 1)
+            v, cores, kind, sample, _ = cpu_arm(cfg, 3, 1)   # ~10 s of CPU work incl. picking the faster threading
             line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}
         emit(line)
     for _, p in pin_in + pin_out + pin_in2 + pin_out2:
