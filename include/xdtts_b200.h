@@ -238,7 +238,8 @@ int xdtts_decoder_last_timing(const xdtts_decoder* h, float* ms, int* steps);
  * (src/lib.rs:83-104); a server doing the same batch after batch would leave the GPU idle during every
  * PCIe copy.  A pipe owns `depth` (1..8; 2 is enough) device-resident slots with one stream each.
  * xdtts_pipe_push enqueues H2D -> [postnet, when pn != null] -> lift -> Griffin-Lim -> D2H for one batch and
- * returns without waiting; it blocks only when every slot is in flight (it then waits for the oldest).
+ * returns without waiting; it blocks only when every slot is in flight (it then waits for the oldest).  The copies of
+ * neighbouring batches overlap kernels; the kernels of consecutive batches run back to back, in push order.
  * All host buffers of a batch -- inputs and outputs -- must stay valid and untouched until that batch has
  * been collected: by xdtts_pipe_pop / xdtts_pipe_flush, or by the push that reuses its slot (`depth` pushes later).
  * Pinned buffers (xdtts_host_alloc) make the copies asynchronous; pageable ones are staged (inputs then

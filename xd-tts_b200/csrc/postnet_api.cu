@@ -515,10 +515,12 @@ struct xdtts_pipe {
         xdtts_gl_plan* gp = nullptr;
         xdtts_postnet_plan* pp = nullptr;
         cudaStream_t s = nullptr;
+        cudaEvent_t computed = nullptr;   // recorded after the slot's kernels, before its device -> host copies
         bool busy = false, staged_wave = false, staged_mel = false;
         std::vector<float*> out_waves, out_mels;
     };
     std::vector<Slot> slots;
+    cudaEvent_t last_computed = nullptr;   // the most recently pushed batch's `computed`
     std::mutex mu;
 };
 
@@ -563,6 +565,7 @@ extern "C" void xdtts_pipe_destroy(xdtts_pipe* q) {
         if (sl.s) cudaStreamSynchronize(sl.s);
         if (sl.gp) xdtts_gl_plan_destroy(sl.gp);
         if (sl.pp) xdtts_postnet_plan_destroy(sl.pp);
+        if (sl.computed) cudaEventDestroy(sl.computed);
         if (sl.s) cudaStreamDestroy(sl.s);
     }
     cudaGetLastError();
@@ -596,8 +599,9 @@ extern "C" int xdtts_pipe_create(xdtts_gl* gl, xdtts_postnet* pn, const int* Ts,
             float* arena = nullptr;
             rc = gl_plan_mel_arena(sl.gp, &arena);
         }
-        if (rc == XDTTS_OK && cudaStreamCreateWithFlags(&sl.s, cudaStreamNonBlocking) != cudaSuccess)
-            rc = fail(XDTTS_ERR_CUDA, "pipe_create: cudaStreamCreate failed");
+        if (rc == XDTTS_OK && (cudaStreamCreateWithFlags(&sl.s, cudaStreamNonBlocking) != cudaSuccess ||
+                               cudaEventCreateWithFlags(&sl.computed, cudaEventDisableTiming) != cudaSuccess))
+            rc = fail(XDTTS_ERR_CUDA, "pipe_create: cudaStreamCreate / cudaEventCreate failed");
         sl.out_waves.resize(B);
         sl.out_mels.resize(B);
     }
@@ -627,9 +631,13 @@ extern "C" int xdtts_pipe_push(xdtts_pipe* q, const float* const* mels, const fl
     rc = gl_plan_mel_arena(sl.gp, &arena);
     if (rc) return rc;
     int flags = 0;
+    // The copies of neighbouring batches overlap kernels, but the KERNELS of two batches must not interleave: every
+    // Griffin-Lim launch is sized to fill the device in one wave, and two such grids sharing the SMs finish later than
+    // the same two grids back to back.  So a slot's kernels wait for the previous batch's kernels (not for its copies).
     if (q->pn) {
         std::lock_guard<std::mutex> lk2(q->pn->mu);
         rc = pn_plan_upload_locked(sl.pp, mels, sl.s);
+        if (rc == XDTTS_OK && q->last_computed) CU(cudaStreamWaitEvent(sl.s, q->last_computed, 0));
         if (rc == XDTTS_OK) rc = pn_enqueue(sl.pp, arena, sl.s);
     } else {
         std::lock_guard<std::mutex> lk2(q->gl->mu);
@@ -642,7 +650,12 @@ extern "C" int xdtts_pipe_push(xdtts_pipe* q, const float* const* mels, const fl
             rc = gl_plan_upload_locked(sl.gp, 2, init_phases, sl.s);
             flags |= XDTTS_RUN_USE_PHASE;
         }
+        if (rc == XDTTS_OK && !q->pn && q->last_computed) CU(cudaStreamWaitEvent(sl.s, q->last_computed, 0));
         if (rc == XDTTS_OK) rc = gl_plan_launch_async(sl.gp, flags, sl.s);
+        if (rc == XDTTS_OK) {
+            CU(cudaEventRecord(sl.computed, sl.s));
+            q->last_computed = sl.computed;
+        }
         if (rc == XDTTS_OK) rc = gl_plan_download_async(sl.gp, out_waves, sl.s, &sl.staged_wave);
     }
     sl.staged_mel = false;
