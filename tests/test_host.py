@@ -31,6 +31,19 @@ def test_library_exports_every_declared_symbol(lib, built):
     assert b"sm_100a" in lib.xdtts_version()
 
 
+def test_header_is_plain_c(built, tmp_path):
+    """The boundary is a C ABI: include/xdtts_b200.h must compile as C99 (no C++, no CUDA or torch types)."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    inc = os.path.join(os.path.dirname(built.__file__), "include")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "xdtts_b200.h"\nint main(void) { xdtts_gl_opts o = {0}; xdtts_decoder_opts d = {0}; (void)o; (void)d; return 0; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)], check=True)
+
+
 def test_mel_filter_bank_matches_golden(lib, golden_dir):
     from xdtts_b200 import griffin_lim
 
