@@ -44,6 +44,44 @@ def test_header_is_plain_c(built, tmp_path):
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)], check=True)
 
 
+def test_c_client_links_and_calls(built, lib, tmp_path):
+    """A plain C program links against the shared library and calls it (the host-only entry points: no GPU needed)."""
+    import shutil
+    import subprocess
+
+    from xdtts_b200 import _ffi, griffin_lim
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    inc = os.path.join(os.path.dirname(built.__file__), "include")
+    libdir = os.path.dirname(_ffi.LIB_PATH)
+    src = tmp_path / "client.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include <stdlib.h>
+#include "xdtts_b200.h"
+int main(void) {
+    float* fb = (float*)malloc(sizeof(float) * 80 * 513);
+    double sum = 0.0;
+    int i, rc = xdtts_mel_filter_bank(22050.0f, 1024, 80, 0.0f, 8000.0f, fb);
+    if (rc != XDTTS_OK) { printf("error %d: %s\n", rc, xdtts_last_error()); return 1; }
+    for (i = 0; i < 80 * 513; i++) sum += fb[i];
+    printf("%s %.9f\n", xdtts_version(), sum);
+    rc = xdtts_mel_filter_bank(22050.0f, 1024, 80, 9000.0f, 8000.0f, fb);     /* fmax <= fmin */
+    printf("%d %s\n", rc, xdtts_last_error());
+    free(fb);
+    return 0;
+}
+""")
+    exe = tmp_path / "client"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-lxdtts_b200",
+                    "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines()
+    ref = griffin_lim.mel.create_mel_filter_bank(22050.0, 1024, 80, 0.0, 8000.0).astype(np.float64).sum()
+    assert out[0].startswith("xdtts_b200") and abs(float(out[0].split()[-1]) - ref) < 1e-6
+    assert out[1].startswith("-1 ") and "fmax" in out[1]
+
+
 def test_mel_filter_bank_matches_golden(lib, golden_dir):
     from xdtts_b200 import griffin_lim
 
