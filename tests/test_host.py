@@ -367,3 +367,65 @@ def test_npy_io_matches_numpy(lib, tmp_path):
     with pytest.raises(XdttsError) as e:
         tacotron2.read_npy(tmp_path / "junk.npy")
     assert e.value.code == ERR_BAD_ARG
+
+
+def test_file_readers_survive_malformed_input(lib, tmp_path):
+    """postnet.onnx and .npy come from disk: mutated / truncated files must produce an error code (or parse), never a
+    crash or a read out of bounds.  400 seeded mutants of each format."""
+    import ctypes
+    import random
+
+    from onnx_writer import postnet_model
+    from oracle import postnet_oracle as po
+    from xdtts_b200._ffi import fptr
+
+    rng = random.Random(7)
+    good = bytes(postnet_model(po.synth_weights(seed=7, channels=(8, 16, 8))))
+    path = str(tmp_path / "m.onnx").encode()
+
+    def mutate(data):
+        d = bytearray(data)
+        mode = rng.randrange(4)
+        if mode == 0:
+            for _ in range(rng.randrange(1, 8)):
+                d[rng.randrange(len(d))] = rng.randrange(256)
+        elif mode == 1:
+            d = d[:rng.randrange(len(d))]
+        elif mode == 2:
+            i = rng.randrange(len(d))
+            d[i:i] = bytes(rng.randrange(256) for _ in range(rng.randrange(1, 16)))
+        else:
+            i = rng.randrange(min(len(d), 400))
+            d[i:i + 1] = b"\xff\xff\xff\xff\xff\x7f"      # a huge varint where a length or key was
+        return bytes(d)
+
+    parsed = 0
+    for _ in range(400):
+        open(path, "wb").write(mutate(good))
+        m = ctypes.c_void_p()
+        rc = lib.xdtts_onnx_postnet_open(path, ctypes.byref(m))
+        assert rc <= 0
+        if rc == 0:
+            parsed += 1
+            n = lib.xdtts_onnx_postnet_n_layers(m)
+            for i in range(max(n, 0)):
+                co, ci, k, hb, hbn = (ctypes.c_int() for _ in range(5))
+                eps = ctypes.c_float()
+                lib.xdtts_onnx_postnet_layer_info(m, i, ctypes.byref(co), ctypes.byref(ci), ctypes.byref(k), ctypes.byref(hb),
+                                                  ctypes.byref(hbn), ctypes.byref(eps))
+                if 0 < co.value * ci.value * k.value < 10 ** 6:
+                    buf = np.empty(co.value * ci.value * k.value, np.float32)
+                    lib.xdtts_onnx_postnet_layer_copy(m, i, 0, fptr(buf))
+            lib.xdtts_onnx_postnet_close(m)
+    assert 0 < parsed < 400          # some mutants are harmless (payload bytes), most are rejected
+    npy = str(tmp_path / "a.npy")
+    np.save(npy, np.arange(12, dtype=np.float32).reshape(3, 4))
+    good = open(npy, "rb").read()
+    for _ in range(400):
+        open(npy, "wb").write(mutate(good))
+        r, c = ctypes.c_int(), ctypes.c_int()
+        rc = lib.xdtts_npy_read_f32(npy.encode(), None, 0, ctypes.byref(r), ctypes.byref(c))
+        assert rc <= 0
+        if rc == 0 and 0 < r.value * c.value < 10 ** 6:
+            buf = np.empty(r.value * c.value, np.float32)
+            lib.xdtts_npy_read_f32(npy.encode(), fptr(buf), buf.size, ctypes.byref(r), ctypes.byref(c))
