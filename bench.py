@@ -532,6 +532,9 @@ def run_gpu(args):
                                              " (one batch at a time, pinned host buffers)"},
                     "peak_normalised_ok": peak_ok},
             "gpu_launches": total_launches,
+            # the same measurement in the other two units people quote for vocoders
+            "frame_iters_per_s": total_frames * it * steps / (dev_ms * 1e-3),
+            "realtime_factor": (dev_ms * 1e-3 / steps) / (world * b * hop * (t - 1) / SR),
             "roofline": {"bound": "hbm", "kernel": "gl_iter_kernel<MID> (one Griffin-Lim iteration)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(cfg), "peak_source": peak_src, "kernel_ms": kern_ms,
