@@ -20,9 +20,9 @@ static void emu_launch(GlParams p, bool reverse_order) {
     typedef Geo<R3> G;
     // one buffer for both exchanges: the emulator always runs the aliased layout (a superset of the
     // hazards of the two-buffer layout; phases are lane-sequential, i.e. warp-synchronous)
-    std::vector<float2> ex1(G::EX1 > G::EX2 ? G::EX1 : G::EX2), r_stg(G::M);
+    std::vector<float2> ex1(G::EX1 > G::EX2 ? G::EX1 : G::EX2);
     std::vector<float2>& ex2 = ex1;
-    std::vector<float> s_stg(G::M);
+    std::vector<float> stg(G::REC_F);   // staged state record [R | S | S_nyq]
     std::vector<Lane<R3>> lanes(32);
     for (int rr = 0; rr < p.n_runs; rr++) {
         const int run_idx = reverse_order ? p.n_runs - 1 - rr : rr;
@@ -39,24 +39,31 @@ static void emu_launch(GlParams p, bool reverse_order) {
             if (old & 1u)
                 for (int l = 0; l < 32; l++) combine_boundary<R3, TRACK_MAX>(lanes[l], l, p, boundary);
         };
-        for (int l = 0; l < 32; l++) stage_issue<R3, MODE>(lanes[l], l, p, foff + r.ta, s_stg.data(), r_stg.data(), nullptr);
+        for (int l = 0; l < 32; l++) stage_issue<R3, MODE>(l, p, foff + r.ta, stg.data(), nullptr);
         bool pref = false;
         for (int t = r.ta; t < r.tb; t++) {
             const long frame = foff + t;
             if (MODE != GL_MODE_INIT) {
                 const bool fetch_next = (t + 1 < r.tb) && (t + 2 <= T - 2);
-                for (int l = 0; l < 32; l++)
-                    phase_f1<R3>(lanes[l], l, p.y_in + yoff, T, t, p.pad_mode, t == r.ta, pref, p.tables, ex1.data());
-                pref = fetch_next;
-                if (fetch_next)
-                    for (int l = 0; l < 32; l++) prefetch_next_block<R3>(lanes[l], l, p.y_in + yoff, T, t, p.pad_mode);
+                if (G::ROT) {
+                    for (int l = 0; l < 32; l++)
+                        phase_f1_rot<R3>(lanes[l], l, p.y_in + yoff, T, t, p.pad_mode, t == r.ta, pref, fetch_next, (t - r.ta) & 3,
+                                         p.tables, ex1.data());
+                    pref = fetch_next;
+                } else {
+                    for (int l = 0; l < 32; l++)
+                        phase_f1<R3>(lanes[l], l, p.y_in + yoff, T, t, p.pad_mode, t == r.ta, pref, p.tables, ex1.data());
+                    pref = fetch_next;
+                    if (fetch_next)
+                        for (int l = 0; l < 32; l++) prefetch_next_block<R3>(lanes[l], l, p.y_in + yoff, T, t, p.pad_mode);
+                }
                 for (int l = 0; l < 32; l++) phase_f2_load<R3>(lanes[l], l, ex1.data());
                 for (int l = 0; l < 32; l++) phase_f2_store<R3>(lanes[l], l, p.tables, ex2.data());
             }
             for (int l = 0; l < 32; l++)
-                phase_f3<R3, MODE, STORE_R>(lanes[l], l, p, r.utt, T, t, frame, p.tables, ex2.data(), s_stg.data(), r_stg.data());
+                phase_f3<R3, MODE, STORE_R>(lanes[l], l, p, r.utt, T, t, frame, p.tables, ex2.data(), stg.data());
             if (t + 1 < r.tb)
-                for (int l = 0; l < 32; l++) stage_issue<R3, MODE>(lanes[l], l, p, frame + 1, s_stg.data(), r_stg.data(), nullptr);
+                for (int l = 0; l < 32; l++) stage_issue<R3, MODE>(l, p, frame + 1, stg.data(), nullptr);
             for (int l = 0; l < 32; l++) phase_f4_load<R3>(lanes[l], l, p.tables, ex2.data());
             for (int l = 0; l < 32; l++) phase_f4_store<R3>(lanes[l], l, ex1.data());
             bool sig = false;
@@ -68,9 +75,13 @@ static void emu_launch(GlParams p, bool reverse_order) {
             }
             if (sig) arrive(run_idx - 1);
         }
+        // the kernel's tail-side fast path (gl_iter.cu): the right neighbour is already in (counter odd) -> finish
+        // the boundary blocks from the register accumulators and only restore the counter's parity
+        const bool ready = r.tb < T && (p.flags[run_idx] & 1u);
         bool sig = false;
-        for (int l = 0; l < 32; l++) sig = emit_tail<R3, TRACK_MAX>(lanes[l], l, p, run_idx, r, yoff, T);
+        for (int l = 0; l < 32; l++) sig = emit_tail<R3, TRACK_MAX>(lanes[l], l, p, run_idx, r, yoff, T, ready);
         if (sig) arrive(run_idx);
+        else if (ready) p.flags[run_idx]++;
         if (TRACK_MAX) {
             float m = 0.f;
             for (int l = 0; l < 32; l++) m = fmaxf(m, lanes[l].amax);
@@ -91,17 +102,13 @@ static int emu_run(const float* s_mag, const float* turns, int T, int n_iter, fl
     build_runs(&T, 1, run_frames, &runs, &foff);
     std::vector<float2> tab = build_tables<R3>();
     std::vector<float> edge = build_edge_scale(G::N);
-    std::vector<float> S((size_t)T * G::M), Sn(T), tu((size_t)T * G::M), tn(T);
-    for (int t = 0; t < T; t++) {
-        for (int k = 0; k < G::M; k++) {
-            S[(size_t)t * G::M + k] = s_mag[(size_t)k * T + t];
-            if (turns) tu[(size_t)t * G::M + k] = turns[(size_t)k * T + t];
+    // per-frame state records [R: 2M floats | S: M floats | S_nyq | 3 pad] and the initial phase [frames][M + 1]
+    std::vector<float> state((size_t)T * G::REC_F, 0.f), tu((size_t)T * K);
+    for (int t = 0; t < T; t++)
+        for (int k = 0; k < K; k++) {
+            state[(size_t)t * G::REC_F + 2 * G::M + k] = s_mag[(size_t)k * T + t];
+            if (turns) tu[(size_t)t * K + k] = turns[(size_t)k * T + t];
         }
-        Sn[t] = s_mag[(size_t)G::M * T + t];
-        if (turns) tn[t] = turns[(size_t)G::M * T + t];
-    }
-    (void)K;
-    std::vector<float2> R((size_t)T * G::M, mk2(0.f, 0.f));
     std::vector<float> ya((size_t)T * G::H, 0.f), yb((size_t)T * G::H, 0.f);
     std::vector<float> halo((size_t)runs.size() * 6 * G::H, 0.f);
     std::vector<unsigned> flags(runs.size(), 0u);
@@ -112,16 +119,13 @@ static int emu_run(const float* s_mag, const float* turns, int T, int n_iter, fl
     p.runs = runs.data();
     p.utt_T = &T;
     p.utt_foff = foff.data();
-    p.S = S.data();
-    p.S_nyq = Sn.data();
-    p.R = R.data();
+    p.state = state.data();
     p.halo = halo.data();
     p.flags = flags.data();
     p.amax = &amax;
     p.edge_scale = edge.data();
     p.tables = tab.data();
     p.turns = turns ? tu.data() : nullptr;
-    p.turns_nyq = turns ? tn.data() : nullptr;
     p.seed = seed;
     p.utt_seed_base = 0;
     p.alpha = momentum / (1.0f + momentum);
@@ -148,7 +152,8 @@ static int emu_run(const float* s_mag, const float* turns, int T, int n_iter, fl
         }
     }
     memcpy(out, yout, sizeof(float) * (size_t)G::H * (T - 1));
-    if (r_out) memcpy(r_out, R.data(), sizeof(float2) * (size_t)T * G::M);
+    if (r_out)
+        for (int t = 0; t < T; t++) memcpy(r_out + (size_t)t * 2 * G::M, &state[(size_t)t * G::REC_F], sizeof(float) * 2 * G::M);
     if (peak) memcpy(peak, &amax, 4);
     return (int)runs.size();
 }

@@ -20,13 +20,20 @@
 #include "gl_tables.h"
 
 namespace xdtts {
-cudaError_t gl_launch_lift(const float*, const float*, const int*, const int*, int, int, int, int, float, int, float*,
-                           float*, cudaStream_t);
+// gl_lift.cu
+std::vector<float> gl_lift_build_image(const float* pinv, int K, int n_mels);
+int gl_lift_tile_frames();
+cudaError_t gl_lift_prepare(int n_mels);
+cudaError_t gl_launch_lift(const float* mel_arena, const float* a_image, const float* pinvT, const int2* tiles, int n_tiles,
+                           const int* utt_T, const int* utt_foff, int n_utt, int max_T, int n_mels, int K, int ld, float power,
+                           int delog, int sm_count, float* S, cudaStream_t s, int* n_kernels);
+bool gl_lift_uses_tensor_cores(int n_mels, int K);
+// gl_aux.cu (S: bin k of frame f at S[f * ld + k], k = 0..K-1)
 cudaError_t gl_launch_nnls(const float*, const int*, const float*, const int*, const float*, const int*, const int*, int, int, int,
-                           int, float, int, float, int, float, float*, float*, cudaStream_t);
+                           int, float, int, float, int, float, float*, int, cudaStream_t);
 cudaError_t gl_launch_nnls_band(const float*, const int*, const float*, int, const int*, const float*, int, const int*, const int*, int,
-                                int, int, int, float, int, float, int, float, float*, float*, cudaStream_t);
-cudaError_t gl_launch_to_frame_major(const float*, const int*, const int*, int, int, int, float*, float*, cudaStream_t);
+                                int, int, int, float, int, float, int, float, float*, int, cudaStream_t);
+cudaError_t gl_launch_to_frame_major(const float*, const int*, const int*, int, int, int, float*, int, cudaStream_t);
 cudaError_t gl_launch_finish(const float*, const int*, const int*, const long long*, const unsigned*, int, int, int, int,
                              float*, cudaStream_t);
 cudaError_t gl_launch_pcm16(const float*, long long, short*, int, cudaStream_t);
@@ -312,6 +319,10 @@ extern "C" int xdtts_gl_create(const float* mel_basis, int n_mels, int K, int no
     std::vector<float2> tab = n_fft == 512 ? build_tables<4>() : (n_fft == 1024 ? build_tables<8>() : build_tables<16>());
     std::vector<float> edge = build_edge_scale(n_fft);
     cudaError_t e = cudaSuccess;
+    std::vector<float> img = gl_lift_build_image(h->pinv.data(), K, n_mels);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_lift_img, img.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_lift_img, img.data(), img.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = gl_lift_prepare(n_mels);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_pinvT, pT.size() * 4);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_tables, tab.size() * sizeof(float2));
     if (e == cudaSuccess) e = cudaMalloc(&h->d_edge, edge.size() * 4);
@@ -351,6 +362,7 @@ extern "C" void xdtts_gl_destroy(xdtts_gl* h) {
     cudaSetDevice(h->device);
     for (xdtts_gl_plan* p : h->cache) xdtts_gl_plan_destroy(p);
     cudaFree(h->d_pinvT);
+    cudaFree(h->d_lift_img);
     cudaFree(h->d_tables);
     cudaFree(h->d_edge);
     cudaFree(h->d_csr); cudaFree(h->d_csc); cudaFree(h->d_csr_val); cudaFree(h->d_csc_val);
@@ -380,9 +392,9 @@ extern "C" void xdtts_gl_plan_destroy(xdtts_gl_plan* p) {
     for (auto& e : p->ev)
         if (e) cudaEventDestroy(e);
     cudaFree(p->d_runs); cudaFree(p->d_T); cudaFree(p->d_foff); cudaFree(p->d_out_off);
-    cudaFree(p->d_mel); cudaFree(p->d_in_mag); cudaFree(p->d_in_phase); cudaFree(p->d_turns); cudaFree(p->d_turns_nyq);
-    cudaFree(p->d_S); cudaFree(p->d_S_nyq); cudaFree(p->d_y[0]); cudaFree(p->d_y[1]); cudaFree(p->d_halo);
-    cudaFree(p->d_out); cudaFree(p->d_R); cudaFree(p->d_flags); cudaFree(p->d_amax); cudaFree(p->d_pcm); cudaFree(p->d_done);
+    cudaFree(p->d_mel); cudaFree(p->d_in_mag); cudaFree(p->d_in_phase); cudaFree(p->d_turns); cudaFree(p->d_lift_tiles);
+    cudaFree(p->d_state); cudaFree(p->d_y[0]); cudaFree(p->d_y[1]); cudaFree(p->d_halo);
+    cudaFree(p->d_out); cudaFree(p->d_flags); cudaFree(p->d_amax); cudaFree(p->d_pcm); cudaFree(p->d_done);
     if (p->h_pcm) cudaFreeHost(p->h_pcm);
     if (p->h_in) cudaFreeHost(p->h_in);
     if (p->h_out) cudaFreeHost(p->h_out);
@@ -460,9 +472,15 @@ int xdtts::gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out)
     ALLOC(p->d_T, B * sizeof(int));
     ALLOC(p->d_foff, B * sizeof(int));
     ALLOC(p->d_out_off, B * sizeof(long long));
-    ALLOC(p->d_S, TT * M * 4);
-    ALLOC(p->d_S_nyq, TT * 4);
-    ALLOC(p->d_R, TT * M * sizeof(float2));
+    // one state record per frame: [R: M float2 | S: M floats | S_nyq + 3 floats of padding] (gl_core.cuh Geo::REC)
+    p->rec_f = (int)(3 * M + 4);
+    ALLOC(p->d_state, TT * (size_t)p->rec_f * 4);
+    {   // frame tiles of the lift: (utterance, first frame), gl_lift_tile_frames() frames each, never across utterances
+        const int tf = gl_lift_tile_frames();
+        for (int b = 0; b < B; b++)
+            for (int t0 = 0; t0 < Ts[b]; t0 += tf) p->lift_tiles.push_back(make_int2(b, t0));
+    }
+    ALLOC(p->d_lift_tiles, p->lift_tiles.size() * sizeof(int2));
     ALLOC(p->d_y[0], TT * H * 4);
     ALLOC(p->d_y[1], TT * H * 4);
     ALLOC(p->d_halo, nr * 6 * H * 4);
@@ -476,7 +494,8 @@ int xdtts::gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out)
     if (e == cudaSuccess) e = cudaMemcpy(p->d_foff, p->foff.data(), B * sizeof(int), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->d_out_off, p->out_off.data(), B * sizeof(long long), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(p->d_flags, 0, nr * sizeof(unsigned));
-    if (e == cudaSuccess) e = cudaMemset(p->d_R, 0, TT * M * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMemset(p->d_state, 0, TT * (size_t)p->rec_f * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_lift_tiles, p->lift_tiles.data(), p->lift_tiles.size() * sizeof(int2), cudaMemcpyHostToDevice);
     for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&p->ev[i]);
     if (e != cudaSuccess) {
         xdtts_gl_plan_destroy(p);
@@ -518,10 +537,7 @@ int xdtts::gl_plan_upload_locked(xdtts_gl_plan* p, int kind, const float* const*
     const size_t rows = kind == 0 ? (size_t)h->n_mels : (size_t)h->K;
     float** dst = kind == 0 ? &p->d_mel : (kind == 1 ? &p->d_in_mag : &p->d_in_phase);
     if (!*dst) CU(cudaMalloc((void**)dst, rows * (size_t)p->total_T * 4));
-    if (kind == 2 && !p->d_turns) {
-        CU(cudaMalloc((void**)&p->d_turns, (size_t)p->total_T * (h->K - 1) * 4));
-        CU(cudaMalloc((void**)&p->d_turns_nyq, (size_t)p->total_T * 4));
-    }
+    if (kind == 2 && !p->d_turns) CU(cudaMalloc((void**)&p->d_turns, (size_t)p->total_T * h->K * 4));   // [frames][K]
     // pageable sources go through one pinned staging buffer so that the copy is a single async DMA
     bool all_pinned = true;
     for (int b = 0; b < p->B; b++) all_pinned = all_pinned && is_pinned(srcs[b]);
@@ -556,40 +572,43 @@ static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid, cud
     const int M = h->K - 1;
     const bool from_mag = flags & XDTTS_RUN_FROM_MAG, use_phase = flags & XDTTS_RUN_USE_PHASE;
     CU(cudaMemsetAsync(p->d_amax, 0, p->B * sizeof(unsigned), s));
+    int lift_kernels = 1;
+    float* d_S = p->d_state + 2 * M;   // the S part of frame 0's record; records are rec_f floats apart
     if (from_mag) {
-        CU(gl_launch_to_frame_major(p->d_in_mag, p->d_T, p->d_foff, p->B, p->max_T, h->K, p->d_S, p->d_S_nyq, s));
+        CU(gl_launch_to_frame_major(p->d_in_mag, p->d_T, p->d_foff, p->B, p->max_T, h->K, d_S, p->rec_f, s));
     } else {
         const bool nnls = h->opts.lift == 1;
-        CU(gl_launch_lift(p->d_mel, h->d_pinvT, p->d_T, p->d_foff, p->B, p->max_T, h->n_mels, h->K, nnls ? 1.0f : h->power, h->opts.delog, p->d_S, p->d_S_nyq, s));
+        CU(gl_launch_lift(p->d_mel, h->d_lift_img, h->d_pinvT, p->d_lift_tiles, (int)p->lift_tiles.size(), p->d_T, p->d_foff, p->B,
+                          p->max_T, h->n_mels, h->K, p->rec_f, nnls ? 1.0f : h->power, h->opts.delog, h->sm_count, d_S, s, &lift_kernels));
+        g_launches += (unsigned long long)(lift_kernels - 1);
         if (nnls) {   // refine the clipped least-squares start in place, then apply the exponent
             const int iters = h->opts.nnls_iters > 0 ? h->opts.nnls_iters : 300;
             if (h->band_rw > 0 && !getenv("XDTTS_NNLS_GENERIC"))
                 CU(gl_launch_nnls_band(p->d_mel, h->d_band_lo, h->d_bandT, h->band_rw, h->d_ell_row, h->d_ell_val, h->band_cw, p->d_T,
                                        p->d_foff, p->B, p->max_T, h->n_mels, h->K, h->power, h->opts.delog, h->lipschitz, iters, 3e-6f,
-                                       p->d_S, p->d_S_nyq, s));
+                                       d_S, p->rec_f, s));
             else
                 CU(gl_launch_nnls(p->d_mel, h->d_csr, h->d_csr_val, h->d_csc, h->d_csc_val, p->d_T, p->d_foff, p->B, p->max_T, h->n_mels,
-                                  h->K, h->power, h->opts.delog, h->lipschitz, iters, 3e-6f, p->d_S, p->d_S_nyq, s));
+                                  h->K, h->power, h->opts.delog, h->lipschitz, iters, 3e-6f, d_S, p->rec_f, s));
             g_launches++;
         }
     }
     g_launches++;
     if (use_phase) {
-        CU(gl_launch_to_frame_major(p->d_in_phase, p->d_T, p->d_foff, p->B, p->max_T, h->K, p->d_turns, p->d_turns_nyq, s));
+        CU(gl_launch_to_frame_major(p->d_in_phase, p->d_T, p->d_foff, p->B, p->max_T, h->K, p->d_turns, h->K, s));
         g_launches++;
     }
     GlParams gp;
     memset(&gp, 0, sizeof(gp));
     gp.n_runs = (int)p->runs.size();
     gp.runs = p->d_runs; gp.utt_T = p->d_T; gp.utt_foff = p->d_foff;
-    gp.S = p->d_S; gp.S_nyq = p->d_S_nyq; gp.R = p->d_R; gp.halo = p->d_halo; gp.flags = p->d_flags; gp.amax = p->d_amax;
+    gp.state = p->d_state; gp.halo = p->d_halo; gp.flags = p->d_flags; gp.amax = p->d_amax;
     gp.edge_scale = h->d_edge; gp.tables = h->d_tables;
-    gp.turns = use_phase ? p->d_turns : nullptr; gp.turns_nyq = use_phase ? p->d_turns_nyq : nullptr;
+    gp.turns = use_phase ? p->d_turns : nullptr;
     gp.seed = h->opts.seed; gp.utt_seed_base = 0;
     gp.alpha = h->momentum / (1.0f + h->momentum);
     gp.inv_n = 1.0f / (float)h->n_fft;
     gp.pad_mode = h->opts.pad_mode;
-    (void)M;
     int mids = 0;
     bool done = false;
     if (p->use_persistent && !(flags & XDTTS_RUN_PER_LAUNCH)) {
@@ -650,7 +669,7 @@ static int plan_launch_graph(xdtts_gl_plan* p, int flags, cudaStream_t s) {
         if (e != cudaSuccess) return fail(XDTTS_ERR_CUDA, "plan_run: graph instantiate: %s", cudaGetErrorString(e));
     }
     CU(cudaGraphLaunch(p->graphs[gi], s));
-    g_launches += (unsigned long long)(h->n_iter + 3 + ((flags & XDTTS_RUN_USE_PHASE) ? 1 : 0));
+    g_launches += (unsigned long long)(h->n_iter + 3 + ((!(flags & XDTTS_RUN_FROM_MAG) && h->opts.lift == 1) ? 1 : 0) + ((flags & XDTTS_RUN_USE_PHASE) ? 1 : 0));
     return XDTTS_OK;
 }
 
@@ -782,12 +801,13 @@ extern "C" int xdtts_gl_plan_peek(xdtts_gl_plan* p, int what, float* out, long l
     if (!p || !out) return fail(XDTTS_ERR_BAD_ARG, "plan_peek: null argument");
     std::lock_guard<std::mutex> lk(p->h->mu);
     const long long M = p->h->K - 1, TT = p->total_T;
-    const void* src = what == 0 ? (const void*)p->d_S : (what == 1 ? (const void*)p->d_S_nyq : (const void*)p->d_R);
     const long long n = what == 0 ? TT * M : (what == 1 ? TT : TT * M * 2);
     if (what < 0 || what > 2 || n != n_floats) return fail(XDTTS_ERR_SHAPE, "plan_peek: what=%d expects %lld floats, got %lld", what, n, n_floats);
     CU(cudaSetDevice(p->h->device));
     CU(cudaStreamSynchronize(p->h->stream));
-    CU(cudaMemcpy(out, src, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    // gather the requested part of every frame's state record [R: 2M floats | S: M floats | S_nyq | pad]
+    const size_t off = what == 0 ? 2 * M : (what == 1 ? 3 * M : 0), width = (what == 0 ? M : (what == 1 ? 1 : 2 * M)) * 4;
+    CU(cudaMemcpy2D(out, width, p->d_state + off, (size_t)p->rec_f * 4, width, (size_t)TT, cudaMemcpyDeviceToHost));
     return XDTTS_OK;
 }
 

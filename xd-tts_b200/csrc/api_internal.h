@@ -43,6 +43,7 @@ struct xdtts_gl {
     xdtts_gl_opts opts{};
     std::vector<float> pinv;        // [K][n_mels] host copy
     float* d_pinvT = nullptr;       // [n_mels][K]
+    float* d_lift_img = nullptr;    // tf32 hi/lo tiles of the pseudo-inverse, pre-swizzled (gl_lift.cu)
     float2* d_tables = nullptr;
     float* d_edge = nullptr;
     int *d_csr = nullptr, *d_csc = nullptr;        // sparse forms of the mel basis for the NNLS lift (rows / columns)
@@ -69,9 +70,12 @@ struct xdtts_gl_plan {
     xdtts::GlRun* d_runs = nullptr;
     int *d_T = nullptr, *d_foff = nullptr;
     long long* d_out_off = nullptr;
-    float *d_mel = nullptr, *d_in_mag = nullptr, *d_in_phase = nullptr, *d_turns = nullptr, *d_turns_nyq = nullptr;
-    float *d_S = nullptr, *d_S_nyq = nullptr, *d_y[2] = {nullptr, nullptr}, *d_halo = nullptr, *d_out = nullptr;
-    float2* d_R = nullptr;
+    float *d_mel = nullptr, *d_in_mag = nullptr, *d_in_phase = nullptr, *d_turns = nullptr;
+    float* d_state = nullptr;        // per-frame records [R | S | S_nyq | pad], rec_f floats each (gl_core.cuh Geo::REC_F)
+    int rec_f = 0;
+    float *d_y[2] = {nullptr, nullptr}, *d_halo = nullptr, *d_out = nullptr;
+    std::vector<int2> lift_tiles;    // (utterance, first frame) of every frame tile of the lift
+    int2* d_lift_tiles = nullptr;
     short* d_pcm = nullptr;          // 16-bit PCM copy of d_out (allocated on first use)
     short* h_pcm = nullptr;
     unsigned *d_flags = nullptr, *d_amax = nullptr, *d_done = nullptr;

@@ -1,7 +1,5 @@
 // Kernels either side of the Griffin-Lim iteration loop (all HBM-bound, one pass each):
-//   * mel -> linear lift   S = max(0, pinv(basis) . delog(mel)) ^ power     (step 1 of
-//     griffin_lim::GriffinLim::infer; the reference's call site is
-//     /root/reference src/lib.rs:141, its parameters come from src/tacotron2/mod.rs:453-456)
+//   * the non-negative least-squares refinement of the mel -> linear lift (the lift itself is gl_lift.cu)
 //   * [K,T] row-major (the reference's ndarray layout) -> frame-major [T][M] + Nyquist column
 //   * peak normalisation of the final waveform (row a8; the caller scales by i16::MAX,
 //     src/lib.rs:153-155)
@@ -11,74 +9,7 @@
 
 namespace xdtts {
 
-// ---------------------------------------------------------------- lift
-// grid (1, ceil(maxT/16), n_utt); thread <-> bins k, k + 128, ...; 16 frames per block.
-// Accumulates in fp64: the pseudo-inverse has 36% negative entries, an fp32 sum
-// loses ~1e-3 relative to cancellation.  The de-logged mel tile is converted to fp64 once, in shared
-// memory, so the inner loop is one coalesced load of the pseudo-inverse column and 16 DFMAs fed by
-// broadcast 128-bit shared loads; the kernel is bound by the fp64 pipe (1.3 G DFMA per 32x1000 batch).
-constexpr int LIFT_TT = 16;
 constexpr int LIFT_MAX_MELS = 256;
-
-__global__ void __launch_bounds__(128) gl_lift_kernel(const float* __restrict__ mel_arena, const float* __restrict__ pinvT,
-                                                      const int* __restrict__ utt_T, const int* __restrict__ utt_foff,
-                                                      int n_mels, int K, float power, int delog, float* __restrict__ S,
-                                                      float* __restrict__ S_nyq) {
-    extern __shared__ __align__(16) double e[];   // [n_mels][LIFT_TT]
-    const int u = blockIdx.z;
-    const int T = utt_T[u];
-    const int t0 = blockIdx.y * LIFT_TT;
-    if (t0 >= T) return;
-    const long foff = utt_foff[u];
-    const float* mel = mel_arena + foff * n_mels;   // [n_mels][T] row-major, as the caller passed it
-    for (int i = threadIdx.x; i < n_mels * LIFT_TT; i += 128) {
-        const int m = i / LIFT_TT, tt = i % LIFT_TT;
-        float v = 0.f;
-        if (t0 + tt < T) {
-            v = mel[(long)m * T + t0 + tt];
-            v = delog == 0 ? expf(v) : (delog == 1 ? powf(10.f, v) : v);
-        }
-        e[i] = (double)v;
-    }
-    __syncthreads();
-    // the de-logged tile is staged once and reused for every block of 128 bins (staging it costs about as much
-    // as one block's multiply-adds)
-    const int M = K - 1;
-    for (int k = threadIdx.x; k < K; k += 128) {
-        double acc[LIFT_TT];
-#pragma unroll
-        for (int tt = 0; tt < LIFT_TT; tt++) acc[tt] = 0.0;
-        const float* col = pinvT + k;
-#pragma unroll 4
-        for (int m = 0; m < n_mels; m++) {
-            const double a = (double)col[(long)m * K];
-            const double2* er = reinterpret_cast<const double2*>(e + m * LIFT_TT);
-#pragma unroll
-            for (int q = 0; q < LIFT_TT / 2; q++) {
-                const double2 x = er[q];
-                acc[2 * q + 0] = fma(a, x.x, acc[2 * q + 0]);
-                acc[2 * q + 1] = fma(a, x.y, acc[2 * q + 1]);
-            }
-        }
-#pragma unroll
-        for (int tt = 0; tt < LIFT_TT; tt++) {
-            if (t0 + tt >= T) break;
-            float s = (float)acc[tt];
-            s = s > 0.f ? (power == 1.0f ? s : powf(s, power)) : 0.f;
-            if (k < M) S[(foff + t0 + tt) * M + k] = s;
-            else S_nyq[foff + t0 + tt] = s;
-        }
-    }
-}
-
-cudaError_t gl_launch_lift(const float* mel_arena, const float* pinvT, const int* utt_T, const int* utt_foff, int n_utt,
-                           int max_T, int n_mels, int K, float power, int delog, float* S, float* S_nyq, cudaStream_t s) {
-    if (n_mels > LIFT_MAX_MELS) return cudaErrorInvalidValue;
-    dim3 grid(1, (max_T + LIFT_TT - 1) / LIFT_TT, n_utt);
-    gl_lift_kernel<<<grid, 128, (size_t)n_mels * LIFT_TT * sizeof(double), s>>>(mel_arena, pinvT, utt_T, utt_foff, n_mels, K, power,
-                                                                               delog, S, S_nyq);
-    return cudaGetLastError();
-}
 
 // ---------------------------------------------------------------- NNLS lift
 // The crate behind griffin_lim::GriffinLim::infer ports librosa, whose mel -> linear step is
@@ -104,7 +35,7 @@ template <int KJ>
 __global__ void __launch_bounds__(128) gl_nnls_kernel(const float* __restrict__ mel_arena, NnlsMat A, const int* __restrict__ utt_T,
                                                       const int* __restrict__ utt_foff, int n_mels, int K, float power, int delog,
                                                       float inv_L, int max_iter, float pgtol_over_L, float* __restrict__ S,
-                                                      float* __restrict__ S_nyq) {
+                                                      int ld) {
     extern __shared__ __align__(16) float nn_sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int u = blockIdx.y, T = utt_T[u], t = blockIdx.x * 4 + warp;
@@ -124,7 +55,7 @@ __global__ void __launch_bounds__(128) gl_nnls_kernel(const float* __restrict__ 
 #pragma unroll
     for (int j = 0; j < KJ; j++) {
         const int k = lane + 32 * j;
-        x[j] = k < M ? S[frame * M + k] : (k == M ? S_nyq[frame] : 0.f);
+        x[j] = k <= M ? S[frame * ld + k] : 0.f;   // k == M: the Nyquist slot of the frame's record
         y[j] = x[j];
     }
     float tk = 1.f;
@@ -180,8 +111,7 @@ __global__ void __launch_bounds__(128) gl_nnls_kernel(const float* __restrict__ 
     for (int j = 0; j < KJ; j++) {
         const int k = lane + 32 * j;
         const float v = x[j] > 0.f ? (power == 1.0f ? x[j] : powf(x[j], power)) : 0.f;
-        if (k < M) S[frame * M + k] = v;
-        else if (k == M) S_nyq[frame] = v;
+        if (k <= M) S[frame * ld + k] = v;
     }
 }
 
@@ -203,7 +133,7 @@ template <int KJ, int CW>
 __global__ void __launch_bounds__(128) gl_nnls_band_kernel(const float* __restrict__ mel_arena, NnlsBand A, const int* __restrict__ utt_T,
                                                            const int* __restrict__ utt_foff, int n_mels, int K, float power, int delog,
                                                            float inv_L, int max_iter, float pgtol_over_L, float* __restrict__ S,
-                                                           float* __restrict__ S_nyq) {
+                                                           int ld) {
     extern __shared__ __align__(16) float nn_sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int u = blockIdx.y, T = utt_T[u], t = blockIdx.x * 4 + warp;
@@ -226,7 +156,7 @@ __global__ void __launch_bounds__(128) gl_nnls_band_kernel(const float* __restri
 #pragma unroll
     for (int j = 0; j < KJ; j++) {
         const int k = lane + 32 * j;
-        x[j] = k < M ? S[frame * M + k] : (k == M ? S_nyq[frame] : 0.f);
+        x[j] = k <= M ? S[frame * ld + k] : 0.f;   // k == M: the Nyquist slot of the frame's record
         y[j] = x[j];
     }
     float tk = 1.f;
@@ -287,15 +217,14 @@ __global__ void __launch_bounds__(128) gl_nnls_band_kernel(const float* __restri
     for (int j = 0; j < KJ; j++) {
         const int k = lane + 32 * j;
         const float v = x[j] > 0.f ? (power == 1.0f ? x[j] : powf(x[j], power)) : 0.f;
-        if (k < M) S[frame * M + k] = v;
-        else if (k == M) S_nyq[frame] = v;
+        if (k <= M) S[frame * ld + k] = v;
     }
 }
 
 // band: [n_mels] row_lo | then nothing else (ints); band_val: [rw][n_mels]; colrow: [cw][K]; colval: [cw][K]
 cudaError_t gl_launch_nnls_band(const float* mel_arena, const int* row_lo, const float* bandT, int rw, const int* col_row,
                                 const float* col_val, int cw, const int* utt_T, const int* utt_foff, int n_utt, int max_T, int n_mels,
-                                int K, float power, int delog, float L, int max_iter, float pgtol, float* S, float* S_nyq,
+                                int K, float power, int delog, float L, int max_iter, float pgtol, float* S, int ld,
                                 cudaStream_t s) {
     if (n_mels > LIFT_MAX_MELS || cw < 1 || cw > 4 || rw < 4 || rw > 64 || (rw & 3)) return cudaErrorInvalidValue;
     NnlsBand A;
@@ -305,7 +234,7 @@ cudaError_t gl_launch_nnls_band(const float* mel_arena, const int* row_lo, const
     const float inv_L = 1.0f / L, tol = pgtol / L;
 #define XD_BAND_LAUNCH(KJ_, CW_)                                                                                                  \
     gl_nnls_band_kernel<KJ_, CW_><<<grid, 128, 4 * (size_t)(32 * KJ_ + 64 + 2 * LIFT_MAX_MELS) * sizeof(float), s>>>(             \
-        mel_arena, A, utt_T, utt_foff, n_mels, K, power, delog, inv_L, max_iter, tol, S, S_nyq)
+        mel_arena, A, utt_T, utt_foff, n_mels, K, power, delog, inv_L, max_iter, tol, S, ld)
 #define XD_BAND_CW(KJ_)                                                                                                           \
     do {                                                                                                                          \
         if (cw <= 2) XD_BAND_LAUNCH(KJ_, 2);                                                                                      \
@@ -322,7 +251,7 @@ cudaError_t gl_launch_nnls_band(const float* mel_arena, const int* row_lo, const
 
 cudaError_t gl_launch_nnls(const float* mel_arena, const int* csr, const float* csr_val, const int* csc, const float* csc_val,
                            const int* utt_T, const int* utt_foff, int n_utt, int max_T, int n_mels, int K, float power, int delog,
-                           float L, int max_iter, float pgtol, float* S, float* S_nyq, cudaStream_t s) {
+                           float L, int max_iter, float pgtol, float* S, int ld, cudaStream_t s) {
     if (n_mels > LIFT_MAX_MELS) return cudaErrorInvalidValue;
     NnlsMat A;
     A.row_ptr = csr; A.row_col = csr + n_mels + 1; A.row_val = csr_val;
@@ -332,7 +261,7 @@ cudaError_t gl_launch_nnls(const float* mel_arena, const int* csr, const float* 
     const float inv_L = 1.0f / L, tol = pgtol / L;
 #define XD_NNLS_LAUNCH(KJ_)                                                                                                   \
     gl_nnls_kernel<KJ_><<<grid, 128, 4 * (size_t)(32 * KJ_ + 2 * LIFT_MAX_MELS) * sizeof(float), s>>>(                          \
-        mel_arena, A, utt_T, utt_foff, n_mels, K, power, delog, inv_L, max_iter, tol, S, S_nyq)
+        mel_arena, A, utt_T, utt_foff, n_mels, K, power, delog, inv_L, max_iter, tol, S, ld)
     if (kj <= 9) XD_NNLS_LAUNCH(9);
     else if (kj <= 17) XD_NNLS_LAUNCH(17);
     else if (kj <= 33) XD_NNLS_LAUNCH(33);
@@ -342,11 +271,12 @@ cudaError_t gl_launch_nnls(const float* mel_arena, const int* csr, const float* 
 }
 
 // ---------------------------------------------------------------- [K,T] -> frame-major
-// src arena: utterance u is a row-major [K][T_u] block at float offset foff[u]*K.
+// src arena: utterance u is a row-major [K][T_u] block at float offset foff[u]*K.  dst: frame-major rows of `ld` floats
+// (bin k of frame f at dst[f * ld + k], k = 0..K-1).
 __global__ void __launch_bounds__(256) gl_to_frame_major_kernel(const float* __restrict__ src_arena,
                                                                 const int* __restrict__ utt_T,
                                                                 const int* __restrict__ utt_foff, int K,
-                                                                float* __restrict__ dst, float* __restrict__ dst_nyq) {
+                                                                float* __restrict__ dst, int ld) {
     __shared__ float tile[32][33];
     const int u = blockIdx.z;
     const int T = utt_T[u];
@@ -360,20 +290,16 @@ __global__ void __launch_bounds__(256) gl_to_frame_major_kernel(const float* __r
         tile[r][tx] = (k < K && t < T) ? src[(long)k * T + t] : 0.f;
     }
     __syncthreads();
-    const int M = K - 1;
     for (int r = ty; r < 32; r += 8) {
         const int t = t0 + r, k = k0 + tx;
-        if (t < T && k < K) {
-            if (k < M) dst[(foff + t) * M + k] = tile[tx][r];
-            else dst_nyq[foff + t] = tile[tx][r];
-        }
+        if (t < T && k < K) dst[(foff + t) * ld + k] = tile[tx][r];   // k == K-1 lands in the Nyquist slot
     }
 }
 
 cudaError_t gl_launch_to_frame_major(const float* src_arena, const int* utt_T, const int* utt_foff, int n_utt, int max_T,
-                                     int K, float* dst, float* dst_nyq, cudaStream_t s) {
+                                     int K, float* dst, int ld, cudaStream_t s) {
     dim3 grid((K + 31) / 32, (max_T + 31) / 32, n_utt);
-    gl_to_frame_major_kernel<<<grid, 256, 0, s>>>(src_arena, utt_T, utt_foff, K, dst, dst_nyq);
+    gl_to_frame_major_kernel<<<grid, 256, 0, s>>>(src_arena, utt_T, utt_foff, K, dst, ld);
     return cudaGetLastError();
 }
 

@@ -37,8 +37,18 @@
 #define XD_HD inline
 #endif
 
+// 1: the frame's samples stay in place in L.raw and the window multiply is instantiated per rotation (phase_f1_rot);
+// 0: L.raw is shifted by one hop per frame (phase_f1 + prefetch_next_block).  Measured on B200 (round 2):
+// n_fft 1024 86.1 -> 85.8 us per launch with rotation, n_fft 2048 367.8 -> 375.7 us (four copies of a window
+// multiply of 64 values cost more instruction-cache misses than the 56 moves they save), hence per geometry.
+#ifndef XDTTS_GL_ROT
+#define XDTTS_GL_ROT(R3) ((R3) != 16)
+#endif
+// keep the 7 pass-2 twiddles in registers for the whole run instead of re-reading them from shared memory twice per
+// frame: n_fft 2048 383 -> 376 us, n_fft 1024 85.8 -> 84.0 us (round 2; in round 1, before the sample registers
+// stopped moving, the extra 14 registers cost more than the loads at n_fft 1024)
 #ifndef XDTTS_GL_TW2_REGS
-#define XDTTS_GL_TW2_REGS(R3) ((R3) == 16)
+#define XDTTS_GL_TW2_REGS(R3) 1
 #endif
 
 namespace xdtts {
@@ -62,22 +72,99 @@ struct Geo {
     static constexpr int TW1_OFF = 0;                     // W_M^{(lane+32 i) k1}, row i*7 + k1-1
     static constexpr int TW2_OFF = TW1_OFF + 7 * NB * 32; // W_{8 R3}^{(lane & (R3-1)) k2}, row k2-1
     static constexpr int RTW_OFF = TW2_OFF + 7 * 32;      // -i W_N^{k(lane,j)} / 2, row j
-    static constexpr int WIN_OFF = RTW_OFF + R3 * 32;     // (w[s], w[s+1]), row i*8 + n1
-    static constexpr int TAB = WIN_OFF + VPL * 32;
-    // keep the 7 pass-2 twiddles in registers for the whole run instead of re-reading them from shared
-    // memory twice per frame: measured faster at N = 2048 (cfg5 478 -> 461 us), slower at N = 1024 (98 -> 102 us)
+    static constexpr int WIN_OFF = RTW_OFF + R3 * 32;     // (w[s], w[s+1]), row i*4 + n1, n1 = 0..3 only:
+                                                          // w[s + N/2] = 1 - w[s] (periodic Hann), so the rows n1+4 are
+                                                          // applied as x - x w with one FFMA and never loaded
+    static constexpr int TAB = WIN_OFF + (VPL / 2) * 32;
+    static constexpr int REC_F = 3 * M + 4;   // floats per frame state record: R (2M) | S (M) | S_nyq + 3 pad
+    static constexpr int REC = 4 * REC_F;     // bytes; a multiple of 16
     static constexpr bool TW2_REGS = XDTTS_GL_TW2_REGS(R3_);
+    static constexpr bool ROT = XDTTS_GL_ROT(R3_);
 };
+
+// Exchange 1 holds, per k1 row, the 8 R3 values m = lane + 32 i of pass 1.  A lane's values of one butterfly pair
+// (i even, i odd) are adjacent, so pass 1 stores and the last inverse pass loads them as ONE 128-bit access; pass 2
+// finds its inputs n2 and n2 + 16/R3*... (m and m + 32) adjacent in the same way.  Conflict-free: a quarter warp
+// touches 8 consecutive 16-byte units.
+template <int R3>
+XD_HD constexpr int ex1_pos(int m) {
+    return (R3 == 4) ? m : 2 * (m & 31) + ((m >> 5) & 1) + 64 * (m >> 6);
+}
+XD_HD float2 mk2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
+XD_HD float4 pack4(float2 a, float2 b) { float4 r; r.x = a.x; r.y = a.y; r.z = b.x; r.w = b.y; return r; }
+
+// pass 1 -> exchange 1: v[i*8 + k1] (already multiplied by its twiddle) goes to row k1, element lane + 32 i
+template <int R3>
+XD_HD void ex1_store_rows(const float2* v, int lane, float2* ex1) {
+    typedef Geo<R3> G;
+    if constexpr (R3 == 4) {
+#pragma unroll
+        for (int k1 = 0; k1 < 8; k1++) ex1[k1 * G::S1 + lane] = v[k1];
+    } else {
+#pragma unroll
+        for (int ip = 0; ip < G::NB / 2; ip++)
+#pragma unroll
+            for (int k1 = 0; k1 < 8; k1++)
+                *reinterpret_cast<float4*>(&ex1[k1 * G::S1 + 2 * lane + 64 * ip]) = pack4(v[(2 * ip) * 8 + k1], v[(2 * ip + 1) * 8 + k1]);
+    }
+}
+// exchange 1 -> last inverse pass: the transpose of ex1_store_rows
+template <int R3>
+XD_HD void ex1_load_rows(float2* v, int lane, const float2* ex1) {
+    typedef Geo<R3> G;
+    if constexpr (R3 == 4) {
+#pragma unroll
+        for (int k1 = 0; k1 < 8; k1++) v[k1] = ex1[k1 * G::S1 + lane];
+    } else {
+#pragma unroll
+        for (int ip = 0; ip < G::NB / 2; ip++)
+#pragma unroll
+            for (int k1 = 0; k1 < 8; k1++) {
+                const float4 q = *reinterpret_cast<const float4*>(&ex1[k1 * G::S1 + 2 * lane + 64 * ip]);
+                v[(2 * ip) * 8 + k1] = mk2(q.x, q.y);
+                v[(2 * ip + 1) * 8 + k1] = mk2(q.z, q.w);
+            }
+    }
+}
+// exchange 1 -> pass 2: butterfly i of a lane reads row k1, elements R3 n2 + n3, n2 = 0..7
+template <int R3>
+XD_HD void ex1_load_cols(float2* v8, int k1, int n3, const float2* ex1) {
+    typedef Geo<R3> G;
+    if constexpr (R3 == 4) {
+#pragma unroll
+        for (int n2 = 0; n2 < 8; n2++) v8[n2] = ex1[k1 * G::S1 + R3 * n2 + n3];
+    } else {
+#pragma unroll
+        for (int n2 = 0; n2 < 8; n2++)
+            if ((((R3 * n2) >> 5) & 1) == 0) {
+                const float4 q = *reinterpret_cast<const float4*>(&ex1[k1 * G::S1 + ex1_pos<R3>(R3 * n2) + 2 * n3]);
+                v8[n2] = mk2(q.x, q.y);
+                v8[n2 + 32 / R3] = mk2(q.z, q.w);
+            }
+    }
+}
+template <int R3>
+XD_HD void ex1_store_cols(const float2* v8, int k1, int n3, float2* ex1) {
+    typedef Geo<R3> G;
+    if constexpr (R3 == 4) {
+#pragma unroll
+        for (int n2 = 0; n2 < 8; n2++) ex1[k1 * G::S1 + R3 * n2 + n3] = v8[n2];
+    } else {
+#pragma unroll
+        for (int n2 = 0; n2 < 8; n2++)
+            if ((((R3 * n2) >> 5) & 1) == 0)
+                *reinterpret_cast<float4*>(&ex1[k1 * G::S1 + ex1_pos<R3>(R3 * n2) + 2 * n3]) = pack4(v8[n2], v8[n2 + 32 / R3]);
+    }
+}
 
 // bin held in pair slot j of a lane after the last forward pass (its partner is M - k)
 template <int R3>
 XD_HD int kslot(int lane, int j) {
     if (lane) return lane + 64 * j;
-    return (j < R3 / 2) ? 64 * j : 32 + 64 * (j - R3 / 2);
+    return (j < R3 / 2) ? 64 * j : 32 + 64 * j;   // lane 0: column 0, then column 32 entered from its upper half (lane0_fix)
 }
 
 // ------------------------------------------------------------------ complex helpers
-XD_HD float2 mk2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
 // Complex add / subtract.  sm_100 has packed fp32x2 instructions (FADD2 / FFMA2 on a 64-bit register
 // pair; a - b = fma(b, -1, a) is exact).  Measured on B200 they cut the FP instruction count of this
 // kernel by 17% but make it SLOWER (cfg2 96.1 -> 106.8 us, cfg5 459 -> 501 us): the packed forms issue
@@ -176,16 +263,16 @@ struct GlParams {
     const int* utt_foff;     // first frame row of the utterance in S / R; its samples start at foff * H
     const float* y_in;       // waveform of the previous iteration
     float* y_out;            // waveform of this iteration
-    const float* S;          // [frames][M] magnitudes, bins 0..M-1
-    const float* S_nyq;      // [frames]    magnitude of bin M
-    float2* R;               // [frames][M] rebuilt spectrum, updated in place; slot 0 = (Re R[0], Re R[M])
+    // per-frame state record, `Geo::REC` bytes, contiguous so that ONE bulk copy stages a frame:
+    //   [R: M float2, rebuilt spectrum, updated in place; slot 0 = (Re R[0], Re R[M])][S: M floats, |S| of bins 0..M-1]
+    //   [S_nyq: |S| of bin M][3 floats of padding]
+    float* state;            // record of frame f at state + f * Geo::REC_F floats
     float* halo;             // [n_runs][2][3*H] partial overlap-add sums at run boundaries
     unsigned* flags;         // [n_runs] arrival counters of the boundary to the right of each run
     unsigned* amax;          // [n_utt] max |y| as float bits (last iteration only)
     const float* edge_scale; // [2][H] 1 / window-sum-square of the first / last hop block
     const float2* tables;    // Geo::TAB constants
-    const float* turns;      // INIT: [frames][M] initial phase in turns, or null -> hashed from seed
-    const float* turns_nyq;  // INIT: [frames]
+    const float* turns;      // INIT: [frames][M + 1] initial phase in turns (bin M last), or null -> hashed from seed
     unsigned long long seed; // INIT: seed of the counter-based phase generator
     int utt_seed_base;       // INIT: global index of utterance 0 (so shards draw distinct phases)
     float* ybuf[2];          // persistent kernel: the two waveform buffers (iteration i reads [(i-1)&1], writes [i&1])
@@ -217,11 +304,17 @@ XD_HD void sincos_turns(float u, float* s, float* c) {
 #endif
 }
 
+// 1 / sqrt(m2) for the unit-modulus projection u / |u| (librosa: angles / (|angles| + tiny)).  One MUFU.RSQ on the
+// device: rsqrtf() wraps the same instruction in a denormal-rescaling sequence (FSETP + 2 predicated FMUL per call,
+// 16 calls per lane and frame), and the m2 > 0 guard cost another FSETP + FSEL.  The floor keeps u = 0 -> 0 (0 * 1e15)
+// and only changes values with |u| < 1e-15, far below the rounding noise of the transform.
 XD_HD float rsqrt_pos(float m2) {
 #if defined(__CUDA_ARCH__)
-    return m2 > 0.f ? rsqrtf(m2) : 0.f;
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(m2, 1e-30f)));
+    return r;
 #else
-    return m2 > 0.f ? 1.0f / sqrtf(m2) : 0.f;
+    return 1.0f / sqrtf(fmaxf(m2, 1e-30f));
 #endif
 }
 
@@ -257,9 +350,8 @@ struct Lane {
     float2 v[Geo<R3>::VPL];          // FFT working set
     float2 raw[Geo<R3>::VPL];        // un-windowed samples of the current frame; three quarters carry over to the next
     float2 acc[3][2 * Geo<R3>::NB];  // overlap-add sums of the three unfinished hop blocks
-    float2 ynew[2 * Geo<R3>::NB];    // newest hop block of the NEXT frame, fetched one frame ahead
+    float2 ynew[2 * Geo<R3>::NB];    // newest hop block of the NEXT frame, fetched one frame ahead (unused when Geo::ROT)
     float2 tw2[7];                   // pass-2 twiddles W_{8 R3}^{(lane & (R3-1)) k2}, k2 = 1..7 (only when Geo::TW2_REGS)
-    float s_nyq;                     // |S| at the Nyquist bin of the frame whose state is staged (lane 0)
     float amax;
 };
 
@@ -289,9 +381,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         ".reg .pred p;\n\t"
         "WAIT_%=:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
+        "@!p bra WAIT_%=;\n\t"
         "}" ::"r"(smem_addr_u32(bar)),
         "r"(parity)
         : "memory");
@@ -303,26 +393,28 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 }
 #endif
 
-// issue the copies of `frame`'s state into the warp's staging area (call after every lane has
-// finished reading the previous contents: the caller puts a warp sync in between)
+// Issue the copy of `frame`'s state record into the warp's staging area (call after every lane has finished
+// reading the previous contents: the caller puts a warp sync in between).  The record is contiguous in HBM and in
+// the staging area -- [R | S | S_nyq] -- so a frame is ONE bulk copy (INIT / FIRST, which have no previous
+// spectrum, copy the [S | S_nyq] tail only): each cp.async.bulk costs ~20 instructions of uniform-register set-up
+// around the one that does the work, and three of them per frame were 4% of the kernel's issue slots.
 template <int R3, int MODE>
-XD_HD void stage_issue(Lane<R3>& L, int lane, const GlParams& p, long frame, float* s_stg, float2* r_stg,
-                       unsigned long long* bar) {
+XD_HD void stage_issue(int lane, const GlParams& p, long frame, float* stg, unsigned long long* bar) {
     typedef Geo<R3> G;
     if (lane == 0) {
-        const float* Srow = p.S + frame * G::M;
-        const float2* Rrow = p.R + frame * G::M;
+        const float* rec = p.state + frame * G::REC_F;
 #if defined(__CUDA_ARCH__)
-        mbar_expect_tx(bar, (unsigned)(G::M * (MODE == GL_MODE_MID ? 12 : 4)));
-        bulk_g2s(s_stg, Srow, (unsigned)(G::M * 4), bar);
-        if (MODE == GL_MODE_MID) bulk_g2s(r_stg, Rrow, (unsigned)(G::M * 8), bar);
+        if (MODE == GL_MODE_MID) {
+            mbar_expect_tx(bar, (unsigned)G::REC);
+            bulk_g2s(stg, rec, (unsigned)G::REC, bar);
+        } else {
+            mbar_expect_tx(bar, (unsigned)(G::M * 4 + 16));
+            bulk_g2s(stg + 2 * G::M, rec + 2 * G::M, (unsigned)(G::M * 4 + 16), bar);
+        }
 #else
         (void)bar;
-        for (int k = 0; k < G::M; k++) s_stg[k] = Srow[k];
-        if (MODE == GL_MODE_MID)
-            for (int k = 0; k < G::M; k++) r_stg[k] = Rrow[k];
+        for (int k = (MODE == GL_MODE_MID ? 0 : 2 * G::M); k < G::REC_F; k++) stg[k] = rec[k];
 #endif
-        L.s_nyq = ld_stream(p.S_nyq + frame);
     }
 }
 
@@ -413,18 +505,81 @@ XD_HD void phase_f1(Lane<R3>& L, int lane, const float* y, int T, int t, int pad
 #pragma unroll
     for (int i = 0; i < G::NB; i++) {
 #pragma unroll
-        for (int n1 = 0; n1 < 8; n1++) {
-            const float2 w = tab[G::WIN_OFF + (i * 8 + n1) * 32 + lane];
-            L.v[i * 8 + n1] = mk2(L.raw[i * 8 + n1].x * w.x, L.raw[i * 8 + n1].y * w.y);
+        for (int n1 = 0; n1 < 4; n1++) {
+            const float2 w = tab[G::WIN_OFF + (i * 4 + n1) * 32 + lane];
+            const float2 lo = L.raw[i * 8 + n1], hi = L.raw[i * 8 + n1 + 4];
+            L.v[i * 8 + n1] = mk2(lo.x * w.x, lo.y * w.y);
+            L.v[i * 8 + n1 + 4] = mk2(fmaf(-hi.x, w.x, hi.x), fmaf(-hi.y, w.y, hi.y));   // x (1 - w)
         }
         Dft<8, false>::run(&L.v[i * 8]);
 #pragma unroll
-        for (int k1 = 0; k1 < 8; k1++) {
-            float2 z = L.v[i * 8 + k1];
-            if (k1) z = cmul(z, tab[G::TW1_OFF + (i * 7 + k1 - 1) * 32 + lane]);
-            ex1[k1 * G::S1 + lane + 32 * i] = z;
+        for (int k1 = 1; k1 < 8; k1++) L.v[i * 8 + k1] = cmul(L.v[i * 8 + k1], tab[G::TW1_OFF + (i * 7 + k1 - 1) * 32 + lane]);
+    }
+    ex1_store_rows<R3>(L.v, lane, ex1);
+}
+
+// ---- F1 with ROTATING sample registers.  Shifting L.raw by one hop costs 6 NB register moves per frame (plus
+// 2 NB to bring in the prefetched block); instead the registers stay put and the frame-relative position n1
+// lives in register (n1 + 2 rho) & 7, rho = (t - ta) & 3.  Register indices must be static, so the window
+// multiply is instantiated four times and selected by a warp-uniform switch.  The group that holds the oldest
+// hop block is dead after the multiply -- the newest block of frame t+1 is loaded straight into it (no ynew).
+template <int R3, int RHO, bool L2LOAD>
+XD_HD void f1_window_rot(Lane<R3>& L, int lane, const float2* tab, const float* y, int t, bool insert, const float2* q,
+                         bool fetch_next) {
+    typedef Geo<R3> G;
+    constexpr int P0 = (2 * RHO) & 7;   // register slot of frame-relative n1 = 0
+    if (insert) {                       // newest hop block of THIS frame was not prefetched (edge frame / first frame)
+#pragma unroll
+        for (int e = 0; e < 2 * G::NB; e++) L.raw[(e % G::NB) * 8 + ((6 + P0) & 7) + e / G::NB] = q[e];
+    }
+#pragma unroll
+    for (int i = 0; i < G::NB; i++) {
+#pragma unroll
+        for (int n1 = 0; n1 < 4; n1++) {
+            const float2 w = tab[G::WIN_OFF + (i * 4 + n1) * 32 + lane];
+            const float2 lo = L.raw[i * 8 + ((n1 + P0) & 7)], hi = L.raw[i * 8 + ((n1 + 4 + P0) & 7)];
+            L.v[i * 8 + n1] = mk2(lo.x * w.x, lo.y * w.y);
+            L.v[i * 8 + n1 + 4] = mk2(fmaf(-hi.x, w.x, hi.x), fmaf(-hi.y, w.y, hi.y));   // x (1 - w)
         }
     }
+    if (fetch_next) {   // hop block t+2 of the signal = newest block of frame t+1, entirely inside the signal
+        const float* yb = y + (long)t * G::H + 2 * G::H + 2 * lane;
+#pragma unroll
+        for (int e = 0; e < 2 * G::NB; e++)
+            L.raw[(e % G::NB) * 8 + P0 + e / G::NB] =
+                ld_y(reinterpret_cast<const float2*>(yb + 16 * R3 * (e / G::NB) + 64 * (e % G::NB)), L2LOAD);
+    }
+}
+
+template <int R3, bool L2LOAD = false>
+XD_HD void phase_f1_rot(Lane<R3>& L, int lane, const float* y, int T, int t, int pad_mode, bool first, bool have_pref,
+                        bool fetch_next, int rho, const float2* tab, float2* ex1) {
+    typedef Geo<R3> G;
+    float2 q[2 * G::NB];
+    const bool insert = first || !have_pref;
+    if (first) {   // rho == 0
+#pragma unroll
+        for (int qi = 0; qi < 3; qi++) {
+            float2 q3[2 * G::NB];
+            load_quarter<R3, L2LOAD>(q3, lane, y, T, t, qi, pad_mode);
+#pragma unroll
+            for (int e = 0; e < 2 * G::NB; e++) L.raw[(e % G::NB) * 8 + 2 * qi + e / G::NB] = q3[e];
+        }
+    }
+    if (insert) load_quarter<R3, L2LOAD>(q, lane, y, T, t, 3, pad_mode);
+    switch (rho) {
+        case 0: f1_window_rot<R3, 0, L2LOAD>(L, lane, tab, y, t, insert, q, fetch_next); break;
+        case 1: f1_window_rot<R3, 1, L2LOAD>(L, lane, tab, y, t, insert, q, fetch_next); break;
+        case 2: f1_window_rot<R3, 2, L2LOAD>(L, lane, tab, y, t, insert, q, fetch_next); break;
+        default: f1_window_rot<R3, 3, L2LOAD>(L, lane, tab, y, t, insert, q, fetch_next); break;
+    }
+#pragma unroll
+    for (int i = 0; i < G::NB; i++) {
+        Dft<8, false>::run(&L.v[i * 8]);
+#pragma unroll
+        for (int k1 = 1; k1 < 8; k1++) L.v[i * 8 + k1] = cmul(L.v[i * 8 + k1], tab[G::TW1_OFF + (i * 7 + k1 - 1) * 32 + lane]);
+    }
+    ex1_store_rows<R3>(L.v, lane, ex1);
 }
 
 // Fetch the newest hop block of frame t+1 (inside the signal by construction: fast path) one frame
@@ -444,8 +599,7 @@ XD_HD void phase_f2_load(Lane<R3>& L, int lane, const float2* ex1) {
 #pragma unroll
     for (int i = 0; i < G::NB; i++) {
         const int k1 = (lane >> G::LN3) + (32 / R3) * i;
-#pragma unroll
-        for (int n2 = 0; n2 < 8; n2++) L.v[i * 8 + n2] = ex1[k1 * G::S1 + R3 * n2 + n3];
+        ex1_load_cols<R3>(&L.v[i * 8], k1, n3, ex1);
     }
 }
 template <int R3>
@@ -465,53 +619,56 @@ XD_HD void phase_f2_store(Lane<R3>& L, int lane, const float2* tab, float2* ex2)
     }
 }
 
-// lane 0 holds the two self-paired butterflies (k mod 64 == 0 and == 32); permute its
-// registers so that "slot j pairs A[j] with B[R3-1-j]" holds for it as for every other lane
+// Lane 0 holds the two self-paired columns (k mod 64 == 0 and == 32): column 0 pairs A[j] with A[R3-j], column 32
+// pairs B[j] with B[R3-1-j].  Every other lane pairs A[j] with B[R3-1-j].  Lane 0 is brought to that form with the
+// FEWEST register moves: the lower half of A and the lower half of B stay where they are -- slots j < R3/2 keep
+// a = A[j] and only need their partner in the b register; slots j >= R3/2 keep b = B[R3-1-j] and process the pair
+// from the other side (a = B[j], the partner of B[R3-1-j]; kslot() names that bin).  So only the upper halves trade
+// places: R3 selects per direction instead of the 3/2 R3 moves of a full re-sort.
 template <int R3>
 XD_HD void lane0_fix(float2* v, bool l0) {
-    float2 A[R3], B[R3];
+    float2 Au[R3 / 2], Bu[R3 / 2];   // upper halves
 #pragma unroll
-    for (int i = 0; i < R3; i++) { A[i] = v[i]; B[i] = v[R3 + i]; }
+    for (int i = 0; i < R3 / 2; i++) { Au[i] = v[R3 / 2 + i]; Bu[i] = v[R3 + R3 / 2 + i]; }
 #pragma unroll
-    for (int i = 0; i < R3 / 2; i++) {
-        if (l0) v[R3 / 2 + i] = B[i];           // A'[R3/2+i] = B[i]
-        if (l0) v[R3 + i] = B[R3 / 2 + i];      // B'[i]      = B[R3/2+i]
-    }
+    for (int i = 0; i < R3 / 2; i++)
+        if (l0) v[R3 / 2 + i] = Bu[i];                            // A'[j] = B[j], j >= R3/2
 #pragma unroll
-    for (int i = R3 / 2; i < R3 - 1; i++)
-        if (l0) v[R3 + i] = A[i + 1];           // B'[i]      = A[i+1]
-    if (l0) v[R3 + R3 - 1] = A[R3 / 2];         // B'[R3-1]   = A[R3/2]
+    for (int i = 0; i < R3 / 2 - 1; i++)
+        if (l0) v[R3 + R3 / 2 + i] = Au[i + 1];                   // B'[m] = A[m+1], m = R3/2 .. R3-2
+    if (l0) v[R3 + R3 - 1] = Au[0];                               // B'[R3-1] = A[R3/2]
 }
 template <int R3>
 XD_HD void lane0_unfix(float2* v, bool l0) {
-    float2 A[R3], B[R3];   // the primed arrays
+    float2 Au[R3 / 2], Bu[R3 / 2];   // upper halves of the primed arrays
 #pragma unroll
-    for (int i = 0; i < R3; i++) { A[i] = v[i]; B[i] = v[R3 + i]; }
+    for (int i = 0; i < R3 / 2; i++) { Au[i] = v[R3 / 2 + i]; Bu[i] = v[R3 + R3 / 2 + i]; }
 #pragma unroll
-    for (int i = 0; i < R3 / 2; i++) {
-        if (l0) v[R3 + i] = A[R3 / 2 + i];          // B[i]        = A'[R3/2+i]
-        if (l0) v[R3 + R3 / 2 + i] = B[i];          // B[R3/2+i]   = B'[i]
-    }
+    for (int i = 0; i < R3 / 2; i++)
+        if (l0) v[R3 + R3 / 2 + i] = Au[i];                       // B[j] = A'[j], j >= R3/2
 #pragma unroll
-    for (int i = R3 / 2; i < R3 - 1; i++)
-        if (l0) v[i + 1] = B[i];                    // A[i+1]      = B'[i]
-    if (l0) v[R3 / 2] = B[R3 - 1];                  // A[R3/2]     = B'[R3-1]
+    for (int i = 0; i < R3 / 2 - 1; i++)
+        if (l0) v[R3 / 2 + i + 1] = Bu[i];                        // A[m+1] = B'[m]
+    if (l0) v[R3 / 2] = Bu[R3 / 2 - 1];                           // A[R3/2] = B'[R3-1]
 }
 
 // F3: pass 3 (radix R3 over n3) -> real-FFT split -> momentum + projection -> inverse split
 //     -> inverse pass 1 -> exchange 2 (in place)
 template <int R3, int MODE, bool STORE_R>
 XD_HD void phase_f3(Lane<R3>& L, int lane, const GlParams& p, int utt, int T, int t, long frame, const float2* tab,
-                    float2* ex2, const float* s_stg, const float2* r_stg) {
+                    float2* ex2, const float* stg) {
     typedef Geo<R3> G;
     const bool l0 = (lane == 0);
     const int qA = lane, qB = lane ? 64 - lane : 32;
     float2* A = &L.v[0];
     float2* B = &L.v[R3];
-    float2* Rrow = p.R + frame * G::M;
+    float2* Rrow = reinterpret_cast<float2*>(p.state + frame * G::REC_F);
+    const float2* r_stg = reinterpret_cast<const float2*>(stg);   // staged record: [R | S | S_nyq]
+    const float* s_stg = stg + 2 * G::M;
 
-    const float s_nyq = L.s_nyq;
-
+    // The 1/N of the inverse transform is NOT applied here: Y = S unit(u) goes through the unnormalised inverse FFT
+    // and the factor is folded into the 1/window-sum-square scale of the store (store_block), which every sample
+    // passes exactly once.
     if (MODE != GL_MODE_INIT) {
 #pragma unroll
         for (int n3 = 0; n3 < R3; n3++) {
@@ -552,21 +709,21 @@ XD_HD void phase_f3(Lane<R3>& L, int lane, const GlParams& p, int utt, int T, in
                 st_stream(Rrow + ka, Ra);
                 st_stream(Rrow + kb, Rb);
             }
-            const float ga = sa_j * p.inv_n * rsqrt_pos(ua.x * ua.x + ua.y * ua.y);
-            const float gb = sb_j * p.inv_n * rsqrt_pos(ub.x * ub.x + ub.y * ub.y);
+            const float ga = sa_j * rsqrt_pos(ua.x * ua.x + ua.y * ua.y);
+            const float gb = sb_j * rsqrt_pos(ub.x * ub.x + ub.y * ub.y);
             Ya = mk2(ua.x * ga, ua.y * ga);
             Yb = mk2(ub.x * gb, ub.y * gb);
             if (j == 0 && l0) {
                 const float y0 = ua.x > 0.f ? 1.f : (ua.x < 0.f ? -1.f : 0.f);
                 const float ym = ua.y > 0.f ? 1.f : (ua.y < 0.f ? -1.f : 0.f);
-                Ya = mk2(y0 * sa_j * p.inv_n, ym * s_nyq * p.inv_n);
+                Ya = mk2(y0 * sa_j, ym * s_stg[G::M]);
             }
         } else {
             float ta_, tb_, tn_ = 0.f;
             if (p.turns) {
-                ta_ = p.turns[frame * G::M + ka];
-                tb_ = p.turns[frame * G::M + kb];
-                if (j == 0 && l0) tn_ = p.turns_nyq[frame];
+                ta_ = p.turns[frame * (G::M + 1) + ka];
+                tb_ = p.turns[frame * (G::M + 1) + kb];
+                if (j == 0 && l0) tn_ = p.turns[frame * (G::M + 1) + G::M];
             } else {
                 ta_ = phase_turn(p.seed, p.utt_seed_base + utt, G::M + 1, t, ka);
                 tb_ = phase_turn(p.seed, p.utt_seed_base + utt, G::M + 1, t, kb);
@@ -574,21 +731,20 @@ XD_HD void phase_f3(Lane<R3>& L, int lane, const GlParams& p, int utt, int T, in
             }
             float sn, cs;
             sincos_turns(ta_, &sn, &cs);
-            Ya = mk2(sa_j * p.inv_n * cs, sa_j * p.inv_n * sn);
+            Ya = mk2(sa_j * cs, sa_j * sn);
             sincos_turns(tb_, &sn, &cs);
-            Yb = mk2(sb_j * p.inv_n * cs, sb_j * p.inv_n * sn);
+            Yb = mk2(sb_j * cs, sb_j * sn);
             if (j == 0 && l0) {   // the inverse real FFT ignores the imaginary part of bins 0 and M
                 sincos_turns(tn_, &sn, &cs);
-                Ya = mk2(Ya.x, s_nyq * p.inv_n * cs);
+                Ya = mk2(Ya.x, s_stg[G::M] * cs);
             }
         }
         // Z[k] = E' + i O',  Z[M-k] = conj(E' - i O'),  E' = Ya + conj Yb,  O' = conj(W^k) (Ya - conj Yb)
         const float2 s2 = mk2(Ya.x + Yb.x, Ya.y - Yb.y);
         const float2 d2 = mk2(Ya.x - Yb.x, Ya.y + Yb.y);
-        const float2 D = mk2(2.f * C.x, -2.f * C.y);       // i conj(W_N^k)
-        const float2 t2 = cmul(D, d2);
-        float2 Za = mk2(s2.x + t2.x, s2.y + t2.y);
-        float2 Zb = mk2(s2.x - t2.x, t2.y - s2.y);
+        const float2 t2 = cmulc(d2, C);                    // d2 * i conj(W_N^k) / 2  (C = -i W_N^k / 2; the 2 is exact in the FFMAs below)
+        float2 Za = mk2(fmaf(2.f, t2.x, s2.x), fmaf(2.f, t2.y, s2.y));
+        float2 Zb = mk2(fmaf(-2.f, t2.x, s2.x), fmaf(2.f, t2.y, -s2.y));
         if (j == 0 && l0) {
             Za = mk2(Ya.x + Ya.y, Ya.x - Ya.y);
             Zb = mk2(2.f * Yb.x, -2.f * Yb.y);
@@ -630,8 +786,7 @@ XD_HD void phase_f4_store(Lane<R3>& L, int lane, float2* ex1) {
     for (int i = 0; i < G::NB; i++) {
         const int k1 = (lane >> G::LN3) + (32 / R3) * i;
         Dft<8, true>::run(&L.v[i * 8]);
-#pragma unroll
-        for (int n2 = 0; n2 < 8; n2++) ex1[k1 * G::S1 + R3 * n2 + n3] = L.v[i * 8 + n2];
+        ex1_store_cols<R3>(&L.v[i * 8], k1, n3, ex1);
     }
 }
 
@@ -639,22 +794,21 @@ XD_HD void phase_f4_store(Lane<R3>& L, int lane, float2* ex1) {
 template <int R3>
 XD_HD void phase_f5(Lane<R3>& L, int lane, const float2* tab, const float2* ex1) {
     typedef Geo<R3> G;
+    ex1_load_rows<R3>(L.v, lane, ex1);
 #pragma unroll
     for (int i = 0; i < G::NB; i++) {
 #pragma unroll
-        for (int k1 = 0; k1 < 8; k1++) {
-            float2 z = ex1[k1 * G::S1 + lane + 32 * i];
-            if (k1) z = cmulc(z, tab[G::TW1_OFF + (i * 7 + k1 - 1) * 32 + lane]);
-            L.v[i * 8 + k1] = z;
-        }
+        for (int k1 = 1; k1 < 8; k1++) L.v[i * 8 + k1] = cmulc(L.v[i * 8 + k1], tab[G::TW1_OFF + (i * 7 + k1 - 1) * 32 + lane]);
     }
 #pragma unroll
     for (int i = 0; i < G::NB; i++) {
         Dft<8, true>::run(&L.v[i * 8]);
 #pragma unroll
-        for (int n1 = 0; n1 < 8; n1++) {
-            const float2 w = tab[G::WIN_OFF + (i * 8 + n1) * 32 + lane];
-            L.v[i * 8 + n1] = mk2(L.v[i * 8 + n1].x * w.x, L.v[i * 8 + n1].y * w.y);
+        for (int n1 = 0; n1 < 4; n1++) {
+            const float2 w = tab[G::WIN_OFF + (i * 4 + n1) * 32 + lane];
+            const float2 lo = L.v[i * 8 + n1], hi = L.v[i * 8 + n1 + 4];
+            L.v[i * 8 + n1] = mk2(lo.x * w.x, lo.y * w.y);
+            L.v[i * 8 + n1 + 4] = mk2(fmaf(-hi.x, w.x, hi.x), fmaf(-hi.y, w.y, hi.y));
         }
     }
 }
@@ -665,7 +819,8 @@ XD_HD int blk_off(int lane, int e) {
     return (e / Geo<R3>::NB) * 16 * R3 + 64 * (e % Geo<R3>::NB) + 2 * lane;
 }
 
-// store one finished hop block (scaled by 1/window-sum-square) and track max |y|
+// store one finished hop block, scaled by 1/(N window-sum-square) -- `scale` alone in the interior, where the
+// window-sum-square is 3/2 exactly, `scale_tab[] * scale` at the first / last block -- and track max |y|
 template <int R3, bool TRACK_MAX>
 XD_HD void store_block(Lane<R3>& L, int lane, const float2* blk, float* ydst, const float* scale_tab, float scale) {
     typedef Geo<R3> G;
@@ -674,8 +829,8 @@ XD_HD void store_block(Lane<R3>& L, int lane, const float2* blk, float* ydst, co
         const int off = blk_off<R3>(lane, e);
         float2 o = blk[e];
         if (scale_tab) {
-            o.x *= scale_tab[off];
-            o.y *= scale_tab[off + 1];
+            o.x *= scale_tab[off] * scale;
+            o.y *= scale_tab[off + 1] * scale;
         } else {
             o.x *= scale;
             o.y *= scale;
@@ -732,19 +887,44 @@ XD_HD bool emit_block(Lane<R3>& L, int lane, const GlParams& p, int run_idx, con
     const bool complete = (r.ta == 0) || (t - 3 >= r.ta);
     if (complete) {
         store_block<R3, TRACK_MAX>(L, lane, out, p.y_out + yoff + (long)b * G::H, b == 0 ? p.edge_scale : nullptr,
-                                   2.0f / 3.0f);
+                                   b == 0 ? p.inv_n : p.inv_n * (2.0f / 3.0f));
         return false;
     }
     store_partial<R3>(lane, out, halo_ptr<R3>(p, run_idx - 1, 1, t - r.ta));
     return t == r.ta + 2;
 }
 
-// end of run; returns true when the caller must signal the boundary to its right
+// end of a run whose right neighbour has already published its three partial blocks (the usual order: a
+// run reaches its third frame long before its left neighbour reaches its last): finish blocks tb-2..tb from
+// the register accumulators + the neighbour's partial sums.  Same operands in the same order as
+// combine_boundary (left + right), so both paths give the same bits.
 template <int R3, bool TRACK_MAX>
-XD_HD bool emit_tail(Lane<R3>& L, int lane, const GlParams& p, int run_idx, const GlRun& r, long yoff, int T) {
+XD_HD void finish_tail_from_registers(Lane<R3>& L, int lane, const GlParams& p, int run_idx, const GlRun& r, long yoff) {
+    typedef Geo<R3> G;
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        const float* rp = halo_ptr<R3>(p, run_idx, 1, q);
+        float2 blk[2 * G::NB];
+#pragma unroll
+        for (int e = 0; e < 2 * G::NB; e++)
+            blk[e] = cadd(L.acc[q][e], ld_l2(reinterpret_cast<const float2*>(rp + blk_off<R3>(lane, e))));
+        store_block<R3, TRACK_MAX>(L, lane, blk, p.y_out + yoff + (long)(r.tb - 2 + q) * G::H, nullptr, p.inv_n * (2.0f / 3.0f));
+    }
+}
+
+// end of run; returns true when the caller must signal the boundary to its right.  neighbour_ready: the
+// run to the right has already published its partial blocks (see finish_tail_from_registers) -- nothing is
+// written to the halo then and the caller only restores the parity of the arrival counter.
+template <int R3, bool TRACK_MAX>
+XD_HD bool emit_tail(Lane<R3>& L, int lane, const GlParams& p, int run_idx, const GlRun& r, long yoff, int T,
+                     bool neighbour_ready = false) {
     typedef Geo<R3> G;
     if (r.tb == T) {   // block T-2 is the last one; it is complete (frames T-3..T-1)
-        store_block<R3, TRACK_MAX>(L, lane, L.acc[0], p.y_out + yoff + (long)(T - 2) * G::H, p.edge_scale + G::H, 0.f);
+        store_block<R3, TRACK_MAX>(L, lane, L.acc[0], p.y_out + yoff + (long)(T - 2) * G::H, p.edge_scale + G::H, p.inv_n);
+        return false;
+    }
+    if (neighbour_ready) {
+        finish_tail_from_registers<R3, TRACK_MAX>(L, lane, p, run_idx, r, yoff);
         return false;
     }
 #pragma unroll
@@ -770,7 +950,7 @@ XD_HD void combine_boundary(Lane<R3>& L, int lane, const GlParams& p, int bounda
             const float2 c = ld_l2(reinterpret_cast<const float2*>(rp + off));
             blk[e] = cadd(a, c);
         }
-        store_block<R3, TRACK_MAX>(L, lane, blk, p.y_out + yoff + (long)(r.tb - 2 + q) * G::H, nullptr, 2.0f / 3.0f);
+        store_block<R3, TRACK_MAX>(L, lane, blk, p.y_out + yoff + (long)(r.tb - 2 + q) * G::H, nullptr, p.inv_n * (2.0f / 3.0f));
     }
 }
 

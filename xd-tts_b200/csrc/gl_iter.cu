@@ -48,27 +48,55 @@ struct GlCfg {
     static constexpr int LATE_PREFETCH = (R3 == 16) ? XDTTS_GL16_LATE : XDTTS_GL8_LATE;   // 0: after F1, 2: after F3, 1: after F4
 };
 
+// ---- run-boundary hand-over.  The three hop blocks that straddle two runs get partial sums from both; the
+// arrival counter of the boundary (flags[], +2 per launch, odd = one side is in) decides who finishes them.
+// A run reaches its THIRD frame (head side done) long before its left neighbour reaches its LAST one, so the
+// usual order is head first, tail second:
+//   head  publishes its partial blocks (fence), bumps the counter and moves on; the counter value it got back is
+//         looked at only when the run ends, so the atomic's round trip is off the warp's critical path;
+//   tail  reads the counter (acquire); odd -> the head is in: it adds the head's partial sums to its register
+//         accumulators and stores the finished blocks -- its own partial sums never go to memory, no fence, no
+//         atomic with a result (a fire-and-forget red.add restores the counter's parity);
+//         even -> the old two-party protocol: publish, fence, atomic; whoever comes second adds left + right.
+// All three paths add (left + right) in that order: bit-identical results.
+__device__ __forceinline__ void fence_release_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// head side: returns the counter value before this arrival (valid in every lane)
+__device__ __forceinline__ unsigned arrive_head(int lane, const GlParams& p, int boundary) {
+    fence_release_gpu();   // publish this lane's partial sums
+    __syncwarp();
+    unsigned old = 0;
+    if (lane == 0) old = atomicAdd(p.flags + boundary, 1u);
+    return old;            // lane 0's value is broadcast when it is consumed (end of the run)
+}
+
 template <int R3, bool TRACK_MAX>
 __device__ __forceinline__ void arrive(Lane<R3>& L, int lane, const GlParams& p, int boundary) {
-    __threadfence();   // publish this lane's partial sums
+    fence_release_gpu();   // publish this lane's partial sums
     __syncwarp();
     unsigned old = 0;
     if (lane == 0) old = atomicAdd(p.flags + boundary, 1u);
     old = __shfl_sync(0xffffffffu, old, 0);
     if (old & 1u) {    // the neighbour was here first: its partial sums are visible after the fence
-        __threadfence();
+        fence_release_gpu();
         combine_boundary<R3, TRACK_MAX>(L, lane, p, boundary);
     }
 }
 
-// shared memory of one CTA, float2 units: [tables][per warp: exchange 1, exchange 2, staged S (M floats), staged R (M float2)]
+// shared memory of one CTA, float2 units: [tables][per warp: exchange 1, exchange 2, staged state record (R | S | S_nyq)]
 // followed by the mbarriers (one for the table copy, one per warp for its state staging)
 template <int R3>
 struct GlSmem {
     typedef Geo<R3> G;
     static constexpr int WARPS = GlCfg<R3>::WARPS;
     static constexpr int EX = GlCfg<R3>::ALIAS ? (G::EX1 > G::EX2 ? G::EX1 : G::EX2) : G::EXW;
-    static constexpr int WARP = EX + G::M / 2 + G::M;               // float2 per warp
+    static constexpr int WARP = EX + G::REC_F / 2;                  // float2 per warp: exchange scratch + the staged state record
     static constexpr int BAR_OFF = G::TAB + WARPS * WARP;           // float2 units (8 bytes each)
     static constexpr size_t BYTES = sizeof(float2) * (size_t)(BAR_OFF + 1 + WARPS);
 };
@@ -76,8 +104,8 @@ struct GlSmem {
 // per-warp view of the CTA's shared memory
 template <int R3>
 struct WarpSmem {
-    float2 *tab, *ex1, *ex2, *r_stg;
-    float* s_stg;
+    float2 *tab, *ex1, *ex2;
+    float* stg;   // staged state record of one frame: [R | S | S_nyq]
     unsigned long long *bar_tab, *bar;
     __device__ __forceinline__ WarpSmem(float2* smem, int warp) {
         typedef Geo<R3> G;
@@ -85,8 +113,7 @@ struct WarpSmem {
         unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + GlSmem<R3>::BAR_OFF);
         ex1 = smem + G::TAB + warp * GlSmem<R3>::WARP;
         ex2 = GlCfg<R3>::ALIAS ? ex1 : ex1 + G::EX1;
-        s_stg = reinterpret_cast<float*>(ex1 + GlSmem<R3>::EX);
-        r_stg = ex1 + GlSmem<R3>::EX + G::M / 2;
+        stg = reinterpret_cast<float*>(ex1 + GlSmem<R3>::EX);
         bar_tab = &bars[0];
         bar = &bars[1 + warp];
     }
@@ -119,16 +146,24 @@ __device__ __forceinline__ void gl_run_frames(Lane<R3>& L, int lane, const GlPar
     constexpr bool ALIAS = GlCfg<R3>::ALIAS;
     const long yoff = foff * G::H;
     float2 *tab = sm.tab, *ex1 = sm.ex1, *ex2 = sm.ex2;
-    stage_issue<R3, MODE>(L, lane, p, foff + r.ta, sm.s_stg, sm.r_stg, sm.bar);
+    stage_issue<R3, MODE>(lane, p, foff + r.ta, sm.stg, sm.bar);
     bool pref = false;
+    unsigned head_old = 0;        // counter value the head-side arrival saw (lane 0), examined after the loop
+    const bool has_left = r.ta > 0, has_right = r.tb < T;
     for (int t = r.ta; t < r.tb; t++) {
         const long frame = foff + t;
         if (MODE != GL_MODE_INIT) {
             const bool fetch_next = (t + 1 < r.tb) && (t + 2 <= T - 2);   // newest hop block of frame t+1 lies inside the signal
-            phase_f1<R3, COHERENT>(L, lane, p.y_in + yoff, T, t, p.pad_mode, t == r.ta, pref, tab, ex1);
-            pref = fetch_next;
-            __syncwarp();
-            if (!GlCfg<R3>::LATE_PREFETCH && fetch_next) prefetch_next_block<R3, COHERENT>(L, lane, p.y_in + yoff, T, t, p.pad_mode);
+            if constexpr (G::ROT) {
+                phase_f1_rot<R3, COHERENT>(L, lane, p.y_in + yoff, T, t, p.pad_mode, t == r.ta, pref, fetch_next, (t - r.ta) & 3, tab, ex1);
+                pref = fetch_next;
+                __syncwarp();
+            } else {
+                phase_f1<R3, COHERENT>(L, lane, p.y_in + yoff, T, t, p.pad_mode, t == r.ta, pref, tab, ex1);
+                pref = fetch_next;
+                __syncwarp();
+                if (!GlCfg<R3>::LATE_PREFETCH && fetch_next) prefetch_next_block<R3, COHERENT>(L, lane, p.y_in + yoff, T, t, p.pad_mode);
+            }
             phase_f2_load<R3>(L, lane, ex1);
             if (ALIAS) __syncwarp();
             phase_f2_store<R3>(L, lane, tab, ex2);
@@ -136,26 +171,42 @@ __device__ __forceinline__ void gl_run_frames(Lane<R3>& L, int lane, const GlPar
         }
         stage_wait(sm.bar, phase);
         phase ^= 1u;
-        phase_f3<R3, MODE, STORE_R>(L, lane, p, r.utt, T, t, frame, tab, ex2, sm.s_stg, sm.r_stg);
+        phase_f3<R3, MODE, STORE_R>(L, lane, p, r.utt, T, t, frame, tab, ex2, sm.stg);
         __syncwarp();   // every lane is done with the staged state (its values fed the stores above)
-        if (t + 1 < r.tb) stage_issue<R3, MODE>(L, lane, p, frame + 1, sm.s_stg, sm.r_stg, sm.bar);
-        if (MODE != GL_MODE_INIT && GlCfg<R3>::LATE_PREFETCH == 2 && pref) prefetch_next_block<R3, COHERENT>(L, lane, p.y_in + yoff, T, t, p.pad_mode);
+        if (t + 1 < r.tb) stage_issue<R3, MODE>(lane, p, frame + 1, sm.stg, sm.bar);
+        if (!G::ROT && MODE != GL_MODE_INIT && GlCfg<R3>::LATE_PREFETCH == 2 && pref) prefetch_next_block<R3, COHERENT>(L, lane, p.y_in + yoff, T, t, p.pad_mode);
         phase_f4_load<R3>(L, lane, tab, ex2);
         if (ALIAS) __syncwarp();
         phase_f4_store<R3>(L, lane, ex1);
         __syncwarp();
-        if (MODE != GL_MODE_INIT && GlCfg<R3>::LATE_PREFETCH == 1 && pref) prefetch_next_block<R3, COHERENT>(L, lane, p.y_in + yoff, T, t, p.pad_mode);
+        if (!G::ROT && MODE != GL_MODE_INIT && GlCfg<R3>::LATE_PREFETCH == 1 && pref) prefetch_next_block<R3, COHERENT>(L, lane, p.y_in + yoff, T, t, p.pad_mode);
         phase_f5<R3>(L, lane, tab, ex1);
         float2 out[2 * G::NB];
         ola_shift<R3>(L, out);
-        if (emit_block<R3, TRACK_MAX>(L, lane, p, run_idx, r, yoff, t, out)) arrive<R3, TRACK_MAX>(L, lane, p, run_idx - 1);
+        if (emit_block<R3, TRACK_MAX>(L, lane, p, run_idx, r, yoff, t, out)) head_old = arrive_head(lane, p, run_idx - 1);
         // the next frame's first shared-memory writes (F1 -> ex1) go to the addresses this same lane read last in F5,
         // so no barrier is needed here -- except in INIT mode with aliased exchange buffers, where the next frame
         // starts with F3's writes to ex2 (= ex1) in a different index mapping than F5's reads (compute-sanitizer
         // racecheck flagged exactly this pair)
         if (ALIAS && MODE == GL_MODE_INIT) __syncwarp();
     }
-    if (emit_tail<R3, TRACK_MAX>(L, lane, p, run_idx, r, yoff, T)) arrive<R3, TRACK_MAX>(L, lane, p, run_idx);
+    if (has_right) {
+        const bool ready = (ld_acquire_gpu(p.flags + run_idx) & 1u) != 0;   // same address in every lane: one request
+        if (emit_tail<R3, TRACK_MAX>(L, lane, p, run_idx, r, yoff, T, ready)) {
+            arrive<R3, TRACK_MAX>(L, lane, p, run_idx);
+        } else if (lane == 0) {
+            asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p.flags + run_idx) : "memory");
+        }
+    } else {
+        emit_tail<R3, TRACK_MAX>(L, lane, p, run_idx, r, yoff, T);
+    }
+    if (has_left) {   // the left neighbour finished its run before this one reached its third frame (rare)
+        head_old = __shfl_sync(0xffffffffu, head_old, 0);
+        if (head_old & 1u) {
+            fence_release_gpu();
+            combine_boundary<R3, TRACK_MAX>(L, lane, p, run_idx - 1);
+        }
+    }
 
     if (TRACK_MAX) {
         float m = L.amax;

@@ -1,0 +1,439 @@
+// mel -> linear lift on the 5th-generation tensor cores:  S = max(0, pinv(basis) . delog(mel)) ^ power
+// (step 1 of griffin_lim::GriffinLim::infer; reference call site
+// /root/reference src/lib.rs:141, parameters from src/tacotron2/mod.rs:453-456).
+//
+// The product is a [bins x n_mels] . [n_mels x frames] GEMM with a tiny inner dimension (80): 82 kFLOP and
+// 2.4 kB per frame, i.e. HBM-bound -- IF the multiply-adds are off the CUDA cores (on the fp32 pipe the 1.3 G
+// FMAs of a 32 x 1000 batch alone take 35 us at 100% issue; the fp64 kernel of round 1 took 220-316 us).
+// One tile of the GEMM is
+//
+//     D[bin 0..127][frame 0..63] = sum_m P[bin][m] * E[frame][m]          (UMMA M = 128 bins, N = 64 frames)
+//
+// with both operands K-major (mel index contiguous) in 128-byte-swizzled shared memory and fp32 accumulation
+// in TMEM.  Precision: the pseudo-inverse has 36% negative entries and the gate is 1e-5 of full
+// scale; a single tf32 pass gives 9e-4, bf16 split in three 2e-5, tf32 split in three 3e-7 (the plain fp32 FMA
+// sum gives 5e-7) -- hence "tf32x3": x = hi + lo, D = Phi Ehi + Phi Elo + Plo Ehi, three passes of
+// tcgen05.mma kind::tf32 into the same accumulator.
+//
+// Work split: CTA (mt, g) owns bin tile mt (its P tile, hi and lo planes, stays in shared memory for the whole
+// kernel: one bulk copy of a pre-swizzled host-built image) and walks frame tiles g, g + G, ...  Bins as the
+// TMEM lane dimension make the epilogue's stores coalesced: for one frame (TMEM column) the 32 lanes of a warp
+// hold 32 consecutive bins = 128 contiguous bytes of the frame-major state record the iteration kernel reads.
+//
+// Warp roles (288 threads, one CTA per SM):
+//     warps 0-3   epilogue     tcgen05.ld (lane quarter = warp) -> clamp -> ^power -> S
+//     warps 4-7   producers    mel [n_mels][T] -> delog -> tf32 hi / lo -> swizzled E tile (2-stage ring)
+//     warp  8     TMEM alloc + one thread issuing the MMAs and commits
+// The Nyquist bin (bin M, a 129th row of the last tile otherwise) is summed by the producers of bin tile 0 on the
+// CUDA cores, from the de-logged values they hold anyway.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "gl_host.h"
+
+namespace xdtts {
+
+namespace {
+
+constexpr int LT_BM = 128;       // bins per tile
+constexpr int LT_BN = 64;        // frames per tile
+constexpr int LT_STAGES = 2;     // E-tile ring
+constexpr int LT_THREADS = 288;
+constexpr int LT_MAX_KB = 3;     // shared memory holds the P tile (2 planes) + the E ring for n_mels <= 96; wider bases take gl_lift_f32_kernel
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], tf32 inputs (fp32 containers, low 13 mantissa bits ignored), fp32 accumulate
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major tile with 128-byte rows (32 tf32) in the 128-byte swizzle: 8-row groups 1024 B apart (SBO), version 1
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+__device__ __forceinline__ float delog_value(float v, int delog) {
+    return delog == 0 ? expf(v) : (delog == 1 ? exp10f(v) : v);
+}
+
+// s ^ power for s > 0 on the special-function unit: 2^(power * log2 s).  ~1e-6 relative at full scale (the gate
+// on S is 1e-5 of full scale, tests/test_gpu_gl.py::test_lift_matches_oracle); powf costs ~40 instructions per
+// value, i.e. more issue time than the whole rest of this kernel.
+__device__ __forceinline__ float pow_pos(float s, float power) {
+    return s > 0.f ? exp2f(power * __log2f(s)) : 0.f;
+}
+
+struct LiftParams {
+    const float* mel_arena;      // utterance u: row-major [n_mels][T_u] at float offset foff[u] * n_mels
+    const float* a_image;        // [n_mt][2 planes][kblocks][128 rows][32] tf32 values, rows pre-swizzled
+    const float* pinv_nyq;       // the pseudo-inverse's row of bin M: entry m at pinv_nyq[m * pinv_ld]
+    int pinv_ld;
+    const int2* tiles;           // frame tiles: (utterance, first frame)
+    const int* utt_T;
+    const int* utt_foff;
+    float* S;                    // frame-major state records: S[(foff + t) * ld + k], k < M
+    int n_tiles, n_mt, groups, n_mels, kblocks, ld, delog;
+    float power;
+};
+
+struct LiftSmem {
+    // [A hi | A lo] then the E ring (per stage [E hi | E lo]); every tile 1024-byte aligned
+    __host__ __device__ static int a_plane(int kblocks) { return kblocks * LT_BM * 128; }
+    __host__ __device__ static int e_plane(int kblocks) { return kblocks * LT_BN * 128; }
+    __host__ __device__ static int bar_off(int kblocks) { return 2 * a_plane(kblocks) + LT_STAGES * 2 * e_plane(kblocks); }
+    __host__ __device__ static int total(int kblocks) { return bar_off(kblocks) + 96 + 4 * 32 * kblocks + 1024; }
+};
+
+__global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int a_plane = LiftSmem::a_plane(p.kblocks), e_plane = LiftSmem::e_plane(p.kblocks);
+    uint8_t* sa = smem;
+    uint8_t* se = smem + 2 * a_plane;
+    uint64_t* bars = (uint64_t*)(smem + LiftSmem::bar_off(p.kblocks));
+    uint64_t* full = bars;            // [2] E stage written (128 producer arrivals)
+    uint64_t* empty = bars + 2;       // [2] E stage consumed (tcgen05.commit)
+    uint64_t* tfull = bars + 4;       // [2] accumulator complete
+    uint64_t* tempty = bars + 6;      // [2] accumulator drained (4 epilogue warps)
+    uint64_t* a_bar = bars + 8;       // P tile landed
+    uint32_t* tmem_ptr = (uint32_t*)(bars + 10);
+    float* wn = (float*)(bars + 12);   // [32 kblocks] the pseudo-inverse's Nyquist row (bin M)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mt = blockIdx.x % p.n_mt, g = blockIdx.x / p.n_mt;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < LT_STAGES; s++) {
+            mbar_init(&full[s], 128);
+            mbar_init(&empty[s], 1);
+            mbar_init(&tfull[s], 1);
+            mbar_init(&tempty[s], 4);
+        }
+        mbar_init(a_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {   // 128 columns: two 128 x 64 fp32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(128u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 32 * p.kblocks; i += LT_THREADS) wn[i] = i < p.n_mels ? p.pinv_nyq[(size_t)i * p.pinv_ld] : 0.f;
+    // the zero padding of the E tiles (mel indices n_mels .. 32 kblocks - 1) is written once: producers only touch k < n_mels
+    for (int i = threadIdx.x; i < LT_STAGES * 2 * e_plane / 16; i += LT_THREADS) reinterpret_cast<uint4*>(se)[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 8) {
+        // ===================== MMA issuer
+        if (lane == 0) {
+            mbar_expect_tx(a_bar, (uint32_t)(2 * a_plane));
+            bulk_g2s(sa, p.a_image + (size_t)mt * (2 * a_plane / 4), (uint32_t)(2 * a_plane), a_bar);
+            // instruction descriptor: D fp32, A/B tf32, both K-major, N = 64, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(LT_BN >> 3) << 17) | ((uint32_t)(LT_BM >> 4) << 24);
+            mbar_wait(a_bar, 0);
+            int it = 0;
+            for (int tile = g; tile < p.n_tiles; tile += p.groups, it++) {
+                const int s = it & 1;
+                const uint32_t ph = (uint32_t)((it >> 1) & 1);
+                mbar_wait(&tempty[s], ph ^ 1u);   // epilogue has drained this accumulator
+                mbar_wait(&full[s], ph);          // producers have written this E stage
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(s * LT_BN);
+                const uint32_t e_hi = smem_u32(se + s * 2 * e_plane), e_lo = e_hi + e_plane;
+                const uint32_t a_hi = smem_u32(sa), a_lo = a_hi + a_plane;
+                uint32_t acc = 0;
+                for (int pass = 0; pass < 3; pass++) {   // Phi Ehi, Phi Elo, Plo Ehi
+                    const uint32_t ab = pass == 2 ? a_lo : a_hi, eb = pass == 1 ? e_lo : e_hi;
+                    for (int kb = 0; kb < p.kblocks; kb++) {
+                        const uint64_t da = umma_desc_sw128(ab + kb * (LT_BM * 128)), db = umma_desc_sw128(eb + kb * (LT_BN * 128));
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {   // UMMA_K = 8 tf32 = 32 B along the swizzled row: +2 in the address field
+                            tc_mma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc);
+                            acc = 1;
+                        }
+                    }
+                }
+                tc_commit(&empty[s]);    // E stage free when these MMAs retire
+                tc_commit(&tfull[s]);    // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== producers: a warp covers 4 mel rows x 8 frames per step (conflict-free swizzled stores,
+        // four full 32-byte sectors per global load).  The loads of tile i+1 are issued before tile i is converted, so
+        // their latency hides behind the conversion, the MMA and the epilogue of the tiles in flight.
+        const int pw = warp - 4;
+        const int m4 = lane & 3, f8 = lane >> 2;
+        const int n_blk = ((p.n_mels + 3) / 4) * (LT_BN / 8);   // (mel group, frame group) blocks per tile, <= 192
+        constexpr int PER = (LT_MAX_KB * 8) * (LT_BN / 8) / 4;   // blocks per producer warp, 48
+        float xn[PER];
+        auto issue_loads = [&](int tile, float* x) {
+            const int2 tl = p.tiles[tile];
+            const int T = p.utt_T[tl.x];
+            const float* mel = p.mel_arena + (size_t)p.utt_foff[tl.x] * p.n_mels;
+#pragma unroll
+            for (int i = 0; i < PER; i++) {
+                const int blk = pw + 4 * i;
+                const int m = (blk >> 3) * 4 + m4, t = tl.y + (blk & 7) * 8 + f8;
+                x[i] = (blk < n_blk && m < p.n_mels && t < T) ? __ldg(mel + (size_t)m * T + t) : -INFINITY;   // -inf: no sample
+            }
+        };
+        if (g < p.n_tiles) issue_loads(g, xn);
+        int it = 0;
+        for (int tile = g; tile < p.n_tiles; tile += p.groups, it++) {
+            const int s = it & 1;
+            float x[PER];
+#pragma unroll
+            for (int i = 0; i < PER; i++) x[i] = xn[i];
+            if (tile + p.groups < p.n_tiles) issue_loads(tile + p.groups, xn);
+            mbar_wait(&empty[s], (uint32_t)((it >> 1) & 1) ^ 1u);
+            uint8_t* ehi = se + s * 2 * e_plane;
+            uint8_t* elo = ehi + e_plane;
+            float nq0 = 0.f, nq1 = 0.f;   // Nyquist-bin partial sums of this lane's two frames (bin tile 0 only)
+#pragma unroll
+            for (int i = 0; i < PER; i++) {
+                const int blk = pw + 4 * i;
+                const int m = (blk >> 3) * 4 + m4, f = (blk & 7) * 8 + f8;
+                if (blk < n_blk && m < p.n_mels) {
+                    const float e = x[i] == -INFINITY ? 0.f : delog_value(x[i], p.delog);
+                    const float hi = to_tf32(e);
+                    const float lo = to_tf32(e - hi);
+                    const int off = (m >> 5) * (LT_BN * 128) + f * 128 + ((((m & 31) >> 2) ^ (f & 7)) << 4) + (m & 3) * 4;
+                    *reinterpret_cast<float*>(ehi + off) = hi;
+                    *reinterpret_cast<float*>(elo + off) = lo;
+                    if (mt == 0) {
+                        if (i & 1) nq1 = fmaf(wn[m], e, nq1);
+                        else nq0 = fmaf(wn[m], e, nq0);
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async proxy
+            mbar_arrive(&full[s]);
+            if (mt == 0) {   // frames (pw + 4 i) & 7: i even -> frame group pw, i odd -> frame group pw + 4; mel rows m4, m4 + 4, ...
+                nq0 += __shfl_xor_sync(0xffffffffu, nq0, 1);
+                nq1 += __shfl_xor_sync(0xffffffffu, nq1, 1);
+                nq0 += __shfl_xor_sync(0xffffffffu, nq0, 2);
+                nq1 += __shfl_xor_sync(0xffffffffu, nq1, 2);
+                const int2 tl = p.tiles[tile];
+                const int T = p.utt_T[tl.x];
+                if (m4 == 0) {
+                    const int fa = pw * 8 + f8, fb = (pw + 4) * 8 + f8;
+                    float* rec = p.S + ((size_t)p.utt_foff[tl.x] + tl.y) * p.ld + p.n_mt * LT_BM;   // slot M of the first frame
+                    if (tl.y + fa < T) rec[(size_t)fa * p.ld] = p.power == 1.0f ? fmaxf(nq0, 0.f) : pow_pos(nq0, p.power);
+                    if (tl.y + fb < T) rec[(size_t)fb * p.ld] = p.power == 1.0f ? fmaxf(nq1, 0.f) : pow_pos(nq1, p.power);
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: TMEM lane quarter q <-> bins mt*128 + 32 q + lane
+        const int q = warp;
+        const int bin = mt * LT_BM + q * 32 + lane;
+        int it = 0;
+        for (int tile = g; tile < p.n_tiles; tile += p.groups, it++) {
+            const int s = it & 1;
+            const int2 tl = p.tiles[tile];
+            const int T = p.utt_T[tl.x];
+            const int nf = min(LT_BN, T - tl.y);
+            float* out = p.S + ((size_t)p.utt_foff[tl.x] + tl.y) * p.ld + bin;
+            mbar_wait(&tfull[s], (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * LT_BN);
+#pragma unroll
+            for (int c0 = 0; c0 < LT_BN; c0 += 16) {
+                uint32_t v[16];
+                tc_ld16(taddr + (uint32_t)c0, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const float x = __uint_as_float(v[i]);
+                    const float r = p.power == 1.0f ? fmaxf(x, 0.f) : pow_pos(x, p.power);
+                    if (c0 + i < nf) __stcs(out + (size_t)(c0 + i) * p.ld, r);   // 32 lanes = 32 consecutive bins of one frame
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[s]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+}
+
+// CUDA-core fp32 form of the same lift (all K bins, Nyquist included): the path for mel bases wider than 96 rows,
+// whose P tile does not fit beside the E ring, and the on-device cross-check of the tensor path (XDTTS_LIFT_F32=1).
+// grid (1, ceil(maxT/16), n_utt); thread <-> bins k, k + 128, ...; 16 frames per block; the plain fp32 FMA sum is
+// 5e-7 of full scale from the fp64 result (the gate is 1e-5).
+constexpr int LF_TT = 16;
+__global__ void __launch_bounds__(128) gl_lift_f32_kernel(const float* __restrict__ mel_arena, const float* __restrict__ pinvT,
+                                                          const int* __restrict__ utt_T, const int* __restrict__ utt_foff,
+                                                          int n_mels, int K, int ld, float power, int delog, float* __restrict__ S) {
+    extern __shared__ __align__(16) float e_sm[];   // [n_mels][LF_TT]
+    const int u = blockIdx.z, T = utt_T[u], t0 = blockIdx.y * LF_TT;
+    if (t0 >= T) return;
+    const size_t foff = (size_t)utt_foff[u];
+    const float* mel = mel_arena + foff * n_mels;
+    for (int i = threadIdx.x; i < n_mels * LF_TT; i += 128) {
+        const int m = i / LF_TT, tt = i % LF_TT;
+        e_sm[i] = (t0 + tt < T) ? delog_value(mel[(size_t)m * T + t0 + tt], delog) : 0.f;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += 128) {
+        float acc[LF_TT];
+#pragma unroll
+        for (int tt = 0; tt < LF_TT; tt++) acc[tt] = 0.f;
+#pragma unroll 4
+        for (int m = 0; m < n_mels; m++) {
+            const float a = pinvT[(size_t)m * K + k];
+            const float4* er = reinterpret_cast<const float4*>(e_sm + m * LF_TT);
+#pragma unroll
+            for (int q = 0; q < LF_TT / 4; q++) {
+                const float4 x = er[q];
+                acc[4 * q + 0] = fmaf(a, x.x, acc[4 * q + 0]);
+                acc[4 * q + 1] = fmaf(a, x.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(a, x.z, acc[4 * q + 2]);
+                acc[4 * q + 3] = fmaf(a, x.w, acc[4 * q + 3]);
+            }
+        }
+#pragma unroll
+        for (int tt = 0; tt < LF_TT; tt++)
+            if (t0 + tt < T) S[(foff + t0 + tt) * ld + k] = power == 1.0f ? fmaxf(acc[tt], 0.f) : pow_pos(acc[tt], power);
+    }
+}
+
+uint32_t tf32_rna_bits(float x) {   // cvt.rna.tf32.f32 on the host: nearest, ties away from zero, 10 mantissa bits
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return u;
+    return (u + 0x1000u) & 0xFFFFE000u;
+}
+
+}  // namespace
+
+// host: the device image of the pseudo-inverse for gl_lift_tc_kernel.  pinv: [K][n_mels] row-major (K = M + 1; the
+// last row is the Nyquist bin and is not part of the image).  Layout [mt][plane hi, lo][kblock][row 0..127][32 floats],
+// each 128-byte row stored with its 16-byte chunks XOR-swizzled by (row & 7) -- what TMA's SWIZZLE_128B would write.
+std::vector<float> gl_lift_build_image(const float* pinv, int K, int n_mels) {
+    const int M = K - 1, n_mt = (M + LT_BM - 1) / LT_BM, kblocks = (n_mels + 31) / 32;
+    std::vector<float> img((size_t)n_mt * 2 * kblocks * LT_BM * 32, 0.f);
+    for (int mt = 0; mt < n_mt; mt++)
+        for (int r = 0; r < LT_BM; r++) {
+            const int bin = mt * LT_BM + r;
+            if (bin >= M) continue;
+            for (int m = 0; m < n_mels; m++) {
+                const float x = pinv[(size_t)bin * n_mels + m];
+                const uint32_t hb = tf32_rna_bits(x);
+                float hi, lo;
+                memcpy(&hi, &hb, 4);
+                const uint32_t lb = tf32_rna_bits(x - hi);
+                memcpy(&lo, &lb, 4);
+                const int kb = m >> 5, kk = m & 31;
+                const size_t row = (size_t)r * 32 + (size_t)((((kk >> 2) ^ (r & 7)) << 2) + (kk & 3));
+                img[(((size_t)mt * 2 + 0) * kblocks + kb) * LT_BM * 32 + row] = hi;
+                img[(((size_t)mt * 2 + 1) * kblocks + kb) * LT_BM * 32 + row] = lo;
+            }
+        }
+    return img;
+}
+
+int gl_lift_tile_frames() { return LT_BN; }
+
+// false: the tensor path does not apply (n_mels > 96, or bins not a multiple of 128): gl_launch_lift takes the fp32 kernel
+bool gl_lift_uses_tensor_cores(int n_mels, int K) {
+    static const bool force_f32 = getenv("XDTTS_LIFT_F32") != nullptr;
+    return !force_f32 && (n_mels + 31) / 32 <= LT_MAX_KB && (K - 1) % LT_BM == 0;
+}
+
+cudaError_t gl_lift_prepare(int n_mels) {
+    const int kblocks = (n_mels + 31) / 32;
+    if (kblocks > LT_MAX_KB) return cudaSuccess;
+    return cudaFuncSetAttribute(gl_lift_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LiftSmem::total(kblocks));
+}
+
+// S[(foff + t) * ld + k] = max(0, sum_m pinv[k][m] delog(mel[m][t])) ^ power for k = 0..M (k = M: the Nyquist slot).
+// pinvT: [n_mels][K] (the transposed pseudo-inverse); a_image: gl_lift_build_image.  *n_kernels: launches made.
+cudaError_t gl_launch_lift(const float* mel_arena, const float* a_image, const float* pinvT, const int2* tiles, int n_tiles,
+                           const int* utt_T, const int* utt_foff, int n_utt, int max_T, int n_mels, int K, int ld, float power,
+                           int delog, int sm_count, float* S, cudaStream_t s, int* n_kernels) {
+    const int M = K - 1;
+    if (!gl_lift_uses_tensor_cores(n_mels, K)) {
+        if (n_mels > 256) return cudaErrorInvalidValue;
+        dim3 grid(1, (max_T + LF_TT - 1) / LF_TT, n_utt);
+        gl_lift_f32_kernel<<<grid, 128, (size_t)n_mels * LF_TT * sizeof(float), s>>>(mel_arena, pinvT, utt_T, utt_foff, n_mels, K, ld,
+                                                                                    power, delog, S);
+        if (n_kernels) *n_kernels = 1;
+        return cudaGetLastError();
+    }
+    LiftParams p;
+    p.mel_arena = mel_arena; p.a_image = a_image; p.tiles = tiles; p.utt_T = utt_T; p.utt_foff = utt_foff; p.S = S;
+    p.n_tiles = n_tiles; p.n_mt = M / LT_BM; p.n_mels = n_mels; p.kblocks = (n_mels + 31) / 32; p.ld = ld;
+    p.delog = delog; p.power = power;
+    p.groups = sm_count / p.n_mt;
+    if (p.groups < 1) p.groups = 1;
+    if (p.groups > n_tiles) p.groups = n_tiles;
+    p.pinv_nyq = pinvT + M; p.pinv_ld = K;
+    gl_lift_tc_kernel<<<p.n_mt * p.groups, LT_THREADS, LiftSmem::total(p.kblocks), s>>>(p);
+    if (n_kernels) *n_kernels = 1;
+    return cudaGetLastError();
+}
+
+}  // namespace xdtts

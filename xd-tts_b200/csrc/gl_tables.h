@@ -33,9 +33,9 @@ std::vector<float2> build_tables() {
             t[G::RTW_OFF + j * 32 + lane] = mk2((float)(-0.5 * std::sin(a)), (float)(-0.5 * std::cos(a)));
         }
         for (int i = 0; i < G::NB; i++)
-            for (int n1 = 0; n1 < 8; n1++) {
+            for (int n1 = 0; n1 < 4; n1++) {   // first half of the window only: w[s + N/2] = 1 - w[s]
                 const int s = 16 * R3 * n1 + 2 * (lane + 32 * i);
-                t[G::WIN_OFF + (i * 8 + n1) * 32 + lane] = mk2((float)hann_periodic(s, G::N), (float)hann_periodic(s + 1, G::N));
+                t[G::WIN_OFF + (i * 4 + n1) * 32 + lane] = mk2((float)hann_periodic(s, G::N), (float)hann_periodic(s + 1, G::N));
             }
     }
     return t;
