@@ -48,6 +48,11 @@ typedef struct xdtts_gl_opts {
     int nnls_iters;          /* lift = 1: iteration cap per frame (0: 300); a frame stops early once its projected gradient
                                 falls below 3e-6 (librosa passes pgtol = 1e-5 to L-BFGS-B; 3e-6 here reaches that
                                 solver's objective, tests/test_oracle.py) */
+    int fixed_seed;          /* when the caller passes no initial phase: 0 (default): every call on the handle draws a NEW phase
+                                field, as the reference does (call c uses seed + c * 0xD1B54A32D192ED03; call 0 uses `seed`)
+                                1: every call draws the field of `seed` (reproducible runs, tests) */
+    int exponent;            /* 0: S = x ^ power (default: the Tacotron convention the call site describes, "tuned by ear ...
+                                1.2-1.7", src/tacotron2/mod.rs:446-449)   1: S = x ^ (1 / power), librosa's mel_to_stft */
 } xdtts_gl_opts;
 
 typedef struct xdtts_gl xdtts_gl;           /* replaces griffin_lim::GriffinLim */
@@ -112,6 +117,9 @@ int xdtts_gl_plan_upload(xdtts_gl_plan* p, int kind, const float* const* srcs);
  * device time and count of the Griffin-Lim launches it covers (the n_iter-2 steady-state launches, or the
  * single persistent launch). */
 int xdtts_gl_plan_run(xdtts_gl_plan* p, int flags, float* ms_total, float* ms_iter, int* n_iter_launches);
+/* device time (CUDA events) of the mel -> linear step (lift, or magnitude transpose, + NNLS when enabled) of the last
+ * XDTTS_RUN_NO_GRAPH pass of this plan */
+int xdtts_gl_plan_lift_ms(const xdtts_gl_plan* p, float* ms);
 int xdtts_gl_plan_download(xdtts_gl_plan* p, float* const* outs);
 int xdtts_gl_plan_download_pcm16(xdtts_gl_plan* p, short* const* outs);   /* after a run: 16-bit PCM of the same waveforms */
 /* debugging / parity: copy device state to host. what: 0 S [T_total][M] frame-major, 1 S Nyquist [T_total],
@@ -253,6 +261,28 @@ int xdtts_pipe_pop(xdtts_pipe* q);      /* wait for the OLDEST batch in flight: 
 int xdtts_pipe_flush(xdtts_pipe* q);    /* wait until every pushed batch is in its host buffers */
 int xdtts_pipe_pending(xdtts_pipe* q);  /* batches in flight (>= 0), or a negative error */
 void xdtts_pipe_destroy(xdtts_pipe* q); /* waits for batches in flight; destroy it before its gl / postnet handles */
+
+/* ---- Multi-GPU: one vocoder per device behind one handle.  The reference is a single process that vocodes one
+ * utterance at a time (src/lib.rs:83-104; "could run in parallel", src/phonemes.rs:677-680); utterances are
+ * independent, so a batch shards across the GPUs of a box without any data-path exchange.
+ * xdtts_pool_create builds one vocoder handle (the arguments of xdtts_gl_create) and one worker thread per device;
+ * devices == null / n_devices == 0 means every visible device.  xdtts_pool_infer_batch assigns the utterances
+ * longest-first to the least-loaded device (ties to the first listed device), runs the sub-batches concurrently and
+ * returns when all are in the caller's buffers.  Every utterance draws the phase stream of its index in THIS call's
+ * batch and all devices use the call's seed, so the output does not depend on how many devices there are (bit for
+ * bit when opts.run_frames fixes the run length; the automatic run length depends on a device's share of the batch). */
+typedef struct xdtts_pool xdtts_pool;
+int xdtts_pool_create(const float* mel_basis, int n_mels, int K, int noverlap, float power, int n_iter, float momentum,
+                      const xdtts_gl_opts* opts_or_null, const int* devices_or_null, int n_devices, xdtts_pool** out);
+void xdtts_pool_destroy(xdtts_pool* p);
+int xdtts_pool_n_devices(const xdtts_pool* p);
+int xdtts_pool_out_len(const xdtts_pool* p, int T);
+/* the device each utterance of a batch with these frame counts is sent to */
+int xdtts_pool_assignment(const xdtts_pool* p, const int* Ts, int B, int* device_of_utt);
+int xdtts_pool_infer_batch(xdtts_pool* p, const float* const* mels, const int* Ts, int B,
+                           const float* const* init_phases_or_null, float* const* outs);
+int xdtts_pool_from_mag_batch(xdtts_pool* p, const float* const* mags, const int* Ts, int B,
+                              const float* const* init_phases_or_null, float* const* outs);
 
 /* .npy I/O for [rows, cols] float32 arrays -- the format of the reference's spectrogram dump
  * (ndarray_npy::write_npy, src/lib.rs:125-139, --output-spectrogram src/bin/app.rs:12-14).

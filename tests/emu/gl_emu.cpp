@@ -126,8 +126,9 @@ static int emu_run(const float* s_mag, const float* turns, int T, int n_iter, fl
     p.edge_scale = edge.data();
     p.tables = tab.data();
     p.turns = turns ? tu.data() : nullptr;
-    p.seed = seed;
-    p.utt_seed_base = 0;
+    const int seed_id = 0;
+    p.seed = &seed;
+    p.utt_seed_id = &seed_id;
     p.alpha = momentum / (1.0f + momentum);
     p.inv_n = 1.0f / (float)G::N;
     p.pad_mode = pad_mode;

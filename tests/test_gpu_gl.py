@@ -129,6 +129,18 @@ def test_seeded_phase_equals_explicit_phase(gl):
         assert np.array_equal(a, b)
     other = make(gl, 1024, 4, seed=78).infer_batch(mels)
     assert not np.array_equal(other[0], seeded[0])
+    # like the reference, a handle draws a NEW phase field on every call (call c: seed + c * 0xD1B54A32D192ED03) ...
+    again = voc.infer_batch(mels)
+    assert not np.array_equal(again[0], seeded[0])
+    s1 = (77 + 0xD1B54A32D192ED03) % 2 ** 64          # call 1: the explicit-phase call in between did not draw
+    want = voc.infer_batch(mels, [o.phase_turns(s1, i, 513, t) for i, t in enumerate(ts)])
+    for a, b in zip(again, want):
+        assert np.array_equal(a, b)
+    # ... unless fixed_seed asks for reproducible calls
+    fixed = make(gl, 1024, 4, seed=77, fixed_seed=True)
+    for _ in range(2):
+        for a, b in zip(fixed.infer_batch(mels), seeded):
+            assert np.array_equal(a, b)
 
 
 def test_options_pad_constant_momentum_zero(gl):
@@ -231,7 +243,7 @@ def test_pcm16_matches_the_callers_cast(gl):
         assert np.array_equal(b, o.pcm16(a))
         assert b.max() == 32767 or b.min() == -32767        # peak-normalised input reaches full scale
     # un-normalised output beyond [-1, 1] saturates instead of wrapping
-    loud = make(gl, 1024, 2, normalise=gl.NORM_NONE)
+    loud = make(gl, 1024, 2, normalise=gl.NORM_NONE, fixed_seed=True)
     big = [np.full((80, 12), 3.0, np.float32)]               # exp(3)^1.7 magnitudes -> |y| >> 1
     y = loud.infer_batch(big)[0]
     p = loud.infer_batch_pcm16(big)[0]
@@ -248,7 +260,7 @@ def test_pcm16_matches_the_callers_cast(gl):
 def test_cfg5_full_size_properties(gl):
     """BASELINE.json configs[4] shape (8 x 80x8000, n_fft 2048, hop 512, 60 iterations): size-independent checks."""
     n_fft, hop, t, b = 2048, 512, 8000, 8
-    voc = make(gl, n_fft, 60)
+    voc = make(gl, n_fft, 60, fixed_seed=True)
     mels = [o.synth_mel(900 + i, 80, t) for i in range(b)]
     ys = voc.infer_batch(mels)
     for y in ys:
@@ -382,7 +394,7 @@ def test_handles_are_thread_safe(gl):
     import threading
 
     basis = basis_for(1024)
-    shared = make(gl, 1024, 5, seed=3)
+    shared = make(gl, 1024, 5, seed=3, fixed_seed=True)
     ts = [21, 64, 9]
     mels = [o.synth_mel(900 + i, 80, t) for i, t in enumerate(ts)]
     want = shared.infer_batch(mels)
@@ -390,7 +402,7 @@ def test_handles_are_thread_safe(gl):
 
     def worker(k):
         try:
-            own = gl.GriffinLim.new(basis, 768, 1.7, 5, 0.99, seed=3)
+            own = gl.GriffinLim.new(basis, 768, 1.7, 5, 0.99, seed=3, fixed_seed=True)
             pipe = shared.pipe(ts, depth=2) if k % 2 == 0 else None
             for _ in range(6):
                 for got in (shared.infer_batch(mels), own.infer_batch(mels)):

@@ -24,7 +24,7 @@ namespace xdtts {
 std::vector<float> gl_lift_build_image(const float* pinv, int K, int n_mels);
 int gl_lift_tile_frames();
 cudaError_t gl_lift_prepare(int n_mels);
-cudaError_t gl_launch_lift(const float* mel_arena, const float* a_image, const float* pinvT, const int2* tiles, int n_tiles,
+cudaError_t gl_launch_lift(const float* mel_arena, const float* a_image, const float* pinvT, const int4* tiles, int n_tiles,
                            const int* utt_T, const int* utt_foff, int n_utt, int max_T, int n_mels, int K, int ld, float power,
                            int delog, int sm_count, float* S, cudaStream_t s, int* n_kernels);
 bool gl_lift_uses_tensor_cores(int n_mels, int K);
@@ -215,7 +215,8 @@ extern "C" int xdtts_gl_create(const float* mel_basis, int n_mels, int K, int no
         if (!std::isfinite(mel_basis[i])) return fail(XDTTS_ERR_BAD_ARG, "gl_create: mel_basis has a non-finite entry");
     if (opts && (opts->delog < 0 || opts->delog > 2 || opts->pad_mode < 0 || opts->pad_mode > 1 || opts->normalise < 0 ||
                  opts->normalise > 1 || opts->run_frames < 0 || opts->persistent < 0 || opts->persistent > 1 || opts->lift < 0 ||
-                 opts->lift > 1 || opts->nnls_iters < 0))
+                 opts->lift > 1 || opts->nnls_iters < 0 || opts->fixed_seed < 0 || opts->fixed_seed > 1 || opts->exponent < 0 ||
+                 opts->exponent > 1))
         return fail(XDTTS_ERR_BAD_ARG, "gl_create: option out of range");
 
     int n_dev = 0;
@@ -234,6 +235,7 @@ extern "C" int xdtts_gl_create(const float* mel_basis, int n_mels, int K, int no
     h->device = device; h->n_mels = n_mels; h->K = K; h->n_fft = n_fft; h->hop = hop; h->n_iter = n_iter;
     h->power = power; h->momentum = momentum; h->sm_count = prop.multiProcessorCount;
     if (opts) h->opts = *opts;
+    if (h->opts.exponent == 1) h->power = 1.0f / power;   // librosa's mel_to_stft convention: S = x ^ (1 / power)
 
     std::vector<double> pv;
     pinv_rows(mel_basis, n_mels, K, &pv);
@@ -392,7 +394,8 @@ extern "C" void xdtts_gl_plan_destroy(xdtts_gl_plan* p) {
     for (auto& e : p->ev)
         if (e) cudaEventDestroy(e);
     cudaFree(p->d_runs); cudaFree(p->d_T); cudaFree(p->d_foff); cudaFree(p->d_out_off);
-    cudaFree(p->d_mel); cudaFree(p->d_in_mag); cudaFree(p->d_in_phase); cudaFree(p->d_turns); cudaFree(p->d_lift_tiles);
+    cudaFree(p->d_mel); cudaFree(p->d_in_mag); cudaFree(p->d_in_phase); cudaFree(p->d_turns); cudaFree(p->d_lift_tiles); cudaFree(p->d_seed);
+    if (p->h_seed) cudaFreeHost(p->h_seed);
     cudaFree(p->d_state); cudaFree(p->d_y[0]); cudaFree(p->d_y[1]); cudaFree(p->d_halo);
     cudaFree(p->d_out); cudaFree(p->d_flags); cudaFree(p->d_amax); cudaFree(p->d_pcm); cudaFree(p->d_done);
     if (p->h_pcm) cudaFreeHost(p->h_pcm);
@@ -475,12 +478,13 @@ int xdtts::gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out)
     // one state record per frame: [R: M float2 | S: M floats | S_nyq + 3 floats of padding] (gl_core.cuh Geo::REC)
     p->rec_f = (int)(3 * M + 4);
     ALLOC(p->d_state, TT * (size_t)p->rec_f * 4);
-    {   // frame tiles of the lift: (utterance, first frame), gl_lift_tile_frames() frames each, never across utterances
+    {   // frame tiles of the lift: (frame row of the utterance, its T, first frame), gl_lift_tile_frames() frames each, never across utterances
         const int tf = gl_lift_tile_frames();
         for (int b = 0; b < B; b++)
-            for (int t0 = 0; t0 < Ts[b]; t0 += tf) p->lift_tiles.push_back(make_int2(b, t0));
+            for (int t0 = 0; t0 < Ts[b]; t0 += tf) p->lift_tiles.push_back(make_int4(p->foff[b], Ts[b], t0, 0));
     }
-    ALLOC(p->d_lift_tiles, p->lift_tiles.size() * sizeof(int2));
+    ALLOC(p->d_lift_tiles, p->lift_tiles.size() * sizeof(int4));
+    ALLOC(p->d_seed, 8 + (size_t)B * sizeof(int));   // [u64 phase seed][int stream index of each utterance]
     ALLOC(p->d_y[0], TT * H * 4);
     ALLOC(p->d_y[1], TT * H * 4);
     ALLOC(p->d_halo, nr * 6 * H * 4);
@@ -495,8 +499,9 @@ int xdtts::gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out)
     if (e == cudaSuccess) e = cudaMemcpy(p->d_out_off, p->out_off.data(), B * sizeof(long long), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(p->d_flags, 0, nr * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemset(p->d_state, 0, TT * (size_t)p->rec_f * 4);
-    if (e == cudaSuccess) e = cudaMemcpy(p->d_lift_tiles, p->lift_tiles.data(), p->lift_tiles.size() * sizeof(int2), cudaMemcpyHostToDevice);
-    for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&p->ev[i]);
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_lift_tiles, p->lift_tiles.data(), p->lift_tiles.size() * sizeof(int4), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&p->h_seed, 8 + (size_t)B * sizeof(int), cudaHostAllocDefault);
+    for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&p->ev[i]);
     if (e != cudaSuccess) {
         xdtts_gl_plan_destroy(p);
         return fail(e == cudaErrorMemoryAllocation ? XDTTS_ERR_OOM : XDTTS_ERR_CUDA, "plan: %s", cudaGetErrorString(e));
@@ -509,6 +514,13 @@ extern "C" int xdtts_gl_plan_create(xdtts_gl* h, const int* Ts, int B, xdtts_gl_
     if (!h || !out) return fail(XDTTS_ERR_BAD_ARG, "plan_create: null argument");
     std::lock_guard<std::mutex> lk(h->mu);
     return gl_plan_build(h, Ts, B, out);
+}
+
+extern "C" int xdtts_gl_plan_lift_ms(const xdtts_gl_plan* p, float* ms) {
+    if (!p || !ms) return fail(XDTTS_ERR_BAD_ARG, "plan_lift_ms: null argument");
+    if (p->lift_ms < 0.f) return fail(XDTTS_ERR_BAD_ARG, "plan_lift_ms: no kernel-by-kernel (XDTTS_RUN_NO_GRAPH) pass has run on this plan");
+    *ms = p->lift_ms;
+    return XDTTS_OK;
 }
 
 extern "C" int xdtts_gl_plan_is_persistent(const xdtts_gl_plan* p) {
@@ -566,6 +578,24 @@ extern "C" int xdtts_gl_plan_upload(xdtts_gl_plan* p, int kind, const float* con
     return gl_plan_upload_locked(p, kind, srcs, nullptr);
 }
 
+// The reference draws new random phases on every call.  Here the phase field is a
+// counter-based generator; the seed of call c on a handle is opts.seed + c * odd constant (call 0 uses opts.seed
+// itself), unless opts.fixed_seed asks for the same field on every call.
+unsigned long long xdtts::gl_draw_seed(xdtts_gl* h) {
+    const unsigned long long c = h->opts.fixed_seed ? 0ull : h->calls.fetch_add(1);
+    return h->opts.seed + c * 0xD1B54A32D192ED03ull;
+}
+
+// seed + stream indices of the next pass of this plan -> device (stream-ordered before the launches that read them).
+// seed_ids == null: utterance b draws stream b.
+int xdtts::gl_plan_set_seed(xdtts_gl_plan* p, unsigned long long seed, const int* seed_ids, cudaStream_t s) {
+    memcpy(p->h_seed, &seed, 8);
+    int* ids = reinterpret_cast<int*>(p->h_seed + 8);
+    for (int b = 0; b < p->B; b++) ids[b] = seed_ids ? seed_ids[b] : b;
+    CU(cudaMemcpyAsync(p->d_seed, p->h_seed, 8 + (size_t)p->B * sizeof(int), cudaMemcpyHostToDevice, s));
+    return XDTTS_OK;
+}
+
 // enqueue the whole pass on the handle's stream; ev[1]/ev[2] bracket the steady-state launches when timed
 static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid, cudaStream_t s) {
     xdtts_gl* h = p->h;
@@ -573,6 +603,7 @@ static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid, cud
     const bool from_mag = flags & XDTTS_RUN_FROM_MAG, use_phase = flags & XDTTS_RUN_USE_PHASE;
     CU(cudaMemsetAsync(p->d_amax, 0, p->B * sizeof(unsigned), s));
     int lift_kernels = 1;
+    if (timed) CU(cudaEventRecord(p->ev[4], s));
     float* d_S = p->d_state + 2 * M;   // the S part of frame 0's record; records are rec_f floats apart
     if (from_mag) {
         CU(gl_launch_to_frame_major(p->d_in_mag, p->d_T, p->d_foff, p->B, p->max_T, h->K, d_S, p->rec_f, s));
@@ -594,6 +625,7 @@ static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid, cud
         }
     }
     g_launches++;
+    if (timed) CU(cudaEventRecord(p->ev[5], s));
     if (use_phase) {
         CU(gl_launch_to_frame_major(p->d_in_phase, p->d_T, p->d_foff, p->B, p->max_T, h->K, p->d_turns, h->K, s));
         g_launches++;
@@ -605,7 +637,8 @@ static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid, cud
     gp.state = p->d_state; gp.halo = p->d_halo; gp.flags = p->d_flags; gp.amax = p->d_amax;
     gp.edge_scale = h->d_edge; gp.tables = h->d_tables;
     gp.turns = use_phase ? p->d_turns : nullptr;
-    gp.seed = h->opts.seed; gp.utt_seed_base = 0;
+    gp.seed = reinterpret_cast<const unsigned long long*>(p->d_seed);
+    gp.utt_seed_id = reinterpret_cast<const int*>(p->d_seed + 8);
     gp.alpha = h->momentum / (1.0f + h->momentum);
     gp.inv_n = 1.0f / (float)h->n_fft;
     gp.pad_mode = h->opts.pad_mode;
@@ -674,9 +707,13 @@ static int plan_launch_graph(xdtts_gl_plan* p, int flags, cudaStream_t s) {
 }
 
 // enqueue the pass on stream s and return without waiting (xdtts_pipe): CUDA graph, or the persistent kernel
-int xdtts::gl_plan_launch_async(xdtts_gl_plan* p, int flags, cudaStream_t s) {
+int xdtts::gl_plan_launch_async(xdtts_gl_plan* p, int flags, cudaStream_t s, const unsigned long long* seed, const int* seed_ids) {
     clear_stale_error(__func__);
     CU(cudaSetDevice(p->h->device));
+    if (!(flags & XDTTS_RUN_USE_PHASE)) {
+        int rc = gl_plan_set_seed(p, seed ? *seed : gl_draw_seed(p->h), seed_ids, s);
+        if (rc) return rc;
+    }
     if (p->use_persistent && !(flags & XDTTS_RUN_PER_LAUNCH)) return plan_enqueue(p, flags, false, nullptr, s);
     return plan_launch_graph(p, flags, s);
 }
@@ -708,10 +745,15 @@ void xdtts::gl_plan_download_finish(xdtts_gl_plan* p, float* const* outs) {
     for (int b = 0; b < p->B; b++) memcpy(outs[b], p->h_out + p->out_off[b], (size_t)p->h->hop * (p->Ts[b] - 1) * 4);
 }
 
-int xdtts::gl_plan_run_locked(xdtts_gl_plan* p, int flags, float* ms_total, float* ms_iter, int* n_iter_launches) {
+int xdtts::gl_plan_run_locked(xdtts_gl_plan* p, int flags, float* ms_total, float* ms_iter, int* n_iter_launches,
+                              const unsigned long long* seed, const int* seed_ids) {
     xdtts_gl* h = p->h;
     clear_stale_error(__func__);
     CU(cudaSetDevice(h->device));
+    if (!(flags & XDTTS_RUN_USE_PHASE)) {
+        int rc = gl_plan_set_seed(p, seed ? *seed : gl_draw_seed(h), seed_ids, h->stream);
+        if (rc) return rc;
+    }
     if ((flags & XDTTS_RUN_FROM_MAG) && !p->d_in_mag) return fail(XDTTS_ERR_BAD_ARG, "plan_run: FROM_MAG without uploaded magnitudes");
     if (!(flags & XDTTS_RUN_FROM_MAG) && !p->d_mel) return fail(XDTTS_ERR_BAD_ARG, "plan_run: no mels uploaded");
     if ((flags & XDTTS_RUN_USE_PHASE) && !p->d_in_phase) return fail(XDTTS_ERR_BAD_ARG, "plan_run: USE_PHASE without uploaded phase");
@@ -728,6 +770,8 @@ int xdtts::gl_plan_run_locked(xdtts_gl_plan* p, int flags, float* ms_total, floa
         CU(cudaStreamSynchronize(s));
         if ((flags & XDTTS_RUN_NO_GRAPH) && ms_iter && mids > 0) CU(cudaEventElapsedTime(ms_iter, p->ev[1], p->ev[2]));
         if ((flags & XDTTS_RUN_NO_GRAPH) && n_iter_launches) *n_iter_launches = mids;
+        p->lift_ms = -1.f;
+        if (flags & XDTTS_RUN_NO_GRAPH) CU(cudaEventElapsedTime(&p->lift_ms, p->ev[4], p->ev[5]));
     } else {
         CU(cudaEventRecord(p->ev[0], s));
         int rc = plan_launch_graph(p, flags, s);
@@ -742,7 +786,7 @@ int xdtts::gl_plan_run_locked(xdtts_gl_plan* p, int flags, float* ms_total, floa
 extern "C" int xdtts_gl_plan_run(xdtts_gl_plan* p, int flags, float* ms_total, float* ms_iter, int* n_iter_launches) {
     if (!p) return fail(XDTTS_ERR_BAD_ARG, "plan_run: plan is null");
     std::lock_guard<std::mutex> lk(p->h->mu);
-    return gl_plan_run_locked(p, flags, ms_total, ms_iter, n_iter_launches);
+    return gl_plan_run_locked(p, flags, ms_total, ms_iter, n_iter_launches, nullptr, nullptr);
 }
 
 int xdtts::gl_plan_download_locked(xdtts_gl_plan* p, float* const* outs) {
@@ -840,8 +884,8 @@ int xdtts::gl_plan_mel_arena(xdtts_gl_plan* p, float** out) {
 }
 
 // ------------------------------------------------------------------ batch entry points
-static int batch_common(xdtts_gl* h, int kind, const float* const* ins, const int* Ts, int B,
-                        const float* const* phases, float* const* outs, short* const* pcm_outs = nullptr) {
+int xdtts::gl_batch_common(xdtts_gl* h, int kind, const float* const* ins, const int* Ts, int B, const float* const* phases,
+                           float* const* outs, short* const* pcm_outs, const unsigned long long* seed, const int* seed_ids) {
     if (!h) return fail(XDTTS_ERR_BAD_ARG, "infer: handle is null");
     if (!ins || !Ts || (!outs && !pcm_outs)) return fail(XDTTS_ERR_BAD_ARG, "infer: null argument");
     if (B < 1) return fail(XDTTS_ERR_BAD_ARG, "infer: B = %d", B);
@@ -859,24 +903,24 @@ static int batch_common(xdtts_gl* h, int kind, const float* const* ins, const in
         if (rc) return rc;
         flags |= XDTTS_RUN_USE_PHASE;
     }
-    rc = gl_plan_run_locked(p, flags, nullptr, nullptr, nullptr);
+    rc = gl_plan_run_locked(p, flags, nullptr, nullptr, nullptr, seed, seed_ids);
     if (rc) return rc;
     return pcm_outs ? plan_download_pcm16_locked(p, pcm_outs) : gl_plan_download_locked(p, outs);
 }
 
 extern "C" int xdtts_gl_infer_batch_pcm16(xdtts_gl* h, const float* const* mels, const int* Ts, int B,
                                           const float* const* init_phases, short* const* outs) {
-    return batch_common(h, 0, mels, Ts, B, init_phases, nullptr, outs);
+    return gl_batch_common(h, 0, mels, Ts, B, init_phases, nullptr, outs, nullptr, nullptr);
 }
 
 extern "C" int xdtts_gl_infer_batch(xdtts_gl* h, const float* const* mels, const int* Ts, int B,
                                     const float* const* init_phases, float* const* outs) {
-    return batch_common(h, 0, mels, Ts, B, init_phases, outs);
+    return gl_batch_common(h, 0, mels, Ts, B, init_phases, outs, nullptr, nullptr, nullptr);
 }
 
 extern "C" int xdtts_gl_from_mag_batch(xdtts_gl* h, const float* const* mags, const int* Ts, int B,
                                        const float* const* init_phases, float* const* outs) {
-    return batch_common(h, 1, mags, Ts, B, init_phases, outs);
+    return gl_batch_common(h, 1, mags, Ts, B, init_phases, outs, nullptr, nullptr, nullptr);
 }
 
 extern "C" int xdtts_gl_infer(xdtts_gl* h, const float* mel, int T, const float* init_phase, float* out, int out_len) {
@@ -887,5 +931,5 @@ extern "C" int xdtts_gl_infer(xdtts_gl* h, const float* mel, int T, const float*
     const float* mels[1] = {mel};
     const float* ph[1] = {init_phase};
     float* outs[1] = {out};
-    return batch_common(h, 0, mels, &T, 1, init_phase ? ph : nullptr, outs);
+    return gl_batch_common(h, 0, mels, &T, 1, init_phase ? ph : nullptr, outs, nullptr, nullptr, nullptr);
 }

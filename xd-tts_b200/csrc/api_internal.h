@@ -55,6 +55,7 @@ struct xdtts_gl {
     float* d_ell_val = nullptr;
     float lipschitz = 0.f;                          // sigma_max(basis)^2
     cudaStream_t stream = nullptr;
+    std::atomic<unsigned long long> calls{0};   // seeded-phase calls made on this handle (advances the phase seed)
     std::mutex mu;
     std::vector<xdtts_gl_plan*> cache;   // plans owned by the batch entry points
 };
@@ -74,8 +75,9 @@ struct xdtts_gl_plan {
     float* d_state = nullptr;        // per-frame records [R | S | S_nyq | pad], rec_f floats each (gl_core.cuh Geo::REC_F)
     int rec_f = 0;
     float *d_y[2] = {nullptr, nullptr}, *d_halo = nullptr, *d_out = nullptr;
-    std::vector<int2> lift_tiles;    // (utterance, first frame) of every frame tile of the lift
-    int2* d_lift_tiles = nullptr;
+    std::vector<int4> lift_tiles;    // (frame row of the utterance, its T, first frame, 0) of every frame tile of the lift
+    int4* d_lift_tiles = nullptr;
+    unsigned char *d_seed = nullptr, *h_seed = nullptr;   // [u64 phase seed][int stream index per utterance], device + pinned
     short* d_pcm = nullptr;          // 16-bit PCM copy of d_out (allocated on first use)
     short* h_pcm = nullptr;
     unsigned *d_flags = nullptr, *d_amax = nullptr, *d_done = nullptr;
@@ -84,7 +86,8 @@ struct xdtts_gl_plan {
     float *h_in = nullptr, *h_out = nullptr;
     size_t h_in_floats = 0;
     cudaGraphExec_t graphs[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float lift_ms = -1.f;            // device time of the mel -> linear step of the last kernel-by-kernel pass
 };
 
 
@@ -92,10 +95,16 @@ namespace xdtts {
 // the *_locked functions expect h->mu to be held
 int gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out);
 int gl_plan_upload_locked(xdtts_gl_plan* p, int kind, const float* const* srcs, cudaStream_t s);   // s == null: the handle's stream
-int gl_plan_launch_async(xdtts_gl_plan* p, int flags, cudaStream_t s);
+// seed / seed_ids: null = the handle's next seed / utterance b draws stream b (a pool passes one seed and global indices)
+int gl_plan_launch_async(xdtts_gl_plan* p, int flags, cudaStream_t s, const unsigned long long* seed = nullptr, const int* seed_ids = nullptr);
+unsigned long long gl_draw_seed(xdtts_gl* h);
+int gl_plan_set_seed(xdtts_gl_plan* p, unsigned long long seed, const int* seed_ids, cudaStream_t s);
+int gl_batch_common(xdtts_gl* h, int kind, const float* const* ins, const int* Ts, int B, const float* const* phases,
+                    float* const* outs, short* const* pcm_outs, const unsigned long long* seed, const int* seed_ids);
 int gl_plan_download_async(xdtts_gl_plan* p, float* const* outs, cudaStream_t s, bool* staged);
 void gl_plan_download_finish(xdtts_gl_plan* p, float* const* outs);
-int gl_plan_run_locked(xdtts_gl_plan* p, int flags, float* ms_total, float* ms_iter, int* n_iter_launches);
+int gl_plan_run_locked(xdtts_gl_plan* p, int flags, float* ms_total, float* ms_iter, int* n_iter_launches,
+                       const unsigned long long* seed = nullptr, const int* seed_ids = nullptr);
 int gl_plan_download_locked(xdtts_gl_plan* p, float* const* outs);
 int gl_cached_plan(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out);
 int gl_plan_mel_arena(xdtts_gl_plan* p, float** out);

@@ -273,8 +273,10 @@ struct GlParams {
     const float* edge_scale; // [2][H] 1 / window-sum-square of the first / last hop block
     const float2* tables;    // Geo::TAB constants
     const float* turns;      // INIT: [frames][M + 1] initial phase in turns (bin M last), or null -> hashed from seed
-    unsigned long long seed; // INIT: seed of the counter-based phase generator
-    int utt_seed_base;       // INIT: global index of utterance 0 (so shards draw distinct phases)
+    // INIT, seeded phase: both live in device memory so that a captured CUDA graph sees the values of the call
+    // that replays it (the seed advances per call; a multi-GPU pool numbers utterances globally)
+    const unsigned long long* seed;   // seed of the counter-based phase generator
+    const int* utt_seed_id;           // [n_utt] stream index of each utterance (its position in the caller's batch)
     float* ybuf[2];          // persistent kernel: the two waveform buffers (iteration i reads [(i-1)&1], writes [i&1])
     unsigned* done;          // persistent kernel: [n_runs] number of iterations each run has completed
     int n_iter;              // persistent kernel: iterations after the initial inverse transform
@@ -725,9 +727,11 @@ XD_HD void phase_f3(Lane<R3>& L, int lane, const GlParams& p, int utt, int T, in
                 tb_ = p.turns[frame * (G::M + 1) + kb];
                 if (j == 0 && l0) tn_ = p.turns[frame * (G::M + 1) + G::M];
             } else {
-                ta_ = phase_turn(p.seed, p.utt_seed_base + utt, G::M + 1, t, ka);
-                tb_ = phase_turn(p.seed, p.utt_seed_base + utt, G::M + 1, t, kb);
-                if (j == 0 && l0) tn_ = phase_turn(p.seed, p.utt_seed_base + utt, G::M + 1, t, G::M);
+                const unsigned long long seed = *p.seed;
+                const int sid = p.utt_seed_id[utt];
+                ta_ = phase_turn(seed, sid, G::M + 1, t, ka);
+                tb_ = phase_turn(seed, sid, G::M + 1, t, kb);
+                if (j == 0 && l0) tn_ = phase_turn(seed, sid, G::M + 1, t, G::M);
             }
             float sn, cs;
             sincos_turns(ta_, &sn, &cs);

@@ -20,10 +20,10 @@
 // TMEM lane dimension make the epilogue's stores coalesced: for one frame (TMEM column) the 32 lanes of a warp
 // hold 32 consecutive bins = 128 contiguous bytes of the frame-major state record the iteration kernel reads.
 //
-// Warp roles (288 threads, one CTA per SM):
+// Warp roles (416 threads, one CTA per SM):
 //     warps 0-3   epilogue     tcgen05.ld (lane quarter = warp) -> clamp -> ^power -> S
-//     warps 4-7   producers    mel [n_mels][T] -> delog -> tf32 hi / lo -> swizzled E tile (2-stage ring)
-//     warp  8     TMEM alloc + one thread issuing the MMAs and commits
+//     warps 4-11  producers    mel [n_mels][T] -> delog -> tf32 hi / lo -> swizzled E tile (2-stage ring)
+//     warp  12    TMEM alloc + one thread issuing the MMAs and commits
 // The Nyquist bin (bin M, a 129th row of the last tile otherwise) is summed by the producers of bin tile 0 on the
 // CUDA cores, from the de-logged values they hold anyway.
 #include <cuda_runtime.h>
@@ -43,7 +43,10 @@ namespace {
 constexpr int LT_BM = 128;       // bins per tile
 constexpr int LT_BN = 64;        // frames per tile
 constexpr int LT_STAGES = 2;     // E-tile ring
-constexpr int LT_THREADS = 288;
+constexpr int LT_EPI_WARPS = 4;   // epilogue warps: lane quarter = warp & 3, column group = warp >> 2 (13 warps keep 128 registers per thread)
+constexpr int LT_PRO_WARPS = 8;   // producer warps: frame groups (warp & 3, + 4), mel half = warp >> 2
+constexpr int LT_THREADS = 32 * (LT_EPI_WARPS + LT_PRO_WARPS + 1);
+constexpr int LT_TILE_SM = 128;  // tile records staged in shared memory per CTA
 constexpr int LT_MAX_KB = 3;     // shared memory holds the P tile (2 planes) + the E ring for n_mels <= 96; wider bases take gl_lift_f32_kernel
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -103,21 +106,24 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
-__device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+// round to tf32 (10 mantissa bits), nearest with ties away from zero -- cvt.rna.tf32.f32, which sm_100 expands
+// into ~15 instructions; for the finite values of this kernel the two integer operations below are the same function
+// (and the host builds the pseudo-inverse image with them, tf32_rna_bits)
+__device__ __forceinline__ float to_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+
+template <int DELOG>
+__device__ __forceinline__ float delog_value(float v) {
+    return DELOG == 0 ? expf(v) : (DELOG == 1 ? exp10f(v) : v);
 }
 
-__device__ __forceinline__ float delog_value(float v, int delog) {
-    return delog == 0 ? expf(v) : (delog == 1 ? exp10f(v) : v);
-}
-
-// s ^ power for s > 0 on the special-function unit: 2^(power * log2 s).  ~1e-6 relative at full scale (the gate
-// on S is 1e-5 of full scale, tests/test_gpu_gl.py::test_lift_matches_oracle); powf costs ~40 instructions per
-// value, i.e. more issue time than the whole rest of this kernel.
+// s ^ power for s > 0 on the special-function unit: 2^(power * log2 s), two MUFU operations and a multiply.  ~1e-6
+// relative at full scale (the gate on S is 1e-5 of full scale, tests/test_gpu_gl.py::test_lift_matches_oracle); powf
+// costs ~40 instructions per value -- more issue time than the rest of the kernel.
 __device__ __forceinline__ float pow_pos(float s, float power) {
-    return s > 0.f ? exp2f(power * __log2f(s)) : 0.f;
+    float l, r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(s));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * power));
+    return s > 0.f ? r : 0.f;
 }
 
 struct LiftParams {
@@ -125,11 +131,9 @@ struct LiftParams {
     const float* a_image;        // [n_mt][2 planes][kblocks][128 rows][32] tf32 values, rows pre-swizzled
     const float* pinv_nyq;       // the pseudo-inverse's row of bin M: entry m at pinv_nyq[m * pinv_ld]
     int pinv_ld;
-    const int2* tiles;           // frame tiles: (utterance, first frame)
-    const int* utt_T;
-    const int* utt_foff;
+    const int4* tiles;           // frame tiles: (first frame row of the utterance, its frame count T, first frame of the tile, 0)
     float* S;                    // frame-major state records: S[(foff + t) * ld + k], k < M
-    int n_tiles, n_mt, groups, n_mels, kblocks, ld, delog;
+    int n_tiles, n_mt, groups, n_mels, kblocks, ld;
     float power;
 };
 
@@ -138,9 +142,10 @@ struct LiftSmem {
     __host__ __device__ static int a_plane(int kblocks) { return kblocks * LT_BM * 128; }
     __host__ __device__ static int e_plane(int kblocks) { return kblocks * LT_BN * 128; }
     __host__ __device__ static int bar_off(int kblocks) { return 2 * a_plane(kblocks) + LT_STAGES * 2 * e_plane(kblocks); }
-    __host__ __device__ static int total(int kblocks) { return bar_off(kblocks) + 96 + 4 * 32 * kblocks + 1024; }
+    __host__ __device__ static int total(int kblocks) { return bar_off(kblocks) + 96 + 4 * 32 * LT_MAX_KB + 4 * 2 * LT_BN + 16 * LT_TILE_SM + 1024; }
 };
 
+template <int DELOG>
 __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -155,25 +160,30 @@ __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftPar
     uint64_t* a_bar = bars + 8;       // P tile landed
     uint32_t* tmem_ptr = (uint32_t*)(bars + 10);
     float* wn = (float*)(bars + 12);   // [32 kblocks] the pseudo-inverse's Nyquist row (bin M)
+    float* nq_sm = wn + 32 * LT_MAX_KB;                  // [2 stages][64 frames] Nyquist partial sums of the upper mel half
+    int4* tile_sm = (int4*)(nq_sm + 2 * LT_BN);   // this CTA's first LT_TILE_SM tile records (a global read per tile and role is a
+                                                    // serialised L2 round trip: a third of all stall samples before they were staged)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mt = blockIdx.x % p.n_mt, g = blockIdx.x / p.n_mt;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < LT_STAGES; s++) {
-            mbar_init(&full[s], 128);
+            mbar_init(&full[s], 32 * LT_PRO_WARPS);
             mbar_init(&empty[s], 1);
             mbar_init(&tfull[s], 1);
-            mbar_init(&tempty[s], 4);
+            mbar_init(&tempty[s], LT_EPI_WARPS);
         }
         mbar_init(a_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {   // 128 columns: two 128 x 64 fp32 accumulators
+    if (warp == LT_EPI_WARPS + LT_PRO_WARPS) {   // 128 columns: two 128 x 64 fp32 accumulators
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(128u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < 32 * p.kblocks; i += LT_THREADS) wn[i] = i < p.n_mels ? p.pinv_nyq[(size_t)i * p.pinv_ld] : 0.f;
+    for (int i = threadIdx.x; i < 32 * LT_MAX_KB; i += LT_THREADS) wn[i] = i < p.n_mels ? p.pinv_nyq[(size_t)i * p.pinv_ld] : 0.f;
+    for (int i = threadIdx.x; i < LT_TILE_SM && g + i * p.groups < p.n_tiles; i += LT_THREADS) tile_sm[i] = p.tiles[g + i * p.groups];
+    auto tile_rec = [&](int it_) -> int4 { return it_ < LT_TILE_SM ? tile_sm[it_] : p.tiles[g + it_ * p.groups]; };
     // the zero padding of the E tiles (mel indices n_mels .. 32 kblocks - 1) is written once: producers only touch k < n_mels
     for (int i = threadIdx.x; i < LT_STAGES * 2 * e_plane / 16; i += LT_THREADS) reinterpret_cast<uint4*>(se)[i] = make_uint4(0, 0, 0, 0);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -182,7 +192,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftPar
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp == 8) {
+    if (warp == LT_EPI_WARPS + LT_PRO_WARPS) {
         // ===================== MMA issuer
         if (lane == 0) {
             mbar_expect_tx(a_bar, (uint32_t)(2 * a_plane));
@@ -216,96 +226,113 @@ __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftPar
                 tc_commit(&tfull[s]);    // accumulator complete -> epilogue
             }
         }
-    } else if (warp >= 4) {
-        // ===================== producers: a warp covers 4 mel rows x 8 frames per step (conflict-free swizzled stores,
-        // four full 32-byte sectors per global load).  The loads of tile i+1 are issued before tile i is converted, so
-        // their latency hides behind the conversion, the MMA and the epilogue of the tiles in flight.
-        const int pw = warp - 4;
+    } else if (warp >= LT_EPI_WARPS) {
+        // ===================== producers.  A warp covers 4 mel rows x 8 frames per step (conflict-free swizzled stores,
+        // four full 32-byte sectors per global load); producer warp pw owns frame groups pw and pw + 4 of the tile, a
+        // lane the frames fa = 8 pw + f8 and fb = fa + 32 and the mel rows m4, m4 + 4, ...  The loads of tile i+1 are
+        // issued before tile i is converted, so their latency hides behind the conversion, MMA and epilogue in flight.
+        const int pw = (warp - LT_EPI_WARPS) & 3, mh = (warp - LT_EPI_WARPS) >> 2;
         const int m4 = lane & 3, f8 = lane >> 2;
-        const int n_blk = ((p.n_mels + 3) / 4) * (LT_BN / 8);   // (mel group, frame group) blocks per tile, <= 192
-        constexpr int PER = (LT_MAX_KB * 8) * (LT_BN / 8) / 4;   // blocks per producer warp, 48
-        float xn[PER];
-        auto issue_loads = [&](int tile, float* x) {
-            const int2 tl = p.tiles[tile];
-            const int T = p.utt_T[tl.x];
-            const float* mel = p.mel_arena + (size_t)p.utt_foff[tl.x] * p.n_mels;
+        const int fa = pw * 8 + f8;
+        constexpr int MGT = LT_MAX_KB * 8;                  // mel groups of 4 in a padded tile (24)
+        constexpr int MG = MGT / (LT_PRO_WARPS / 4);        // ... of which this warp converts MG, starting at mg0
+        const int mg0 = mh * MG;
+        const int mgroups = (p.n_mels + 3) / 4;
+        float wreg[MG];                          // this lane's entries of the pseudo-inverse's Nyquist row
 #pragma unroll
-            for (int i = 0; i < PER; i++) {
-                const int blk = pw + 4 * i;
-                const int m = (blk >> 3) * 4 + m4, t = tl.y + (blk & 7) * 8 + f8;
-                x[i] = (blk < n_blk && m < p.n_mels && t < T) ? __ldg(mel + (size_t)m * T + t) : -INFINITY;   // -inf: no sample
+        for (int mg = 0; mg < MG; mg++) wreg[mg] = wn[(mg0 + mg) * 4 + m4];
+        float xn[2 * MG];
+        auto issue_loads = [&](int it_, float* x) {
+            const int4 tl = tile_rec(it_);
+            const int T = tl.y;
+            const bool va = tl.z + fa < T, vb = tl.z + fa + 32 < T;
+            const float* src = p.mel_arena + (size_t)tl.x * p.n_mels + (size_t)(mg0 * 4 + m4) * T + tl.z + fa;
+#pragma unroll
+            for (int mg = 0; mg < MG; mg++) {
+                const bool mv = mg0 + mg < mgroups && (mg0 + mg) * 4 + m4 < p.n_mels;
+                x[2 * mg] = (mv && va) ? __ldg(src) : -INFINITY;          // -inf: no sample
+                x[2 * mg + 1] = (mv && vb) ? __ldg(src + 32) : -INFINITY;
+                src += 4 * (size_t)T;
             }
         };
-        if (g < p.n_tiles) issue_loads(g, xn);
+        if (g < p.n_tiles) issue_loads(0, xn);
         int it = 0;
         for (int tile = g; tile < p.n_tiles; tile += p.groups, it++) {
             const int s = it & 1;
-            float x[PER];
+            float x[2 * MG];
 #pragma unroll
-            for (int i = 0; i < PER; i++) x[i] = xn[i];
-            if (tile + p.groups < p.n_tiles) issue_loads(tile + p.groups, xn);
+            for (int i = 0; i < 2 * MG; i++) x[i] = xn[i];
+            if (tile + p.groups < p.n_tiles) issue_loads(it + 1, xn);
             mbar_wait(&empty[s], (uint32_t)((it >> 1) & 1) ^ 1u);
-            uint8_t* ehi = se + s * 2 * e_plane;
-            uint8_t* elo = ehi + e_plane;
-            float nq0 = 0.f, nq1 = 0.f;   // Nyquist-bin partial sums of this lane's two frames (bin tile 0 only)
+            uint8_t* ehi = se + s * 2 * e_plane + fa * 128 + m4 * 4;
+            float nq0 = 0.f, nq1 = 0.f;   // Nyquist-bin partial sums of this lane's two frames
 #pragma unroll
-            for (int i = 0; i < PER; i++) {
-                const int blk = pw + 4 * i;
-                const int m = (blk >> 3) * 4 + m4, f = (blk & 7) * 8 + f8;
-                if (blk < n_blk && m < p.n_mels) {
-                    const float e = x[i] == -INFINITY ? 0.f : delog_value(x[i], p.delog);
-                    const float hi = to_tf32(e);
-                    const float lo = to_tf32(e - hi);
-                    const int off = (m >> 5) * (LT_BN * 128) + f * 128 + ((((m & 31) >> 2) ^ (f & 7)) << 4) + (m & 3) * 4;
-                    *reinterpret_cast<float*>(ehi + off) = hi;
-                    *reinterpret_cast<float*>(elo + off) = lo;
-                    if (mt == 0) {
-                        if (i & 1) nq1 = fmaf(wn[m], e, nq1);
-                        else nq0 = fmaf(wn[m], e, nq0);
+            for (int mg = 0; mg < MG; mg++) {
+                const int mgg = mg0 + mg;
+                if (mgg < mgroups && mgg * 4 + m4 < p.n_mels) {
+                    // row f of K-block mgg >> 3, 16-byte chunk (mgg & 7) ^ (f & 7) (both frames have f & 7 == f8), element m4
+                    const int off = (mgg >> 3) * (LT_BN * 128) + (((mgg & 7) ^ f8) << 4);
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const float v = x[2 * mg + h];
+                        float e = delog_value<DELOG>(v);               // exp(-inf) = 0: no branch
+                        if (DELOG == 2) e = v == -INFINITY ? 0.f : e;
+                        const float hi = to_tf32(e);
+                        const float lo = to_tf32(e - hi);
+                        *reinterpret_cast<float*>(ehi + off + h * (32 * 128)) = hi;
+                        *reinterpret_cast<float*>(ehi + e_plane + off + h * (32 * 128)) = lo;
+                        if (h) nq1 = fmaf(wreg[mg], e, nq1);
+                        else nq0 = fmaf(wreg[mg], e, nq0);
                     }
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async proxy
             mbar_arrive(&full[s]);
-            if (mt == 0) {   // frames (pw + 4 i) & 7: i even -> frame group pw, i odd -> frame group pw + 4; mel rows m4, m4 + 4, ...
+            if (mt == 0) {   // the Nyquist bin (slot M of the frame's record): sum over the four lanes that share a frame,
+                             // then over the two warps that share the frame (one per half of the mel rows)
                 nq0 += __shfl_xor_sync(0xffffffffu, nq0, 1);
                 nq1 += __shfl_xor_sync(0xffffffffu, nq1, 1);
                 nq0 += __shfl_xor_sync(0xffffffffu, nq0, 2);
                 nq1 += __shfl_xor_sync(0xffffffffu, nq1, 2);
-                const int2 tl = p.tiles[tile];
-                const int T = p.utt_T[tl.x];
-                if (m4 == 0) {
-                    const int fa = pw * 8 + f8, fb = (pw + 4) * 8 + f8;
-                    float* rec = p.S + ((size_t)p.utt_foff[tl.x] + tl.y) * p.ld + p.n_mt * LT_BM;   // slot M of the first frame
-                    if (tl.y + fa < T) rec[(size_t)fa * p.ld] = p.power == 1.0f ? fmaxf(nq0, 0.f) : pow_pos(nq0, p.power);
-                    if (tl.y + fb < T) rec[(size_t)fb * p.ld] = p.power == 1.0f ? fmaxf(nq1, 0.f) : pow_pos(nq1, p.power);
+                float* part = nq_sm + s * LT_BN;   // the upper half's partial sums of this stage
+                if (mh == 1 && m4 == 0) { part[fa] = nq0; part[fa + 32] = nq1; }
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + pw), "r"(64) : "memory");   // the two warps of frame groups (pw, pw + 4)
+                const int4 tl = tile_rec(it);
+                if (mh == 0 && m4 == 0) {
+                    nq0 += part[fa];
+                    nq1 += part[fa + 32];
+                    float* rec = p.S + ((size_t)tl.x + tl.z + fa) * p.ld + p.n_mt * LT_BM;
+                    if (tl.z + fa < tl.y) rec[0] = p.power == 1.0f ? fmaxf(nq0, 0.f) : pow_pos(nq0, p.power);
+                    if (tl.z + fa + 32 < tl.y) rec[(size_t)32 * p.ld] = p.power == 1.0f ? fmaxf(nq1, 0.f) : pow_pos(nq1, p.power);
                 }
             }
         }
     } else {
         // ===================== epilogue: TMEM lane quarter q <-> bins mt*128 + 32 q + lane
-        const int q = warp;
+        const int q = warp & 3, ch = warp >> 2;                   // lane quarter, column half
+        constexpr int CW = LT_BN / (LT_EPI_WARPS / 4);            // columns per epilogue warp
         const int bin = mt * LT_BM + q * 32 + lane;
+        const bool plain = p.power == 1.0f;
         int it = 0;
         for (int tile = g; tile < p.n_tiles; tile += p.groups, it++) {
             const int s = it & 1;
-            const int2 tl = p.tiles[tile];
-            const int T = p.utt_T[tl.x];
-            const int nf = min(LT_BN, T - tl.y);
-            float* out = p.S + ((size_t)p.utt_foff[tl.x] + tl.y) * p.ld + bin;
+            const int4 tl = tile_rec(it);
+            const int nf = min(LT_BN, tl.y - tl.z) - ch * CW;   // frames of this warp's columns that exist
+            float* out = p.S + ((size_t)tl.x + tl.z + ch * CW) * p.ld + bin;
             mbar_wait(&tfull[s], (uint32_t)((it >> 1) & 1));
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * LT_BN);
-#pragma unroll
-            for (int c0 = 0; c0 < LT_BN; c0 += 16) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * LT_BN + ch * CW);
+#pragma unroll 1
+            for (int c0 = 0; c0 < CW; c0 += 16) {
                 uint32_t v[16];
                 tc_ld16(taddr + (uint32_t)c0, v);
                 tc_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
-                    const float x = __uint_as_float(v[i]);
-                    const float r = p.power == 1.0f ? fmaxf(x, 0.f) : pow_pos(x, p.power);
-                    if (c0 + i < nf) __stcs(out + (size_t)(c0 + i) * p.ld, r);   // 32 lanes = 32 consecutive bins of one frame
+                    const float xv = __uint_as_float(v[i]);
+                    const float r = plain ? fmaxf(xv, 0.f) : pow_pos(xv, p.power);
+                    if (c0 + i < nf) __stcs(out, r);   // 32 lanes = 32 consecutive bins of one frame: one 128-byte line
+                    out += p.ld;
                 }
             }
             tc_fence_before();
@@ -316,7 +343,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftPar
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+    if (warp == LT_EPI_WARPS + LT_PRO_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
 }
 
 // CUDA-core fp32 form of the same lift (all K bins, Nyquist included): the path for mel bases wider than 96 rows,
@@ -324,9 +351,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftPar
 // grid (1, ceil(maxT/16), n_utt); thread <-> bins k, k + 128, ...; 16 frames per block; the plain fp32 FMA sum is
 // 5e-7 of full scale from the fp64 result (the gate is 1e-5).
 constexpr int LF_TT = 16;
+template <int DELOG>
 __global__ void __launch_bounds__(128) gl_lift_f32_kernel(const float* __restrict__ mel_arena, const float* __restrict__ pinvT,
                                                           const int* __restrict__ utt_T, const int* __restrict__ utt_foff,
-                                                          int n_mels, int K, int ld, float power, int delog, float* __restrict__ S) {
+                                                          int n_mels, int K, int ld, float power, float* __restrict__ S) {
     extern __shared__ __align__(16) float e_sm[];   // [n_mels][LF_TT]
     const int u = blockIdx.z, T = utt_T[u], t0 = blockIdx.y * LF_TT;
     if (t0 >= T) return;
@@ -334,7 +362,7 @@ __global__ void __launch_bounds__(128) gl_lift_f32_kernel(const float* __restric
     const float* mel = mel_arena + foff * n_mels;
     for (int i = threadIdx.x; i < n_mels * LF_TT; i += 128) {
         const int m = i / LF_TT, tt = i % LF_TT;
-        e_sm[i] = (t0 + tt < T) ? delog_value(mel[(size_t)m * T + t0 + tt], delog) : 0.f;
+        e_sm[i] = (t0 + tt < T) ? delog_value<DELOG>(mel[(size_t)m * T + t0 + tt]) : 0.f;
     }
     __syncthreads();
     for (int k = threadIdx.x; k < K; k += 128) {
@@ -406,32 +434,40 @@ bool gl_lift_uses_tensor_cores(int n_mels, int K) {
 cudaError_t gl_lift_prepare(int n_mels) {
     const int kblocks = (n_mels + 31) / 32;
     if (kblocks > LT_MAX_KB) return cudaSuccess;
-    return cudaFuncSetAttribute(gl_lift_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LiftSmem::total(kblocks));
+    cudaError_t e = cudaFuncSetAttribute(gl_lift_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, LiftSmem::total(kblocks));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gl_lift_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LiftSmem::total(kblocks));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gl_lift_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, LiftSmem::total(kblocks));
+    return e;
 }
 
 // S[(foff + t) * ld + k] = max(0, sum_m pinv[k][m] delog(mel[m][t])) ^ power for k = 0..M (k = M: the Nyquist slot).
 // pinvT: [n_mels][K] (the transposed pseudo-inverse); a_image: gl_lift_build_image.  *n_kernels: launches made.
-cudaError_t gl_launch_lift(const float* mel_arena, const float* a_image, const float* pinvT, const int2* tiles, int n_tiles,
+cudaError_t gl_launch_lift(const float* mel_arena, const float* a_image, const float* pinvT, const int4* tiles, int n_tiles,
                            const int* utt_T, const int* utt_foff, int n_utt, int max_T, int n_mels, int K, int ld, float power,
                            int delog, int sm_count, float* S, cudaStream_t s, int* n_kernels) {
     const int M = K - 1;
     if (!gl_lift_uses_tensor_cores(n_mels, K)) {
         if (n_mels > 256) return cudaErrorInvalidValue;
         dim3 grid(1, (max_T + LF_TT - 1) / LF_TT, n_utt);
-        gl_lift_f32_kernel<<<grid, 128, (size_t)n_mels * LF_TT * sizeof(float), s>>>(mel_arena, pinvT, utt_T, utt_foff, n_mels, K, ld,
-                                                                                    power, delog, S);
+        const size_t sm = (size_t)n_mels * LF_TT * sizeof(float);
+        if (delog == 0) gl_lift_f32_kernel<0><<<grid, 128, sm, s>>>(mel_arena, pinvT, utt_T, utt_foff, n_mels, K, ld, power, S);
+        else if (delog == 1) gl_lift_f32_kernel<1><<<grid, 128, sm, s>>>(mel_arena, pinvT, utt_T, utt_foff, n_mels, K, ld, power, S);
+        else gl_lift_f32_kernel<2><<<grid, 128, sm, s>>>(mel_arena, pinvT, utt_T, utt_foff, n_mels, K, ld, power, S);
         if (n_kernels) *n_kernels = 1;
         return cudaGetLastError();
     }
     LiftParams p;
-    p.mel_arena = mel_arena; p.a_image = a_image; p.tiles = tiles; p.utt_T = utt_T; p.utt_foff = utt_foff; p.S = S;
+    p.mel_arena = mel_arena; p.a_image = a_image; p.tiles = tiles; p.S = S;
     p.n_tiles = n_tiles; p.n_mt = M / LT_BM; p.n_mels = n_mels; p.kblocks = (n_mels + 31) / 32; p.ld = ld;
-    p.delog = delog; p.power = power;
+    p.power = power;
     p.groups = sm_count / p.n_mt;
     if (p.groups < 1) p.groups = 1;
     if (p.groups > n_tiles) p.groups = n_tiles;
     p.pinv_nyq = pinvT + M; p.pinv_ld = K;
-    gl_lift_tc_kernel<<<p.n_mt * p.groups, LT_THREADS, LiftSmem::total(p.kblocks), s>>>(p);
+    const int grid = p.n_mt * p.groups, sm = LiftSmem::total(p.kblocks);
+    if (delog == 0) gl_lift_tc_kernel<0><<<grid, LT_THREADS, sm, s>>>(p);
+    else if (delog == 1) gl_lift_tc_kernel<1><<<grid, LT_THREADS, sm, s>>>(p);
+    else gl_lift_tc_kernel<2><<<grid, LT_THREADS, sm, s>>>(p);
     if (n_kernels) *n_kernels = 1;
     return cudaGetLastError();
 }

@@ -49,6 +49,8 @@ class GlOpts(ctypes.Structure):
         ("persistent", ctypes.c_int),
         ("lift", ctypes.c_int),
         ("nnls_iters", ctypes.c_int),
+        ("fixed_seed", ctypes.c_int),
+        ("exponent", ctypes.c_int),
     ]
 
 
@@ -73,6 +75,15 @@ SIGNATURES = {
     "xdtts_gl_from_mag_batch": (ctypes.c_int, [_vp, _fpp, _ip, ctypes.c_int, _fpp, _fpp]),
     "xdtts_gl_infer_batch_pcm16": (ctypes.c_int, [_vp, _fpp, _ip, ctypes.c_int, _fpp, _spp]),
     "xdtts_gl_plan_download_pcm16": (ctypes.c_int, [_vp, _spp]),
+    "xdtts_gl_plan_lift_ms": (ctypes.c_int, [_vp, _fp]),
+    "xdtts_pool_create": (ctypes.c_int, [_fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
+                                         ctypes.c_float, ctypes.POINTER(GlOpts), _ip, ctypes.c_int, ctypes.POINTER(_vp)]),
+    "xdtts_pool_destroy": (None, [_vp]),
+    "xdtts_pool_n_devices": (ctypes.c_int, [_vp]),
+    "xdtts_pool_out_len": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "xdtts_pool_assignment": (ctypes.c_int, [_vp, _ip, ctypes.c_int, _ip]),
+    "xdtts_pool_infer_batch": (ctypes.c_int, [_vp, _fpp, _ip, ctypes.c_int, _fpp, _fpp]),
+    "xdtts_pool_from_mag_batch": (ctypes.c_int, [_vp, _fpp, _ip, ctypes.c_int, _fpp, _fpp]),
     "xdtts_gl_plan_create": (ctypes.c_int, [_vp, _ip, ctypes.c_int, ctypes.POINTER(_vp)]),
     "xdtts_gl_plan_destroy": (None, [_vp]),
     "xdtts_gl_plan_upload": (ctypes.c_int, [_vp, ctypes.c_int, _fpp]),

@@ -58,14 +58,15 @@ class GriffinLim:
 
     @classmethod
     def new(cls, mel_basis, noverlap, power, iter, momentum, *, delog=DELOG_EXP, pad_mode=PAD_REFLECT,  # noqa: A002
-            normalise=NORM_PEAK, seed=0, run_frames=0, persistent=False, lift=LIFT_PINV, nnls_iters=0, device=0):
+            normalise=NORM_PEAK, seed=0, run_frames=0, persistent=False, lift=LIFT_PINV, nnls_iters=0, fixed_seed=False,
+            exponent=0, device=0):
         """GriffinLim::new(mel_basis, noverlap, power, iter, momentum) (src/tacotron2/mod.rs:456)."""
         lib = load_library()
         basis = np.ascontiguousarray(mel_basis, dtype=np.float32)
         if basis.ndim != 2:
             raise XdttsError(_ffi.ERR_SHAPE, "mel_basis must be 2-D [n_mels, K]")
         opts = GlOpts(int(delog), int(pad_mode), int(normalise), int(run_frames), int(seed), int(bool(persistent)), int(lift),
-                      int(nnls_iters))
+                      int(nnls_iters), int(bool(fixed_seed)), int(exponent))
         h = ctypes.c_void_p()
         check(lib.xdtts_gl_create(fptr(basis), basis.shape[0], basis.shape[1], int(noverlap), float(power), int(iter),
                                   float(momentum), ctypes.byref(opts), int(device), ctypes.byref(h)))
@@ -181,6 +182,12 @@ class GlPlan:
         a = (ctypes.c_int * 4)()
         check(load_library().xdtts_gl_plan_info(self._p, a))
         return dict(n_runs=a[0], run_frames=a[1], ctas=a[2], total_frames=a[3])
+
+    def lift_ms(self):
+        """Device time of the mel -> linear step of the last run(RUN_NO_GRAPH) of this plan."""
+        ms = ctypes.c_float()
+        check(load_library().xdtts_gl_plan_lift_ms(self._p, ctypes.byref(ms)))
+        return ms.value
 
     def is_persistent(self):
         """True when run() vocodes the plan with the single cooperative launch (all runs resident at once)."""
@@ -340,3 +347,69 @@ class Pipe:
         if rc < 0:
             check(rc)
         return rc
+
+
+class GriffinLimPool:
+    """One vocoder per GPU behind one handle (xdtts_pool_*): `infer_batch` shards the utterances over the devices
+    (longest first to the least-loaded device, no data-path exchange -- SURVEY.md section 8e) and returns the
+    waveforms in the caller's order.  Same constructor arguments as GriffinLim.new, plus the device list."""
+
+    def __init__(self, handle, n_mels, k_bins, hop):
+        self._h, self.n_mels, self.k_bins, self.hop = handle, n_mels, k_bins, hop
+
+    @classmethod
+    def new(cls, mel_basis, noverlap, power, iter, momentum, *, devices=None, delog=DELOG_EXP, pad_mode=PAD_REFLECT,  # noqa: A002
+            normalise=NORM_PEAK, seed=0, run_frames=0, lift=LIFT_PINV, nnls_iters=0, fixed_seed=False, exponent=0):
+        lib = load_library()
+        basis = np.ascontiguousarray(mel_basis, dtype=np.float32)
+        if basis.ndim != 2:
+            raise XdttsError(_ffi.ERR_SHAPE, "mel_basis must be 2-D [n_mels, K]")
+        opts = GlOpts(int(delog), int(pad_mode), int(normalise), int(run_frames), int(seed), 0, int(lift), int(nnls_iters),
+                      int(bool(fixed_seed)), int(exponent))
+        devs = list(devices) if devices is not None else []
+        d_arr = (ctypes.c_int * max(len(devs), 1))(*devs) if devs else None
+        h = ctypes.c_void_p()
+        check(lib.xdtts_pool_create(fptr(basis), basis.shape[0], basis.shape[1], int(noverlap), float(power), int(iter),
+                                    float(momentum), ctypes.byref(opts), d_arr, len(devs), ctypes.byref(h)))
+        return cls(h, basis.shape[0], basis.shape[1], 2 * (basis.shape[1] - 1) - int(noverlap))
+
+    def close(self):
+        if self._h:
+            load_library().xdtts_pool_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def n_devices(self):
+        return load_library().xdtts_pool_n_devices(self._h)
+
+    def assignment(self, frame_counts):
+        ts = [int(t) for t in frame_counts]
+        t_arr = (ctypes.c_int * len(ts))(*ts)
+        out = (ctypes.c_int * len(ts))()
+        check(load_library().xdtts_pool_assignment(self._h, t_arr, len(ts), out))
+        return list(out)
+
+    def _run(self, fn, ins, rows, what, init_phases):
+        lib = load_library()
+        ins = [_as_f32_2d(a, rows, what) for a in ins]
+        ts = [a.shape[1] for a in ins]
+        outs = [np.empty(max(self.hop * (t - 1), 0), dtype=np.float32) for t in ts]
+        phs = None
+        if init_phases is not None:
+            phs = [_as_f32_2d(a, self.k_bins, "init_phase") for a in init_phases]
+            if [a.shape[1] for a in phs] != ts:
+                raise XdttsError(_ffi.ERR_SHAPE, "init_phases do not match the inputs' frame counts")
+        t_arr = (ctypes.c_int * len(ts))(*ts)
+        check(getattr(lib, fn)(self._h, fptr_array(ins), t_arr, len(ins), None if phs is None else fptr_array(phs), fptr_array(outs)))
+        return outs
+
+    def infer_batch(self, mels, init_phases=None):
+        return self._run("xdtts_pool_infer_batch", mels, self.n_mels, "mel", init_phases)
+
+    def from_magnitude_batch(self, mags, init_phases=None):
+        return self._run("xdtts_pool_from_mag_batch", mags, self.k_bins, "magnitude", init_phases)
