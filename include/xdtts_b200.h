@@ -277,6 +277,9 @@ int xdtts_pool_create(const float* mel_basis, int n_mels, int K, int noverlap, f
 void xdtts_pool_destroy(xdtts_pool* p);
 int xdtts_pool_n_devices(const xdtts_pool* p);
 int xdtts_pool_out_len(const xdtts_pool* p, int T);
+/* the assignment rule alone (host only, no GPU needed): slot 0..n_slots-1 of every utterance -- longest first to the
+ * least-loaded slot, ties to the lowest slot; what xdtts_b200/shard.py applies across processes */
+int xdtts_shard_assign(const int* Ts, int B, int n_slots, int* slot_of_utt);
 /* the device each utterance of a batch with these frame counts is sent to */
 int xdtts_pool_assignment(const xdtts_pool* p, const int* Ts, int B, int* device_of_utt);
 int xdtts_pool_infer_batch(xdtts_pool* p, const float* const* mels, const int* Ts, int B,

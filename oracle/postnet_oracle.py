@@ -69,10 +69,12 @@ def postnet(mel, layers, eps=BN_EPS, dtype=np.float32):
     x = np.asarray(mel, dtype=dtype)
     n = len(layers)
     for i, l in enumerate(layers):
-        y = conv1d_same(x, l["w"].astype(dtype), l["b"].astype(dtype))
-        inv = 1.0 / np.sqrt(l["var"].astype(dtype) + dtype(eps))
-        y = (y - l["mean"].astype(dtype)[:, None]) * (l["gamma"].astype(dtype) * inv)[:, None] + l[
-            "beta"
-        ].astype(dtype)[:, None]
+        bias = l["b"].astype(dtype) if l.get("b") is not None else np.zeros(l["w"].shape[0], dtype)
+        y = conv1d_same(x, l["w"].astype(dtype), bias)
+        if l.get("gamma") is not None:   # a layer without BatchNormalization: an export with the statistics folded in
+            inv = 1.0 / np.sqrt(l["var"].astype(dtype) + dtype(eps))
+            y = (y - l["mean"].astype(dtype)[:, None]) * (l["gamma"].astype(dtype) * inv)[:, None] + l[
+                "beta"
+            ].astype(dtype)[:, None]
         x = np.tanh(y) if i < n - 1 else y
     return (np.asarray(mel, dtype=dtype) + x).astype(dtype)

@@ -74,8 +74,11 @@ def node(op, inputs, outputs, attrs=(), name=""):
     return body
 
 
-def postnet_model(layers, eps=1e-5, prefix="postnet.convolutions", raw=True, with_bn=True):
-    """bytes of a ModelProto for the postnet with the given layers (dicts w,b,gamma,beta,mean,var)."""
+def postnet_model(layers, eps=1e-5, prefix="postnet.convolutions", raw=True, with_bn=True, activation="Tanh", residual=True,
+                  extra_op=None, dropout=False):
+    """bytes of a ModelProto for the postnet with the given layers (dicts w,b,gamma,beta,mean,var).
+    activation / residual / extra_op build graphs that are NOT the Tacotron2 postnet (the reader must reject them);
+    dropout inserts the inference-mode Dropout nodes some exporters keep."""
     nodes, inits = [], []
     x = "mel"
     n = len(layers)
@@ -98,12 +101,23 @@ def postnet_model(layers, eps=1e-5, prefix="postnet.convolutions", raw=True, wit
             z = "bn_%d" % i
             nodes.append(node("BatchNormalization", [y] + names, [z], [attr_float("epsilon", eps), attr_float("momentum", 0.9)]))
             y = z
-        if i < n - 1:
+        if i < n - 1 and activation:
             z = "tanh_%d" % i
-            nodes.append(node("Tanh", [y], [z]))
+            nodes.append(node(activation, [y], [z]))
+            y = z
+        if dropout:
+            z = "drop_%d" % i
+            nodes.append(node("Dropout", [y], [z]))
+            y = z
+        if extra_op and i == 1:
+            z = "extra_%d" % i
+            nodes.append(node(extra_op, [y], [z]))
             y = z
         x = y
-    nodes.append(node("Add", ["mel", x], ["mel_outputs_postnet"]))
+    if residual:
+        nodes.append(node("Add", ["mel", x], ["mel_outputs_postnet"]))
+    else:
+        nodes.append(node("Identity", [x], ["mel_outputs_postnet"]))
     graph = b"".join(_ld(1, nd) for nd in nodes) + _str(2, "torch_jit") + b"".join(_ld(5, t) for t in inits)
     graph += _ld(11, _str(1, "mel")) + _ld(12, _str(1, "mel_outputs_postnet"))   # ValueInfoProto names only
     model = _int(1, 7) + _str(2, "pytorch") + _str(3, "1.13") + _ld(7, graph) + _ld(8, _str(1, "") + _int(2, 13))

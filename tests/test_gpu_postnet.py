@@ -252,3 +252,17 @@ def test_cfg3_full_size_batch(taco, layers):
     assert worst < 2e-4, worst
     assert np.array_equal(tc.run(mels[17]), outs[17])
     assert np.abs(outs[5] - po.postnet(mels[5], layers, dtype=np.float64)).max() < TOL[0]
+
+
+def test_load_files_written_by_pytorch(taco, golden_dir):
+    """Postnet.load (xdtts_postnet_create_from_onnx) on ONNX files serialised by PyTorch's exporter -- BatchNorm kept and
+    BatchNorm folded -- reproduces PyTorch's own output of that module (tests/make_foreign_onnx.py)."""
+    import os
+
+    g = np.load(os.path.join(golden_dir, "postnet_torch_export.npz"))
+    for tag in ("bn", "fused"):
+        post = taco.Postnet.load(os.path.join(golden_dir, "postnet_torch_export_%s.onnx" % tag))
+        y = post.run(g["x"])
+        assert y.shape == g["y"].shape
+        assert np.abs(y - g["y"]).max() < 2e-4, tag
+        post.close()

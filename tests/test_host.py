@@ -336,7 +336,46 @@ def test_onnx_postnet_reader(lib, tmp_path):
     trunc.write_bytes(postnet_model(layers)[:200000])
     with pytest.raises(XdttsError):
         tacotron2.read_onnx_postnet(trunc)
-    assert ERR_UNSUPPORTED < 0
+    # the graph must BE the postnet the device computes: another activation, a missing residual or a foreign operator is
+    # rejected instead of loading into a network that computes something else (inference-mode Dropout is accepted)
+    small = [dict(l) for l in po.synth_weights(seed=3, channels=(8, 16, 16, 8))]
+    ok = tmp_path / "dropout.onnx"
+    ok.write_bytes(postnet_model(small, dropout=True))
+    assert len(tacotron2.read_onnx_postnet(ok)) == 3
+    for kw, word in ((dict(activation="Relu"), "Relu"), (dict(activation=None), "Tanh"), (dict(residual=False), "residual"),
+                     (dict(extra_op="Sigmoid"), "Sigmoid"), (dict(extra_op="Tanh"), "Tanh")):
+        path = tmp_path / "wrong.onnx"
+        path.write_bytes(postnet_model(small, **kw))
+        with pytest.raises(XdttsError) as e:
+            tacotron2.read_onnx_postnet(path)
+        assert e.value.code == ERR_UNSUPPORTED and word in e.value.message, (kw, e.value.message)
+
+
+def test_onnx_reader_on_files_written_by_pytorch(lib, golden_dir):
+    """A FOREIGN encoder: tests/golden/postnet_torch_export_*.onnx were serialised by PyTorch's ONNX exporter
+    (tests/make_foreign_onnx.py), not by tests/onnx_writer.py -- initializer names, packing, attribute order and the
+    BatchNorm folding are the exporter's, not ours."""
+    from xdtts_b200 import tacotron2
+
+    g = np.load(os.path.join(golden_dir, "postnet_torch_export.npz"))
+    bn = tacotron2.read_onnx_postnet(os.path.join(golden_dir, "postnet_torch_export_bn.onnx"))
+    assert len(bn) == 5
+    for i, l in enumerate(bn):
+        for k, name in (("w", "w"), ("b", "b"), ("gamma", "gamma"), ("beta", "beta"), ("mean", "mean"), ("var", "var")):
+            assert np.array_equal(l[k], g["%s%d" % (name, i)]), (i, k)
+        assert abs(l["eps"] - 1e-5) < 1e-9
+    fused = tacotron2.read_onnx_postnet(os.path.join(golden_dir, "postnet_torch_export_fused.onnx"))
+    assert len(fused) == 5 and all("gamma" not in l for l in fused)
+    for i, l in enumerate(fused):   # the exporter folded BatchNorm into the convolution: W' = W g / sqrt(var + eps), ...
+        sc = g["gamma%d" % i].astype(np.float64) / np.sqrt(g["var%d" % i].astype(np.float64) + 1e-5)
+        assert np.allclose(l["w"], g["w%d" % i] * sc[:, None, None], rtol=1e-5, atol=1e-6)
+        assert np.allclose(l["b"], (g["b%d" % i] - g["mean%d" % i]) * sc + g["beta%d" % i], rtol=1e-5, atol=1e-6)
+    # and the oracle run on the layers we read reproduces PyTorch's own output of that graph
+    from oracle import postnet_oracle as po
+
+    for layers in (bn, fused):
+        y = po.postnet(g["x"], layers, dtype=np.float64)
+        assert np.abs(y - g["y"]).max() < 1e-5
 
 
 def test_npy_io_matches_numpy(lib, tmp_path):

@@ -70,3 +70,28 @@ def test_two_rank_gloo_job(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
+
+
+def test_c_abi_assignment_matches_the_python_rule(built):
+    """xdtts_shard_assign (what xdtts_pool_infer_batch applies across the GPUs of one process) == shard.shard_utterances
+    (what bench.py applies across ranks): one rule, two hosts."""
+    import ctypes
+
+    import numpy as np
+
+    from xdtts_b200 import _ffi, shard
+
+    lib = _ffi.load_library()
+    rng = np.random.default_rng(5)
+    for trial in range(40):
+        b = int(rng.integers(1, 70))
+        n = int(rng.integers(1, 9))
+        ts = [int(x) for x in rng.integers(4, 3000, b)]
+        if trial % 5 == 0:
+            ts = [1000] * b                                     # the benchmark's uniform batches: ties everywhere
+        t_arr = (ctypes.c_int * b)(*ts)
+        out = (ctypes.c_int * b)()
+        _ffi.check(lib.xdtts_shard_assign(t_arr, b, n, out))
+        for r in range(n):
+            assert [i for i in range(b) if out[i] == r] == shard.shard_utterances(ts, n, r)
+    assert lib.xdtts_shard_assign(None, 3, 2, None) == _ffi.ERR_BAD_ARG

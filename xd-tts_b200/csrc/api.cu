@@ -18,6 +18,7 @@
 #include "api_internal.h"
 #include "gl_host.h"
 #include "gl_tables.h"
+#include "host_copy.h"
 
 namespace xdtts {
 // gl_lift.cu
@@ -396,6 +397,9 @@ extern "C" void xdtts_gl_plan_destroy(xdtts_gl_plan* p) {
     cudaFree(p->d_runs); cudaFree(p->d_T); cudaFree(p->d_foff); cudaFree(p->d_out_off);
     cudaFree(p->d_mel); cudaFree(p->d_in_mag); cudaFree(p->d_in_phase); cudaFree(p->d_turns); cudaFree(p->d_lift_tiles); cudaFree(p->d_seed);
     if (p->h_seed) cudaFreeHost(p->h_seed);
+    for (cudaEvent_t e : p->out_ev)
+        if (e) cudaEventDestroy(e);
+    if (p->h_in_busy) cudaEventDestroy(p->h_in_busy);
     cudaFree(p->d_state); cudaFree(p->d_y[0]); cudaFree(p->d_y[1]); cudaFree(p->d_halo);
     cudaFree(p->d_out); cudaFree(p->d_flags); cudaFree(p->d_amax); cudaFree(p->d_pcm); cudaFree(p->d_done);
     if (p->h_pcm) cudaFreeHost(p->h_pcm);
@@ -550,21 +554,34 @@ int xdtts::gl_plan_upload_locked(xdtts_gl_plan* p, int kind, const float* const*
     float** dst = kind == 0 ? &p->d_mel : (kind == 1 ? &p->d_in_mag : &p->d_in_phase);
     if (!*dst) CU(cudaMalloc((void**)dst, rows * (size_t)p->total_T * 4));
     if (kind == 2 && !p->d_turns) CU(cudaMalloc((void**)&p->d_turns, (size_t)p->total_T * h->K * 4));   // [frames][K]
-    // pageable sources go through one pinned staging buffer so that the copy is a single async DMA
+    // pageable sources go through the plan's pinned staging buffer: helper threads copy utterance by utterance, and an
+    // utterance goes on the bus (async DMA) as soon as it is staged, while the next ones are still being copied
     bool all_pinned = true;
     for (int b = 0; b < p->B; b++) all_pinned = all_pinned && is_pinned(srcs[b]);
     if (!all_pinned) {
         const size_t need = rows * (size_t)p->total_T;
+        if (p->h_in_busy) CU(cudaEventSynchronize(p->h_in_busy));   // the previous upload's DMA still reads the staging buffer
         if (p->h_in_floats < need) {
             if (p->h_in) cudaFreeHost(p->h_in);
             p->h_in = nullptr; p->h_in_floats = 0;
             CU(cudaHostAlloc((void**)&p->h_in, need * 4, cudaHostAllocDefault));
             p->h_in_floats = need;
         }
-        for (int b = 0; b < p->B; b++)
-            memcpy(p->h_in + rows * (size_t)p->foff[b], srcs[b], rows * (size_t)p->Ts[b] * 4);
-        CU(cudaMemcpyAsync(*dst, p->h_in, need * 4, cudaMemcpyHostToDevice, s));
-        CU(cudaStreamSynchronize(s));   // the staging buffer is reused by the next upload
+        if (!p->h_in_busy) CU(cudaEventCreateWithFlags(&p->h_in_busy, cudaEventDisableTiming));
+        std::vector<std::atomic<int>> pending(p->B);
+        for (int b = 0; b < p->B; b++) {
+            pending[b].store(0);
+            host_copy_async(p->h_in + rows * (size_t)p->foff[b], srcs[b], rows * (size_t)p->Ts[b] * 4, &pending[b]);
+        }
+        cudaError_t ce = cudaSuccess;
+        for (int b = 0; b < p->B; b++) {
+            host_copy_wait(&pending[b]);      // every chunk must be done before this function returns, error or not
+            if (ce == cudaSuccess)
+                ce = cudaMemcpyAsync(*dst + rows * (size_t)p->foff[b], p->h_in + rows * (size_t)p->foff[b], rows * (size_t)p->Ts[b] * 4,
+                                     cudaMemcpyHostToDevice, s);
+        }
+        CU(ce);
+        CU(cudaEventRecord(p->h_in_busy, s));
     } else {
         for (int b = 0; b < p->B; b++)
             CU(cudaMemcpyAsync(*dst + rows * (size_t)p->foff[b], srcs[b], rows * (size_t)p->Ts[b] * 4, cudaMemcpyHostToDevice, s));
@@ -597,7 +614,8 @@ int xdtts::gl_plan_set_seed(xdtts_gl_plan* p, unsigned long long seed, const int
 }
 
 // enqueue the whole pass on the handle's stream; ev[1]/ev[2] bracket the steady-state launches when timed
-static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid, cudaStream_t s) {
+static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid, cudaStream_t s, bool capturing = false) {
+    unsigned long long launched = 0;   // added to the process-wide counter at the end -- not at all while capturing a graph
     xdtts_gl* h = p->h;
     const int M = h->K - 1;
     const bool from_mag = flags & XDTTS_RUN_FROM_MAG, use_phase = flags & XDTTS_RUN_USE_PHASE;
@@ -611,7 +629,7 @@ static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid, cud
         const bool nnls = h->opts.lift == 1;
         CU(gl_launch_lift(p->d_mel, h->d_lift_img, h->d_pinvT, p->d_lift_tiles, (int)p->lift_tiles.size(), p->d_T, p->d_foff, p->B,
                           p->max_T, h->n_mels, h->K, p->rec_f, nnls ? 1.0f : h->power, h->opts.delog, h->sm_count, d_S, s, &lift_kernels));
-        g_launches += (unsigned long long)(lift_kernels - 1);
+        launched += (unsigned long long)(lift_kernels - 1);
         if (nnls) {   // refine the clipped least-squares start in place, then apply the exponent
             const int iters = h->opts.nnls_iters > 0 ? h->opts.nnls_iters : 300;
             if (h->band_rw > 0 && !getenv("XDTTS_NNLS_GENERIC"))
@@ -621,14 +639,14 @@ static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid, cud
             else
                 CU(gl_launch_nnls(p->d_mel, h->d_csr, h->d_csr_val, h->d_csc, h->d_csc_val, p->d_T, p->d_foff, p->B, p->max_T, h->n_mels,
                                   h->K, h->power, h->opts.delog, h->lipschitz, iters, 3e-6f, d_S, p->rec_f, s));
-            g_launches++;
+            launched++;
         }
     }
-    g_launches++;
+    launched++;
     if (timed) CU(cudaEventRecord(p->ev[5], s));
     if (use_phase) {
         CU(gl_launch_to_frame_major(p->d_in_phase, p->d_T, p->d_foff, p->B, p->max_T, h->K, p->d_turns, h->K, s));
-        g_launches++;
+        launched++;
     }
     GlParams gp;
     memset(&gp, 0, sizeof(gp));
@@ -652,7 +670,7 @@ static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid, cud
         CU(gl_launch_persistent(h->n_fft, gp, h->sm_count, s, &fits));
         if (fits) {
             if (timed) CU(cudaEventRecord(p->ev[2], s));
-            g_launches++;
+            launched++;
             mids = 1;
             done = true;
         } else {
@@ -662,22 +680,23 @@ static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid, cud
     if (!done) {
         gp.y_in = p->d_y[1]; gp.y_out = p->d_y[0];
         CU(gl_launch_iteration(h->n_fft, GL_MODE_INIT, h->n_iter == 0, gp, s));
-        g_launches++;
+        launched++;
         for (int it = 1; it <= h->n_iter; it++) {
             gp.y_in = p->d_y[(it - 1) & 1];
             gp.y_out = p->d_y[it & 1];
             const bool last = it == h->n_iter;
             if (timed && it == 2) CU(cudaEventRecord(p->ev[1], s));
             CU(gl_launch_iteration(h->n_fft, it == 1 ? GL_MODE_FIRST : GL_MODE_MID, last, gp, s));
-            g_launches++;
+            launched++;
             if (it >= 2 && !last) mids++;
             if (timed && it == h->n_iter - 1 && it >= 2) CU(cudaEventRecord(p->ev[2], s));
         }
     }
     CU(gl_launch_finish(p->d_y[h->n_iter & 1], p->d_T, p->d_foff, p->d_out_off, p->d_amax, p->B, p->max_T, h->hop,
                         h->opts.normalise == 0, p->d_out, s));
-    g_launches++;
+    launched++;
     if (n_mid) *n_mid = mids;
+    if (!capturing) g_launches += launched;
     return XDTTS_OK;
 }
 
@@ -688,9 +707,7 @@ static int plan_launch_graph(xdtts_gl_plan* p, int flags, cudaStream_t s) {
     if (!p->graphs[gi]) {
         cudaGraph_t g = nullptr;
         CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        const unsigned long long before = g_launches.load();
-        int rc = plan_enqueue(p, flags, false, nullptr, s);
-        g_launches = before;   // captured, not launched
+        int rc = plan_enqueue(p, flags, false, nullptr, s, true);   // captured, not launched: not counted
         cudaError_t e = cudaStreamEndCapture(s, &g);
         if (rc) {
             if (g) cudaGraphDestroy(g);
@@ -735,14 +752,28 @@ int xdtts::gl_plan_download_async(xdtts_gl_plan* p, float* const* outs, cudaStre
         for (int b = 0; b < p->B; b++)
             CU(cudaMemcpyAsync(outs[b], p->d_out + p->out_off[b], (size_t)h->hop * (p->Ts[b] - 1) * 4, cudaMemcpyDeviceToHost, s));
     } else {
+        // utterance by utterance into the pinned staging buffer, an event after each: gl_plan_download_finish hands an
+        // utterance to the copy threads as soon as its DMA is done, while the following ones are still on the bus
         if (!p->h_out) CU(cudaHostAlloc((void**)&p->h_out, (size_t)p->out_total * 4, cudaHostAllocDefault));
-        CU(cudaMemcpyAsync(p->h_out, p->d_out, (size_t)p->out_total * 4, cudaMemcpyDeviceToHost, s));
+        if (p->out_ev.empty()) {
+            p->out_ev.resize(p->B, nullptr);
+            for (int b = 0; b < p->B; b++) CU(cudaEventCreateWithFlags(&p->out_ev[b], cudaEventDisableTiming));
+        }
+        for (int b = 0; b < p->B; b++) {
+            CU(cudaMemcpyAsync(p->h_out + p->out_off[b], p->d_out + p->out_off[b], (size_t)h->hop * (p->Ts[b] - 1) * 4, cudaMemcpyDeviceToHost, s));
+            CU(cudaEventRecord(p->out_ev[b], s));
+        }
     }
     return XDTTS_OK;
 }
 
 void xdtts::gl_plan_download_finish(xdtts_gl_plan* p, float* const* outs) {
-    for (int b = 0; b < p->B; b++) memcpy(outs[b], p->h_out + p->out_off[b], (size_t)p->h->hop * (p->Ts[b] - 1) * 4);
+    std::atomic<int> pending{0};
+    for (int b = 0; b < p->B; b++) {
+        if (!p->out_ev.empty()) cudaEventSynchronize(p->out_ev[b]);
+        host_copy_async(outs[b], p->h_out + p->out_off[b], (size_t)p->h->hop * (p->Ts[b] - 1) * 4, &pending);
+    }
+    host_copy_wait(&pending);
 }
 
 int xdtts::gl_plan_run_locked(xdtts_gl_plan* p, int flags, float* ms_total, float* ms_iter, int* n_iter_launches,
@@ -798,8 +829,8 @@ int xdtts::gl_plan_download_locked(xdtts_gl_plan* p, float* const* outs) {
     bool staged = false;
     int rc = gl_plan_download_async(p, outs, h->stream, &staged);
     if (rc) return rc;
+    if (staged) gl_plan_download_finish(p, outs);   // overlaps the host copies with the DMA of the following utterances
     CU(cudaStreamSynchronize(h->stream));
-    if (staged) gl_plan_download_finish(p, outs);
     return XDTTS_OK;
 }
 

@@ -85,6 +85,8 @@ struct xdtts_gl_plan {
     // pinned staging for pageable callers
     float *h_in = nullptr, *h_out = nullptr;
     size_t h_in_floats = 0;
+    cudaEvent_t h_in_busy = nullptr;         // recorded after the DMA that reads h_in
+    std::vector<cudaEvent_t> out_ev;         // per utterance: its device -> h_out copy is done
     cudaGraphExec_t graphs[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float lift_ms = -1.f;            // device time of the mel -> linear step of the last kernel-by-kernel pass

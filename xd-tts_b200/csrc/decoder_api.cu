@@ -177,6 +177,7 @@ extern "C" int xdtts_decoder_max_steps(const xdtts_decoder* h) {
 
 extern "C" int xdtts_decoder_last_timing(const xdtts_decoder* h, float* ms, int* steps) {
     if (!h) return fail(XDTTS_ERR_BAD_ARG, "decoder_last_timing: handle is null");
+    std::lock_guard<std::mutex> lk(const_cast<xdtts_decoder*>(h)->mu);
     if (ms) *ms = h->last_ms;
     if (steps) *steps = h->last_steps;
     return XDTTS_OK;

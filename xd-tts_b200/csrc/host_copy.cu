@@ -1,0 +1,108 @@
+// see host_copy.h
+#include "host_copy.h"
+
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace xdtts {
+namespace {
+
+struct Chunk {
+    void* dst;
+    const void* src;
+    size_t bytes;
+    std::atomic<int>* pending;
+};
+
+class Copier {
+  public:
+    Copier() {
+        int n = 4;
+        if (const char* e = getenv("XDTTS_COPY_THREADS")) n = atoi(e);
+        const int hw = (int)std::thread::hardware_concurrency();
+        if (hw > 0 && n > hw) n = hw;
+        if (n < 0) n = 0;
+        for (int i = 0; i < n; i++) threads_.emplace_back([this] { loop(); });
+    }
+    ~Copier() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    void push(const Chunk& c) {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            q_.push_back(c);
+        }
+        cv_.notify_one();
+    }
+    bool run_one() {   // the waiting caller copies too
+        Chunk c;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            if (q_.empty()) return false;
+            c = q_.front();
+            q_.pop_front();
+        }
+        memcpy(c.dst, c.src, c.bytes);
+        c.pending->fetch_sub(1, std::memory_order_release);
+        return true;
+    }
+    int threads() const { return (int)threads_.size(); }
+
+  private:
+    void loop() {
+        for (;;) {
+            Chunk c;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this] { return stop_ || !q_.empty(); });
+                if (stop_ && q_.empty()) return;
+                c = q_.front();
+                q_.pop_front();
+            }
+            memcpy(c.dst, c.src, c.bytes);
+            c.pending->fetch_sub(1, std::memory_order_release);
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<Chunk> q_;
+    std::vector<std::thread> threads_;
+    bool stop_ = false;
+};
+
+Copier& copier() {
+    static Copier* c = new Copier();   // never destroyed: helper threads must not be joined from a static destructor
+    return *c;
+}
+
+}  // namespace
+
+void host_copy_async(void* dst, const void* src, size_t bytes, std::atomic<int>* pending) {
+    const size_t chunk = 512 * 1024;
+    Copier& c = copier();
+    for (size_t off = 0; off < bytes; off += chunk) {
+        const size_t n = bytes - off < chunk ? bytes - off : chunk;
+        pending->fetch_add(1, std::memory_order_relaxed);
+        c.push(Chunk{(char*)dst + off, (const char*)src + off, n, pending});
+    }
+}
+
+void host_copy_wait(std::atomic<int>* pending) {
+    Copier& c = copier();
+    while (pending->load(std::memory_order_acquire) > 0)
+        if (!c.run_one()) std::this_thread::yield();
+}
+
+int host_copy_threads() { return copier().threads(); }
+
+}  // namespace xdtts

@@ -4,10 +4,13 @@
 // -- without ONNX Runtime or protobuf: a ~200-line reader of the protobuf wire format for the handful
 // of ModelProto / GraphProto / NodeProto / TensorProto fields that matter.
 //
-// The graph is matched structurally, not by initializer names (exporters rename them): every `Conv`
-// node in graph order is a layer (inputs X, W, B); a `BatchNormalization` node consuming the Conv's
-// output supplies (scale, B, mean, var) and the `epsilon` attribute; Tanh / Add / Identity / Dropout
-// nodes are what the device path implements itself.  Host-only code: usable (and tested) without a GPU.
+// The graph is matched structurally, not by initializer names (exporters rename them), and it is VALIDATED: the
+// nodes are walked along the dataflow from the graph input and must spell Conv [-> BatchNormalization] -> Tanh for
+// every layer but the last, then the residual Add of the graph input -- the function the device kernels compute.
+// Anything else (another activation, no residual, an extra operator) is rejected with XDTTS_ERR_UNSUPPORTED instead
+// of loading into a network that computes something different.  Host-only code: usable (and tested) without a GPU.
+// Read against two encoders: tests/onnx_writer.py (hand-rolled) and PyTorch's own serializer
+// (tests/make_foreign_onnx.py -> tests/golden/postnet_torch_export_*.onnx).
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -205,6 +208,16 @@ extern "C" int xdtts_onnx_postnet_open(const char* path, xdtts_onnx_postnet** ou
 
     std::map<std::string, Tensor> init;
     std::vector<Node> nodes;
+    std::vector<std::string> g_in, g_out;   // GraphProto.input / .output (ValueInfoProto.name)
+    auto value_name = [](Span v) {
+        std::string name;
+        uint32_t vf, vw;
+        while (v.field(&vf, &vw)) {
+            if (vf == 1 && vw == 2) name = v.str();
+            else v.skip(vw);
+        }
+        return name;
+    };
     while (graph.field(&f, &w)) {
         if (f == 1 && w == 2) {
             Node n;
@@ -215,6 +228,10 @@ extern "C" int xdtts_onnx_postnet_open(const char* path, xdtts_onnx_postnet** ou
             Tensor t;
             if (!parse_tensor(graph.bytes(), &name, &t)) return fail(XDTTS_ERR_BAD_ARG, "onnx_postnet_open: malformed TensorProto");
             init[name] = std::move(t);
+        } else if (f == 11 && w == 2) {
+            g_in.push_back(value_name(graph.bytes()));
+        } else if (f == 12 && w == 2) {
+            g_out.push_back(value_name(graph.bytes()));
         } else {
             graph.skip(w);
         }
@@ -233,12 +250,62 @@ extern "C" int xdtts_onnx_postnet_open(const char* path, xdtts_onnx_postnet** ou
         return XDTTS_OK;
     };
 
+    // The device path is fixed: out = x + L_{n-1}(tanh(L_{n-2}(... tanh(L_0(x))))), L = Conv [-> BatchNormalization].  The
+    // graph must BE that -- walked along its dataflow from the (single) non-initializer input: Conv, then optionally the
+    // BatchNormalization of its output, then Tanh after every layer but the last, a final Add of the graph input, and
+    // nothing else but Identity / Dropout (inference: identity).  Any other operator, a missing activation or a missing
+    // residual would load without complaint otherwise and silently produce a different mel_outputs_postnet.
+    std::string x_name;
+    for (const std::string& nm : g_in)
+        if (init.find(nm) == init.end()) {   // old exporters list the initializers as graph inputs too
+            if (!x_name.empty()) return fail(XDTTS_ERR_UNSUPPORTED, "onnx_postnet_open: more than one graph input ('%s', '%s')", x_name.c_str(), nm.c_str());
+            x_name = nm;
+        }
+    if (x_name.empty()) return fail(XDTTS_ERR_BAD_ARG, "onnx_postnet_open: the graph has no input");
     xdtts_onnx_postnet* m = new xdtts_onnx_postnet();
     int rc = XDTTS_OK;
+    std::string cur = x_name;          // tensor the walk stands on
+    std::vector<bool> has_tanh;        // per layer
+    bool bn_allowed = false, residual = false;
     for (size_t i = 0; i < nodes.size() && rc == XDTTS_OK; i++) {
         const Node& n = nodes[i];
-        if (n.op != "Conv") continue;
-        if (n.in.size() < 2 || n.out.empty()) { rc = fail(XDTTS_ERR_BAD_ARG, "onnx_postnet_open: Conv node without weights"); break; }
+        if (residual) { rc = fail(XDTTS_ERR_UNSUPPORTED, "onnx_postnet_open: operator %s after the residual Add", n.op.c_str()); break; }
+        if (n.out.empty() || n.in.empty()) { rc = fail(XDTTS_ERR_BAD_ARG, "onnx_postnet_open: %s node without input or output", n.op.c_str()); break; }
+        if (n.op == "Identity" || n.op == "Dropout") {
+            if (n.in[0] != cur) { rc = fail(XDTTS_ERR_UNSUPPORTED, "onnx_postnet_open: %s node off the main path ('%s')", n.op.c_str(), n.in[0].c_str()); break; }
+            cur = n.out[0];
+            continue;
+        }
+        if (n.op == "Tanh") {
+            if (n.in[0] != cur || m->layers.empty() || has_tanh.back()) { rc = fail(XDTTS_ERR_UNSUPPORTED, "onnx_postnet_open: Tanh that does not follow a convolution layer"); break; }
+            has_tanh.back() = true;
+            bn_allowed = false;
+            cur = n.out[0];
+            continue;
+        }
+        if (n.op == "Add") {
+            const bool ok = n.in.size() == 2 && ((n.in[0] == x_name && n.in[1] == cur) || (n.in[1] == x_name && n.in[0] == cur));
+            if (!ok || m->layers.empty() || has_tanh.back()) { rc = fail(XDTTS_ERR_UNSUPPORTED, "onnx_postnet_open: Add is not the residual (graph input + last layer)"); break; }
+            residual = true;
+            cur = n.out[0];
+            continue;
+        }
+        if (n.op == "BatchNormalization") {
+            if (n.in.size() < 5 || n.in[0] != cur || !bn_allowed) { rc = fail(XDTTS_ERR_UNSUPPORTED, "onnx_postnet_open: BatchNormalization that does not directly follow a Conv"); break; }
+            Layer& L = m->layers.back();
+            rc = get(n.in[1], (size_t)L.cout, "BatchNormalization scale", &L.gamma);
+            if (rc == XDTTS_OK) rc = get(n.in[2], (size_t)L.cout, "BatchNormalization bias", &L.beta);
+            if (rc == XDTTS_OK) rc = get(n.in[3], (size_t)L.cout, "BatchNormalization mean", &L.mean);
+            if (rc == XDTTS_OK) rc = get(n.in[4], (size_t)L.cout, "BatchNormalization var", &L.var);
+            L.eps = n.epsilon;
+            bn_allowed = false;
+            cur = n.out[0];
+            continue;
+        }
+        if (n.op != "Conv") { rc = fail(XDTTS_ERR_UNSUPPORTED, "onnx_postnet_open: operator %s is not part of a Tacotron2 postnet (Conv, BatchNormalization, Tanh, Add, Identity, Dropout)", n.op.c_str()); break; }
+        if (n.in[0] != cur) { rc = fail(XDTTS_ERR_UNSUPPORTED, "onnx_postnet_open: Conv reads '%s', not the previous layer's output", n.in[0].c_str()); break; }
+        if (!m->layers.empty() && !has_tanh.back()) { rc = fail(XDTTS_ERR_UNSUPPORTED, "onnx_postnet_open: layer %zu is not followed by Tanh (only the last layer may be linear)", m->layers.size() - 1); break; }
+        if (n.in.size() < 2) { rc = fail(XDTTS_ERR_BAD_ARG, "onnx_postnet_open: Conv node without weights"); break; }
         auto wt = init.find(n.in[1]);
         if (wt == init.end() || wt->second.dims.size() != 3) { rc = fail(XDTTS_ERR_UNSUPPORTED, "onnx_postnet_open: Conv weight '%s' is not a 3-D initializer (Conv1d expected)", n.in[1].c_str()); break; }
         Layer L;
@@ -250,17 +317,15 @@ extern "C" int xdtts_onnx_postnet_open(const char* path, xdtts_onnx_postnet** ou
         rc = get(n.in[1], (size_t)L.cout * L.cin * L.k, "Conv weight", &L.w);
         if (rc == XDTTS_OK && n.in.size() > 2 && !n.in[2].empty()) rc = get(n.in[2], (size_t)L.cout, "Conv bias", &L.b);
         if (rc != XDTTS_OK) break;
-        for (const Node& bn : nodes) {   // the BatchNormalization that consumes this Conv's output, if any
-            if (bn.op != "BatchNormalization" || bn.in.size() < 5 || bn.in[0] != n.out[0]) continue;
-            rc = get(bn.in[1], (size_t)L.cout, "BatchNormalization scale", &L.gamma);
-            if (rc == XDTTS_OK) rc = get(bn.in[2], (size_t)L.cout, "BatchNormalization bias", &L.beta);
-            if (rc == XDTTS_OK) rc = get(bn.in[3], (size_t)L.cout, "BatchNormalization mean", &L.mean);
-            if (rc == XDTTS_OK) rc = get(bn.in[4], (size_t)L.cout, "BatchNormalization var", &L.var);
-            L.eps = bn.epsilon;
-            break;
-        }
-        if (rc == XDTTS_OK) m->layers.push_back(std::move(L));
+        m->layers.push_back(std::move(L));
+        has_tanh.push_back(false);
+        bn_allowed = true;
+        cur = n.out[0];
     }
+    if (rc == XDTTS_OK && !m->layers.empty() && !residual)
+        rc = fail(XDTTS_ERR_UNSUPPORTED, "onnx_postnet_open: %s has no residual Add of the graph input (mel_outputs_postnet = mel + postnet(mel))", path);
+    if (rc == XDTTS_OK && !m->layers.empty() && (g_out.size() != 1 || g_out[0] != cur))
+        rc = fail(XDTTS_ERR_UNSUPPORTED, "onnx_postnet_open: the graph output is not the residual sum");
     if (rc == XDTTS_OK && m->layers.empty()) rc = fail(XDTTS_ERR_BAD_ARG, "onnx_postnet_open: %s has no Conv node", path);
     for (size_t l = 1; rc == XDTTS_OK && l < m->layers.size(); l++) {
         if (m->layers[l].cin != m->layers[l - 1].cout) rc = fail(XDTTS_ERR_SHAPE, "onnx_postnet_open: layer %zu takes %d channels, layer %zu makes %d", l, m->layers[l].cin, l - 1, m->layers[l - 1].cout);

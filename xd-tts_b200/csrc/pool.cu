@@ -84,6 +84,13 @@ static void worker_main(xdtts_pool* p, xdtts_pool::Worker* w) {
     }
 }
 
+// host-only: the assignment rule by itself (slot index 0..n_slots-1 per utterance)
+extern "C" int xdtts_shard_assign(const int* Ts, int B, int n_slots, int* slot_of_utt) {
+    if (!Ts || !slot_of_utt || B < 1 || n_slots < 1) return fail(XDTTS_ERR_BAD_ARG, "shard_assign: bad argument");
+    lpt_assign(Ts, B, n_slots, slot_of_utt);
+    return XDTTS_OK;
+}
+
 extern "C" void xdtts_pool_destroy(xdtts_pool* p) {
     if (!p) return;
     {

@@ -546,9 +546,9 @@ static int pn_download_async(xdtts_postnet_plan* p, const float* src, float* con
 // wait for the batch in `sl` and finish the staged copies of pageable destinations
 static int pipe_collect(xdtts_pipe* q, xdtts_pipe::Slot& sl) {
     if (!sl.busy) return XDTTS_OK;
-    sl.busy = false;
     CU(cudaSetDevice(q->gl->device));
-    CU(cudaStreamSynchronize(sl.s));
+    CU(cudaStreamSynchronize(sl.s));     // on failure the slot stays busy: the batch is not silently dropped
+    sl.busy = false;
     if (sl.staged_wave) gl_plan_download_finish(sl.gp, sl.out_waves.data());
     if (sl.staged_mel) {
         const size_t C0 = q->pn->ch[0];
@@ -631,39 +631,42 @@ extern "C" int xdtts_pipe_push(xdtts_pipe* q, const float* const* mels, const fl
     rc = gl_plan_mel_arena(sl.gp, &arena);
     if (rc) return rc;
     int flags = 0;
+    // From here on work may already be queued on the slot's stream: every failure goes through the clean-up below
+    // (wait for the stream) before returning, so nothing of a half-submitted batch touches the caller's buffers later.
+    auto cuda_rc = [&](cudaError_t e, const char* what) {
+        return e == cudaSuccess ? XDTTS_OK : fail(e == cudaErrorMemoryAllocation ? XDTTS_ERR_OOM : XDTTS_ERR_CUDA, "pipe_push: %s: %s", what, cudaGetErrorString(e));
+    };
     // The copies of neighbouring batches overlap kernels, but the KERNELS of two batches must not interleave: every
     // Griffin-Lim launch is sized to fill the device in one wave, and two such grids sharing the SMs finish later than
     // the same two grids back to back.  So a slot's kernels wait for the previous batch's kernels (not for its copies).
     if (q->pn) {
         std::lock_guard<std::mutex> lk2(q->pn->mu);
         rc = pn_plan_upload_locked(sl.pp, mels, sl.s);
-        if (rc == XDTTS_OK && q->last_computed) CU(cudaStreamWaitEvent(sl.s, q->last_computed, 0));
+        if (rc == XDTTS_OK && q->last_computed) rc = cuda_rc(cudaStreamWaitEvent(sl.s, q->last_computed, 0), "cudaStreamWaitEvent");
         if (rc == XDTTS_OK) rc = pn_enqueue(sl.pp, arena, sl.s);
     } else {
         std::lock_guard<std::mutex> lk2(q->gl->mu);
         rc = gl_plan_upload_locked(sl.gp, 0, mels, sl.s);
     }
-    if (rc) return rc;
-    {
+    if (rc == XDTTS_OK) {
         std::lock_guard<std::mutex> lk2(q->gl->mu);
         if (init_phases) {
             rc = gl_plan_upload_locked(sl.gp, 2, init_phases, sl.s);
             flags |= XDTTS_RUN_USE_PHASE;
         }
-        if (rc == XDTTS_OK && !q->pn && q->last_computed) CU(cudaStreamWaitEvent(sl.s, q->last_computed, 0));
+        if (rc == XDTTS_OK && !q->pn && q->last_computed) rc = cuda_rc(cudaStreamWaitEvent(sl.s, q->last_computed, 0), "cudaStreamWaitEvent");
         if (rc == XDTTS_OK) rc = gl_plan_launch_async(sl.gp, flags, sl.s);
-        if (rc == XDTTS_OK) {
-            CU(cudaEventRecord(sl.computed, sl.s));
-            q->last_computed = sl.computed;
-        }
+        if (rc == XDTTS_OK) rc = cuda_rc(cudaEventRecord(sl.computed, sl.s), "cudaEventRecord");
+        if (rc == XDTTS_OK) q->last_computed = sl.computed;
         if (rc == XDTTS_OK) rc = gl_plan_download_async(sl.gp, out_waves, sl.s, &sl.staged_wave);
     }
     sl.staged_mel = false;
     if (rc == XDTTS_OK && out_mels) rc = pn_download_async(sl.pp, arena, out_mels, sl.s, &sl.staged_mel);
     if (rc) {
+        const std::string msg = xdtts_last_error();
         cudaStreamSynchronize(sl.s);   // leave nothing of a half-submitted batch in flight
         cudaGetLastError();
-        return rc;
+        return fail(rc, "%s", msg.c_str());
     }
     for (int b = 0; b < q->B; b++) {
         sl.out_waves[b] = out_waves[b];

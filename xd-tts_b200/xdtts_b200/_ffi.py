@@ -81,6 +81,7 @@ SIGNATURES = {
     "xdtts_pool_destroy": (None, [_vp]),
     "xdtts_pool_n_devices": (ctypes.c_int, [_vp]),
     "xdtts_pool_out_len": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "xdtts_shard_assign": (ctypes.c_int, [_ip, ctypes.c_int, ctypes.c_int, _ip]),
     "xdtts_pool_assignment": (ctypes.c_int, [_vp, _ip, ctypes.c_int, _ip]),
     "xdtts_pool_infer_batch": (ctypes.c_int, [_vp, _fpp, _ip, ctypes.c_int, _fpp, _fpp]),
     "xdtts_pool_from_mag_batch": (ctypes.c_int, [_vp, _fpp, _ip, ctypes.c_int, _fpp, _fpp]),
