@@ -47,6 +47,7 @@ CONFIGS = {
 POSTNET_FLOP_PER_FRAME = 8683520.0   # 2 * 5 * (80*512 + 3*512*512 + 512*80)
 FALLBACK_BF16_TFLOPS = 1590.0        # B200_PROFILING.md fallback (burst)
 POWER, MOMENTUM, N_MELS, SR, FMAX = 1.7, 0.99, 80, 22050.0, 8000.0
+STRONG_BATCH = 256                   # BASELINE.json configs[3]: batch = 256 sharded across the GPUs
 FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -113,16 +114,41 @@ def synth_encoder_outputs(seed, t_enc):
     return (0.5 * rng.standard_normal((t_enc, 512))).astype(np.float32), (0.5 * rng.standard_normal((t_enc, 128))).astype(np.float32)
 
 
-def decoder_leg(device, with_cpu):
-    """The decoder loop (SURVEY.md 8f N1): 1000 steps of the Tacotron2 decoder in one persistent kernel, for one
-    utterance (the reference's shape) and for 8 in lockstep.  Device time = CUDA events around the launch."""
-    from xdtts_b200 import tacotron2
+def measured_l2_read_gbs(torch, device):
+    """Read bandwidth of the L2 on this GPU, measured live: repeated reductions over a 64 MB tensor (fits the 126 MB L2,
+    so every pass after the first is served from it).  A library kernel, used ONLY to calibrate the decoder's floor."""
+    x = torch.empty(16 * 1024 * 1024, dtype=torch.float32, device="cuda:%d" % device).normal_()
+    for _ in range(3):
+        x.sum()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = None
+    for _ in range(5):
+        e0.record()
+        for _ in range(4):
+            x.sum()
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / 4
+        best = ms if best is None or ms < best else best
+    return x.numel() * 4 / (best * 1e-3) / 1e9
 
+
+DEC_BARRIERS_PER_STEP, DEC_BARRIER_US = 7, 1.23   # grid barriers per decoder step; one barrier with empty stages (DESIGN.md 3.4)
+
+
+def decoder_leg(ctx, with_cpu):
+    """The decoder loop (SURVEY.md 8f N1): 1000 steps of the Tacotron2 decoder in one persistent kernel, for one
+    utterance (the reference's shape) and for 8 in lockstep.  Device time = CUDA events around the launch.
+    Its 72.7 MB of weights stay in the L2 (ncu: 0.15% DRAM throughput, 93% L2 hits), so it is reported against (i) weights /
+    measured L2 read bandwidth -- the bound it sits under -- and (ii) the grid-barrier floor, not against HBM."""
+    tacotron2 = ctx.tacotron2
+    device = ctx.local_rank
     wt = synth_decoder_weights()
     dec = tacotron2.Decoder.from_weights(wt, gate_threshold=0.999999, max_steps=DEC_STEPS, seed=1, device=device)
-    out = {"bound": "hbm", "kernel": "dec_persist_kernel (one cooperative launch = %d decoder steps, 7 grid barriers per step)" % DEC_STEPS,
+    out = {"bound": "l2 (the 72.7 MB of weights are re-read from the L2 every step; %d dependent grid-wide hops per step)" % DEC_BARRIERS_PER_STEP,
+           "kernel": "dec_persist_kernel (one cooperative launch = %d decoder steps, %d grid barriers per step)" % (DEC_STEPS, DEC_BARRIERS_PER_STEP),
            "workload": "Tacotron2 decoder loop, t_enc=%d (%d unpadded), %d steps, fp32, synthetic weights" % (DEC_T_ENC, DEC_UNPADDED, DEC_STEPS),
-           "algorithmic_bytes_per_step": DEC_WEIGHT_BYTES}
+           "weight_bytes_per_step": DEC_WEIGHT_BYTES}
     for nb in (1, 8):
         enc = [synth_encoder_outputs(100 + i, DEC_T_ENC) for i in range(nb)]
         best = None
@@ -132,10 +158,19 @@ def decoder_leg(device, with_cpu):
             best = ms if best is None or ms < best else best
         assert steps == DEC_STEPS and all(m.shape == (80, DEC_STEPS) and np.isfinite(m).all() for m in mels)
         out["b%d" % nb] = {"ms": best, "us_per_step": best * 1e3 / DEC_STEPS, "frames_per_s": nb * DEC_STEPS / (best * 1e-3)}
-    peak, src = measured_peak()
-    out["achieved"] = DEC_WEIGHT_BYTES / (out["b1"]["us_per_step"] * 1e-6) / 1e9
-    out.update({"peak": peak, "unit": "GB/s", "frac": out["achieved"] / peak, "peak_source": src,
-                "note": "weights (72.7 MB) are re-read every step; achieved above the HBM peak would mean they are served from the 126 MB L2"})
+    l2 = measured_l2_read_gbs(ctx.torch, device)
+    us = out["b1"]["us_per_step"]
+    l2_floor = DEC_WEIGHT_BYTES / (l2 * 1e9) * 1e6
+    bar_floor = DEC_BARRIERS_PER_STEP * DEC_BARRIER_US
+    out["floors"] = {"l2_read_gbs_measured": l2, "l2_us_per_step": l2_floor, "barrier_us_per_step": bar_floor,
+                     "how": "L2: 64 MB torch reduction repeated in this process; barrier: %d x %.2f us, this kernel's barrier with "
+                            "the stage bodies compiled out (DESIGN.md 3.4)" % (DEC_BARRIERS_PER_STEP, DEC_BARRIER_US)}
+    out["frac"] = l2_floor / us                     # of the L2-read floor: the roofline this loop is actually under
+    out["achieved"] = DEC_WEIGHT_BYTES / (us * 1e-6) / 1e9
+    out["peak"] = l2
+    out["unit"] = "GB/s (L2 read, measured live)"
+    out["frac_of_barrier_floor"] = bar_floor / us
+    out["note"] = "achieved / peak are L2 figures, NOT HBM: the weights never leave the L2 (ncu: DRAM throughput 0.15%, L2 hit rate 93%)"
     if with_cpu:
         from oracle import decoder_oracle as d   # CPU baseline leg only
 
@@ -266,12 +301,16 @@ def pinned_array(lib, shape):
 
 
 # ------------------------------------------------------------------------------- CPU arm
-def cpu_arm(cfg, steps, warmup, sample_utts=None):
-    """Oracle C port (OpenMP) on this host: returns (frames/s, cores, kind, sample description, ms/step)."""
+def cpu_arm(cfg, steps, warmup, sample_utts=None, candidates=True):
+    """The reference's path on this host's cores.  The Rust crate cannot be built here, so three CPU implementations of
+    the same step are timed on a bounded sample and the FASTEST is quoted: the oracle's C/OpenMP
+    port (rebuilt with -march=native on this host), torchaudio.functional.griffinlim (MKL FFT, all threads) and the
+    numpy/scipy oracle (pocketfft, workers = cores).  Returns (frames/s, cores, kind, sample description, ms/step, all)."""
     from oracle import c_oracle, gl_oracle as o
 
     b, t, n_fft, it = CONFIGS[cfg]
     c_oracle.build()
+    native = c_oracle.use_native_build()
     cores = c_oracle.num_threads()
     basis = o.create_mel_filter_bank(SR, n_fft, N_MELS, 0.0, FMAX)
     pinv = o.pinv_basis(basis).astype(np.float32)
@@ -297,24 +336,60 @@ def cpu_arm(cfg, steps, warmup, sample_utts=None):
     def per_batch():    # one thread per utterance
         c_oracle.infer_batch(pinv, cpu_postnet(mels), turns, hop, POWER, it, MOMENTUM)
 
+    tried = {}
     best = None
     for name, fn in (("threads over utterances", per_batch), ("threads over frames", per_utt)):
         fn()
         t0 = time.perf_counter()
         fn()
         dt = time.perf_counter() - t0
+        tried["C/OpenMP port, " + name] = n * t / dt
         if best is None or dt < best[1]:
             best = (name, dt, fn)
     name, _, fn = best
+    label = "C/OpenMP port of the oracle (%s), %s" % ("-march=native" if native else "x86-64-v3", name)
+    if candidates:
+        # the two library-backed implementations, on a smaller sample (they are several times slower)
+        try:
+            import torch
+            import torchaudio
+
+            torch.set_num_threads(cores)
+            nb = min(n, 4)
+            win = torch.hann_window(n_fft, periodic=True)
+
+            def ta():
+                pm = cpu_postnet(mels[:nb])
+                s_lin = np.maximum(np.einsum("km,bmt->bkt", pinv, np.exp(pm)), 0.0) ** POWER
+                torchaudio.functional.griffinlim(torch.from_numpy(s_lin.astype(np.float32)), win, n_fft, hop, n_fft, 1.0, it, MOMENTUM,
+                                                 hop * (t - 1), True)
+
+            ta()
+            t0 = time.perf_counter()
+            ta()
+            tried["torchaudio.functional.griffinlim (%d threads)" % cores] = nb * t / (time.perf_counter() - t0)
+        except Exception as e:  # noqa: BLE001
+            tried["torchaudio.functional.griffinlim"] = "unavailable: %r" % (e,)
+        try:
+            def sp():
+                pm = cpu_postnet(mels[:2])
+                for i in range(2):
+                    o.infer(pm[i], basis, n_fft - hop, POWER, it, MOMENTUM, turns[i], dtype=np.float32, workers=cores)
+
+            t0 = time.perf_counter()
+            sp()
+            tried["numpy/scipy oracle (pocketfft, workers=%d)" % cores] = 2 * t / (time.perf_counter() - t0)
+        except Exception as e:  # noqa: BLE001
+            tried["numpy/scipy oracle"] = "unavailable: %r" % (e,)
     for _ in range(max(0, warmup - 1)):
         fn()
     t0 = time.perf_counter()
     for _ in range(steps):
         fn()
     dt = (time.perf_counter() - t0) / steps
-    sample = "%d of %d utterances x %d frames x %d iters per step, C/OpenMP port of the oracle%s, %s" % (
-        n, b, t, it, " after the numpy/BLAS postnet" if layers else "", name)
-    return n * t / dt, cores, "port", sample, dt * 1e3
+    sample = "%d of %d utterances x %d frames x %d iters per step, %s%s; fastest of the candidates" % (
+        n, b, t, it, label, " after the numpy/BLAS postnet" if layers else "")
+    return n * t / dt, cores, "port", sample, dt * 1e3, tried
 
 
 def run_reference(args):
@@ -327,21 +402,236 @@ def run_reference(args):
     cfg = args.config
     b, t, n_fft, it = CONFIGS[cfg]
     steps, warmup = args.steps, args.warmup
-    v, cores, kind, sample, ms = cpu_arm(cfg, steps, warmup)
+    v, cores, kind, sample, ms, tried = cpu_arm(cfg, steps, warmup)
     line = {
         "impl": "reference", "metric": "audio frames/sec", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(cfg, b, t, n_fft, it)},
-        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample, "candidates": tried},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "reference Rust crate (griffin-lim 0.2.0) cannot be built here (no cargo, not vendored): CPU arm is the oracle's C/OpenMP port",
+        "note": "reference Rust crate (griffin-lim 0.2.0) cannot be built here (no cargo, not vendored): CPU arm is the fastest of "
+                "three CPU implementations of the same step (cpu_baseline.candidates, frames/s)",
     }
     emit(line)
 
 
 # ------------------------------------------------------------------------------- GPU arm
+class Ctx:
+    pass
+
+
+def measure(ctx, cfg, utt_ids, steps, warmup, *, kernel=True, blocking=True, pipe=True, tag=""):
+    """One configuration on this rank's GPU: resident (device-timed) pass, the iteration kernel's steady-state duration,
+    the lift, and the end-to-end calls.  Returns this rank's raw numbers (times in ms; the caller reduces over ranks)."""
+    torch, lib, _ffi, griffin_lim, tacotron2, shard = ctx.torch, ctx.lib, ctx.ffi, ctx.griffin_lim, ctx.tacotron2, ctx.shard
+    _, t, n_fft, it = CONFIGS[cfg]
+    hop, k = n_fft // 4, n_fft // 2 + 1
+    with_postnet = cfg == "cfg3"
+    basis = griffin_lim.mel.create_mel_filter_bank(SR, n_fft, N_MELS, 0.0, FMAX)
+    voc = griffin_lim.GriffinLim.new(basis, n_fft - hop, POWER, it, MOMENTUM, seed=shard.rank_seed(0, ctx.rank), device=ctx.local_rank)
+    mels = [bench_mel(i, t) for i in utt_ids]
+    b = len(mels)
+    frames = b * t
+    r = {"b": b, "frames": frames, "t": t, "n_fft": n_fft, "it": it, "hop": hop, "k": k}
+    plan = voc.plan([t] * b)
+    r["info"] = plan.info()
+    post = pplan = None
+    if with_postnet:
+        post = tacotron2.Postnet.from_layers(synth_postnet_layers(), device=ctx.local_rank)
+        pplan = post.plan([t] * b)
+        pplan.upload(mels)
+    else:
+        plan.upload(0, mels)
+
+    def step():
+        """one pass of the path over the resident batch -> device milliseconds"""
+        ms_pn = pplan.run(feed=plan) if with_postnet else 0.0   # writes mel_outputs_postnet into the vocoder's arena
+        return ms_pn + plan.run(0)[0]
+
+    for _ in range(warmup):
+        step()
+    sampler = ClockSampler(ctx.local_rank)
+    ctx.barrier()
+    sampler.start()
+    launches0 = lib.xdtts_kernel_launches()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(steps):
+        dev_ms += step()
+    ctx.barrier()
+    r["wall_ms"] = (time.perf_counter() - t0) * 1e3
+    r["dev_ms"] = dev_ms
+    r["launches"] = lib.xdtts_kernel_launches() - launches0
+    r["clocks"] = sampler.stop()
+
+    if kernel:
+        # steady-state duration of the iteration kernel, live, two ways:
+        #  (1) as launched in the timed region -- inside the plan's CUDA graph: CUDA events around the graph of the full pass
+        #      and around the graph of a pass with half the iterations (same batch, same kernels); the difference divided by
+        #      the extra launches is the average duration of one steady-state launch where the product runs it;
+        #  (2) kernel-by-kernel stream launches with events around the n_iter - 2 steady-state launches (adds the
+        #      stream's launch-to-launch gap to every kernel: an upper bound, kept as kernel_ms_stream_launches).
+        if with_postnet:
+            plan.upload(0, mels)      # any mel will do for the timing: the arithmetic does not depend on the values
+        iter_ms, iter_n, lift = 0.0, 0, []
+        for _ in range(max(2, min(steps, 5))):
+            _, mi, n = plan.run(_ffi.RUN_NO_GRAPH)
+            iter_ms += mi
+            iter_n += n
+            lift.append(plan.lift_ms())
+        r["kern_stream_ms"] = iter_ms / max(iter_n, 1)
+        r["lift_ms"] = min(lift)
+        it_half = it // 2
+        voc_half = griffin_lim.GriffinLim.new(basis, n_fft - hop, POWER, it_half, MOMENTUM, seed=shard.rank_seed(0, ctx.rank),
+                                              device=ctx.local_rank)
+        plan_half = voc_half.plan([t] * b)
+        plan_half.upload(0, mels)
+        for _ in range(2):
+            plan_half.run(0)
+            plan.run(0)
+        t_full = min(plan.run(0)[0] for _ in range(5))
+        t_half = min(plan_half.run(0)[0] for _ in range(5))
+        r["kern_ms"] = (t_full - t_half) / (it - it_half)
+        r["it_half"] = it_half
+        plan_half.close()
+        voc_half.close()
+
+    out_len = hop * (t - 1)
+    r["out_len"] = out_len
+    pins = []
+    if blocking or pipe:
+        pin_in = [pinned_array(lib, (N_MELS, t)) for _ in range(b)]
+        for (a, _), m in zip(pin_in, mels):
+            a[...] = m
+        pin_out = [pinned_array(lib, (out_len,)) for _ in range(b)]
+        pins += pin_in + pin_out
+        in_ptrs = _ffi.fptr_array([a for a, _ in pin_in])
+        out_ptrs = _ffi.fptr_array([a for a, _ in pin_out])
+        t_arr = (ctypes.c_int * b)(*([t] * b))
+        peak_ok = True
+
+    if blocking:
+        # end to end through the blocking batch call, pinned and PAGEABLE host buffers (what a Rust caller's ndarray /
+        # Vec buffers are: staged by the library's copy threads, overlapped with the DMA)
+        def call(ip, op):
+            if with_postnet:
+                _ffi.check(lib.xdtts_tail_infer_batch(post._h, voc._h, ip, t_arr, b, None, None, op))
+            else:
+                _ffi.check(lib.xdtts_gl_infer_batch(voc._h, ip, t_arr, b, None, op))
+
+        for _ in range(warmup):
+            call(in_ptrs, out_ptrs)
+        ctx.barrier()
+        t1 = time.perf_counter()
+        for _ in range(steps):
+            call(in_ptrs, out_ptrs)
+        ctx.barrier()
+        r["call_ms"] = (time.perf_counter() - t1) * 1e3
+        peak_ok = all(abs(float(np.abs(a).max()) - 1.0) < 1e-5 for a, _ in pin_out)
+        pg_in = [np.array(m) for m in mels]
+        pg_out = [np.zeros(out_len, np.float32) for _ in range(b)]      # touched once: the pages exist (a caller reusing its buffers)
+        pg_ip, pg_op = _ffi.fptr_array(pg_in), _ffi.fptr_array(pg_out)
+        for _ in range(warmup):
+            call(pg_ip, pg_op)
+        ctx.barrier()
+        t1 = time.perf_counter()
+        for _ in range(steps):
+            call(pg_ip, pg_op)
+        ctx.barrier()
+        r["call_pageable_ms"] = (time.perf_counter() - t1) * 1e3
+        peak_ok = peak_ok and all(abs(float(np.abs(a).max()) - 1.0) < 1e-5 for a in pg_out)
+
+    if pipe:
+        # end to end, streaming (the headline e2e): xdtts_pipe_push, two batches in flight, each with its own
+        # pinned host buffers; every step's H2D and D2H are inside the timed region and overlap the kernels of
+        # the neighbouring steps.  Same kernels, same results as the blocking call above (tests/test_gpu_postnet.py).
+        pin_in2 = [pinned_array(lib, (N_MELS, t)) for _ in range(b)]
+        for (a, _), m in zip(pin_in2, mels):
+            a[...] = m
+        pin_out2 = [pinned_array(lib, (out_len,)) for _ in range(b)]
+        pins += pin_in2 + pin_out2
+        sets = [(in_ptrs, out_ptrs), (_ffi.fptr_array([a for a, _ in pin_in2]), _ffi.fptr_array([a for a, _ in pin_out2]))]
+        for a, _ in pin_out + pin_out2:
+            a[...] = 0.0
+        q = ctypes.c_void_p()
+        _ffi.check(lib.xdtts_pipe_create(voc._h, post._h if with_postnet else None, t_arr, b, 2, ctypes.byref(q)))
+        for i in range(warmup):
+            _ffi.check(lib.xdtts_pipe_push(q, sets[i % 2][0], None, None, sets[i % 2][1]))
+        _ffi.check(lib.xdtts_pipe_flush(q))
+        ctx.barrier()
+        t1 = time.perf_counter()
+        for i in range(steps):
+            _ffi.check(lib.xdtts_pipe_push(q, sets[i % 2][0], None, None, sets[i % 2][1]))
+        _ffi.check(lib.xdtts_pipe_flush(q))
+        ctx.barrier()
+        r["e2e_ms"] = (time.perf_counter() - t1) * 1e3
+        lib.xdtts_pipe_destroy(q)
+        peak_ok = peak_ok and all(abs(float(np.abs(a).max()) - 1.0) < 1e-5 for a, _ in pin_out + pin_out2)
+    if blocking or pipe:
+        r["peak_ok"] = peak_ok
+
+    if with_postnet:   # the tensor-core leg (BASELINE.json configs[2]): postnet alone, device time by CUDA events
+        r["pn_ms"] = min(pplan.run(feed=plan) for _ in range(5))
+        pplan.close()
+        post.close()
+    for _, ptr in pins:
+        lib.xdtts_host_free(ptr)
+    plan.close()
+    voc.close()
+    return r
+
+
+def dropin_leg(ctx, with_cpu):
+    """The reference's actual call: GriffinLim::infer(&mel) on ONE utterance with ordinary (pageable) host arrays
+    (src/lib.rs:141; create_griffin_lim's 30 iterations, src/tacotron2/mod.rs:456) -- xdtts_gl_infer, B = 1."""
+    griffin_lim, _ffi = ctx.griffin_lim, ctx.ffi
+    n_fft, hop, it = 1024, 256, 30
+    basis = griffin_lim.mel.create_mel_filter_bank(SR, n_fft, N_MELS, 0.0, FMAX)
+    out = {"api": "xdtts_gl_infer (B = 1), pageable numpy buffers, %d iterations (the shipped configuration)" % it, "cases": {}}
+    for t in (200, 1000):
+        voc = griffin_lim.GriffinLim.new(basis, n_fft - hop, POWER, it, MOMENTUM, device=ctx.local_rank)
+        mel = bench_mel(0, t)
+        for _ in range(5):
+            voc.infer(mel)
+        n = 30
+        t0 = time.perf_counter()
+        for _ in range(n):
+            y = voc.infer(mel)
+        ms = (time.perf_counter() - t0) * 1e3 / n
+        plan = voc.plan([t])
+        plan.upload(0, [mel])
+        for _ in range(3):
+            plan.run(0)
+        dev = min(plan.run(0)[0] for _ in range(10))
+        # latency floor of this shape: 31 dependent launches, each at least one frame-chain long; the one-warp-per-run
+        # mapping gives T / (resident warps) frames per warp, never fewer than 4
+        info = plan.info()
+        case = {"T": t, "ms_per_call": ms, "device_ms": dev, "frames_per_s": t / (ms * 1e-3),
+                "realtime_factor": (ms * 1e-3) / (hop * (t - 1) / SR), "us_per_launch": dev * 1e3 / (it + 1),
+                "runs": info["n_runs"], "run_frames": info["run_frames"], "peak_normalised_ok": bool(abs(float(np.abs(y).max()) - 1.0) < 1e-5)}
+        if with_cpu:
+            from oracle import c_oracle, gl_oracle as o
+
+            c_oracle.build()
+            pinv = o.pinv_basis(basis).astype(np.float32)
+            tu = o.phase_turns(0, 0, n_fft // 2 + 1, t)
+            c_oracle.infer(pinv, mel, tu, hop, POWER, it, MOMENTUM)
+            t0 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                c_oracle.infer(pinv, mel, tu, hop, POWER, it, MOMENTUM)
+            cms = (time.perf_counter() - t0) * 1e3 / reps
+            case["cpu_port_ms_per_call"] = cms
+            case["cpu_port_cores"] = c_oracle.num_threads()
+            case["speedup_vs_cpu_port"] = cms / ms
+        out["cases"]["T%d" % t] = case
+        plan.close()
+        voc.close()
+    return out
+
+
 def run_gpu(args):
     import torch
 
@@ -365,36 +655,9 @@ def run_gpu(args):
         g.build_cuda()
     from xdtts_b200 import _ffi, griffin_lim, shard, tacotron2
 
-    lib = _ffi.load_library()
-    cfg = args.config
-    b, t, n_fft, it = CONFIGS[cfg]
-    hop, k = n_fft // 4, n_fft // 2 + 1
-    steps, warmup = args.steps, max(args.warmup, 3)
-
-    basis = griffin_lim.mel.create_mel_filter_bank(SR, n_fft, N_MELS, 0.0, FMAX)
-    voc = griffin_lim.GriffinLim.new(basis, n_fft - hop, POWER, it, MOMENTUM, seed=shard.rank_seed(0, rank), device=local_rank)
-    # the job: world * b utterances (weak scaling: b per GPU); this rank vocodes its shard, no data crosses GPUs
-    mine = shard.shard_utterances([t] * (world * b), world, rank)
-    mels = [bench_mel(i, t) for i in mine]
-    b = len(mine)
-    frames = b * t
-
-    # ---- device-resident arm: plan with the mels already in HBM
-    plan = voc.plan([t] * b)
-    info = plan.info()
-    with_postnet = cfg == "cfg3"
-    post = pplan = None
-    if with_postnet or (world == 1 and n_fft == 1024):
-        post = tacotron2.Postnet.from_layers(synth_postnet_layers(), device=local_rank)
-        pplan = post.plan([t] * b)
-        pplan.upload(mels)
-    if not with_postnet:
-        plan.upload(0, mels)
-
-    def step():
-        """one pass of the path over the resident batch -> device milliseconds"""
-        ms_pn = pplan.run(feed=plan) if with_postnet else 0.0   # writes mel_outputs_postnet into the vocoder's arena
-        return ms_pn + plan.run(0)[0]
+    ctx = Ctx()
+    ctx.torch, ctx.lib, ctx.ffi, ctx.griffin_lim, ctx.tacotron2, ctx.shard = torch, _ffi.load_library(), _ffi, griffin_lim, tacotron2, shard
+    ctx.rank, ctx.local_rank, ctx.world = rank, local_rank, world
 
     def barrier():
         torch.cuda.synchronize()
@@ -402,163 +665,146 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(warmup):
-        step()
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    launches0 = lib.xdtts_kernel_launches()
-    t0 = time.perf_counter()
-    dev_ms = 0.0
-    for _ in range(steps):
-        dev_ms += step()
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    launches = lib.xdtts_kernel_launches() - launches0
-    clocks = sampler.stop()
+    ctx.barrier = barrier
+    cfg = args.config
+    b, t, n_fft, it = CONFIGS[cfg]
+    hop, k = n_fft // 4, n_fft // 2 + 1
+    steps, warmup = args.steps, max(args.warmup, 3)
+    strong = args.scaling == "strong"
+    # the job: weak scaling = b utterances per GPU (world * b in total); strong = STRONG_BATCH utterances in total
+    # (BASELINE.json configs[3]: batch = 256 sharded across the GPUs).  This rank vocodes its shard; no data crosses GPUs.
+    total_utts = STRONG_BATCH if strong else world * b
+    mine = shard.shard_utterances([t] * total_utts, world, rank)
+    main = measure(ctx, cfg, mine, steps, warmup)
 
-    # ---- steady-state duration of the iteration kernel, live, two ways:
-    #  (1) as launched in the timed region -- inside the plan's CUDA graph: CUDA events around the graph of the full pass
-    #      and around the graph of a pass with half the iterations (same batch, same kernels); the difference divided by
-    #      the extra launches is the average duration of one steady-state launch where the product runs it;
-    #  (2) kernel-by-kernel stream launches with events around the n_iter - 2 steady-state launches (adds the
-    #      stream's launch-to-launch gap to every kernel: an upper bound, kept as kernel_ms_stream_launches).
-    iter_ms, iter_n = 0.0, 0
-    for _ in range(max(2, min(steps, 5))):
-        _, mi, n = plan.run(_ffi.RUN_NO_GRAPH)
-        iter_ms += mi
-        iter_n += n
-    kern_stream_ms = iter_ms / max(iter_n, 1)
-    it_half = it // 2
-    voc_half = griffin_lim.GriffinLim.new(basis, n_fft - hop, POWER, it_half, MOMENTUM, seed=shard.rank_seed(0, rank), device=local_rank)
-    plan_half = voc_half.plan([t] * b)
-    plan_half.upload(0, mels)
-    if with_postnet:
-        plan.upload(0, mels)      # any mel will do for the timing: the arithmetic does not depend on the values
-    for _ in range(2):
-        plan_half.run(0)
-        plan.run(0)
-    t_full = min(plan.run(0)[0] for _ in range(5))
-    t_half = min(plan_half.run(0)[0] for _ in range(5))
-    kern_ms = (t_full - t_half) / (it - it_half)
-    plan_half.close()
-    voc_half.close()
+    def reduce(r, keys):
+        vals = [r.get(key, 0.0) for key in keys]
+        fr, la, vals = shard.reduce_counters(r["frames"], r.get("launches", 0), vals, device="cuda")   # the job's single collective
+        return fr, la, dict(zip(keys, vals))
 
-    # ---- end to end through the public call, pinned host buffers
-    pin_in = [pinned_array(lib, (N_MELS, t)) for _ in range(b)]
-    for (a, _), m in zip(pin_in, mels):
-        a[...] = m
-    out_len = hop * (t - 1)
-    pin_out = [pinned_array(lib, (out_len,)) for _ in range(b)]
-    in_ptrs = _ffi.fptr_array([a for a, _ in pin_in])
-    out_ptrs = _ffi.fptr_array([a for a, _ in pin_out])
-    t_arr = (ctypes.c_int * b)(*([t] * b))
+    keys = ["dev_ms", "wall_ms", "e2e_ms", "kern_ms", "call_ms", "call_pageable_ms", "kern_stream_ms", "lift_ms"]
+    total_frames, total_launches, red = reduce(main, keys)
 
-    def e2e_step():
-        if with_postnet:
-            _ffi.check(lib.xdtts_tail_infer_batch(post._h, voc._h, in_ptrs, t_arr, b, None, None, out_ptrs))
-        else:
-            _ffi.check(lib.xdtts_gl_infer_batch(voc._h, in_ptrs, t_arr, b, None, out_ptrs))
+    # ---- every N: the other scaling mode as a sub-object (resident + streaming e2e only), so that one run per N gives both
+    # curves of BASELINE.json configs[3] ("weak and strong")
+    other = None
+    if cfg == "cfg2" and not args.no_extras:
+        o_total = world * b if strong else STRONG_BATCH
+        o_mine = shard.shard_utterances([t] * o_total, world, rank)
+        o_r = measure(ctx, cfg, o_mine, max(3, steps // 2), 3, kernel=False, blocking=False, pipe=True)
+        o_frames, _, o_red = reduce(o_r, ["dev_ms", "e2e_ms"])
+        o_steps = max(3, steps // 2)
+        other = {"scaling": "weak" if strong else "strong", "utterances_total": o_total, "utterances_this_gpu": len(o_mine),
+                 "value": o_frames * o_steps / (o_red["dev_ms"] * 1e-3), "e2e": o_frames * o_steps / (o_red["e2e_ms"] * 1e-3),
+                 "unit": "frames/s", "ms_per_step": o_red["dev_ms"] / o_steps, "runs": o_r["info"]["n_runs"],
+                 "run_frames": o_r["info"]["run_frames"],
+                 "note": "same kernels; the limiter of strong scaling is the per-GPU batch shrinking below one resident wave of "
+                         "full-length runs (run_frames falls, run-boundary overhead rises), not communication: there is none"}
 
-    for _ in range(warmup):
-        e2e_step()
-    barrier()
-    t1 = time.perf_counter()
-    for _ in range(steps):
-        e2e_step()
-    barrier()
-    call_ms = (time.perf_counter() - t1) * 1e3
-    peak_ok = all(abs(float(np.abs(a).max()) - 1.0) < 1e-5 for a, _ in pin_out)
-
-    # ---- end to end, streaming (the headline e2e): xdtts_pipe_push, two batches in flight, each with its own
-    # pinned host buffers; every step's H2D and D2H are inside the timed region and overlap the kernels of
-    # the neighbouring steps.  Same kernels, same results as the blocking call above (tests/test_gpu_postnet.py).
-    pin_in2 = [pinned_array(lib, (N_MELS, t)) for _ in range(b)]
-    for (a, _), m in zip(pin_in2, mels):
-        a[...] = m
-    pin_out2 = [pinned_array(lib, (out_len,)) for _ in range(b)]
-    sets = [(in_ptrs, out_ptrs), (_ffi.fptr_array([a for a, _ in pin_in2]), _ffi.fptr_array([a for a, _ in pin_out2]))]
-    for a, _ in pin_out + pin_out2:
-        a[...] = 0.0
-    pipe = ctypes.c_void_p()
-    _ffi.check(lib.xdtts_pipe_create(voc._h, post._h if with_postnet else None, t_arr, b, 2, ctypes.byref(pipe)))
-    for i in range(warmup):
-        _ffi.check(lib.xdtts_pipe_push(pipe, sets[i % 2][0], None, None, sets[i % 2][1]))
-    _ffi.check(lib.xdtts_pipe_flush(pipe))
-    barrier()
-    t1 = time.perf_counter()
-    for i in range(steps):
-        _ffi.check(lib.xdtts_pipe_push(pipe, sets[i % 2][0], None, None, sets[i % 2][1]))
-    _ffi.check(lib.xdtts_pipe_flush(pipe))
-    barrier()
-    e2e_ms = (time.perf_counter() - t1) * 1e3
-    lib.xdtts_pipe_destroy(pipe)
-    peak_ok = peak_ok and all(abs(float(np.abs(a).max()) - 1.0) < 1e-5 for a, _ in pin_out + pin_out2)
-
-    # ---- the tensor-core leg (BASELINE.json configs[2]): postnet alone, device time by CUDA events
-    pn_ms = None
-    if pplan is not None:
-        if not with_postnet:
-            for _ in range(3):
-                pplan.run()
-        pn_ms = min((pplan.run(feed=plan) if with_postnet else pplan.run()) for _ in range(5))
-
-    # ---- next row N1: the decoder loop that produces the mels this path consumes
-    dec_line = decoder_leg(local_rank, not args.no_cpu) if (world == 1 and cfg == "cfg2" and not args.no_decoder) else None
-
-    # ---- reduce over ranks: time = max, frames = sum
-    total_frames, total_launches, (dev_ms, wall_ms, e2e_ms, kern_ms, call_ms, kern_stream_ms) = shard.reduce_counters(
-        frames, launches, [dev_ms, wall_ms, e2e_ms, kern_ms, call_ms, kern_stream_ms], device="cuda")   # the single collective of the job
+    # ---- N = 1 only: the other BASELINE configurations and the next-row legs, live in the same process
+    extras = {}
+    if world == 1 and cfg == "cfg2" and not args.no_extras:
+        for c2, st in (("cfg3", max(3, steps // 2)), ("cfg5", max(3, steps // 4))):
+            b2 = CONFIGS[c2][0]
+            extras[c2] = (measure(ctx, c2, list(range(b2)), st, 3), st)
+        extras["dropin"] = dropin_leg(ctx, not args.no_cpu)
+    dec_line = decoder_leg(ctx, not args.no_cpu) if (world == 1 and cfg == "cfg2" and not args.no_decoder) else None
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        alg_bytes = frames * (20 * k + 8 * hop)      # per steady-state launch on one GPU
-        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+
+        def roof(r, kern_ms):
+            alg = r["frames"] * (20 * r["k"] + 8 * r["hop"])      # per steady-state launch on one GPU
+            ach = alg / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+            return {"bound": "hbm", "kernel": "gl_iter_kernel<MID> (one Griffin-Lim iteration)", "achieved": ach, "peak": peak,
+                    "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic(r["cfg"]),
+                    "traffic_how": "static: dram__bytes_read + dram__bytes_write of one launch from the committed ncu --set full capture "
+                                   "(profiles/roofline_traffic.json), not measured in this run",
+                    "peak_source": peak_src, "kernel_ms": kern_ms,
+                    "kernel_ms_how": "(CUDA-graph pass with %d iterations - pass with %d) / %d, CUDA events on the library's stream" % (
+                        r["it"], r["it_half"], r["it"] - r["it_half"]),
+                    "algorithmic_bytes_per_launch": alg}
+
+        def lift_obj(r, lift_ms):
+            alg = r["frames"] * 4 * (N_MELS + r["k"])            # 4 (80 + K) bytes per frame
+            ach = alg / (lift_ms * 1e-3) / 1e9
+            return {"bound": "hbm", "kernel": "gl_lift_tc_kernel (tcgen05 kind::tf32, hi/lo split, 3 passes; exp prologue, clamp + ^1.7 epilogue)",
+                    "ms": lift_ms, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
+                    "algorithmic_bytes": alg, "how": "CUDA events around the launch in a kernel-by-kernel pass (best of 5)"}
+
+        def postnet_obj(r):
+            tpeak, tsrc = measured_tensor_peak()
+            tf = POSTNET_FLOP_PER_FRAME * r["frames"] / (r["pn_ms"] * 1e-3) / 1e12
+            return {"bound": "tensor", "kernel": "pn_conv_tc_kernel x5 + input staging (tcgen05 bf16x3: 3 MMA passes per layer)",
+                    "ms": r["pn_ms"], "frames_per_s": r["frames"] / (r["pn_ms"] * 1e-3), "achieved": tf, "executed": 3 * tf,
+                    "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak, "frac_executed": 3 * tf / tpeak,
+                    "peak_source": tsrc, "algorithmic_flop_per_frame": POSTNET_FLOP_PER_FRAME, "in_timed_step": True}
+
+        def e2e_obj(r, red_, st, frames_total):
+            o_ = {"value": frames_total * st / (red_["e2e_ms"] * 1e-3), "unit": "frames/s",
+                  "h2d_bytes_per_step": r["b"] * N_MELS * r["t"] * 4, "d2h_bytes_per_step": r["b"] * r["out_len"] * 4,
+                  "ms_per_step": red_["e2e_ms"] / st,
+                  "api": "xdtts_pipe_push%s, 2 batches in flight, pinned host buffers; flushed inside the timed region" % (
+                      " (postnet + vocoder)" if r["cfg"] == "cfg3" else ""),
+                  "peak_normalised_ok": r.get("peak_ok")}
+            if "call_ms" in red_ and red_["call_ms"] > 0:
+                name = "xdtts_tail_infer_batch" if r["cfg"] == "cfg3" else "xdtts_gl_infer_batch"
+                o_["blocking_call"] = {"value": frames_total * st / (red_["call_ms"] * 1e-3), "ms_per_step": red_["call_ms"] / st,
+                                       "api": name + " (one batch at a time, pinned host buffers)"}
+                o_["blocking_call_pageable"] = {
+                    "value": frames_total * st / (red_["call_pageable_ms"] * 1e-3), "ms_per_step": red_["call_pageable_ms"] / st,
+                    "ratio_to_pinned": red_["call_ms"] / red_["call_pageable_ms"],
+                    "api": name + " (one batch at a time, PAGEABLE host buffers -- a Rust caller's ndarray / Vec -- staged by the "
+                                  "library's copy threads and overlapped with the DMA)"}
+            return o_
+
+        main["cfg"] = cfg
+        main["it_half"] = main.get("it_half", it // 2)
         line = {
-            "metric": "audio frames/sec", "value": total_frames * steps / (dev_ms * 1e-3), "unit": "frames/s",
-            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": dev_ms / steps,
-            "wall_ms_per_step": wall_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(cfg, b, t, n_fft, it), "utterances_per_gpu": b,
-                       "l2": "no flush needed: per-step state %.0f MB > 126 MB L2" % ((20 * k + 8 * hop) * frames / 1e6),
-                       "runs": info["n_runs"], "run_frames": info["run_frames"], "ctas": info["ctas"]},
-            "e2e": {"value": total_frames * steps / (e2e_ms * 1e-3), "unit": "frames/s",
-                    "h2d_bytes_per_step": b * N_MELS * t * 4, "d2h_bytes_per_step": b * out_len * 4,
-                    "ms_per_step": e2e_ms / steps,
-                    "api": "xdtts_pipe_push%s, 2 batches in flight, pinned host buffers; flushed inside the timed region" % (
-                        " (postnet + vocoder)" if with_postnet else ""),
-                    "blocking_call": {"value": total_frames * steps / (call_ms * 1e-3), "ms_per_step": call_ms / steps,
-                                      "api": ("xdtts_tail_infer_batch" if with_postnet else "xdtts_gl_infer_batch") +
-                                             " (one batch at a time, pinned host buffers)"},
-                    "peak_normalised_ok": peak_ok},
+            "metric": "audio frames/sec", "value": total_frames * steps / (red["dev_ms"] * 1e-3), "unit": "frames/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": red["dev_ms"] / steps,
+            "wall_ms_per_step": red["wall_ms"] / steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(cfg, b, t, n_fft, it)},
+            "plan": {"utterances_this_gpu": main["b"], "utterances_total": total_utts,
+                     "l2": "no flush needed: per-step state %.0f MB > 126 MB L2" % ((20 * k + 8 * hop) * main["frames"] / 1e6),
+                     "runs": main["info"]["n_runs"], "run_frames": main["info"]["run_frames"], "ctas": main["info"]["ctas"]},
+            "e2e": e2e_obj(main, red, steps, total_frames),
             "gpu_launches": total_launches,
             # the same measurement in the other two units people quote for vocoders
-            "frame_iters_per_s": total_frames * it * steps / (dev_ms * 1e-3),
-            "realtime_factor": (dev_ms * 1e-3 / steps) / (world * b * hop * (t - 1) / SR),
-            "roofline": {"bound": "hbm", "kernel": "gl_iter_kernel<MID> (one Griffin-Lim iteration)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(cfg), "peak_source": peak_src, "kernel_ms": kern_ms,
-                         "kernel_ms_how": "(CUDA-graph pass with %d iterations - pass with %d) / %d, CUDA events on the library's stream" % (it, it_half, it - it_half),
-                         "kernel_ms_stream_launches": kern_stream_ms,
-                         "algorithmic_bytes_per_launch": alg_bytes},
-            "clocks": clocks,
+            "frame_iters_per_s": total_frames * it * steps / (red["dev_ms"] * 1e-3),
+            "realtime_factor": (red["dev_ms"] * 1e-3 / steps) / (total_utts * hop * (t - 1) / SR),
+            "roofline": roof(main, red["kern_ms"]),
+            "lift": lift_obj(main, red["lift_ms"]),
+            "clocks": main["clocks"],
         }
-        if pn_ms is not None:
-            tpeak, tsrc = measured_tensor_peak()
-            tf = POSTNET_FLOP_PER_FRAME * frames / (pn_ms * 1e-3) / 1e12
-            line["postnet"] = {"bound": "tensor", "kernel": "pn_conv_tc_kernel x5 + input staging (tcgen05 bf16x3: 3 MMA passes per layer)",
-                               "ms": pn_ms, "frames_per_s": frames / (pn_ms * 1e-3), "achieved": tf, "executed": 3 * tf,
-                               "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak, "frac_executed": 3 * tf / tpeak,
-                               "peak_source": tsrc, "algorithmic_flop_per_frame": POSTNET_FLOP_PER_FRAME,
-                               "in_timed_step": with_postnet}
+        line["roofline"]["kernel_ms_stream_launches"] = red["kern_stream_ms"]
+        if other is not None:
+            line["strong_scaling" if other["scaling"] == "strong" else "weak_scaling"] = other
+        if "pn_ms" in main:
+            line["postnet"] = postnet_obj(main)
+        for c2 in ("cfg3", "cfg5"):
+            if c2 in extras:
+                r2, st = extras[c2]
+                r2["cfg"] = c2
+                b2, t2, n2, it2 = CONFIGS[c2]
+                red2 = {key: r2.get(key, 0.0) for key in keys}
+                sub = {"config": {"workload": workload_name(c2, b2, t2, n2, it2)}, "value": r2["frames"] * st / (r2["dev_ms"] * 1e-3),
+                       "unit": "frames/s", "steps": st, "ms_per_step": r2["dev_ms"] / st, "e2e": e2e_obj(r2, red2, st, r2["frames"]),
+                       "roofline": roof(r2, r2["kern_ms"]), "lift": lift_obj(r2, r2["lift_ms"]), "clocks": r2["clocks"],
+                       "plan": {"runs": r2["info"]["n_runs"], "run_frames": r2["info"]["run_frames"], "ctas": r2["info"]["ctas"]}}
+                sub["roofline"]["kernel_ms_stream_launches"] = r2["kern_stream_ms"]
+                if "pn_ms" in r2:
+                    sub["postnet"] = postnet_obj(r2)
+                line[c2] = sub
+        if "dropin" in extras:
+            line["dropin"] = extras["dropin"]
         if dec_line is not None:
             line["decoder"] = dec_line
         if world == 1 and not args.no_cpu:
-            v, cores, kind, sample, _ = cpu_arm(cfg, 3, 1)   # ~10 s of CPU work incl. picking the faster threading
-            line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}
+            v, cores, kind, sample, _, tried = cpu_arm(cfg, 3, 1)   # ~15 s of CPU work incl. picking the fastest implementation
+            line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample, "candidates": tried}
         emit(line)
-    for _, p in pin_in + pin_out + pin_in2 + pin_out2:
-        lib.xdtts_host_free(p)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -596,6 +842,8 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-decoder", action="store_true", help="skip the decoder-loop leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the cfg3 / cfg5 / drop-in / other-scaling sub-objects")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N > 1: 32 utterances per GPU (weak) or 256 in total (strong)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -64,7 +64,7 @@ static void cfft(const plan_t *p, cpx *x, cpx *y, int inverse) {
     while (n_left >= 4) {
         const int q = n_left / 4; /* butterflies per stride block */
         for (int j = 0; j < q; j++) {
-            cpx w1 = p->tw[(j * s) % m], w2 = p->tw[(2 * j * s) % m], w3 = p->tw[(3 * j * s) % m];
+            cpx w1 = p->tw[j * s], w2 = p->tw[2 * j * s], w3 = p->tw[3 * j * s];   /* 3 j s < 3 m / 4: no wrap */
             if (inverse) { w1.im = -w1.im; w2.im = -w2.im; w3.im = -w3.im; }
             for (int k = 0; k < s; k++) {
                 const cpx c0 = a[k + s * (j)], c1 = a[k + s * (j + q)];

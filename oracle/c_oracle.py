@@ -23,6 +23,24 @@ def build(force=False):
     return _SO
 
 
+def use_native_build():
+    """Timed CPU arm only (bench.py): rebuild the port with -march=native ON THE HOST THAT RUNS IT (the portable build
+    that travels with the repo targets x86-64-v3) and load that one.  Falls back to the portable build."""
+    global _lib, _SO
+    src = os.path.join(_HERE, "c", "gl_oracle.c")
+    out = os.path.join(_HERE, "_build", "libgl_oracle_native.so")
+    try:
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-fopenmp", "-fPIC", "-std=gnu11", "-shared", "-o", out, src, "-lm"],
+                              stderr=subprocess.DEVNULL)
+        _SO, _lib = out, None
+        lib()
+        return True
+    except Exception:  # noqa: BLE001
+        _SO, _lib = os.path.join(_HERE, "_build", "libgl_oracle.so"), None
+        return False
+
+
 def lib():
     global _lib
     if _lib is None:

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-CH = (8, 16, 16, 16, 16, 8)
+CH = (16, 32, 32, 32, 32, 16)   # the device postnet takes channel counts that are multiples of 16
 
 
 class ConvNorm(nn.Module):

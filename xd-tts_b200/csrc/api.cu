@@ -424,9 +424,10 @@ int xdtts::gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out)
     p->h = h; p->B = B; p->Ts.assign(Ts, Ts + B); p->total_T = (int)total;
     for (int b = 0; b < B; b++) p->max_T = Ts[b] > p->max_T ? Ts[b] : p->max_T;
     // Runs: one warp each.  A fixed run length (option / environment) gives results that do not depend on
-    // the batch; the automatic choice fills the resident warp slots of the device exactly once (as many
-    // runs as fit, utterances split in proportion to their length), or uses 64-frame runs over several
-    // waves when the batch is larger than that.
+    // the batch; the automatic choice fills the resident warp slots of the device a whole number of times
+    // (one wave for up to 64 frames per slot, else the fewest waves that keep runs at <= 64 frames;
+    // utterances split in proportion to their length): a partial last wave leaves SMs idle for a run's
+    // duration (256 x 1000 frames as 4000 runs of 64 = 2.25 waves; as 5328 runs of 48 = 3 full waves).
     int rf = h->opts.run_frames;
     if (const char* env = getenv("XDTTS_GL_RUN_FRAMES")) rf = atoi(env);
     if (rf > 0) {
@@ -434,7 +435,8 @@ int xdtts::gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out)
         build_runs(Ts, B, rf, &p->runs, &p->foff);
     } else {
         const long long resident = (long long)h->sm_count * gl_resident_warps_per_sm(h->n_fft);
-        const long long target = total <= resident * 64 ? resident : (total + 63) / 64;
+        const long long waves = (total + resident * 64 - 1) / (resident * 64);
+        const long long target = resident * (waves < 1 ? 1 : waves);
         std::vector<int> counts(B);
         long long used = 0;
         for (int b = 0; b < B; b++) {
@@ -445,7 +447,7 @@ int xdtts::gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out)
         }
         // hand the slots the floors left over to the utterances with the longest runs (largest frames per run first,
         // ties by index: deterministic), so that a resident wave is filled exactly
-        if (total <= resident * 64) {
+        {
             for (long long left = target - used; left > 0; left--) {
                 int best = -1;
                 for (int b = 0; b < B; b++) {

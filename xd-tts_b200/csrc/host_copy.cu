@@ -22,9 +22,11 @@ struct Chunk {
 class Copier {
   public:
     Copier() {
-        int n = 4;
-        if (const char* e = getenv("XDTTS_COPY_THREADS")) n = atoi(e);
+        // enough threads to keep up with the DMA engine (~25 GB/s per direction; one thread copies ~5 GB/s): half the
+        // cores, at most 8.  XDTTS_COPY_THREADS overrides (0: the calling thread copies alone).
         const int hw = (int)std::thread::hardware_concurrency();
+        int n = hw > 0 ? (hw / 2 < 8 ? (hw / 2 < 1 ? 1 : hw / 2) : 8) : 4;
+        if (const char* e = getenv("XDTTS_COPY_THREADS")) n = atoi(e);
         if (hw > 0 && n > hw) n = hw;
         if (n < 0) n = 0;
         for (int i = 0; i < n; i++) threads_.emplace_back([this] { loop(); });
