@@ -573,7 +573,7 @@ int xdtts::gl_plan_upload_locked(xdtts_gl_plan* p, int kind, const float* const*
         std::vector<std::atomic<int>> pending(p->B);
         for (int b = 0; b < p->B; b++) {
             pending[b].store(0);
-            host_copy_async(p->h_in + rows * (size_t)p->foff[b], srcs[b], rows * (size_t)p->Ts[b] * 4, &pending[b]);
+            host_copy_async(p->h_in + rows * (size_t)p->foff[b], srcs[b], rows * (size_t)p->Ts[b] * 4, &pending[b], true);
         }
         cudaError_t ce = cudaSuccess;
         for (int b = 0; b < p->B; b++) {

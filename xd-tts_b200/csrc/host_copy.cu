@@ -1,7 +1,10 @@
 // see host_copy.h
 #include "host_copy.h"
 
+#include <emmintrin.h>
+
 #include <condition_variable>
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
@@ -17,7 +20,31 @@ struct Chunk {
     const void* src;
     size_t bytes;
     std::atomic<int>* pending;
+    bool stream;   // destination is a DMA staging buffer: write it with non-temporal stores
 };
+
+// memcpy whose stores bypass the caches.  A staging buffer filled with ordinary stores sits, dirty, in the private caches
+// of the cores that wrote it; the DMA engine then has to snoop every line out of them -- measured on the B200 host:
+// 10 MB staged by 8 threads left the host -> device copy at 8 GB/s instead of 46 GB/s.  SSE2 is baseline x86-64.
+void copy_chunk(const Chunk& c) {
+    if (!c.stream || ((uintptr_t)c.dst & 15) || (c.bytes & 15)) {
+        memcpy(c.dst, c.src, c.bytes);
+        return;
+    }
+    __m128i* d = (__m128i*)c.dst;
+    const __m128i* s = (const __m128i*)c.src;
+    const size_t n = c.bytes / 16;
+    size_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        const __m128i a = _mm_loadu_si128(s + i), b = _mm_loadu_si128(s + i + 1), e = _mm_loadu_si128(s + i + 2), f = _mm_loadu_si128(s + i + 3);
+        _mm_stream_si128(d + i, a);
+        _mm_stream_si128(d + i + 1, b);
+        _mm_stream_si128(d + i + 2, e);
+        _mm_stream_si128(d + i + 3, f);
+    }
+    for (; i < n; i++) _mm_stream_si128(d + i, _mm_loadu_si128(s + i));
+    _mm_sfence();
+}
 
 class Copier {
   public:
@@ -54,7 +81,7 @@ class Copier {
             c = q_.front();
             q_.pop_front();
         }
-        memcpy(c.dst, c.src, c.bytes);
+        copy_chunk(c);
         c.pending->fetch_sub(1, std::memory_order_release);
         return true;
     }
@@ -71,7 +98,7 @@ class Copier {
                 c = q_.front();
                 q_.pop_front();
             }
-            memcpy(c.dst, c.src, c.bytes);
+            copy_chunk(c);
             c.pending->fetch_sub(1, std::memory_order_release);
         }
     }
@@ -89,13 +116,13 @@ Copier& copier() {
 
 }  // namespace
 
-void host_copy_async(void* dst, const void* src, size_t bytes, std::atomic<int>* pending) {
+void host_copy_async(void* dst, const void* src, size_t bytes, std::atomic<int>* pending, bool to_staging) {
     const size_t chunk = 512 * 1024;
     Copier& c = copier();
     for (size_t off = 0; off < bytes; off += chunk) {
         const size_t n = bytes - off < chunk ? bytes - off : chunk;
         pending->fetch_add(1, std::memory_order_relaxed);
-        c.push(Chunk{(char*)dst + off, (const char*)src + off, n, pending});
+        c.push(Chunk{(char*)dst + off, (const char*)src + off, n, pending, to_staging});
     }
 }
 

@@ -11,7 +11,8 @@ namespace xdtts {
 
 // memcpy(dst, src, bytes) on the helper threads, in chunks; *pending is incremented once per chunk before the call
 // returns and decremented as chunks complete (the caller waits for it to reach zero)
-void host_copy_async(void* dst, const void* src, size_t bytes, std::atomic<int>* pending);
+// to_staging: dst is a pinned buffer a DMA will read next -> non-temporal stores (see host_copy.cu)
+void host_copy_async(void* dst, const void* src, size_t bytes, std::atomic<int>* pending, bool to_staging = false);
 // wait until *pending == 0 (the calling thread helps with queued chunks meanwhile)
 void host_copy_wait(std::atomic<int>* pending);
 int host_copy_threads();
