@@ -238,6 +238,23 @@ int xdtts_decoder_max_steps(const xdtts_decoder* h);   /* frame capacity the out
 int xdtts_decoder_infer_batch(xdtts_decoder* h, const float* const* memory, const float* const* processed_memory, int t_enc,
                               const int* unpadded_len, int B, float* const* out_mels, int* n_frames,
                               float* const* out_gates_or_null, float* const* out_align_or_null);
+/* Tacotron2::load for the decoder (src/tacotron2/mod.rs:251-254 opens decoder_iter.onnx as an ort::Session): reads the
+ * weights out of the ONNX file with the library's own protobuf reader and builds the device decoder from them.  Tensors are
+ * found by their role in the dataflow between the graph's named inputs and outputs (the names run_decoder feeds and reads,
+ * src/tacotron2/mod.rs:285-341), not by initializer names; an LSTM cell may be an ONNX LSTM operator (gate order i, o, f, c,
+ * re-ordered here) or its Gemm / Add / Split decomposition.  Fails with XDTTS_ERR_UNSUPPORTED when the graph is not that
+ * decoder step or its dimensions are not Tacotron2's. */
+int xdtts_decoder_create_from_onnx(const char* path, const xdtts_decoder_opts* opts_or_null, int device, xdtts_decoder** out);
+/* host-only access to the same reader (no GPU needed) */
+typedef struct xdtts_onnx_decoder xdtts_onnx_decoder;
+int xdtts_onnx_decoder_open(const char* path, xdtts_onnx_decoder** out);
+void xdtts_onnx_decoder_close(xdtts_onnx_decoder* m);
+/* dims10: mel channels, prenet, encoder embedding, attention rnn, decoder rnn, attention dim, location filters, location
+ * kernel, LSTM encoding (0: Gemm decomposition, 1: LSTM operators), 1 when the graph draws the prenet dropout mask itself */
+int xdtts_onnx_decoder_dims(const xdtts_onnx_decoder* m, int* dims10);
+/* which: index of the field in the decoder weight struct above (0 prenet1 ... 17 gate_b), in its layouts.  out == null:
+ * returns the number of floats; else copies them (capacity in floats) and returns the count; negative on error */
+long long xdtts_onnx_decoder_tensor(const xdtts_onnx_decoder* m, int which, float* out_or_null, long long capacity);
 /* device time (CUDA events around the persistent kernel launches) and steps executed by the last call */
 int xdtts_decoder_last_timing(const xdtts_decoder* h, float* ms, int* steps);
 

@@ -158,3 +158,30 @@ def test_errors(taco, weights):
     with pytest.raises(XdttsError) as e:
         taco.Decoder.from_weights(weights, gate_threshold=1.5)
     assert e.value.code == ERR_BAD_ARG
+
+
+@pytest.mark.parametrize("use_lstm_op", [False, True])
+def test_decoder_from_onnx_equals_from_weights(taco, weights, tmp_path, use_lstm_op):
+    """xdtts_decoder_create_from_onnx (Tacotron2::load for decoder_iter.onnx, src/tacotron2/mod.rs:251-254) on a FULL-SIZE
+    file written here by PyTorch's ONNX serializer from the same weights -- with the LSTM cells as ONNX LSTM operators
+    (gate order i, o, f, c: NVIDIA's export script) and as their Gemm / Split decomposition -- gives, bit for bit, the
+    decoder built from the arrays."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import make_foreign_decoder_onnx as gen
+
+    path = tmp_path / "decoder_iter.onnx"
+    gen.build(gen.FULL, str(path), weights=weights, use_lstm_op=use_lstm_op)
+    assert path.stat().st_size > 70e6                                   # 18.2 M fp32 weights
+    dims, got = taco.read_onnx_decoder(path)
+    assert dims["lstm_form"] == int(use_lstm_op) and dims["has_dropout"] == 1
+    for name in taco.DECODER_TENSORS:
+        assert np.array_equal(got[name], np.asarray(weights[name], np.float32).ravel()), name
+    mem, pm = d.synth_encoder_outputs(5, 30)
+    a = taco.Decoder.from_onnx(path, gate_threshold=0.999999, max_steps=12, seed=4)
+    b = taco.Decoder.from_weights(weights, gate_threshold=0.999999, max_steps=12, seed=4)
+    ya, yb = a.run(mem, pm, 27), b.run(mem, pm, 27)
+    assert ya.shape == (80, 12) and np.array_equal(ya, yb)
+    a.close()
+    b.close()

@@ -378,6 +378,48 @@ def test_onnx_reader_on_files_written_by_pytorch(lib, golden_dir):
         assert np.abs(y - g["y"]).max() < 1e-5
 
 
+def test_decoder_onnx_reader_on_files_written_by_pytorch(lib, golden_dir, tmp_path):
+    """decoder_iter.onnx (src/tacotron2/mod.rs:251-254): the reader finds every weight by its role in the dataflow, in both
+    encodings of the LSTM cells -- ONNX LSTM operators (NVIDIA's export script; gate order i, o, f, c) and the Gemm / Split
+    decomposition of today's PyTorch exporter -- on files serialised by PyTorch itself (tests/make_foreign_decoder_onnx.py)."""
+    from xdtts_b200 import tacotron2
+    from xdtts_b200._ffi import ERR_BAD_ARG, ERR_UNSUPPORTED, XdttsError
+
+    want = np.load(os.path.join(golden_dir, "decoder_iter_small.npz"))
+    for tag, form in (("cells", 0), ("lstm", 1)):
+        dims, got = tacotron2.read_onnx_decoder(os.path.join(golden_dir, "decoder_iter_small_%s.onnx" % tag))
+        assert dims == dict(n_mel=8, prenet=16, enc=24, att_rnn=32, dec_rnn=40, att_dim=12, loc_f=6, loc_k=7, lstm_form=form, has_dropout=1)
+        for name in tacotron2.DECODER_TENSORS:
+            assert np.array_equal(got[name], want[name].ravel()), (tag, name)
+    # a postnet is not a decoder; the LFS pointer the reference ships; a decoder is not a postnet
+    with pytest.raises(XdttsError) as e:
+        tacotron2.read_onnx_decoder(os.path.join(golden_dir, "postnet_torch_export_bn.onnx"))
+    assert e.value.code == ERR_UNSUPPORTED and "decoder_input" in e.value.message
+    ptr = tmp_path / "decoder_iter.onnx"
+    ptr.write_text("version https://git-lfs.github.com/spec/v1\noid sha256:0000\nsize 72800000\n")
+    with pytest.raises(XdttsError) as e:
+        tacotron2.read_onnx_decoder(ptr)
+    assert e.value.code == ERR_BAD_ARG and "LFS" in e.value.message
+    with pytest.raises(XdttsError) as e:
+        tacotron2.read_onnx_postnet(os.path.join(golden_dir, "decoder_iter_small_lstm.onnx"))
+    assert e.value.code == ERR_UNSUPPORTED
+    # truncated / mutated files never crash the reader
+    raw = open(os.path.join(golden_dir, "decoder_iter_small_lstm.onnx"), "rb").read()
+    rng = np.random.default_rng(1)
+    for i in range(60):
+        b = bytearray(raw[: int(rng.integers(50, len(raw)))] if i % 2 else raw)
+        for _ in range(int(rng.integers(1, 6))):
+            b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        path = tmp_path / "mut.onnx"
+        path.write_bytes(bytes(b))
+        m = ctypes.c_void_p()
+        rc = lib.xdtts_onnx_decoder_open(str(path).encode(), ctypes.byref(m))
+        if rc == 0:
+            lib.xdtts_onnx_decoder_close(m)
+        else:
+            assert rc in (ERR_BAD_ARG, ERR_UNSUPPORTED, -2)
+
+
 def test_npy_io_matches_numpy(lib, tmp_path):
     """The reference dumps mels with ndarray_npy::write_npy (src/lib.rs:132): our writer/reader interoperate with numpy."""
     from xdtts_b200 import tacotron2

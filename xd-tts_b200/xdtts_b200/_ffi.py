@@ -110,6 +110,11 @@ SIGNATURES = {
     "xdtts_onnx_postnet_layer_info": (ctypes.c_int, [_vp, ctypes.c_int, _ip, _ip, _ip, _ip, _ip, _fp]),
     "xdtts_onnx_postnet_layer_copy": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _fp]),
     "xdtts_tail_infer_batch": (ctypes.c_int, [_vp, _vp, _fpp, _ip, ctypes.c_int, _fpp, _fpp, _fpp]),
+    "xdtts_decoder_create_from_onnx": (ctypes.c_int, [ctypes.c_char_p, _vp, ctypes.c_int, ctypes.POINTER(_vp)]),
+    "xdtts_onnx_decoder_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    "xdtts_onnx_decoder_close": (None, [_vp]),
+    "xdtts_onnx_decoder_dims": (ctypes.c_int, [_vp, _ip]),
+    "xdtts_onnx_decoder_tensor": (ctypes.c_longlong, [_vp, ctypes.c_int, _fp, ctypes.c_longlong]),
     "xdtts_decoder_create": (ctypes.c_int, [ctypes.POINTER(DecoderWeights), ctypes.POINTER(DecoderOpts), ctypes.c_int,
                                             ctypes.POINTER(_vp)]),
     "xdtts_decoder_destroy": (None, [_vp]),

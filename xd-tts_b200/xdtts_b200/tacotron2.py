@@ -159,6 +159,15 @@ class Decoder:
         check(lib.xdtts_decoder_create(ctypes.byref(w), ctypes.byref(opts), int(device), ctypes.byref(h)))
         return cls(h, lib.xdtts_decoder_max_steps(h))
 
+    @classmethod
+    def from_onnx(cls, path, *, gate_threshold=GATE_THRESHOLD, max_steps=MAX_DECODER_STEPS, prenet_dropout=True, seed=0, device=0):
+        """The decoder part of Tacotron2::load (src/tacotron2/mod.rs:251-254): `path` is decoder_iter.onnx."""
+        lib = load_library()
+        opts = DecoderOpts(float(gate_threshold), int(max_steps), 0 if prenet_dropout else 1, int(seed))
+        h = ctypes.c_void_p()
+        check(lib.xdtts_decoder_create_from_onnx(str(path).encode(), ctypes.byref(opts), int(device), ctypes.byref(h)))
+        return cls(h, lib.xdtts_decoder_max_steps(h))
+
     def close(self):
         if self._h:
             load_library().xdtts_decoder_destroy(self._h)
@@ -332,3 +341,32 @@ def synthesize_batch(decoder, post, vocoder, memories, processed_memories, unpad
     if short:
         raise XdttsError(_ffi.ERR_SHAPE, "utterances %s stopped after fewer than 4 frames: too short to vocode" % short)
     return infer_tail_batch(post, vocoder, mels, init_phases, return_mels=return_mels)
+
+
+DECODER_TENSORS = ("prenet1", "prenet2", "att_w_ih", "att_w_hh", "att_b_ih", "att_b_hh", "query", "v", "loc_conv", "loc_dense",
+                   "dec_w_ih", "dec_w_hh", "dec_b_ih", "dec_b_hh", "proj_w", "proj_b", "gate_w", "gate_b")
+
+
+def read_onnx_decoder(path):
+    """(dims, weights) of a decoder_iter.onnx: the library's own ONNX reader, host only.  weights: flat float32 arrays in
+    the order and layouts of include/xdtts_b200.h `xdtts_decoder_weights` (LSTM gate order i, f, g, o)."""
+    lib = load_library()
+    m = ctypes.c_void_p()
+    check(lib.xdtts_onnx_decoder_open(str(path).encode(), ctypes.byref(m)))
+    try:
+        d = (ctypes.c_int * 10)()
+        check(lib.xdtts_onnx_decoder_dims(m, d))
+        dims = dict(zip(("n_mel", "prenet", "enc", "att_rnn", "dec_rnn", "att_dim", "loc_f", "loc_k", "lstm_form", "has_dropout"), list(d)))
+        weights = {}
+        for i, name in enumerate(DECODER_TENSORS):
+            n = lib.xdtts_onnx_decoder_tensor(m, i, None, 0)
+            if n < 0:
+                check(int(n))
+            a = np.empty(int(n), np.float32)
+            got = lib.xdtts_onnx_decoder_tensor(m, i, fptr(a), int(n))
+            if got < 0:
+                check(int(got))
+            weights[name] = a
+        return dims, weights
+    finally:
+        lib.xdtts_onnx_decoder_close(m)
