@@ -26,6 +26,17 @@ for n_fft, t in ((1024, 77), (2048, 40)):
     (y,) = voc.from_magnitude_batch([s], [tu])
     err = float(np.sqrt(np.mean((y - ref) ** 2)) / np.abs(ref).max())
     print("%s parity n_fft=%d rel rms %.2e %s" % (tag, n_fft, err, "OK" if err < 2e-6 else "FAIL"))
+# lift accuracy against the fp64 oracle (the gate of tests/test_gpu_gl.py::test_lift_matches_oracle is 1e-5 of full scale)
+for seed in (5, 6):
+    basis = o.create_mel_filter_bank(22050.0, 1024, 80, 0.0, 8000.0)
+    mel = o.synth_mel(seed, 80, 150)
+    voc = griffin_lim.GriffinLim.new(basis, 768, 1.7, 0, 0.99)
+    plan = voc.plan([150])
+    plan.upload(0, [mel])
+    plan.run(0)
+    got = np.concatenate([plan.peek(0).T, plan.peek(1)[None, :]], 0)
+    ref = o.lift_pinv_clamp(mel, basis, 1.7, dtype=np.float64)
+    print("%s lift max err / full scale %.2e" % (tag, np.abs(got - ref).max() / ref.max()))
 peak = bench.measured_peak()[0]
 for cfg in (sys.argv[1:] or ["cfg2", "cfg5"]):
     b, t, n_fft, it = bench.CONFIGS[cfg]

@@ -173,8 +173,8 @@ def build(dims, path, seed=3, t_enc=9, weights=None, use_lstm_op=False):
                          (d.decoder_rnn.bias_hh, "dec_b_hh"), (d.linear_projection.linear_layer.weight, "proj_w"),
                          (d.linear_projection.linear_layer.bias, "proj_b"), (d.gate_layer.linear_layer.bias, "gate_b")):
                 t.copy_(torch.from_numpy(np.asarray(weights[k], np.float32)))
-            d.attention_layer.v.linear_layer.weight.copy_(torch.from_numpy(np.asarray(weights["v"], np.float32))[None, :])
-            d.gate_layer.linear_layer.weight.copy_(torch.from_numpy(np.asarray(weights["gate_w"], np.float32))[None, :])
+            d.attention_layer.v.linear_layer.weight.copy_(torch.from_numpy(np.asarray(weights["v"], np.float32)).reshape(1, -1))
+            d.gate_layer.linear_layer.weight.copy_(torch.from_numpy(np.asarray(weights["gate_w"], np.float32)).reshape(1, -1))
     if use_lstm_op:
         m.convert_cells()
     z = lambda *s: torch.zeros(*s)  # noqa: E731

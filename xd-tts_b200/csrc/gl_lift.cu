@@ -7,7 +7,7 @@
 // FMAs of a 32 x 1000 batch alone take 35 us at 100% issue; the fp64 kernel of round 1 took 220-316 us).
 // One tile of the GEMM is
 //
-//     D[bin 0..127][frame 0..63] = sum_m P[bin][m] * E[frame][m]          (UMMA M = 128 bins, N = 64 frames)
+//     D[bin 0..127][frame 0..31] = sum_m P[bin][m] * E[frame][m]          (UMMA M = 128 bins, N = 32 frames)
 //
 // with both operands K-major (mel index contiguous) in 128-byte-swizzled shared memory and fp32 accumulation
 // in TMEM.  Precision: the pseudo-inverse has 36% negative entries and the gate is 1e-5 of full
@@ -22,7 +22,7 @@
 //
 // Warp roles (416 threads, one CTA per SM):
 //     warps 0-3   epilogue     tcgen05.ld (lane quarter = warp) -> clamp -> ^power -> S
-//     warps 4-11  producers    mel [n_mels][T] -> delog -> tf32 hi / lo -> swizzled E tile (2-stage ring)
+//     warps 4-11  producers    mel [n_mels][T] -> delog -> tf32 hi / lo -> swizzled E tile (4-stage ring, loads 3 tiles ahead)
 //     warp  12    TMEM alloc + one thread issuing the MMAs and commits
 // The Nyquist bin (bin M, a 129th row of the last tile otherwise) is summed by the producers of bin tile 0 on the
 // CUDA cores, from the de-logged values they hold anyway.
@@ -40,10 +40,17 @@ namespace xdtts {
 
 namespace {
 
+// timing experiments only (tools/build_lift_variants.py): bit 0 skips the MMAs, bit 1 the epilogue's math and stores,
+// bit 2 the producers' conversion and shared-memory stores.  0 in the product.
+#ifndef XDTTS_LIFT_SKIP
+#define XDTTS_LIFT_SKIP 0
+#endif
+
 constexpr int LT_BM = 128;       // bins per tile
 constexpr int LT_BN = 64;        // frames per tile
-constexpr int LT_STAGES = 2;     // E-tile ring
-constexpr int LT_EPI_WARPS = 4;   // epilogue warps: lane quarter = warp & 3, column group = warp >> 2 (13 warps keep 128 registers per thread)
+constexpr int LT_STAGES = 2;     // E-tile ring and TMEM accumulators
+constexpr int LT_AHEAD = 1;      // tiles whose mel loads are in flight ahead of the conversion
+constexpr int LT_EPI_WARPS = 4;   // epilogue warps: TMEM lane quarter = warp (13 warps keep 128 registers per thread)
 constexpr int LT_PRO_WARPS = 8;   // producer warps: frame groups (warp & 3, + 4), mel half = warp >> 2
 constexpr int LT_THREADS = 32 * (LT_EPI_WARPS + LT_PRO_WARPS + 1);
 constexpr int LT_TILE_SM = 128;  // tile records staged in shared memory per CTA
@@ -64,10 +71,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "{\n\t"
         ".reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"   // %2: suspend-time hint (ns): sleep instead of spinning
         "@!p bra WAIT_%=;\n\t"
         "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(100000u)
         : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -111,19 +118,30 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 // (and the host builds the pseudo-inverse image with them, tf32_rna_bits)
 __device__ __forceinline__ float to_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 
+// e^v (DELOG 0) / 10^v (DELOG 1) in six instructions: 2^t with t = v * c split so that the rounding of the product
+// is carried into a first-order correction -- t = fl(v c_hi), r = (v c_hi - t) + v c_lo exactly, e = 2^t (1 + r ln 2).
+// ~1.5 ulp (ex2.approx is 2 ulp), against ~15 instructions for expf(); exp(-inf) = 0 without a branch.
 template <int DELOG>
 __device__ __forceinline__ float delog_value(float v) {
-    return DELOG == 0 ? expf(v) : (DELOG == 1 ? exp10f(v) : v);
+    if (DELOG == 2) return v;
+    const float c_hi = DELOG == 0 ? 1.4426950216293335f : 3.3219280242919922f;      // log2(e), log2(10) rounded to fp32
+    const float c_lo = DELOG == 0 ? 1.9259629911266175e-8f : 7.0595369550985533e-8f; // ... and what the rounding dropped
+    const float t = v * c_hi;
+    float r = fmaf(v, c_hi, -t);
+    r = fmaf(v, c_lo, r);
+    float p;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(t));
+    return v == -INFINITY ? 0.f : fmaf(p, r * 0.69314718055994531f, p);
 }
 
 // s ^ power for s > 0 on the special-function unit: 2^(power * log2 s), two MUFU operations and a multiply.  ~1e-6
 // relative at full scale (the gate on S is 1e-5 of full scale, tests/test_gpu_gl.py::test_lift_matches_oracle); powf
 // costs ~40 instructions per value -- more issue time than the rest of the kernel.
 __device__ __forceinline__ float pow_pos(float s, float power) {
-    float l, r;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(s));
+    float l, r;   // max(s, 0) -> log2 = -inf at 0 -> 2^-inf = 0: the clamp needs no select
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(fmaxf(s, 0.f)));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * power));
-    return s > 0.f ? r : 0.f;
+    return r;
 }
 
 struct LiftParams {
@@ -142,7 +160,7 @@ struct LiftSmem {
     __host__ __device__ static int a_plane(int kblocks) { return kblocks * LT_BM * 128; }
     __host__ __device__ static int e_plane(int kblocks) { return kblocks * LT_BN * 128; }
     __host__ __device__ static int bar_off(int kblocks) { return 2 * a_plane(kblocks) + LT_STAGES * 2 * e_plane(kblocks); }
-    __host__ __device__ static int total(int kblocks) { return bar_off(kblocks) + 96 + 4 * 32 * LT_MAX_KB + 4 * 2 * LT_BN + 16 * LT_TILE_SM + 1024; }
+    __host__ __device__ static int total(int kblocks) { return bar_off(kblocks) + 8 * (4 * LT_STAGES + 4) + 4 * 32 * LT_MAX_KB + 4 * LT_STAGES * LT_BN + 16 * LT_TILE_SM + 1024; }
 };
 
 template <int DELOG>
@@ -153,16 +171,16 @@ __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftPar
     uint8_t* sa = smem;
     uint8_t* se = smem + 2 * a_plane;
     uint64_t* bars = (uint64_t*)(smem + LiftSmem::bar_off(p.kblocks));
-    uint64_t* full = bars;            // [2] E stage written (128 producer arrivals)
-    uint64_t* empty = bars + 2;       // [2] E stage consumed (tcgen05.commit)
-    uint64_t* tfull = bars + 4;       // [2] accumulator complete
-    uint64_t* tempty = bars + 6;      // [2] accumulator drained (4 epilogue warps)
-    uint64_t* a_bar = bars + 8;       // P tile landed
-    uint32_t* tmem_ptr = (uint32_t*)(bars + 10);
-    float* wn = (float*)(bars + 12);   // [32 kblocks] the pseudo-inverse's Nyquist row (bin M)
-    float* nq_sm = wn + 32 * LT_MAX_KB;                  // [2 stages][64 frames] Nyquist partial sums of the upper mel half
-    int4* tile_sm = (int4*)(nq_sm + 2 * LT_BN);   // this CTA's first LT_TILE_SM tile records (a global read per tile and role is a
-                                                    // serialised L2 round trip: a third of all stall samples before they were staged)
+    uint64_t* full = bars;                       // [S] E stage written (all producer threads arrive)
+    uint64_t* empty = bars + LT_STAGES;          // [S] E stage consumed (tcgen05.commit)
+    uint64_t* tfull = bars + 2 * LT_STAGES;      // [S] accumulator complete
+    uint64_t* tempty = bars + 3 * LT_STAGES;     // [S] accumulator drained (the epilogue warps)
+    uint64_t* a_bar = bars + 4 * LT_STAGES;      // P tile landed
+    uint32_t* tmem_ptr = (uint32_t*)(bars + 4 * LT_STAGES + 2);
+    float* wn = (float*)(bars + 4 * LT_STAGES + 4);        // [32 LT_MAX_KB] the pseudo-inverse's Nyquist row (bin M)
+    float* nq_sm = wn + 32 * LT_MAX_KB;                     // [S][LT_BN] Nyquist partial sums of the upper mel half
+    int4* tile_sm = (int4*)(nq_sm + LT_STAGES * LT_BN);     // this CTA's first LT_TILE_SM tile records (a global read per tile and
+                                                            // role is a serialised L2 round trip: a third of all stall samples before)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mt = blockIdx.x % p.n_mt, g = blockIdx.x / p.n_mt;
@@ -177,8 +195,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftPar
         mbar_init(a_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == LT_EPI_WARPS + LT_PRO_WARPS) {   // 128 columns: two 128 x 64 fp32 accumulators
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(128u) : "memory");
+    if (warp == LT_EPI_WARPS + LT_PRO_WARPS) {   // LT_STAGES accumulators of 128 lanes x LT_BN fp32 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)(LT_STAGES * LT_BN)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (int i = threadIdx.x; i < 32 * LT_MAX_KB; i += LT_THREADS) wn[i] = i < p.n_mels ? p.pinv_nyq[(size_t)i * p.pinv_ld] : 0.f;
@@ -191,19 +209,19 @@ __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftPar
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    const int my_tiles = g < p.n_tiles ? (p.n_tiles - g + p.groups - 1) / p.groups : 0;   // tiles g, g + G, ... of this CTA
 
     if (warp == LT_EPI_WARPS + LT_PRO_WARPS) {
         // ===================== MMA issuer
         if (lane == 0) {
             mbar_expect_tx(a_bar, (uint32_t)(2 * a_plane));
             bulk_g2s(sa, p.a_image + (size_t)mt * (2 * a_plane / 4), (uint32_t)(2 * a_plane), a_bar);
-            // instruction descriptor: D fp32, A/B tf32, both K-major, N = 64, M = 128
+            // instruction descriptor: D fp32, A/B tf32, both K-major, N = LT_BN, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(LT_BN >> 3) << 17) | ((uint32_t)(LT_BM >> 4) << 24);
             mbar_wait(a_bar, 0);
-            int it = 0;
-            for (int tile = g; tile < p.n_tiles; tile += p.groups, it++) {
-                const int s = it & 1;
-                const uint32_t ph = (uint32_t)((it >> 1) & 1);
+            for (int it = 0; it < my_tiles; it++) {
+                const int s = it % LT_STAGES;
+                const uint32_t ph = (uint32_t)((it / LT_STAGES) & 1);
                 mbar_wait(&tempty[s], ph ^ 1u);   // epilogue has drained this accumulator
                 mbar_wait(&full[s], ph);          // producers have written this E stage
                 tc_fence_after();
@@ -217,7 +235,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftPar
                         const uint64_t da = umma_desc_sw128(ab + kb * (LT_BM * 128)), db = umma_desc_sw128(eb + kb * (LT_BN * 128));
 #pragma unroll
                         for (int k = 0; k < 4; k++) {   // UMMA_K = 8 tf32 = 32 B along the swizzled row: +2 in the address field
-                            tc_mma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc);
+                            if (!(XDTTS_LIFT_SKIP & 1)) tc_mma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc);
                             acc = 1;
                         }
                     }
@@ -228,61 +246,68 @@ __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftPar
         }
     } else if (warp >= LT_EPI_WARPS) {
         // ===================== producers.  A warp covers 4 mel rows x 8 frames per step (conflict-free swizzled stores,
-        // four full 32-byte sectors per global load); producer warp pw owns frame groups pw and pw + 4 of the tile, a
-        // lane the frames fa = 8 pw + f8 and fb = fa + 32 and the mel rows m4, m4 + 4, ...  The loads of tile i+1 are
-        // issued before tile i is converted, so their latency hides behind the conversion, MMA and epilogue in flight.
+        // four full 32-byte sectors per global load); producer warp w owns frame group w & 3 of the tile (a lane: frame
+        // f = 8 (w & 3) + lane / 4) and the mel-row groups of half w >> 2 (a lane: rows 4 mg + lane % 4).  Loads run
+        // LT_AHEAD tiles ahead of the conversion, so DRAM latency hides behind the tiles in flight.
         const int pw = (warp - LT_EPI_WARPS) & 3, mh = (warp - LT_EPI_WARPS) >> 2;
         const int m4 = lane & 3, f8 = lane >> 2;
-        const int fa = pw * 8 + f8;
+        constexpr int FG = LT_BN / 32;                      // frame groups of 8 per producer warp: frames 8 pw + f8 + 32 h
+        const int f = pw * 8 + f8;
         constexpr int MGT = LT_MAX_KB * 8;                  // mel groups of 4 in a padded tile (24)
         constexpr int MG = MGT / (LT_PRO_WARPS / 4);        // ... of which this warp converts MG, starting at mg0
         const int mg0 = mh * MG;
         const int mgroups = (p.n_mels + 3) / 4;
-        float wreg[MG];                          // this lane's entries of the pseudo-inverse's Nyquist row
+        float wreg[MG];                                     // this lane's entries of the pseudo-inverse's Nyquist row
 #pragma unroll
         for (int mg = 0; mg < MG; mg++) wreg[mg] = wn[(mg0 + mg) * 4 + m4];
-        float xn[2 * MG];
+        float xq[LT_AHEAD][FG * MG];
         auto issue_loads = [&](int it_, float* x) {
             const int4 tl = tile_rec(it_);
             const int T = tl.y;
-            const bool va = tl.z + fa < T, vb = tl.z + fa + 32 < T;
-            const float* src = p.mel_arena + (size_t)tl.x * p.n_mels + (size_t)(mg0 * 4 + m4) * T + tl.z + fa;
+            const float* src = p.mel_arena + (size_t)tl.x * p.n_mels + tl.z + f;   // row 0 of the utterance, this lane's first frame
+            int off = (mg0 * 4 + m4) * T;   // 32-bit: a plan holds fewer than 2^31 / K frames
 #pragma unroll
             for (int mg = 0; mg < MG; mg++) {
-                const bool mv = mg0 + mg < mgroups && (mg0 + mg) * 4 + m4 < p.n_mels;
-                x[2 * mg] = (mv && va) ? __ldg(src) : -INFINITY;          // -inf: no sample
-                x[2 * mg + 1] = (mv && vb) ? __ldg(src + 32) : -INFINITY;
-                src += 4 * (size_t)T;
+                const bool mv = (mg0 + mg) * 4 + m4 < p.n_mels;
+#pragma unroll
+                for (int h = 0; h < FG; h++) x[FG * mg + h] = (mv && tl.z + f + 32 * h < T) ? __ldg(src + off + 32 * h) : -INFINITY;   // -inf: no sample
+                off += 4 * T;
             }
         };
-        if (g < p.n_tiles) issue_loads(0, xn);
-        int it = 0;
-        for (int tile = g; tile < p.n_tiles; tile += p.groups, it++) {
-            const int s = it & 1;
-            float x[2 * MG];
 #pragma unroll
-            for (int i = 0; i < 2 * MG; i++) x[i] = xn[i];
-            if (tile + p.groups < p.n_tiles) issue_loads(it + 1, xn);
-            mbar_wait(&empty[s], (uint32_t)((it >> 1) & 1) ^ 1u);
-            uint8_t* ehi = se + s * 2 * e_plane + fa * 128 + m4 * 4;
-            float nq0 = 0.f, nq1 = 0.f;   // Nyquist-bin partial sums of this lane's two frames
+        for (int a = 0; a < LT_AHEAD; a++)
+            if (a < my_tiles) issue_loads(a, xq[a]);
+        for (int it = 0; it < my_tiles; it++) {
+            const int s = it % LT_STAGES;
+            float x[FG * MG];
+#pragma unroll
+            for (int i = 0; i < FG * MG; i++) x[i] = xq[0][i];
+#pragma unroll
+            for (int a = 0; a + 1 < LT_AHEAD; a++)
+#pragma unroll
+                for (int i = 0; i < FG * MG; i++) xq[a][i] = xq[a + 1][i];
+            if (it + LT_AHEAD < my_tiles) issue_loads(it + LT_AHEAD, xq[LT_AHEAD - 1]);
+            mbar_wait(&empty[s], (uint32_t)((it / LT_STAGES) & 1) ^ 1u);
+            uint8_t* ehi = se + s * 2 * e_plane + f * 128 + m4 * 4;
+            float nq[FG];   // Nyquist-bin partial sums of this lane's frames
+#pragma unroll
+            for (int h = 0; h < FG; h++) nq[h] = 0.f;
 #pragma unroll
             for (int mg = 0; mg < MG; mg++) {
                 const int mgg = mg0 + mg;
-                if (mgg < mgroups && mgg * 4 + m4 < p.n_mels) {
-                    // row f of K-block mgg >> 3, 16-byte chunk (mgg & 7) ^ (f & 7) (both frames have f & 7 == f8), element m4
+                if (!(XDTTS_LIFT_SKIP & 4) && mgg < mgroups && mgg * 4 + m4 < p.n_mels) {
+                    // row f of K-block mgg >> 3, 16-byte chunk (mgg & 7) ^ (f & 7) (f & 7 == f8 for every h), element m4
                     const int off = (mgg >> 3) * (LT_BN * 128) + (((mgg & 7) ^ f8) << 4);
 #pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const float v = x[2 * mg + h];
-                        float e = delog_value<DELOG>(v);               // exp(-inf) = 0: no branch
+                    for (int h = 0; h < FG; h++) {
+                        const float v = x[FG * mg + h];
+                        float e = delog_value<DELOG>(v);               // -inf (no sample) -> 0
                         if (DELOG == 2) e = v == -INFINITY ? 0.f : e;
                         const float hi = to_tf32(e);
                         const float lo = to_tf32(e - hi);
                         *reinterpret_cast<float*>(ehi + off + h * (32 * 128)) = hi;
                         *reinterpret_cast<float*>(ehi + e_plane + off + h * (32 * 128)) = lo;
-                        if (h) nq1 = fmaf(wreg[mg], e, nq1);
-                        else nq0 = fmaf(wreg[mg], e, nq0);
+                        nq[h] = fmaf(wreg[mg], e, nq[h]);
                     }
                 }
             }
@@ -290,49 +315,53 @@ __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftPar
             mbar_arrive(&full[s]);
             if (mt == 0) {   // the Nyquist bin (slot M of the frame's record): sum over the four lanes that share a frame,
                              // then over the two warps that share the frame (one per half of the mel rows)
-                nq0 += __shfl_xor_sync(0xffffffffu, nq0, 1);
-                nq1 += __shfl_xor_sync(0xffffffffu, nq1, 1);
-                nq0 += __shfl_xor_sync(0xffffffffu, nq0, 2);
-                nq1 += __shfl_xor_sync(0xffffffffu, nq1, 2);
                 float* part = nq_sm + s * LT_BN;   // the upper half's partial sums of this stage
-                if (mh == 1 && m4 == 0) { part[fa] = nq0; part[fa + 32] = nq1; }
-                asm volatile("bar.sync %0, %1;" ::"r"(1 + pw), "r"(64) : "memory");   // the two warps of frame groups (pw, pw + 4)
-                const int4 tl = tile_rec(it);
-                if (mh == 0 && m4 == 0) {
-                    nq0 += part[fa];
-                    nq1 += part[fa + 32];
-                    float* rec = p.S + ((size_t)tl.x + tl.z + fa) * p.ld + p.n_mt * LT_BM;
-                    if (tl.z + fa < tl.y) rec[0] = p.power == 1.0f ? fmaxf(nq0, 0.f) : pow_pos(nq0, p.power);
-                    if (tl.z + fa + 32 < tl.y) rec[(size_t)32 * p.ld] = p.power == 1.0f ? fmaxf(nq1, 0.f) : pow_pos(nq1, p.power);
+#pragma unroll
+                for (int h = 0; h < FG; h++) {
+                    nq[h] += __shfl_xor_sync(0xffffffffu, nq[h], 1);
+                    nq[h] += __shfl_xor_sync(0xffffffffu, nq[h], 2);
+                    if (mh == 1 && m4 == 0) part[f + 32 * h] = nq[h];
                 }
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + pw), "r"(64) : "memory");   // the two warps of frame group pw
+                const int4 tl = tile_rec(it);
+#pragma unroll
+                for (int h = 0; h < FG; h++)
+                    if (mh == 0 && m4 == 0 && tl.z + f + 32 * h < tl.y) {
+                        const float v = nq[h] + part[f + 32 * h];
+                        p.S[((size_t)tl.x + tl.z + f + 32 * h) * p.ld + p.n_mt * LT_BM] = p.power == 1.0f ? fmaxf(v, 0.f) : pow_pos(v, p.power);
+                    }
             }
         }
     } else {
         // ===================== epilogue: TMEM lane quarter q <-> bins mt*128 + 32 q + lane
-        const int q = warp & 3, ch = warp >> 2;                   // lane quarter, column half
-        constexpr int CW = LT_BN / (LT_EPI_WARPS / 4);            // columns per epilogue warp
+        const int q = warp & 3;
         const int bin = mt * LT_BM + q * 32 + lane;
         const bool plain = p.power == 1.0f;
-        int it = 0;
-        for (int tile = g; tile < p.n_tiles; tile += p.groups, it++) {
-            const int s = it & 1;
+        for (int it = 0; it < my_tiles; it++) {
+            const int s = it % LT_STAGES;
             const int4 tl = tile_rec(it);
-            const int nf = min(LT_BN, tl.y - tl.z) - ch * CW;   // frames of this warp's columns that exist
-            float* out = p.S + ((size_t)tl.x + tl.z + ch * CW) * p.ld + bin;
-            mbar_wait(&tfull[s], (uint32_t)((it >> 1) & 1));
+            const int nf = min(LT_BN, tl.y - tl.z);   // frames of this tile that exist
+            float* out = p.S + ((size_t)tl.x + tl.z) * p.ld + bin;
+            mbar_wait(&tfull[s], (uint32_t)((it / LT_STAGES) & 1));
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * LT_BN + ch * CW);
-#pragma unroll 1
-            for (int c0 = 0; c0 < CW; c0 += 16) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * LT_BN);
+            const bool full_tile = nf >= LT_BN;   // all but an utterance's last tile
+#pragma unroll
+            for (int c0 = 0; c0 < ((XDTTS_LIFT_SKIP & 2) ? 0 : LT_BN); c0 += 16) {
                 uint32_t v[16];
                 tc_ld16(taddr + (uint32_t)c0, v);
                 tc_wait_ld();
+                float r[16];
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const float xv = __uint_as_float(v[i]);
-                    const float r = plain ? fmaxf(xv, 0.f) : pow_pos(xv, p.power);
-                    if (c0 + i < nf) __stcs(out, r);   // 32 lanes = 32 consecutive bins of one frame: one 128-byte line
-                    out += p.ld;
+                for (int i = 0; i < 16; i++) r[i] = plain ? fmaxf(__uint_as_float(v[i]), 0.f) : pow_pos(__uint_as_float(v[i]), p.power);
+                // 32 lanes = 32 consecutive bins of one frame: every store is one 128-byte line
+                if (full_tile) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) __stcs(out + (c0 + i) * p.ld, r[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; i++)
+                        if (c0 + i < nf) __stcs(out + (c0 + i) * p.ld, r[i]);
                 }
             }
             tc_fence_before();
@@ -343,7 +372,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftPar
 
     tc_fence_before();
     __syncthreads();
-    if (warp == LT_EPI_WARPS + LT_PRO_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+    if (warp == LT_EPI_WARPS + LT_PRO_WARPS)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(LT_STAGES * LT_BN)) : "memory");
 }
 
 // CUDA-core fp32 form of the same lift (all K bins, Nyquist included): the path for mel bases wider than 96 rows,
