@@ -19,7 +19,7 @@ layers = po.synth_weights(seed=7)
 for n_fft, ts in ((1024, [37, 4, 150]), (2048, [21, 9]), (512, [30])):
     hop, k = n_fft // 4, n_fft // 2 + 1
     basis = o.create_mel_filter_bank(22050.0, n_fft, 80, 0.0, 8000.0)
-    voc = griffin_lim.GriffinLim.new(basis, n_fft - hop, 1.7, 3, 0.99, run_frames=5)
+    voc = griffin_lim.GriffinLim.new(basis, n_fft - hop, 1.7, 3, 0.99, run_frames=5, fixed_seed=True)
     mels = [o.synth_mel(i, 80, t) for i, t in enumerate(ts)]
     ys = voc.infer_batch(mels)
     ys2 = voc.infer_batch(mels, [o.phase_turns(0, i, k, t) for i, t in enumerate(ts)])

