@@ -68,8 +68,10 @@ struct Geo {
     static constexpr int EX1 = 8 * S1;        // exchange-1 size, complex elements
     static constexpr int EX2 = R3 * S2;       // exchange-2 size
     static constexpr int EXW = EX1 + EX2;     // per-warp exchange scratch
-    // constant tables, float2 units, laid out [row][32 lanes]
-    static constexpr int TW1_OFF = 0;                     // W_M^{(lane+32 i) k1}, row i*7 + k1-1
+    // constant tables, float2 units.  Rows that a lane reads together are PAIRED into 16-byte entries ([pair][32 lanes]
+    // of float4), so that they arrive with one 128-bit shared load: per butterfly i the pass-1 twiddles k1 = (1,2), (3,4),
+    // (5,6) then k1 = 7 alone; the window rows n1 = (0,1), (2,3); the split twiddles j = (0,1), (2,3), ...
+    static constexpr int TW1_OFF = 0;                     // W_M^{(lane+32 i) k1}: block i at 7*32*i = [3 pairs][32] float4 + [32] float2
     static constexpr int TW2_OFF = TW1_OFF + 7 * NB * 32; // W_{8 R3}^{(lane & (R3-1)) k2}, row k2-1
     static constexpr int RTW_OFF = TW2_OFF + 7 * 32;      // -i W_N^{k(lane,j)} / 2, row j
     static constexpr int WIN_OFF = RTW_OFF + R3 * 32;     // (w[s], w[s+1]), row i*4 + n1, n1 = 0..3 only:
@@ -92,6 +94,22 @@ XD_HD constexpr int ex1_pos(int m) {
 }
 XD_HD float2 mk2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
 XD_HD float4 pack4(float2 a, float2 b) { float4 r; r.x = a.x; r.y = a.y; r.z = b.x; r.w = b.y; return r; }
+
+// paired table rows (see Geo): `base` = float2 offset of the block, entry `pair` of this lane -> the two float2 rows
+XD_HD void tab_pair(const float2* tab, int base, int pair, int lane, float2* a, float2* b) {
+    const float4 q = *reinterpret_cast<const float4*>(&tab[base + 64 * pair + 2 * lane]);
+    *a = mk2(q.x, q.y);
+    *b = mk2(q.z, q.w);
+}
+// the seven pass-1 twiddles of butterfly i: tw[k1 - 1]
+template <int R3>
+XD_HD void load_tw1(const float2* tab, int i, int lane, float2* tw) {
+    const int base = Geo<R3>::TW1_OFF + i * 7 * 32;
+    tab_pair(tab, base, 0, lane, &tw[0], &tw[1]);
+    tab_pair(tab, base, 1, lane, &tw[2], &tw[3]);
+    tab_pair(tab, base, 2, lane, &tw[4], &tw[5]);
+    tw[6] = tab[base + 6 * 32 + lane];
+}
 
 // pass 1 -> exchange 1: v[i*8 + k1] (already multiplied by its twiddle) goes to row k1, element lane + 32 i
 template <int R3>
@@ -507,15 +525,24 @@ XD_HD void phase_f1(Lane<R3>& L, int lane, const float* y, int T, int t, int pad
 #pragma unroll
     for (int i = 0; i < G::NB; i++) {
 #pragma unroll
-        for (int n1 = 0; n1 < 4; n1++) {
-            const float2 w = tab[G::WIN_OFF + (i * 4 + n1) * 32 + lane];
-            const float2 lo = L.raw[i * 8 + n1], hi = L.raw[i * 8 + n1 + 4];
-            L.v[i * 8 + n1] = mk2(lo.x * w.x, lo.y * w.y);
-            L.v[i * 8 + n1 + 4] = mk2(fmaf(-hi.x, w.x, hi.x), fmaf(-hi.y, w.y, hi.y));   // x (1 - w)
+        for (int np = 0; np < 2; np++) {
+            float2 wp[2];
+            tab_pair(tab, G::WIN_OFF + i * 4 * 32, np, lane, &wp[0], &wp[1]);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int n1 = 2 * np + h;
+                const float2 w = wp[h];
+                const float2 lo = L.raw[i * 8 + n1], hi = L.raw[i * 8 + n1 + 4];
+                L.v[i * 8 + n1] = mk2(lo.x * w.x, lo.y * w.y);
+                L.v[i * 8 + n1 + 4] = mk2(fmaf(-hi.x, w.x, hi.x), fmaf(-hi.y, w.y, hi.y));   // x (1 - w)
+            }
         }
         Dft<8, false>::run(&L.v[i * 8]);
 #pragma unroll
-        for (int k1 = 1; k1 < 8; k1++) L.v[i * 8 + k1] = cmul(L.v[i * 8 + k1], tab[G::TW1_OFF + (i * 7 + k1 - 1) * 32 + lane]);
+        float2 tw[7];
+        load_tw1<R3>(tab, i, lane, tw);
+#pragma unroll
+        for (int k1 = 1; k1 < 8; k1++) L.v[i * 8 + k1] = cmul(L.v[i * 8 + k1], tw[k1 - 1]);
     }
     ex1_store_rows<R3>(L.v, lane, ex1);
 }
@@ -537,11 +564,17 @@ XD_HD void f1_window_rot(Lane<R3>& L, int lane, const float2* tab, const float* 
 #pragma unroll
     for (int i = 0; i < G::NB; i++) {
 #pragma unroll
-        for (int n1 = 0; n1 < 4; n1++) {
-            const float2 w = tab[G::WIN_OFF + (i * 4 + n1) * 32 + lane];
-            const float2 lo = L.raw[i * 8 + ((n1 + P0) & 7)], hi = L.raw[i * 8 + ((n1 + 4 + P0) & 7)];
-            L.v[i * 8 + n1] = mk2(lo.x * w.x, lo.y * w.y);
-            L.v[i * 8 + n1 + 4] = mk2(fmaf(-hi.x, w.x, hi.x), fmaf(-hi.y, w.y, hi.y));   // x (1 - w)
+        for (int np = 0; np < 2; np++) {
+            float2 wp[2];
+            tab_pair(tab, G::WIN_OFF + i * 4 * 32, np, lane, &wp[0], &wp[1]);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int n1 = 2 * np + h;
+                const float2 w = wp[h];
+                const float2 lo = L.raw[i * 8 + ((n1 + P0) & 7)], hi = L.raw[i * 8 + ((n1 + 4 + P0) & 7)];
+                L.v[i * 8 + n1] = mk2(lo.x * w.x, lo.y * w.y);
+                L.v[i * 8 + n1 + 4] = mk2(fmaf(-hi.x, w.x, hi.x), fmaf(-hi.y, w.y, hi.y));   // x (1 - w)
+            }
         }
     }
     if (fetch_next) {   // hop block t+2 of the signal = newest block of frame t+1, entirely inside the signal
@@ -579,7 +612,10 @@ XD_HD void phase_f1_rot(Lane<R3>& L, int lane, const float* y, int T, int t, int
     for (int i = 0; i < G::NB; i++) {
         Dft<8, false>::run(&L.v[i * 8]);
 #pragma unroll
-        for (int k1 = 1; k1 < 8; k1++) L.v[i * 8 + k1] = cmul(L.v[i * 8 + k1], tab[G::TW1_OFF + (i * 7 + k1 - 1) * 32 + lane]);
+        float2 tw[7];
+        load_tw1<R3>(tab, i, lane, tw);
+#pragma unroll
+        for (int k1 = 1; k1 < 8; k1++) L.v[i * 8 + k1] = cmul(L.v[i * 8 + k1], tw[k1 - 1]);
     }
     ex1_store_rows<R3>(L.v, lane, ex1);
 }
@@ -682,11 +718,13 @@ XD_HD void phase_f3(Lane<R3>& L, int lane, const GlParams& p, int utt, int T, in
         lane0_fix<R3>(L.v, l0);
     }
 
+    float2 Cpair[2];
 #pragma unroll
     for (int j = 0; j < R3; j++) {
         const int ka = kslot<R3>(lane, j);
         const int kb = (l0 && j == 0) ? G::M / 2 : G::M - ka;
-        const float2 C = tab[G::RTW_OFF + j * 32 + lane];   // -i W_N^k / 2
+        if ((j & 1) == 0) tab_pair(tab, G::RTW_OFF, j >> 1, lane, &Cpair[0], &Cpair[1]);
+        const float2 C = Cpair[j & 1];   // -i W_N^k / 2
         const float sa_j = s_stg[ka], sb_j = s_stg[kb];      // staged |S| at bins k and M-k
         float2 Ya, Yb;
         if (MODE != GL_MODE_INIT) {
@@ -802,17 +840,26 @@ XD_HD void phase_f5(Lane<R3>& L, int lane, const float2* tab, const float2* ex1)
 #pragma unroll
     for (int i = 0; i < G::NB; i++) {
 #pragma unroll
-        for (int k1 = 1; k1 < 8; k1++) L.v[i * 8 + k1] = cmulc(L.v[i * 8 + k1], tab[G::TW1_OFF + (i * 7 + k1 - 1) * 32 + lane]);
+        float2 tw[7];
+        load_tw1<R3>(tab, i, lane, tw);
+#pragma unroll
+        for (int k1 = 1; k1 < 8; k1++) L.v[i * 8 + k1] = cmulc(L.v[i * 8 + k1], tw[k1 - 1]);
     }
 #pragma unroll
     for (int i = 0; i < G::NB; i++) {
         Dft<8, true>::run(&L.v[i * 8]);
 #pragma unroll
-        for (int n1 = 0; n1 < 4; n1++) {
-            const float2 w = tab[G::WIN_OFF + (i * 4 + n1) * 32 + lane];
-            const float2 lo = L.v[i * 8 + n1], hi = L.v[i * 8 + n1 + 4];
-            L.v[i * 8 + n1] = mk2(lo.x * w.x, lo.y * w.y);
-            L.v[i * 8 + n1 + 4] = mk2(fmaf(-hi.x, w.x, hi.x), fmaf(-hi.y, w.y, hi.y));
+        for (int np = 0; np < 2; np++) {
+            float2 wp[2];
+            tab_pair(tab, G::WIN_OFF + i * 4 * 32, np, lane, &wp[0], &wp[1]);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int n1 = 2 * np + h;
+                const float2 w = wp[h];
+                const float2 lo = L.v[i * 8 + n1], hi = L.v[i * 8 + n1 + 4];
+                L.v[i * 8 + n1] = mk2(lo.x * w.x, lo.y * w.y);
+                L.v[i * 8 + n1 + 4] = mk2(fmaf(-hi.x, w.x, hi.x), fmaf(-hi.y, w.y, hi.y));
+            }
         }
     }
 }

@@ -17,11 +17,16 @@ template <int R3>
 std::vector<float2> build_tables() {
     typedef Geo<R3> G;
     std::vector<float2> t(G::TAB);
+    // paired rows: entry `pair` of a block holds rows (2 pair, 2 pair + 1) of one lane in 16 consecutive bytes (gl_core.cuh tab_pair)
+    auto put_pair = [&](int base, int row, int lane, float2 v) { t[base + 64 * (row >> 1) + 2 * lane + (row & 1)] = v; };
     for (int lane = 0; lane < 32; lane++) {
         for (int i = 0; i < G::NB; i++)
             for (int k1 = 1; k1 < 8; k1++) {
                 const double a = -2.0 * M_PI * (double)((lane + 32 * i) * k1) / (double)G::M;
-                t[G::TW1_OFF + (i * 7 + k1 - 1) * 32 + lane] = mk2((float)std::cos(a), (float)std::sin(a));
+                const float2 v = mk2((float)std::cos(a), (float)std::sin(a));
+                const int base = G::TW1_OFF + i * 7 * 32;
+                if (k1 < 7) put_pair(base, k1 - 1, lane, v);       // (1,2) (3,4) (5,6)
+                else t[base + 6 * 32 + lane] = v;                  // k1 = 7 alone
             }
         for (int k2 = 1; k2 < 8; k2++) {
             const double a = -2.0 * M_PI * (double)((lane & (R3 - 1)) * k2) / (double)(8 * R3);
@@ -30,12 +35,12 @@ std::vector<float2> build_tables() {
         for (int j = 0; j < R3; j++) {
             const int k = kslot<R3>(lane, j);
             const double a = 2.0 * M_PI * (double)k / (double)G::N;   // W_N^k = cos a - i sin a
-            t[G::RTW_OFF + j * 32 + lane] = mk2((float)(-0.5 * std::sin(a)), (float)(-0.5 * std::cos(a)));
+            put_pair(G::RTW_OFF, j, lane, mk2((float)(-0.5 * std::sin(a)), (float)(-0.5 * std::cos(a))));
         }
         for (int i = 0; i < G::NB; i++)
             for (int n1 = 0; n1 < 4; n1++) {   // first half of the window only: w[s + N/2] = 1 - w[s]
                 const int s = 16 * R3 * n1 + 2 * (lane + 32 * i);
-                t[G::WIN_OFF + (i * 4 + n1) * 32 + lane] = mk2((float)hann_periodic(s, G::N), (float)hann_periodic(s + 1, G::N));
+                put_pair(G::WIN_OFF + i * 4 * 32, n1, lane, mk2((float)hann_periodic(s, G::N), (float)hann_periodic(s + 1, G::N)));
             }
     }
     return t;

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "api_internal.h"
+#include "host_copy.h"
 #include "postnet.h"
 
 using namespace xdtts;
@@ -79,6 +80,7 @@ struct xdtts_postnet_plan {
     float *xin_f32 = nullptr, *act_f32[2] = {nullptr, nullptr};     // CUDA-core path
     CUtensorMap tm_a_hi[PN_MAX_LAYERS], tm_a_lo[PN_MAX_LAYERS];
     float *h_in = nullptr, *h_out = nullptr;                        // pinned staging
+    cudaEvent_t h_in_busy = nullptr;                                // recorded after the DMA that reads h_in
     cudaEvent_t ev[2] = {nullptr, nullptr};
 };
 
@@ -210,6 +212,7 @@ extern "C" void xdtts_postnet_plan_destroy(xdtts_postnet_plan* p) {
         if (p->ev[i]) cudaEventDestroy(p->ev[i]);
     }
     if (p->h_in) cudaFreeHost(p->h_in);
+    if (p->h_in_busy) cudaEventDestroy(p->h_in_busy);
     if (p->h_out) cudaFreeHost(p->h_out);
     delete p;
 }
@@ -310,11 +313,24 @@ static int pn_plan_upload_locked(xdtts_postnet_plan* p, const float* const* srcs
     const size_t C0 = h->ch[0];
     bool all_pinned = true;
     for (int b = 0; b < p->B; b++) all_pinned = all_pinned && is_pinned(srcs[b]);
-    if (!all_pinned) {
+    if (!all_pinned) {   // pageable: staged by the copy threads with non-temporal stores, utterance by utterance (host_copy.h)
+        if (p->h_in_busy) CU(cudaEventSynchronize(p->h_in_busy));   // the previous upload's DMA still reads the staging buffer
         if (!p->h_in) CU(cudaHostAlloc((void**)&p->h_in, C0 * (size_t)p->total_T * 4, cudaHostAllocDefault));
-        for (int b = 0; b < p->B; b++) memcpy(p->h_in + C0 * (size_t)p->foff[b], srcs[b], C0 * (size_t)p->Ts[b] * 4);
-        CU(cudaMemcpyAsync(p->d_mel, p->h_in, C0 * (size_t)p->total_T * 4, cudaMemcpyHostToDevice, s));
-        CU(cudaStreamSynchronize(s));   // the staging buffer is reused by the next upload
+        if (!p->h_in_busy) CU(cudaEventCreateWithFlags(&p->h_in_busy, cudaEventDisableTiming));
+        std::vector<std::atomic<int>> pending(p->B);
+        for (int b = 0; b < p->B; b++) {
+            pending[b].store(0);
+            host_copy_async(p->h_in + C0 * (size_t)p->foff[b], srcs[b], C0 * (size_t)p->Ts[b] * 4, &pending[b], true);
+        }
+        cudaError_t ce = cudaSuccess;
+        for (int b = 0; b < p->B; b++) {
+            host_copy_wait(&pending[b]);
+            if (ce == cudaSuccess)
+                ce = cudaMemcpyAsync(p->d_mel + C0 * (size_t)p->foff[b], p->h_in + C0 * (size_t)p->foff[b], C0 * (size_t)p->Ts[b] * 4,
+                                     cudaMemcpyHostToDevice, s);
+        }
+        CU(ce);
+        CU(cudaEventRecord(p->h_in_busy, s));
     } else {
         for (int b = 0; b < p->B; b++)
             CU(cudaMemcpyAsync(p->d_mel + C0 * (size_t)p->foff[b], srcs[b], C0 * (size_t)p->Ts[b] * 4, cudaMemcpyHostToDevice, s));
