@@ -32,7 +32,16 @@ extern "C" {
 #define XDTTS_ERR_UNSUPPORTED (-5) /* n_fft not in {512,1024,2048}, hop != n_fft/4, n_mels > 256 */
 
 /* Options whose value the un-vendored crate fixes internally (SURVEY.md section 7 "unknowns");
- * defaults (all zero) are the librosa-0.9.2 behaviour the crate ports. */
+ * defaults (all zero) are the librosa-0.9.2 behaviour the crate ports -- WITH ONE DELIBERATE EXCEPTION:
+ *
+ *   lift = 0, the default, is the mel-filterbank PSEUDO-INVERSE lift this back end was specified with.  The crate behind
+ *   GriffinLim::infer most likely does what librosa's mel_to_stft does (non-negative least squares: least-squares start +
+ *   L-BFGS-B; its dependencies lbfgsb and ndarray-linalg are in Cargo.lock:888,1006).  The two give different magnitudes
+ *   (about 2% apart on speech-like mels, up to 70% on random ones), i.e. with the defaults this library does NOT reproduce
+ *   the reference's audio sample for sample.  Set lift = 1 for the librosa-faithful lift (costs +0.2 ms per 32 x 1000
+ *   frames on speech-like input); the Rust shim exposes it as the cargo feature `nnls-lift` / XDTTS_B200_LIFT=nnls.
+ *   Likewise `exponent` selects between S = x^power (default, the call site's reading) and librosa's x^(1/power).
+ *   Which combination the crate really uses is what tools/capture_reference_fixtures.sh + test_reference_fixtures decide. */
 typedef struct xdtts_gl_opts {
     int delog;               /* 0: exp (Tacotron2 ln-mel, default)  1: 10^x  2: mel is already linear */
     int pad_mode;            /* 0: reflect (librosa 0.9.2 stft)     1: constant zero */
