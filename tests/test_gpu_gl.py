@@ -505,3 +505,36 @@ def test_large_batch_whole_wave_plan(gl):
     for y in ys[1:]:
         assert rel_rms(y, ys[0]) < 2e-6                            # utterances may be cut at different frames: equal up to rounding
     assert rel_rms(ys[0], ref) < 2e-5
+
+
+@pytest.mark.parametrize("n_fft", [512, 2048])
+def test_lift_other_geometries_and_ragged_tiles(gl, n_fft):
+    """The tensor-core lift at 2 and 8 bin tiles, utterances that end inside a 64-frame tile, one frame count below a tile and
+    one exactly on a tile boundary; and the CUDA-core form of the same lift (mel bases wider than 96 rows take it) agrees."""
+    k = n_fft // 2 + 1
+    basis = basis_for(n_fft)
+    ts = [4, 63, 64, 65, 131]
+    mels = [o.synth_mel(40 + i, 80, t) for i, t in enumerate(ts)]
+    voc = make(gl, n_fft, 0)
+    plan = voc.plan(ts)
+    plan.upload(0, mels)
+    plan.run(0)
+    s_dev, s_nyq = plan.peek(0), plan.peek(1)
+    off = 0
+    for mel in mels:
+        t = mel.shape[1]
+        ref = o.lift_pinv_clamp(mel, basis, 1.7, dtype=np.float64)
+        got = np.concatenate([s_dev[off:off + t].T, s_nyq[None, off:off + t]], 0)
+        assert got.shape == (k, t)
+        assert np.abs(got - ref).max() / ref.max() < 1e-5, (n_fft, t)
+        off += t
+    # a 100-row basis does not fit the tensor path's shared memory: the fp32 kernel computes the same function
+    wide = o.create_mel_filter_bank(22050.0, n_fft, 100, 0.0, 8000.0)
+    vw = gl.GriffinLim.new(wide, n_fft - n_fft // 4, 1.7, 0, 0.99)
+    mw = o.synth_mel(77, 100, 70)
+    pw = vw.plan([70])
+    pw.upload(0, [mw])
+    pw.run(0)
+    ref = o.lift_pinv_clamp(mw, wide, 1.7, dtype=np.float64)
+    got = np.concatenate([pw.peek(0).T, pw.peek(1)[None, :]], 0)
+    assert np.abs(got - ref).max() / ref.max() < 1e-5
