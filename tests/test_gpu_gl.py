@@ -528,13 +528,15 @@ def test_lift_other_geometries_and_ragged_tiles(gl, n_fft):
         assert got.shape == (k, t)
         assert np.abs(got - ref).max() / ref.max() < 1e-5, (n_fft, t)
         off += t
-    # a 100-row basis does not fit the tensor path's shared memory: the fp32 kernel computes the same function
-    wide = o.create_mel_filter_bank(22050.0, n_fft, 100, 0.0, 8000.0)
-    vw = gl.GriffinLim.new(wide, n_fft - n_fft // 4, 1.7, 0, 0.99)
-    mw = o.synth_mel(77, 100, 70)
-    pw = vw.plan([70])
-    pw.upload(0, [mw])
-    pw.run(0)
-    ref = o.lift_pinv_clamp(mw, wide, 1.7, dtype=np.float64)
-    got = np.concatenate([pw.peek(0).T, pw.peek(1)[None, :]], 0)
-    assert np.abs(got - ref).max() / ref.max() < 1e-5
+    # wider bases: 100 rows (14 K chunks: the tensor kernel's four-chunks-per-producer form, two bin tiles per CTA at
+    # n_fft 2048) and 140 rows (beyond the tensor path: the fp32 CUDA-core kernel) compute the same function
+    for rows in (100, 140):
+        wide = o.create_mel_filter_bank(22050.0, n_fft, rows, 0.0, 8000.0)
+        vw = gl.GriffinLim.new(wide, n_fft - n_fft // 4, 1.7, 0, 0.99)
+        mw = o.synth_mel(77, rows, 70)
+        pw = vw.plan([70])
+        pw.upload(0, [mw])
+        pw.run(0)
+        ref = o.lift_pinv_clamp(mw, wide, 1.7, dtype=np.float64)
+        got = np.concatenate([pw.peek(0).T, pw.peek(1)[None, :]], 0)
+        assert np.abs(got - ref).max() / ref.max() < 1e-5, rows

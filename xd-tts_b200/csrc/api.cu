@@ -22,10 +22,10 @@
 
 namespace xdtts {
 // gl_lift.cu
-std::vector<float> gl_lift_build_image(const float* pinv, int K, int n_mels);
+std::vector<float> gl_lift_build_image(const float* pinv, int K, int n_mels, float* p_exp);
 int gl_lift_tile_frames();
 cudaError_t gl_lift_prepare(int n_mels);
-cudaError_t gl_launch_lift(const float* mel_arena, const float* a_image, const float* pinvT, const int4* tiles, int n_tiles,
+cudaError_t gl_launch_lift(const float* mel_arena, const float* a_image, float p_exp, const float* pinvT, const int4* tiles, int n_tiles,
                            const int* utt_T, const int* utt_foff, int n_utt, int max_T, int n_mels, int K, int ld, float power,
                            int delog, int sm_count, float* S, cudaStream_t s, int* n_kernels);
 bool gl_lift_uses_tensor_cores(int n_mels, int K);
@@ -322,7 +322,7 @@ extern "C" int xdtts_gl_create(const float* mel_basis, int n_mels, int K, int no
     std::vector<float2> tab = n_fft == 512 ? build_tables<4>() : (n_fft == 1024 ? build_tables<8>() : build_tables<16>());
     std::vector<float> edge = build_edge_scale(n_fft);
     cudaError_t e = cudaSuccess;
-    std::vector<float> img = gl_lift_build_image(h->pinv.data(), K, n_mels);
+    std::vector<float> img = gl_lift_build_image(h->pinv.data(), K, n_mels, &h->lift_p_exp);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_lift_img, img.size() * 4);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_lift_img, img.data(), img.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = gl_lift_prepare(n_mels);
@@ -629,7 +629,7 @@ static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid, cud
         CU(gl_launch_to_frame_major(p->d_in_mag, p->d_T, p->d_foff, p->B, p->max_T, h->K, d_S, p->rec_f, s));
     } else {
         const bool nnls = h->opts.lift == 1;
-        CU(gl_launch_lift(p->d_mel, h->d_lift_img, h->d_pinvT, p->d_lift_tiles, (int)p->lift_tiles.size(), p->d_T, p->d_foff, p->B,
+        CU(gl_launch_lift(p->d_mel, h->d_lift_img, h->lift_p_exp, h->d_pinvT, p->d_lift_tiles, (int)p->lift_tiles.size(), p->d_T, p->d_foff, p->B,
                           p->max_T, h->n_mels, h->K, p->rec_f, nnls ? 1.0f : h->power, h->opts.delog, h->sm_count, d_S, s, &lift_kernels));
         launched += (unsigned long long)(lift_kernels - 1);
         if (nnls) {   // refine the clipped least-squares start in place, then apply the exponent

@@ -43,7 +43,8 @@ struct xdtts_gl {
     xdtts_gl_opts opts{};
     std::vector<float> pinv;        // [K][n_mels] host copy
     float* d_pinvT = nullptr;       // [n_mels][K]
-    float* d_lift_img = nullptr;    // tf32 hi/lo tiles of the pseudo-inverse, pre-swizzled (gl_lift.cu)
+    float* d_lift_img = nullptr;    // fp16 hi/lo tiles of the scaled pseudo-inverse in the MMA's operand layout (gl_lift.cu)
+    float lift_p_exp = 0.f;         // ... which holds pinv * 2^lift_p_exp
     float2* d_tables = nullptr;
     float* d_edge = nullptr;
     int *d_csr = nullptr, *d_csc = nullptr;        // sparse forms of the mel basis for the NNLS lift (rows / columns)

@@ -4,28 +4,37 @@
 //
 // The product is a [bins x n_mels] . [n_mels x frames] GEMM with a tiny inner dimension (80): 82 kFLOP and
 // 2.4 kB per frame, i.e. HBM-bound -- IF the multiply-adds are off the CUDA cores (on the fp32 pipe the 1.3 G
-// FMAs of a 32 x 1000 batch alone take 35 us at 100% issue; the fp64 kernel of round 1 took 220-316 us).
-// One tile of the GEMM is
+// FMAs of a 32 x 1000 batch alone take 35 us at 100% issue; the fp64 kernel of round 1 took 220-316 us) AND the
+// de-logged mel tile is produced once per frame, not once per bin tile.  The second condition is a shared-memory
+// question: the pseudo-inverse P must stay resident next to the ring of mel tiles.
 //
-//     D[bin 0..127][frame 0..31] = sum_m P[bin][m] * E[frame][m]          (UMMA M = 128 bins, N = 32 frames)
+// Precision: P has 36% negative entries and the gate is 1e-5 of full scale, so one low-precision
+// pass is not enough (tf32: 9e-4).  Both operands are split in two fp16 halves, x = hi + lo with hi = fp16(x),
+// lo = fp16(x - hi): 22 significant bits, and D = Phi Ehi + Phi Elo + Plo Ehi in three passes of
+// tcgen05.mma kind::f16 into one fp32 accumulator -- 3e-7 of full scale, the same as the tf32 split this kernel
+// used before, at HALF the shared-memory bytes per element (4 instead of 8).  That is what lets ONE CTA hold all
+// four 128-bin tiles of P at n_fft 1024 (160 KB) beside a two-stage ring of 64-frame mel tiles (40 KB): before,
+// each of the four bin-tile CTAs of a frame tile repeated the exp / split / store of the same mel tile and the
+// kernel was issue-bound on exactly that work (45 us; now one conversion per frame).
+// fp16 has 5 exponent bits, so both operands are scaled by exact powers of two: P once on the host (largest entry
+// into [2^12, 2^13)), every frame of E by its own 2^(8 - ceil(log2 max_m E[m])) (a frame is a column of the GEMM, so
+// a per-frame factor commutes with it); the epilogue folds both exponents into the log2 it takes for ^power anyway.
 //
-// with both operands K-major (mel index contiguous) in 128-byte-swizzled shared memory and fp32 accumulation
-// in TMEM.  Precision: the pseudo-inverse has 36% negative entries and the gate is 1e-5 of full
-// scale; a single tf32 pass gives 9e-4, bf16 split in three 2e-5, tf32 split in three 3e-7 (the plain fp32 FMA
-// sum gives 5e-7) -- hence "tf32x3": x = hi + lo, D = Phi Ehi + Phi Elo + Plo Ehi, three passes of
-// tcgen05.mma kind::tf32 into the same accumulator.
+// One tile of the GEMM is D[bin 0..127][frame 0..63] = sum_m P[bin][m] E[frame][m] (UMMA M = 128 bins, N = 64
+// frames, K = 16 per instruction), both operands K-major in the un-swizzled core-matrix layout (8 rows x 16 bytes
+// contiguous; K-direction stride LBO, row-group stride SBO = 128 B): any n_mels that is a multiple of 16 is a
+// whole number of instructions (80 = 5), no padding to a swizzle atom, and a producer thread's 8 consecutive mel
+// rows of one frame are one conflict-free 16-byte shared-memory store.
+// Bins as the TMEM lane dimension make the epilogue's stores coalesced: for one frame (TMEM column) the 32 lanes
+// of a warp hold 32 consecutive bins = 128 contiguous bytes of the frame-major state record the iteration kernel reads.
 //
-// Work split: CTA (mt, g) owns bin tile mt (its P tile, hi and lo planes, stays in shared memory for the whole
-// kernel: one bulk copy of a pre-swizzled host-built image) and walks frame tiles g, g + G, ...  Bins as the
-// TMEM lane dimension make the epilogue's stores coalesced: for one frame (TMEM column) the 32 lanes of a warp
-// hold 32 consecutive bins = 128 contiguous bytes of the frame-major state record the iteration kernel reads.
-//
-// Warp roles (416 threads, one CTA per SM):
-//     warps 0-3   epilogue     tcgen05.ld (lane quarter = warp) -> clamp -> ^power -> S
-//     warps 4-11  producers    mel [n_mels][T] -> delog -> tf32 hi / lo -> swizzled E tile (4-stage ring, loads 3 tiles ahead)
-//     warp  12    TMEM alloc + one thread issuing the MMAs and commits
-// The Nyquist bin (bin M, a 129th row of the last tile otherwise) is summed by the producers of bin tile 0 on the
+// Warp roles (608 threads, one CTA per SM; CTA (part, g) owns bin tiles part*nbt .. +nbt-1 and frame tiles g, g+G, ...):
+//     warps 0-7    epilogue     tcgen05.ld (lane quarter = warp & 3, column half = warp >> 2) -> clamp -> ^power -> S
+//     warps 8-17   producers    mel [n_mels][T] -> per-frame scale -> delog -> fp16 hi / lo -> E tile (loads one tile ahead)
+//     warp  18     TMEM alloc + one thread issuing the bulk copy of P, the MMAs and the commits
+// The Nyquist bin (bin M, a 129th row of the last tile otherwise) is summed by the producers of part 0 on the
 // CUDA cores, from the de-logged values they hold anyway.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -41,20 +50,24 @@ namespace xdtts {
 namespace {
 
 // timing experiments only (tools/build_lift_variants.py): bit 0 skips the MMAs, bit 1 the epilogue's math and stores,
-// bit 2 the producers' conversion and shared-memory stores.  0 in the product.
+// bit 2 the producers' conversion.  0 in the product.
 #ifndef XDTTS_LIFT_SKIP
 #define XDTTS_LIFT_SKIP 0
 #endif
 
 constexpr int LT_BM = 128;       // bins per tile
 constexpr int LT_BN = 64;        // frames per tile
-constexpr int LT_STAGES = 2;     // E-tile ring and TMEM accumulators
-constexpr int LT_AHEAD = 1;      // tiles whose mel loads are in flight ahead of the conversion
-constexpr int LT_EPI_WARPS = 4;   // epilogue warps: TMEM lane quarter = warp (13 warps keep 128 registers per thread)
-constexpr int LT_PRO_WARPS = 8;   // producer warps: frame groups (warp & 3, + 4), mel half = warp >> 2
+constexpr int LT_STAGES = 2;     // E-tile ring and TMEM accumulator sets
+constexpr int LT_MAX_BT = 4;     // bin tiles resident per CTA (TMEM: LT_STAGES * 4 * 64 = 512 columns)
+constexpr int LT_TILE_SM = 64;   // tile records staged in shared memory per CTA
+constexpr int LT_MAX_KC = 16;    // K chunks of 8 mel rows: n_mels <= 128; wider bases take gl_lift_f32_kernel
+constexpr int LT_EPI_WARPS = 8;
+constexpr int LT_PRO_WARPS = 10;
+constexpr int LT_PGROUPS = LT_PRO_WARPS * 32 / LT_BN;   // producer thread (frame f, chunk group cg): chunks cg, cg + 5, ...
 constexpr int LT_THREADS = 32 * (LT_EPI_WARPS + LT_PRO_WARPS + 1);
-constexpr int LT_TILE_SM = 128;  // tile records staged in shared memory per CTA
-constexpr int LT_MAX_KB = 3;     // shared memory holds the P tile (2 planes) + the E ring for n_mels <= 96; wider bases take gl_lift_f32_kernel
+constexpr int LT_CF_RING = 2 * LT_STAGES;   // per-frame exponents: written up to 2 stages ahead of the epilogue that reads them
+constexpr int LT_E_SHIFT = 8;    // a frame's largest de-logged value lands in (2^7, 2^8]
+constexpr int LT_SMEM_MAX = 232448;   // 227 KB
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -87,16 +100,30 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem], tf32 inputs (fp32 containers, low 13 mantissa bits ignored), fp32 accumulate
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem], fp16 inputs, fp32 accumulate.  The two shared-memory descriptors share their high word.
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
         "}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
     asm volatile(
@@ -108,31 +135,32 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major tile with 128-byte rows (32 tf32) in the 128-byte swizzle: 8-row groups 1024 B apart (SBO), version 1
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
+// Shared-memory descriptors (K-major operand in the un-swizzled layout): a core matrix is 8 rows x 16 bytes, contiguous
+// (128 B); the two core matrices one instruction reads along K are LBO bytes apart, consecutive 8-row groups SBO bytes
+// apart.  Low word: address >> 4 (bits 0-13), LBO >> 4 (bits 16-29); high word: SBO >> 4 (bits 0-13), version 1 (bit 14),
+// layout type 0 = no swizzle (bits 29-31).
 
-// round to tf32 (10 mantissa bits), nearest with ties away from zero -- cvt.rna.tf32.f32, which sm_100 expands
-// into ~15 instructions; for the finite values of this kernel the two integer operations below are the same function
-// (and the host builds the pseudo-inverse image with them, tf32_rna_bits)
-__device__ __forceinline__ float to_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
-
-// e^v (DELOG 0) / 10^v (DELOG 1) in six instructions: 2^t with t = v * c split so that the rounding of the product
-// is carried into a first-order correction -- t = fl(v c_hi), r = (v c_hi - t) + v c_lo exactly, e = 2^t (1 + r ln 2).
-// ~1.5 ulp (ex2.approx is 2 ulp), against ~15 instructions for expf(); exp(-inf) = 0 without a branch.
+// The de-log as 2^t: t = v * c with the rounding of the product carried into a first-order correction --
+// t = fl(v c_hi), r = (v c_hi - t) + v c_lo exactly, e = 2^t (1 + r ln 2).  ~1.5 ulp (ex2.approx is 2 ulp), seven
+// instructions with the frame's power-of-two scale against ~15 for expf().
 template <int DELOG>
-__device__ __forceinline__ float delog_value(float v) {
-    if (DELOG == 2) return v;
-    const float c_hi = DELOG == 0 ? 1.4426950216293335f : 3.3219280242919922f;      // log2(e), log2(10) rounded to fp32
-    const float c_lo = DELOG == 0 ? 1.9259629911266175e-8f : 7.0595369550985533e-8f; // ... and what the rounding dropped
-    const float t = v * c_hi;
-    float r = fmaf(v, c_hi, -t);
-    r = fmaf(v, c_lo, r);
+struct Delog {
+    static constexpr float c_hi = DELOG == 0 ? 1.4426950216293335f : 3.3219280242919922f;       // log2(e), log2(10) rounded to fp32
+    static constexpr float c_lo = DELOG == 0 ? 1.9259629911266175e-8f : 7.0595369550985533e-8f;  // ... and what the rounding dropped
+};
+template <int DELOG>
+__device__ __forceinline__ float delog_scaled(float v, float sc) {   // delog(v) * sc, sc a power of two (exact); -inf (no sample) -> 0
+    if (DELOG == 2) return v == -INFINITY ? 0.f : v * sc;
+    const float t = v * Delog<DELOG>::c_hi;
+    float r = fmaf(v, Delog<DELOG>::c_hi, -t);
+    r = fmaf(v, Delog<DELOG>::c_lo, r);
     float p;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(t));
+    p *= sc;   // not 2^(t - shift): that subtraction rounds the exponent at 2^-21 for the very values that matter
     return v == -INFINITY ? 0.f : fmaf(p, r * 0.69314718055994531f, p);
 }
+template <int DELOG>
+__device__ __forceinline__ float delog_value(float v) { return delog_scaled<DELOG>(v, 1.f); }
 
 // s ^ power for s > 0 on the special-function unit: 2^(power * log2 s), two MUFU operations and a multiply.  ~1e-6
 // relative at full scale (the gate on S is 1e-5 of full scale, tests/test_gpu_gl.py::test_lift_matches_oracle); powf
@@ -143,225 +171,274 @@ __device__ __forceinline__ float pow_pos(float s, float power) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * power));
     return r;
 }
+__device__ __forceinline__ float exp2_int(int e) {   // 2^e, e clamped to the normal range
+    return __int_as_float(min(max(e + 127, 1), 254) << 23);
+}
 
 struct LiftParams {
     const float* mel_arena;      // utterance u: row-major [n_mels][T_u] at float offset foff[u] * n_mels
-    const float* a_image;        // [n_mt][2 planes][kblocks][128 rows][32] tf32 values, rows pre-swizzled
+    const uint8_t* a_image;      // [n_mt][2 planes][kchunks][128 rows][8 fp16]: the scaled pseudo-inverse, hi / lo halves
     const float* pinv_nyq;       // the pseudo-inverse's row of bin M: entry m at pinv_nyq[m * pinv_ld]
     int pinv_ld;
     const int4* tiles;           // frame tiles: (first frame row of the utterance, its frame count T, first frame of the tile, 0)
     float* S;                    // frame-major state records: S[(foff + t) * ld + k], k < M
-    int n_tiles, n_mt, groups, n_mels, kblocks, ld;
+    int n_tiles, n_mt, nbt, n_part, groups, n_mels, kchunks, ld;
     float power;
+    float p_exp;                 // the image holds P * 2^p_exp
 };
 
 struct LiftSmem {
-    // [A hi | A lo] then the E ring (per stage [E hi | E lo]); every tile 1024-byte aligned
-    __host__ __device__ static int a_plane(int kblocks) { return kblocks * LT_BM * 128; }
-    __host__ __device__ static int e_plane(int kblocks) { return kblocks * LT_BN * 128; }
-    __host__ __device__ static int bar_off(int kblocks) { return 2 * a_plane(kblocks) + LT_STAGES * 2 * e_plane(kblocks); }
-    __host__ __device__ static int total(int kblocks) { return bar_off(kblocks) + 8 * (4 * LT_STAGES + 4) + 4 * 32 * LT_MAX_KB + 4 * LT_STAGES * LT_BN + 16 * LT_TILE_SM + 1024; }
+    // [P: nbt tiles x (hi | lo)] then the E ring (per stage [hi | lo]), then barriers and the small tables
+    __host__ __device__ static int a_tile(int kchunks) { return 2 * kchunks * LT_BM * 16; }
+    __host__ __device__ static int e_plane(int kchunks) { return kchunks * LT_BN * 16; }
+    __host__ __device__ static int bar_off(int nbt, int kchunks) { return nbt * a_tile(kchunks) + LT_STAGES * 2 * e_plane(kchunks); }
+    static constexpr int N_BARS = 3 * LT_STAGES + LT_STAGES * LT_MAX_BT + LT_MAX_BT;
+    static constexpr int BAR_SLOTS = (N_BARS + 1 + 1) & ~1;   // barriers + the TMEM address, padded to 16 bytes
+    static constexpr int TAIL = 8 * BAR_SLOTS + 4 * (8 * LT_MAX_KC + 2 * 2 * LT_PGROUPS * LT_BN + LT_CF_RING * LT_BN) + 16 * LT_TILE_SM;
+    __host__ __device__ static int total(int nbt, int kchunks) { return bar_off(nbt, kchunks) + TAIL + 16; }
 };
 
-template <int DELOG>
+template <int DELOG, int CPT>   // CPT: K chunks per producer thread (ceil(kchunks / LT_PGROUPS))
 __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int a_plane = LiftSmem::a_plane(p.kblocks), e_plane = LiftSmem::e_plane(p.kblocks);
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 15) & ~(uintptr_t)15);
+    const int a_tile = LiftSmem::a_tile(p.kchunks), e_plane = LiftSmem::e_plane(p.kchunks);
     uint8_t* sa = smem;
-    uint8_t* se = smem + 2 * a_plane;
-    uint64_t* bars = (uint64_t*)(smem + LiftSmem::bar_off(p.kblocks));
-    uint64_t* full = bars;                       // [S] E stage written (all producer threads arrive)
-    uint64_t* empty = bars + LT_STAGES;          // [S] E stage consumed (tcgen05.commit)
-    uint64_t* tfull = bars + 2 * LT_STAGES;      // [S] accumulator complete
-    uint64_t* tempty = bars + 3 * LT_STAGES;     // [S] accumulator drained (the epilogue warps)
-    uint64_t* a_bar = bars + 4 * LT_STAGES;      // P tile landed
-    uint32_t* tmem_ptr = (uint32_t*)(bars + 4 * LT_STAGES + 2);
-    float* wn = (float*)(bars + 4 * LT_STAGES + 4);        // [32 LT_MAX_KB] the pseudo-inverse's Nyquist row (bin M)
-    float* nq_sm = wn + 32 * LT_MAX_KB;                     // [S][LT_BN] Nyquist partial sums of the upper mel half
-    int4* tile_sm = (int4*)(nq_sm + LT_STAGES * LT_BN);     // this CTA's first LT_TILE_SM tile records (a global read per tile and
-                                                            // role is a serialised L2 round trip: a third of all stall samples before)
+    uint8_t* se = smem + p.nbt * a_tile;
+    uint64_t* bars = (uint64_t*)(smem + LiftSmem::bar_off(p.nbt, p.kchunks));
+    uint64_t* full = bars;                               // [S] E stage written (one arrival per producer warp)
+    uint64_t* empty = bars + LT_STAGES;                  // [S] E stage consumed (tcgen05.commit)
+    uint64_t* tempty = bars + 2 * LT_STAGES;             // [S] accumulator set drained (the epilogue warps)
+    uint64_t* tfull = bars + 3 * LT_STAGES;              // [S][LT_MAX_BT] accumulator of one bin tile complete
+    uint64_t* a_bar = tfull + LT_STAGES * LT_MAX_BT;     // [LT_MAX_BT] bin tile of P landed
+    uint32_t* tmem_ptr = (uint32_t*)(a_bar + LT_MAX_BT);
+    float* wn = (float*)(bars + LiftSmem::BAR_SLOTS);       // [8 LT_MAX_KC] the pseudo-inverse's Nyquist row (bin M)
+    float* pmax = wn + 8 * LT_MAX_KC;                    // [2][LT_PGROUPS][LT_BN] per-group maxima of a frame's mel column
+    float* nqp = pmax + 2 * LT_PGROUPS * LT_BN;          // [2][LT_PGROUPS][LT_BN] per-group partial sums of the Nyquist bin
+    float* cfac = nqp + 2 * LT_PGROUPS * LT_BN;          // [LT_CF_RING][LT_BN] power of two the epilogue owes each frame
+    int4* tile_sm = (int4*)(cfac + LT_CF_RING * LT_BN);  // this CTA's first LT_TILE_SM tile records (a global read per tile and
+                                                         // role is a serialised L2 round trip)
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mt = blockIdx.x % p.n_mt, g = blockIdx.x / p.n_mt;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // the shuffle tells the compiler it is warp-uniform
+    const int part = blockIdx.x % p.n_part, g = blockIdx.x / p.n_part;
+    const int nbt = p.nbt;
+    const uint32_t tmem_cols = nbt * LT_STAGES * LT_BN <= 128 ? 128u : (nbt * LT_STAGES * LT_BN <= 256 ? 256u : 512u);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < LT_STAGES; s++) {
-            mbar_init(&full[s], 32 * LT_PRO_WARPS);
+            mbar_init(&full[s], LT_PRO_WARPS);
             mbar_init(&empty[s], 1);
-            mbar_init(&tfull[s], 1);
             mbar_init(&tempty[s], LT_EPI_WARPS);
+            for (int b = 0; b < LT_MAX_BT; b++) mbar_init(&tfull[s * LT_MAX_BT + b], 1);
         }
-        mbar_init(a_bar, 1);
+        for (int b = 0; b < LT_MAX_BT; b++) mbar_init(&a_bar[b], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == LT_EPI_WARPS + LT_PRO_WARPS) {   // LT_STAGES accumulators of 128 lanes x LT_BN fp32 columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)(LT_STAGES * LT_BN)) : "memory");
+    if (warp == LT_EPI_WARPS + LT_PRO_WARPS) {   // LT_STAGES sets of nbt accumulators, 128 lanes x LT_BN fp32 columns each
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < 32 * LT_MAX_KB; i += LT_THREADS) wn[i] = i < p.n_mels ? p.pinv_nyq[(size_t)i * p.pinv_ld] : 0.f;
+    for (int i = threadIdx.x; i < 8 * LT_MAX_KC; i += LT_THREADS) wn[i] = i < p.n_mels ? p.pinv_nyq[(size_t)i * p.pinv_ld] : 0.f;
     for (int i = threadIdx.x; i < LT_TILE_SM && g + i * p.groups < p.n_tiles; i += LT_THREADS) tile_sm[i] = p.tiles[g + i * p.groups];
     auto tile_rec = [&](int it_) -> int4 { return it_ < LT_TILE_SM ? tile_sm[it_] : p.tiles[g + it_ * p.groups]; };
-    // the zero padding of the E tiles (mel indices n_mels .. 32 kblocks - 1) is written once: producers only touch k < n_mels
-    for (int i = threadIdx.x; i < LT_STAGES * 2 * e_plane / 16; i += LT_THREADS) reinterpret_cast<uint4*>(se)[i] = make_uint4(0, 0, 0, 0);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
     const int my_tiles = g < p.n_tiles ? (p.n_tiles - g + p.groups - 1) / p.groups : 0;   // tiles g, g + G, ... of this CTA
 
     if (warp == LT_EPI_WARPS + LT_PRO_WARPS) {
-        // ===================== MMA issuer
-        if (lane == 0) {
-            mbar_expect_tx(a_bar, (uint32_t)(2 * a_plane));
-            bulk_g2s(sa, p.a_image + (size_t)mt * (2 * a_plane / 4), (uint32_t)(2 * a_plane), a_bar);
-            // instruction descriptor: D fp32, A/B tf32, both K-major, N = LT_BN, M = 128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(LT_BN >> 3) << 17) | ((uint32_t)(LT_BM >> 4) << 24);
-            mbar_wait(a_bar, 0);
-            for (int it = 0; it < my_tiles; it++) {
-                const int s = it % LT_STAGES;
-                const uint32_t ph = (uint32_t)((it / LT_STAGES) & 1);
-                mbar_wait(&tempty[s], ph ^ 1u);   // epilogue has drained this accumulator
-                mbar_wait(&full[s], ph);          // producers have written this E stage
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(s * LT_BN);
-                const uint32_t e_hi = smem_u32(se + s * 2 * e_plane), e_lo = e_hi + e_plane;
-                const uint32_t a_hi = smem_u32(sa), a_lo = a_hi + a_plane;
-                uint32_t acc = 0;
-                for (int pass = 0; pass < 3; pass++) {   // Phi Ehi, Phi Elo, Plo Ehi
-                    const uint32_t ab = pass == 2 ? a_lo : a_hi, eb = pass == 1 ? e_lo : e_hi;
-                    for (int kb = 0; kb < p.kblocks; kb++) {
-                        const uint64_t da = umma_desc_sw128(ab + kb * (LT_BM * 128)), db = umma_desc_sw128(eb + kb * (LT_BN * 128));
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {   // UMMA_K = 8 tf32 = 32 B along the swizzled row: +2 in the address field
-                            if (!(XDTTS_LIFT_SKIP & 1)) tc_mma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc);
-                            acc = 1;
-                        }
-                    }
-                }
-                tc_commit(&empty[s]);    // E stage free when these MMAs retire
-                tc_commit(&tfull[s]);    // accumulator complete -> epilogue
+        // ===================== MMA issuer.  The whole warp walks the loop (warp-uniform control flow and operands: the
+        // descriptors live in uniform registers, ~3 instructions per MMA; issued from inside a one-lane branch each MMA cost
+        // ~20 dependent instructions of one warp = 120 cycles against the 32 the tensor pipe needs); one elected lane issues.
+        const bool leader = elect_one();
+        if (leader) {
+            for (int b = 0; b < nbt; b++) {   // one bulk copy per bin tile: the first MMAs start when a quarter of P has landed
+                mbar_expect_tx(&a_bar[b], (uint32_t)a_tile);
+                bulk_g2s(sa + b * a_tile, p.a_image + (size_t)(part * nbt + b) * a_tile, (uint32_t)a_tile, &a_bar[b]);
             }
         }
-    } else if (warp >= LT_EPI_WARPS) {
-        // ===================== producers.  A warp covers 4 mel rows x 8 frames per step (conflict-free swizzled stores,
-        // four full 32-byte sectors per global load); producer warp w owns frame group w & 3 of the tile (a lane: frame
-        // f = 8 (w & 3) + lane / 4) and the mel-row groups of half w >> 2 (a lane: rows 4 mg + lane % 4).  Loads run
-        // LT_AHEAD tiles ahead of the conversion, so DRAM latency hides behind the tiles in flight.
-        const int pw = (warp - LT_EPI_WARPS) & 3, mh = (warp - LT_EPI_WARPS) >> 2;
-        const int m4 = lane & 3, f8 = lane >> 2;
-        constexpr int FG = LT_BN / 32;                      // frame groups of 8 per producer warp: frames 8 pw + f8 + 32 h
-        const int f = pw * 8 + f8;
-        constexpr int MGT = LT_MAX_KB * 8;                  // mel groups of 4 in a padded tile (24)
-        constexpr int MG = MGT / (LT_PRO_WARPS / 4);        // ... of which this warp converts MG, starting at mg0
-        const int mg0 = mh * MG;
-        const int mgroups = (p.n_mels + 3) / 4;
-        float wreg[MG];                                     // this lane's entries of the pseudo-inverse's Nyquist row
+        // instruction descriptor: D fp32, A/B fp16, both K-major, N = LT_BN, M = 128
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(LT_BN >> 3) << 17) | ((uint32_t)(LT_BM >> 4) << 24);
+        constexpr uint32_t A_LBO = LT_BM * 16, E_LBO = LT_BN * 16, SBO = 128;
+        constexpr uint32_t A_HI = ((A_LBO >> 4) << 16), E_HI = ((E_LBO >> 4) << 16);   // low words' LBO fields
+        constexpr uint32_t D_HI = (SBO >> 4) | (1u << 14);                               // high word: SBO, version 1
+        const int ksteps = p.kchunks >> 1;
+        const uint32_t sa_u = smem_u32(sa), se_u = smem_u32(se);
+        for (int it = 0; it < my_tiles; it++) {
+            const int s = it % LT_STAGES;
+            const uint32_t ph = (uint32_t)((it / LT_STAGES) & 1);
+            mbar_wait(&tempty[s], ph ^ 1u);   // epilogue has drained this accumulator set
+            mbar_wait(&full[s], ph);          // producers have written this E stage
+            tc_fence_after();
+            const uint32_t e_hi = ((se_u + (uint32_t)(s * 2 * e_plane)) >> 4) | E_HI, e_lo = e_hi + (uint32_t)(e_plane >> 4);
+            for (int b = 0; b < nbt; b++) {
+                mbar_wait(&a_bar[b], 0);
+                const uint32_t d_tmem = tmem_base + (uint32_t)((s * nbt + b) * LT_BN);
+                const uint32_t a_hi = ((sa_u + (uint32_t)(b * a_tile)) >> 4) | A_HI, a_lo = a_hi + (uint32_t)(a_tile >> 5);
+                if (leader) {
 #pragma unroll
-        for (int mg = 0; mg < MG; mg++) wreg[mg] = wn[(mg0 + mg) * 4 + m4];
-        float xq[LT_AHEAD][FG * MG];
+                    for (int pass = 0; pass < 3; pass++) {   // Phi Ehi, Phi Elo, Plo Ehi
+                        const uint32_t ab = pass == 2 ? a_lo : a_hi, eb = pass == 1 ? e_lo : e_hi;
+#pragma unroll
+                        for (int k = 0; k < LT_MAX_KC / 2; k++)   // UMMA_K = 16 fp16 = two K chunks: the address field moves by 2 LBO
+                            if (k < ksteps && !(XDTTS_LIFT_SKIP & 1))
+                                tc_mma_f16(d_tmem, ab + (uint32_t)k * (2 * A_LBO >> 4), eb + (uint32_t)k * (2 * E_LBO >> 4), D_HI, idesc, (pass | k) ? 1u : 0u);
+                    }
+                    tc_commit(&tfull[s * LT_MAX_BT + b]);   // this bin tile's accumulator complete -> epilogue
+                }
+            }
+            if (leader) tc_commit(&empty[s]);    // E stage free when these MMAs retire
+            __syncwarp();
+        }
+    } else if (warp >= LT_EPI_WARPS) {
+        // ===================== producers.  Thread (f, cg): frame f of the tile, K chunks cg, cg + 5, ... (8 mel rows each).
+        // A warp's 32 lanes are 32 consecutive frames of one mel row: every global load is one 128-byte line, every
+        // shared-memory store 32 consecutive 16-byte core-matrix rows.  Loads run one tile ahead of the conversion.
+        const int ptid = threadIdx.x - 32 * LT_EPI_WARPS;
+        const int f = ptid & (LT_BN - 1), cg = ptid / LT_BN;
+        constexpr int NX = CPT * 8;
+        constexpr bool AHEAD = CPT <= 2;                 // the prefetched tile lives in registers
+        float wreg[NX];                                  // this thread's entries of the pseudo-inverse's Nyquist row
+#pragma unroll
+        for (int j = 0; j < CPT; j++)
+#pragma unroll
+            for (int r = 0; r < 8; r++) wreg[8 * j + r] = (cg + LT_PGROUPS * j) < p.kchunks ? wn[(cg + LT_PGROUPS * j) * 8 + r] : 0.f;
         auto issue_loads = [&](int it_, float* x) {
             const int4 tl = tile_rec(it_);
             const int T = tl.y;
-            const float* src = p.mel_arena + (size_t)tl.x * p.n_mels + tl.z + f;   // row 0 of the utterance, this lane's first frame
-            int off = (mg0 * 4 + m4) * T;   // 32-bit: a plan holds fewer than 2^31 / K frames
+            const bool fv = tl.z + f < T;
+            const float* src = p.mel_arena + (size_t)tl.x * p.n_mels + tl.z + f;   // row 0 of the utterance, this thread's frame
 #pragma unroll
-            for (int mg = 0; mg < MG; mg++) {
-                const bool mv = (mg0 + mg) * 4 + m4 < p.n_mels;
+            for (int j = 0; j < CPT; j++)
 #pragma unroll
-                for (int h = 0; h < FG; h++) x[FG * mg + h] = (mv && tl.z + f + 32 * h < T) ? __ldg(src + off + 32 * h) : -INFINITY;   // -inf: no sample
-                off += 4 * T;
+                for (int r = 0; r < 8; r++) {
+                    const int m = (cg + LT_PGROUPS * j) * 8 + r;   // 32-bit offsets: a plan holds fewer than 2^31 / K frames
+                    x[8 * j + r] = (fv && m < p.n_mels) ? __ldg(src + m * T) : -INFINITY;   // -inf: no sample
+                }
+        };
+        float xq[NX];
+        if (AHEAD && my_tiles > 0) issue_loads(0, xq);
+        float nq_prev = 0.f, sh_prev = 0.f;   // cg == 0: the Nyquist partial sum and 2^shift of the previous tile
+        int4 tl_prev = make_int4(0, 0, 0, 0);
+        auto finish_nyquist = [&](int it_prev) {   // after the producers' barrier that follows tile it_prev
+            if (part == 0 && cg == 0 && tl_prev.z + f < tl_prev.y) {
+                float v = nq_prev;
+                const float* pp = nqp + (it_prev & 1) * LT_PGROUPS * LT_BN + f;
+#pragma unroll
+                for (int c = 1; c < LT_PGROUPS; c++) v += pp[c * LT_BN];
+                p.S[((size_t)tl_prev.x + tl_prev.z + f) * p.ld + p.n_mt * LT_BM] =
+                    p.power == 1.0f ? fmaxf(v * sh_prev, 0.f) : pow_pos(v * sh_prev, p.power);
             }
         };
-#pragma unroll
-        for (int a = 0; a < LT_AHEAD; a++)
-            if (a < my_tiles) issue_loads(a, xq[a]);
         for (int it = 0; it < my_tiles; it++) {
             const int s = it % LT_STAGES;
-            float x[FG * MG];
+            float x[NX];
+            if (AHEAD) {
 #pragma unroll
-            for (int i = 0; i < FG * MG; i++) x[i] = xq[0][i];
+                for (int i = 0; i < NX; i++) x[i] = xq[i];
+                if (it + 1 < my_tiles) issue_loads(it + 1, xq);
+            } else {
+                issue_loads(it, x);
+            }
+            // the frame's exponent: every value of the column is scaled by 2^-shift so that the largest lands in (2^7, 2^8]
+            float mx = DELOG == 2 ? 0.f : -INFINITY;
 #pragma unroll
-            for (int a = 0; a + 1 < LT_AHEAD; a++)
+            for (int i = 0; i < NX; i++) mx = DELOG == 2 ? fmaxf(mx, x[i] == -INFINITY ? 0.f : fabsf(x[i])) : fmaxf(mx, x[i]);
+            float* pm = pmax + (it & 1) * LT_PGROUPS * LT_BN + f;
+            pm[cg * LT_BN] = mx;
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * LT_PRO_WARPS) : "memory");
 #pragma unroll
-                for (int i = 0; i < FG * MG; i++) xq[a][i] = xq[a + 1][i];
-            if (it + LT_AHEAD < my_tiles) issue_loads(it + LT_AHEAD, xq[LT_AHEAD - 1]);
+            for (int c = 0; c < LT_PGROUPS; c++) mx = fmaxf(mx, pm[c * LT_BN]);
+            float shift;
+            if (DELOG == 2) shift = (float)((int)((__float_as_uint(mx) >> 23) & 0xFFu) - 126);   // mx < 2^shift
+            else shift = ceilf(mx * Delog<DELOG>::c_hi);
+            shift = fminf(fmaxf(shift, -100.f), 118.f) - (float)LT_E_SHIFT;
+            const float sc = __int_as_float((127 - (int)shift) << 23);   // 2^-shift
+            if (it > 0) finish_nyquist(it - 1);
             mbar_wait(&empty[s], (uint32_t)((it / LT_STAGES) & 1) ^ 1u);
-            uint8_t* ehi = se + s * 2 * e_plane + f * 128 + m4 * 4;
-            float nq[FG];   // Nyquist-bin partial sums of this lane's frames
+            uint8_t* ehi = se + s * 2 * e_plane + f * 16;
+            float nq = 0.f;
 #pragma unroll
-            for (int h = 0; h < FG; h++) nq[h] = 0.f;
+            for (int j = 0; j < CPT; j++) {
+                const int c = cg + LT_PGROUPS * j;
+                if (!(XDTTS_LIFT_SKIP & 4) && c < p.kchunks) {
+                    uint32_t hw[4], lw[4];
 #pragma unroll
-            for (int mg = 0; mg < MG; mg++) {
-                const int mgg = mg0 + mg;
-                if (!(XDTTS_LIFT_SKIP & 4) && mgg < mgroups && mgg * 4 + m4 < p.n_mels) {
-                    // row f of K-block mgg >> 3, 16-byte chunk (mgg & 7) ^ (f & 7) (f & 7 == f8 for every h), element m4
-                    const int off = (mgg >> 3) * (LT_BN * 128) + (((mgg & 7) ^ f8) << 4);
-#pragma unroll
-                    for (int h = 0; h < FG; h++) {
-                        const float v = x[FG * mg + h];
-                        float e = delog_value<DELOG>(v);               // -inf (no sample) -> 0
-                        if (DELOG == 2) e = v == -INFINITY ? 0.f : e;
-                        const float hi = to_tf32(e);
-                        const float lo = to_tf32(e - hi);
-                        *reinterpret_cast<float*>(ehi + off + h * (32 * 128)) = hi;
-                        *reinterpret_cast<float*>(ehi + e_plane + off + h * (32 * 128)) = lo;
-                        nq[h] = fmaf(wreg[mg], e, nq[h]);
+                    for (int r = 0; r < 8; r += 2) {
+                        const float e0 = delog_scaled<DELOG>(x[8 * j + r], sc), e1 = delog_scaled<DELOG>(x[8 * j + r + 1], sc);
+                        nq = fmaf(wreg[8 * j + r], e0, nq);
+                        nq = fmaf(wreg[8 * j + r + 1], e1, nq);
+                        const __half2 h = __floats2half2_rn(e0, e1);
+                        const float2 hf = __half22float2(h);
+                        const __half2 l = __floats2half2_rn(e0 - hf.x, e1 - hf.y);
+                        hw[r >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+                        lw[r >> 1] = *reinterpret_cast<const uint32_t*>(&l);
                     }
+                    *reinterpret_cast<uint4*>(ehi + c * (LT_BN * 16)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    *reinterpret_cast<uint4*>(ehi + e_plane + c * (LT_BN * 16)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                 }
             }
+            // D = (P 2^p_exp)(E 2^-shift): the accumulator owes 2^(shift - p_exp).  A factor, not an exponent added to the
+            // epilogue's log2: log2 of the raw accumulator (~2^20) would be rounded at 2^-19, 1e-6 of the result after ^power
+            if (cg == 0) cfac[(it % LT_CF_RING) * LT_BN + f] = exp2_int((int)shift - (int)p.p_exp);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async proxy
-            mbar_arrive(&full[s]);
-            if (mt == 0) {   // the Nyquist bin (slot M of the frame's record): sum over the four lanes that share a frame,
-                             // then over the two warps that share the frame (one per half of the mel rows)
-                float* part = nq_sm + s * LT_BN;   // the upper half's partial sums of this stage
-#pragma unroll
-                for (int h = 0; h < FG; h++) {
-                    nq[h] += __shfl_xor_sync(0xffffffffu, nq[h], 1);
-                    nq[h] += __shfl_xor_sync(0xffffffffu, nq[h], 2);
-                    if (mh == 1 && m4 == 0) part[f + 32 * h] = nq[h];
-                }
-                asm volatile("bar.sync %0, %1;" ::"r"(1 + pw), "r"(64) : "memory");   // the two warps of frame group pw
-                const int4 tl = tile_rec(it);
-#pragma unroll
-                for (int h = 0; h < FG; h++)
-                    if (mh == 0 && m4 == 0 && tl.z + f + 32 * h < tl.y) {
-                        const float v = nq[h] + part[f + 32 * h];
-                        p.S[((size_t)tl.x + tl.z + f + 32 * h) * p.ld + p.n_mt * LT_BM] = p.power == 1.0f ? fmaxf(v, 0.f) : pow_pos(v, p.power);
-                    }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+            if (cg == 0) {
+                nq_prev = nq;
+                sh_prev = exp2_int((int)shift);
+                tl_prev = tile_rec(it);
+            } else {
+                nqp[((it & 1) * LT_PGROUPS + cg) * LT_BN + f] = nq;
             }
         }
+        if (my_tiles > 0) {
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * LT_PRO_WARPS) : "memory");
+            finish_nyquist(my_tiles - 1);
+        }
     } else {
-        // ===================== epilogue: TMEM lane quarter q <-> bins mt*128 + 32 q + lane
-        const int q = warp & 3;
-        const int bin = mt * LT_BM + q * 32 + lane;
+        // ===================== epilogue: TMEM lane quarter q <-> bins bt*128 + 32 q + lane; column half ch
+        const int q = warp & 3, ch = warp >> 2;
+        constexpr int CW = LT_BN / (LT_EPI_WARPS / 4);
         const bool plain = p.power == 1.0f;
         for (int it = 0; it < my_tiles; it++) {
             const int s = it % LT_STAGES;
+            const uint32_t ph = (uint32_t)((it / LT_STAGES) & 1);
             const int4 tl = tile_rec(it);
-            const int nf = min(LT_BN, tl.y - tl.z);   // frames of this tile that exist
-            float* out = p.S + ((size_t)tl.x + tl.z) * p.ld + bin;
-            mbar_wait(&tfull[s], (uint32_t)((it / LT_STAGES) & 1));
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * LT_BN);
-            const bool full_tile = nf >= LT_BN;   // all but an utterance's last tile
+            const int nf = min(LT_BN, tl.y - tl.z) - ch * CW;   // frames of this warp's columns that exist
+            const bool full_tile = nf >= CW;                    // all but an utterance's last tile
+            float* out0 = p.S + ((size_t)tl.x + tl.z + ch * CW) * p.ld + (part * nbt) * LT_BM + q * 32 + lane;
+            const float4* cf4 = reinterpret_cast<const float4*>(cfac + (it % LT_CF_RING) * LT_BN + ch * CW);
+            for (int b = 0; b < nbt; b++) {
+                mbar_wait(&tfull[s * LT_MAX_BT + b], ph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((s * nbt + b) * LT_BN + ch * CW);
+                float* out = out0 + b * LT_BM;
 #pragma unroll
-            for (int c0 = 0; c0 < ((XDTTS_LIFT_SKIP & 2) ? 0 : LT_BN); c0 += 16) {
-                uint32_t v[16];
-                tc_ld16(taddr + (uint32_t)c0, v);
-                tc_wait_ld();
-                float r[16];
+                for (int c0 = 0; c0 < ((XDTTS_LIFT_SKIP & 2) ? 0 : CW); c0 += 16) {
+                    uint32_t v[16];
+                    tc_ld16(taddr + (uint32_t)c0, v);
+                    float cf[16];
 #pragma unroll
-                for (int i = 0; i < 16; i++) r[i] = plain ? fmaxf(__uint_as_float(v[i]), 0.f) : pow_pos(__uint_as_float(v[i]), p.power);
-                // 32 lanes = 32 consecutive bins of one frame: every store is one 128-byte line
-                if (full_tile) {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) __stcs(out + (c0 + i) * p.ld, r[i]);
-                } else {
+                    for (int i = 0; i < 4; i++) {
+                        const float4 c = cf4[(c0 >> 2) + i];
+                        cf[4 * i] = c.x; cf[4 * i + 1] = c.y; cf[4 * i + 2] = c.z; cf[4 * i + 3] = c.w;
+                    }
+                    tc_wait_ld();
+                    float r[16];
 #pragma unroll
                     for (int i = 0; i < 16; i++)
-                        if (c0 + i < nf) __stcs(out + (c0 + i) * p.ld, r[i]);
+                        r[i] = plain ? fmaxf(__uint_as_float(v[i]) * cf[i], 0.f) : pow_pos(__uint_as_float(v[i]) * cf[i], p.power);
+                    // 32 lanes = 32 consecutive bins of one frame: every store is one 128-byte line
+                    if (full_tile) {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) __stcs(out + (c0 + i) * p.ld, r[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; i++)
+                            if (c0 + i < nf) __stcs(out + (c0 + i) * p.ld, r[i]);
+                    }
                 }
             }
             tc_fence_before();
@@ -373,7 +450,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftPar
     tc_fence_before();
     __syncthreads();
     if (warp == LT_EPI_WARPS + LT_PRO_WARPS)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(LT_STAGES * LT_BN)) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
 }
 
 // CUDA-core fp32 form of the same lift (all K bins, Nyquist included): the path for mel bases wider than 96 rows,
@@ -418,64 +495,76 @@ __global__ void __launch_bounds__(128) gl_lift_f32_kernel(const float* __restric
     }
 }
 
-uint32_t tf32_rna_bits(float x) {   // cvt.rna.tf32.f32 on the host: nearest, ties away from zero, 10 mantissa bits
-    uint32_t u;
-    memcpy(&u, &x, 4);
-    if ((u & 0x7F800000u) == 0x7F800000u) return u;
-    return (u + 0x1000u) & 0xFFFFE000u;
-}
-
 }  // namespace
 
 // host: the device image of the pseudo-inverse for gl_lift_tc_kernel.  pinv: [K][n_mels] row-major (K = M + 1; the
-// last row is the Nyquist bin and is not part of the image).  Layout [mt][plane hi, lo][kblock][row 0..127][32 floats],
-// each 128-byte row stored with its 16-byte chunks XOR-swizzled by (row & 7) -- what TMA's SWIZZLE_128B would write.
-std::vector<float> gl_lift_build_image(const float* pinv, int K, int n_mels) {
-    const int M = K - 1, n_mt = (M + LT_BM - 1) / LT_BM, kblocks = (n_mels + 31) / 32;
-    std::vector<float> img((size_t)n_mt * 2 * kblocks * LT_BM * 32, 0.f);
-    for (int mt = 0; mt < n_mt; mt++)
-        for (int r = 0; r < LT_BM; r++) {
-            const int bin = mt * LT_BM + r;
-            if (bin >= M) continue;
-            for (int m = 0; m < n_mels; m++) {
-                const float x = pinv[(size_t)bin * n_mels + m];
-                const uint32_t hb = tf32_rna_bits(x);
-                float hi, lo;
-                memcpy(&hi, &hb, 4);
-                const uint32_t lb = tf32_rna_bits(x - hi);
-                memcpy(&lo, &lb, 4);
-                const int kb = m >> 5, kk = m & 31;
-                const size_t row = (size_t)r * 32 + (size_t)((((kk >> 2) ^ (r & 7)) << 2) + (kk & 3));
-                img[(((size_t)mt * 2 + 0) * kblocks + kb) * LT_BM * 32 + row] = hi;
-                img[(((size_t)mt * 2 + 1) * kblocks + kb) * LT_BM * 32 + row] = lo;
-            }
+// last row is the Nyquist bin and is not part of the image).  Layout [bin tile][plane hi, lo][K chunk][row 0..127][8 fp16]
+// (core matrices of 8 rows x 16 bytes, un-swizzled); values are pinv * 2^(*p_exp), the power of two that brings the
+// largest entry into [2^12, 2^13) -- fp16 has 5 exponent bits, and the low halves should stay out of its subnormals.
+std::vector<float> gl_lift_build_image(const float* pinv, int K, int n_mels, float* p_exp) {
+    const int M = K - 1, n_mt = (M + LT_BM - 1) / LT_BM, kchunks = 2 * ((n_mels + 15) / 16);
+    float amax = 0.f;
+    for (size_t i = 0; i < (size_t)M * n_mels; i++)
+        if (std::isfinite(pinv[i])) amax = std::max(amax, std::fabs(pinv[i]));
+    int ex = 0;
+    if (amax > 0.f) std::frexp(amax, &ex);   // amax in [2^(ex-1), 2^ex)
+    const int pe = amax > 0.f ? 13 - ex : 0;
+    *p_exp = (float)pe;
+    std::vector<float> img((size_t)n_mt * 2 * kchunks * LT_BM * 8 / 2, 0.f);   // fp16 pairs in float-sized slots
+    uint16_t* h16 = reinterpret_cast<uint16_t*>(img.data());
+    for (int bin = 0; bin < M; bin++) {
+        const int mt = bin / LT_BM, r = bin % LT_BM;
+        for (int m = 0; m < n_mels; m++) {
+            const float x = std::ldexp(pinv[(size_t)bin * n_mels + m], pe);
+            const __half hi = __float2half_rn(x);
+            const __half lo = __float2half_rn(x - __half2float(hi));
+            const size_t at = ((((size_t)mt * 2 + 0) * kchunks + (m >> 3)) * LT_BM + r) * 8 + (m & 7);
+            memcpy(&h16[at], &hi, 2);
+            memcpy(&h16[at + (size_t)kchunks * LT_BM * 8], &lo, 2);
         }
+    }
     return img;
 }
 
 int gl_lift_tile_frames() { return LT_BN; }
 
-// false: the tensor path does not apply (n_mels > 96, or bins not a multiple of 128): gl_launch_lift takes the fp32 kernel
+// bin tiles one CTA keeps resident: the largest of 4, 2, 1 that divides the tile count and fits shared memory
+static int lift_bin_tiles_per_cta(int n_mt, int kchunks) {
+    for (int nbt = LT_MAX_BT; nbt > 1; nbt >>= 1)
+        if (n_mt % nbt == 0 && LiftSmem::total(nbt, kchunks) <= LT_SMEM_MAX) return nbt;
+    return 1;
+}
+
+// false: the tensor path does not apply (n_mels > 128, or bins not a multiple of 128): gl_launch_lift takes the fp32 kernel
 bool gl_lift_uses_tensor_cores(int n_mels, int K) {
     static const bool force_f32 = getenv("XDTTS_LIFT_F32") != nullptr;
-    return !force_f32 && (n_mels + 31) / 32 <= LT_MAX_KB && (K - 1) % LT_BM == 0;
+    return !force_f32 && (n_mels + 7) / 8 <= LT_MAX_KC && (K - 1) % LT_BM == 0;
+}
+
+template <int DELOG, int CPT>
+static cudaError_t lift_attr(int bytes) {
+    return cudaFuncSetAttribute(gl_lift_tc_kernel<DELOG, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 cudaError_t gl_lift_prepare(int n_mels) {
-    const int kblocks = (n_mels + 31) / 32;
-    if (kblocks > LT_MAX_KB) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(gl_lift_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, LiftSmem::total(kblocks));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gl_lift_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LiftSmem::total(kblocks));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gl_lift_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, LiftSmem::total(kblocks));
+    if ((n_mels + 7) / 8 > LT_MAX_KC) return cudaSuccess;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = lift_attr<0, 2>(LT_SMEM_MAX);
+    if (e == cudaSuccess) e = lift_attr<1, 2>(LT_SMEM_MAX);
+    if (e == cudaSuccess) e = lift_attr<2, 2>(LT_SMEM_MAX);
+    if (e == cudaSuccess) e = lift_attr<0, 4>(LT_SMEM_MAX);
+    if (e == cudaSuccess) e = lift_attr<1, 4>(LT_SMEM_MAX);
+    if (e == cudaSuccess) e = lift_attr<2, 4>(LT_SMEM_MAX);
     return e;
 }
 
 // S[(foff + t) * ld + k] = max(0, sum_m pinv[k][m] delog(mel[m][t])) ^ power for k = 0..M (k = M: the Nyquist slot).
-// pinvT: [n_mels][K] (the transposed pseudo-inverse); a_image: gl_lift_build_image.  *n_kernels: launches made.
-cudaError_t gl_launch_lift(const float* mel_arena, const float* a_image, const float* pinvT, const int4* tiles, int n_tiles,
+// pinvT: [n_mels][K] (the transposed pseudo-inverse); a_image, p_exp: gl_lift_build_image.  *n_kernels: launches made.
+cudaError_t gl_launch_lift(const float* mel_arena, const float* a_image, float p_exp, const float* pinvT, const int4* tiles, int n_tiles,
                            const int* utt_T, const int* utt_foff, int n_utt, int max_T, int n_mels, int K, int ld, float power,
                            int delog, int sm_count, float* S, cudaStream_t s, int* n_kernels) {
     const int M = K - 1;
+    if (n_kernels) *n_kernels = 1;
     if (!gl_lift_uses_tensor_cores(n_mels, K)) {
         if (n_mels > 256) return cudaErrorInvalidValue;
         dim3 grid(1, (max_T + LF_TT - 1) / LF_TT, n_utt);
@@ -483,22 +572,29 @@ cudaError_t gl_launch_lift(const float* mel_arena, const float* a_image, const f
         if (delog == 0) gl_lift_f32_kernel<0><<<grid, 128, sm, s>>>(mel_arena, pinvT, utt_T, utt_foff, n_mels, K, ld, power, S);
         else if (delog == 1) gl_lift_f32_kernel<1><<<grid, 128, sm, s>>>(mel_arena, pinvT, utt_T, utt_foff, n_mels, K, ld, power, S);
         else gl_lift_f32_kernel<2><<<grid, 128, sm, s>>>(mel_arena, pinvT, utt_T, utt_foff, n_mels, K, ld, power, S);
-        if (n_kernels) *n_kernels = 1;
         return cudaGetLastError();
     }
     LiftParams p;
-    p.mel_arena = mel_arena; p.a_image = a_image; p.tiles = tiles; p.S = S;
-    p.n_tiles = n_tiles; p.n_mt = M / LT_BM; p.n_mels = n_mels; p.kblocks = (n_mels + 31) / 32; p.ld = ld;
-    p.power = power;
-    p.groups = sm_count / p.n_mt;
+    p.mel_arena = mel_arena; p.a_image = reinterpret_cast<const uint8_t*>(a_image); p.tiles = tiles; p.S = S;
+    p.n_tiles = n_tiles; p.n_mt = M / LT_BM; p.n_mels = n_mels; p.kchunks = 2 * ((n_mels + 15) / 16); p.ld = ld;
+    p.power = power; p.p_exp = p_exp;
+    p.nbt = lift_bin_tiles_per_cta(p.n_mt, p.kchunks);
+    p.n_part = p.n_mt / p.nbt;
+    p.groups = sm_count / p.n_part;
     if (p.groups < 1) p.groups = 1;
     if (p.groups > n_tiles) p.groups = n_tiles;
     p.pinv_nyq = pinvT + M; p.pinv_ld = K;
-    const int grid = p.n_mt * p.groups, sm = LiftSmem::total(p.kblocks);
-    if (delog == 0) gl_lift_tc_kernel<0><<<grid, LT_THREADS, sm, s>>>(p);
-    else if (delog == 1) gl_lift_tc_kernel<1><<<grid, LT_THREADS, sm, s>>>(p);
-    else gl_lift_tc_kernel<2><<<grid, LT_THREADS, sm, s>>>(p);
-    if (n_kernels) *n_kernels = 1;
+    const int grid = p.n_part * p.groups, sm = LiftSmem::total(p.nbt, p.kchunks);
+    const bool wide = p.kchunks > 2 * LT_PGROUPS;   // more than two K chunks per producer thread
+#define XDTTS_LIFT_LAUNCH(D)                                                              \
+    do {                                                                                  \
+        if (wide) gl_lift_tc_kernel<D, 4><<<grid, LT_THREADS, sm, s>>>(p);                \
+        else gl_lift_tc_kernel<D, 2><<<grid, LT_THREADS, sm, s>>>(p);                     \
+    } while (0)
+    if (delog == 0) XDTTS_LIFT_LAUNCH(0);
+    else if (delog == 1) XDTTS_LIFT_LAUNCH(1);
+    else XDTTS_LIFT_LAUNCH(2);
+#undef XDTTS_LIFT_LAUNCH
     return cudaGetLastError();
 }
 
