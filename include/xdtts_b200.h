@@ -129,6 +129,9 @@ int xdtts_gl_plan_run(xdtts_gl_plan* p, int flags, float* ms_total, float* ms_it
 /* device time (CUDA events) of the mel -> linear step (lift, or magnitude transpose, + NNLS when enabled) of the last
  * XDTTS_RUN_NO_GRAPH pass of this plan */
 int xdtts_gl_plan_lift_ms(const xdtts_gl_plan* p, float* ms);
+/* measurement: the same step of this plan launched reps times back to back (after one warm-up), device time per launch --
+ * CUDA events around the whole train, so the ~7 us of launch and event latency a single bracketed launch carries is amortised */
+int xdtts_gl_plan_time_lift(xdtts_gl_plan* p, int reps, float* ms_per_launch);
 int xdtts_gl_plan_download(xdtts_gl_plan* p, float* const* outs);
 int xdtts_gl_plan_download_pcm16(xdtts_gl_plan* p, short* const* outs);   /* after a run: 16-bit PCM of the same waveforms */
 /* debugging / parity: copy device state to host. what: 0 S [T_total][M] frame-major, 1 S Nyquist [T_total],

@@ -57,8 +57,9 @@ for cfg in (sys.argv[1:] or ["cfg2", "cfg5"]):
     for _ in range(5):
         plan.run(_ffi.RUN_NO_GRAPH)
         lifts.append(plan.lift_ms())
-    lift = min(lifts)
-    print("%s %s: lift %.1f us = %.0f GB/s (%.3f of peak)" % (tag, cfg, lift * 1e3, b * t * 4 * (80 + k) / lift / 1e6, b * t * 4 * (80 + k) / lift / 1e6 / peak))
+    lift1 = min(lifts)                                   # one launch between two events: + ~7 us of launch / event latency
+    lift = min(plan.time_lift(20) for _ in range(3)) if hasattr(plan, "time_lift") else lift1
+    print("%s %s: lift %.1f us = %.0f GB/s (%.3f of peak); single bracketed launch %.1f us" % (tag, cfg, lift * 1e3, b * t * 4 * (80 + k) / lift / 1e6, b * t * 4 * (80 + k) / lift / 1e6 / peak, lift1 * 1e3))
     alg = b * t * (20 * k + 8 * hop)
     info = plan.info()
     print("%s %s: step %.3f ms (%.2f M frames/s), iteration kernel %.2f us, %.0f GB/s = %.3f of %.0f, runs %d x %d frames, %d CTAs"

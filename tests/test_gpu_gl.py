@@ -483,6 +483,7 @@ def test_exponent_convention_and_lift_timing(gl):
             plan.lift_ms()                                         # no kernel-by-kernel pass yet
         plan.run(_ffi.RUN_NO_GRAPH)
         assert 0.0 < plan.lift_ms() < 50.0
+        assert 0.0 < plan.time_lift(3) < 50.0                  # the same step, three launches back to back, per launch
         ref = o.lift_pinv_clamp(mel, basis, p, dtype=np.float64)
         got = np.concatenate([plan.peek(0).T, plan.peek(1)[None, :]], 0)
         assert np.abs(got - ref).max() / ref.max() < 1e-5

@@ -23,9 +23,9 @@
 namespace xdtts {
 // gl_lift.cu
 std::vector<float> gl_lift_build_image(const float* pinv, int K, int n_mels, float* p_exp);
-int gl_lift_tile_frames();
+int gl_lift_tile_frames(const int* Ts, int B, int n_mels, int K, int sm_count);
 cudaError_t gl_lift_prepare(int n_mels);
-cudaError_t gl_launch_lift(const float* mel_arena, const float* a_image, float p_exp, const float* pinvT, const int4* tiles, int n_tiles,
+cudaError_t gl_launch_lift(const float* mel_arena, const float* a_image, float p_exp, const float* pinvT, const int4* tiles, int n_tiles, int tile_frames,
                            const int* utt_T, const int* utt_foff, int n_utt, int max_T, int n_mels, int K, int ld, float power,
                            int delog, int sm_count, float* S, cudaStream_t s, int* n_kernels);
 bool gl_lift_uses_tensor_cores(int n_mels, int K);
@@ -484,10 +484,11 @@ int xdtts::gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out)
     // one state record per frame: [R: M float2 | S: M floats | S_nyq + 3 floats of padding] (gl_core.cuh Geo::REC)
     p->rec_f = (int)(3 * M + 4);
     ALLOC(p->d_state, TT * (size_t)p->rec_f * 4);
-    {   // frame tiles of the lift: (frame row of the utterance, its T, first frame), gl_lift_tile_frames() frames each, never across utterances
-        const int tf = gl_lift_tile_frames();
+    {   // frame tiles of the lift: (frame row of the utterance, its T, first frame, frames in the tile), never across utterances;
+        // the extent is chosen per plan so that the tile count fills the CTAs' last round (gl_lift_tile_frames)
+        const int tf = p->lift_tile_frames = gl_lift_tile_frames(Ts, B, h->n_mels, h->K, h->sm_count);
         for (int b = 0; b < B; b++)
-            for (int t0 = 0; t0 < Ts[b]; t0 += tf) p->lift_tiles.push_back(make_int4(p->foff[b], Ts[b], t0, 0));
+            for (int t0 = 0; t0 < Ts[b]; t0 += tf) p->lift_tiles.push_back(make_int4(p->foff[b], Ts[b], t0, std::min(tf, Ts[b] - t0)));
     }
     ALLOC(p->d_lift_tiles, p->lift_tiles.size() * sizeof(int4));
     ALLOC(p->d_seed, 8 + (size_t)B * sizeof(int));   // [u64 phase seed][int stream index of each utterance]
@@ -526,6 +527,29 @@ extern "C" int xdtts_gl_plan_lift_ms(const xdtts_gl_plan* p, float* ms) {
     if (!p || !ms) return fail(XDTTS_ERR_BAD_ARG, "plan_lift_ms: null argument");
     if (p->lift_ms < 0.f) return fail(XDTTS_ERR_BAD_ARG, "plan_lift_ms: no kernel-by-kernel (XDTTS_RUN_NO_GRAPH) pass has run on this plan");
     *ms = p->lift_ms;
+    return XDTTS_OK;
+}
+
+static int plan_enqueue_lift(xdtts_gl_plan* p, int flags, cudaStream_t s, unsigned long long* launched);
+
+extern "C" int xdtts_gl_plan_time_lift(xdtts_gl_plan* p, int reps, float* ms_per_launch) {
+    if (!p || !ms_per_launch) return fail(XDTTS_ERR_BAD_ARG, "plan_time_lift: null argument");
+    if (reps < 1 || reps > 10000) return fail(XDTTS_ERR_BAD_ARG, "plan_time_lift: reps must be in 1..10000");
+    xdtts_gl* h = p->h;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    unsigned long long launched = 0;
+    int rc = plan_enqueue_lift(p, 0, s, &launched);   // warm-up
+    CU(cudaEventRecord(p->ev[4], s));
+    for (int i = 0; i < reps && !rc; i++) rc = plan_enqueue_lift(p, 0, s, &launched);
+    if (rc) return rc;
+    CU(cudaEventRecord(p->ev[5], s));
+    CU(cudaStreamSynchronize(s));
+    g_launches += launched;
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, p->ev[4], p->ev[5]));
+    *ms_per_launch = ms / (float)reps;
     return XDTTS_OK;
 }
 
@@ -615,23 +639,20 @@ int xdtts::gl_plan_set_seed(xdtts_gl_plan* p, unsigned long long seed, const int
     return XDTTS_OK;
 }
 
-// enqueue the whole pass on the handle's stream; ev[1]/ev[2] bracket the steady-state launches when timed
-static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid, cudaStream_t s, bool capturing = false) {
-    unsigned long long launched = 0;   // added to the process-wide counter at the end -- not at all while capturing a graph
+// the mel -> linear step of a pass (lift, or the transpose of caller-supplied magnitudes; + NNLS when enabled); *launched += kernels
+static int plan_enqueue_lift(xdtts_gl_plan* p, int flags, cudaStream_t s, unsigned long long* launched) {
     xdtts_gl* h = p->h;
     const int M = h->K - 1;
-    const bool from_mag = flags & XDTTS_RUN_FROM_MAG, use_phase = flags & XDTTS_RUN_USE_PHASE;
-    CU(cudaMemsetAsync(p->d_amax, 0, p->B * sizeof(unsigned), s));
+    const bool from_mag = flags & XDTTS_RUN_FROM_MAG;
     int lift_kernels = 1;
-    if (timed) CU(cudaEventRecord(p->ev[4], s));
     float* d_S = p->d_state + 2 * M;   // the S part of frame 0's record; records are rec_f floats apart
     if (from_mag) {
         CU(gl_launch_to_frame_major(p->d_in_mag, p->d_T, p->d_foff, p->B, p->max_T, h->K, d_S, p->rec_f, s));
     } else {
         const bool nnls = h->opts.lift == 1;
-        CU(gl_launch_lift(p->d_mel, h->d_lift_img, h->lift_p_exp, h->d_pinvT, p->d_lift_tiles, (int)p->lift_tiles.size(), p->d_T, p->d_foff, p->B,
+        CU(gl_launch_lift(p->d_mel, h->d_lift_img, h->lift_p_exp, h->d_pinvT, p->d_lift_tiles, (int)p->lift_tiles.size(), p->lift_tile_frames, p->d_T, p->d_foff, p->B,
                           p->max_T, h->n_mels, h->K, p->rec_f, nnls ? 1.0f : h->power, h->opts.delog, h->sm_count, d_S, s, &lift_kernels));
-        launched += (unsigned long long)(lift_kernels - 1);
+        *launched += (unsigned long long)(lift_kernels - 1);
         if (nnls) {   // refine the clipped least-squares start in place, then apply the exponent
             const int iters = h->opts.nnls_iters > 0 ? h->opts.nnls_iters : 300;
             if (h->band_rw > 0 && !getenv("XDTTS_NNLS_GENERIC"))
@@ -641,10 +662,25 @@ static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid, cud
             else
                 CU(gl_launch_nnls(p->d_mel, h->d_csr, h->d_csr_val, h->d_csc, h->d_csc_val, p->d_T, p->d_foff, p->B, p->max_T, h->n_mels,
                                   h->K, h->power, h->opts.delog, h->lipschitz, iters, 3e-6f, d_S, p->rec_f, s));
-            launched++;
+            (*launched)++;
         }
     }
-    launched++;
+    (*launched)++;
+    return XDTTS_OK;
+}
+
+// enqueue the whole pass on the handle's stream; ev[1]/ev[2] bracket the steady-state launches when timed
+static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid, cudaStream_t s, bool capturing = false) {
+    unsigned long long launched = 0;   // added to the process-wide counter at the end -- not at all while capturing a graph
+    xdtts_gl* h = p->h;
+    const int M = h->K - 1;
+    const bool from_mag = flags & XDTTS_RUN_FROM_MAG, use_phase = flags & XDTTS_RUN_USE_PHASE;
+    CU(cudaMemsetAsync(p->d_amax, 0, p->B * sizeof(unsigned), s));
+    if (timed) CU(cudaEventRecord(p->ev[4], s));
+    {
+        int rc = plan_enqueue_lift(p, flags, s, &launched);
+        if (rc) return rc;
+    }
     if (timed) CU(cudaEventRecord(p->ev[5], s));
     if (use_phase) {
         CU(gl_launch_to_frame_major(p->d_in_phase, p->d_T, p->d_foff, p->B, p->max_T, h->K, p->d_turns, h->K, s));

@@ -78,6 +78,7 @@ struct xdtts_gl_plan {
     float *d_y[2] = {nullptr, nullptr}, *d_halo = nullptr, *d_out = nullptr;
     std::vector<int4> lift_tiles;    // (frame row of the utterance, its T, first frame, 0) of every frame tile of the lift
     int4* d_lift_tiles = nullptr;
+    int lift_tile_frames = 64;
     unsigned char *d_seed = nullptr, *h_seed = nullptr;   // [u64 phase seed][int stream index per utterance], device + pinned
     short* d_pcm = nullptr;          // 16-bit PCM copy of d_out (allocated on first use)
     short* h_pcm = nullptr;

@@ -28,17 +28,19 @@
 // Bins as the TMEM lane dimension make the epilogue's stores coalesced: for one frame (TMEM column) the 32 lanes
 // of a warp hold 32 consecutive bins = 128 contiguous bytes of the frame-major state record the iteration kernel reads.
 //
-// Warp roles (608 threads, one CTA per SM; CTA (part, g) owns bin tiles part*nbt .. +nbt-1 and frame tiles g, g+G, ...):
-//     warps 0-7    epilogue     tcgen05.ld (lane quarter = warp & 3, column half = warp >> 2) -> clamp -> ^power -> S
-//     warps 8-17   producers    mel [n_mels][T] -> per-frame scale -> delog -> fp16 hi / lo -> E tile (loads one tile ahead)
-//     warp  18     TMEM alloc + one thread issuing the bulk copy of P, the MMAs and the commits
+// Warp roles (864 threads, one CTA per SM; CTA (part, g) owns bin tiles part*nbt .. +nbt-1 and frame tiles g, g+G, ...):
+//     warps 0-15   epilogue     tcgen05.ld (lane quarter = warp & 3) -> clamp -> ^power -> S
+//     warps 16-25  producers    mel [n_mels][T] -> per-frame scale -> delog -> fp16 hi / lo -> E tile (loads one tile ahead)
+//     warp  26     TMEM alloc + one thread issuing the bulk copy of P, the MMAs and the commits
 // The Nyquist bin (bin M, a 129th row of the last tile otherwise) is summed by the producers of part 0 on the
 // CUDA cores, from the de-logged values they hold anyway.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -50,9 +52,18 @@ namespace xdtts {
 namespace {
 
 // timing experiments only (tools/build_lift_variants.py): bit 0 skips the MMAs, bit 1 the epilogue's math and stores,
-// bit 2 the producers' conversion.  0 in the product.
+// bit 2 the producers' conversion; bits 3 / 4 / 5 only the epilogue's stores / special-function math / TMEM loads.  0 in the product.
 #ifndef XDTTS_LIFT_SKIP
 #define XDTTS_LIFT_SKIP 0
+#endif
+
+#ifdef XDTTS_LIFT_TRACE
+__device__ __forceinline__ long long lt_gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define LT_GSTAMP(role, k) do { p.trace[(((size_t)blockIdx.x * 4 + (role)) * 32 + 31) * 2 + (k)] = lt_gtime(); } while (0)
+#define LT_STAMP(role, it_, k) do { if ((it_) < 31) p.trace[(((size_t)blockIdx.x * 4 + (role)) * 32 + (it_)) * 2 + (k)] = clock64(); } while (0)
+#else
+#define LT_STAMP(role, it_, k) do { } while (0)
+#define LT_GSTAMP(role, k) do { } while (0)
 #endif
 
 constexpr int LT_BM = 128;       // bins per tile
@@ -61,7 +72,7 @@ constexpr int LT_STAGES = 2;     // E-tile ring and TMEM accumulator sets
 constexpr int LT_MAX_BT = 4;     // bin tiles resident per CTA (TMEM: LT_STAGES * 4 * 64 = 512 columns)
 constexpr int LT_TILE_SM = 64;   // tile records staged in shared memory per CTA
 constexpr int LT_MAX_KC = 16;    // K chunks of 8 mel rows: n_mels <= 128; wider bases take gl_lift_f32_kernel
-constexpr int LT_EPI_WARPS = 8;
+constexpr int LT_EPI_WARPS = 16;
 constexpr int LT_PRO_WARPS = 10;
 constexpr int LT_PGROUPS = LT_PRO_WARPS * 32 / LT_BN;   // producer thread (frame f, chunk group cg): chunks cg, cg + 5, ...
 constexpr int LT_THREADS = 32 * (LT_EPI_WARPS + LT_PRO_WARPS + 1);
@@ -125,11 +136,14 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]),
+          "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]),
+          "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
 }
@@ -180,11 +194,15 @@ struct LiftParams {
     const uint8_t* a_image;      // [n_mt][2 planes][kchunks][128 rows][8 fp16]: the scaled pseudo-inverse, hi / lo halves
     const float* pinv_nyq;       // the pseudo-inverse's row of bin M: entry m at pinv_nyq[m * pinv_ld]
     int pinv_ld;
-    const int4* tiles;           // frame tiles: (first frame row of the utterance, its frame count T, first frame of the tile, 0)
+    const int4* tiles;           // frame tiles: (first frame row of the utterance, its frame count T, first frame of the tile, frames in the tile <= 64)
     float* S;                    // frame-major state records: S[(foff + t) * ld + k], k < M
     int n_tiles, n_mt, nbt, n_part, groups, n_mels, kchunks, ld;
+    int mma_n;                   // UMMA N: the largest tile extent of the plan, rounded up to 16
     float power;
     float p_exp;                 // the image holds P * 2^p_exp
+#ifdef XDTTS_LIFT_TRACE
+    long long* trace;            // timing experiments: [cta][role 4][tile 32][2] clock64 stamps
+#endif
 };
 
 struct LiftSmem {
@@ -198,7 +216,9 @@ struct LiftSmem {
     __host__ __device__ static int total(int nbt, int kchunks) { return bar_off(nbt, kchunks) + TAIL + 16; }
 };
 
-template <int DELOG, int CPT>   // CPT: K chunks per producer thread (ceil(kchunks / LT_PGROUPS))
+// CPT: K chunks per producer thread (ceil(kchunks / LT_PGROUPS)); LD: floats between the records of consecutive frames
+// (0: p.ld at run time; as a constant, the epilogue's 64 stores per warp and bin tile are one instruction each)
+template <int DELOG, int CPT, int LD>
 __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 15) & ~(uintptr_t)15);
@@ -222,7 +242,32 @@ __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftPar
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // the shuffle tells the compiler it is warp-uniform
     const int part = blockIdx.x % p.n_part, g = blockIdx.x / p.n_part;
     const int nbt = p.nbt;
+    const int ld = LD ? LD : p.ld;
+    if (threadIdx.x == 0) LT_GSTAMP(0, 0);
     const uint32_t tmem_cols = nbt * LT_STAGES * LT_BN <= 128 ? 128u : (nbt * LT_STAGES * LT_BN <= 256 ? 256u : 512u);
+
+    const int my_tiles = g < p.n_tiles ? (p.n_tiles - g + p.groups - 1) / p.groups : 0;   // tiles g, g + G, ... of this CTA
+
+    // producer thread (f, cg): frame f of a tile, K chunks cg, cg + 5, ... (8 mel rows each).  The loads of the CTA's first tile go
+    // out before anything else: their ~3 us (cold HBM, one line per mel row) then overlap the set-up below instead of following it.
+    const int ptid = threadIdx.x - 32 * LT_EPI_WARPS;
+    const int f = ptid & (LT_BN - 1), cg = ptid / LT_BN;
+    constexpr int NX = CPT * 8;
+    constexpr bool AHEAD = CPT <= 2;                 // the prefetched tile lives in registers
+    auto issue_loads_rec = [&](const int4 tl, float* x) {
+        const int T = tl.y;
+        const bool fv = f < tl.w && tl.z + f < T;
+        const float* src = p.mel_arena + (size_t)tl.x * p.n_mels + tl.z + f;   // row 0 of the utterance, this thread's frame
+#pragma unroll
+        for (int j = 0; j < CPT; j++)
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const int m = (cg + LT_PGROUPS * j) * 8 + r;   // 32-bit offsets: a plan holds fewer than 2^31 / K frames
+                x[8 * j + r] = (fv && m < p.n_mels) ? __ldg(src + m * T) : -INFINITY;   // -inf: no sample
+            }
+    };
+    float xq[NX];
+    if (AHEAD && my_tiles > 0 && warp >= LT_EPI_WARPS && warp < LT_EPI_WARPS + LT_PRO_WARPS) issue_loads_rec(__ldg(&p.tiles[g]), xq);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < LT_STAGES; s++) {
@@ -245,7 +290,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftPar
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
-    const int my_tiles = g < p.n_tiles ? (p.n_tiles - g + p.groups - 1) / p.groups : 0;   // tiles g, g + G, ... of this CTA
+    if (threadIdx.x == 0) LT_GSTAMP(1, 0);
 
     if (warp == LT_EPI_WARPS + LT_PRO_WARPS) {
         // ===================== MMA issuer.  The whole warp walks the loop (warp-uniform control flow and operands: the
@@ -258,8 +303,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftPar
                 bulk_g2s(sa + b * a_tile, p.a_image + (size_t)(part * nbt + b) * a_tile, (uint32_t)a_tile, &a_bar[b]);
             }
         }
-        // instruction descriptor: D fp32, A/B fp16, both K-major, N = LT_BN, M = 128
-        const uint32_t idesc = (1u << 4) | ((uint32_t)(LT_BN >> 3) << 17) | ((uint32_t)(LT_BM >> 4) << 24);
+        // instruction descriptor: D fp32, A/B fp16, both K-major, N = the plan's tile extent, M = 128
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(p.mma_n >> 3) << 17) | ((uint32_t)(LT_BM >> 4) << 24);
         constexpr uint32_t A_LBO = LT_BM * 16, E_LBO = LT_BN * 16, SBO = 128;
         constexpr uint32_t A_HI = ((A_LBO >> 4) << 16), E_HI = ((E_LBO >> 4) << 16);   // low words' LBO fields
         constexpr uint32_t D_HI = (SBO >> 4) | (1u << 14);                               // high word: SBO, version 1
@@ -268,12 +313,19 @@ __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftPar
         for (int it = 0; it < my_tiles; it++) {
             const int s = it % LT_STAGES;
             const uint32_t ph = (uint32_t)((it / LT_STAGES) & 1);
-            mbar_wait(&tempty[s], ph ^ 1u);   // epilogue has drained this accumulator set
-            mbar_wait(&full[s], ph);          // producers have written this E stage
+            if (lane == 0) {   // one lane polls (32 spinning lanes cost this scheduler 15% of its issue slots), the rest wait at the warp barrier
+                mbar_wait(&tempty[s], ph ^ 1u);   // epilogue has drained this accumulator set
+                mbar_wait(&full[s], ph);          // producers have written this E stage
+            }
+            __syncwarp();
             tc_fence_after();
+            if (lane == 0) LT_STAMP(1, it, 0);
             const uint32_t e_hi = ((se_u + (uint32_t)(s * 2 * e_plane)) >> 4) | E_HI, e_lo = e_hi + (uint32_t)(e_plane >> 4);
             for (int b = 0; b < nbt; b++) {
-                mbar_wait(&a_bar[b], 0);
+                if (it == 0) {
+                    if (lane == 0) mbar_wait(&a_bar[b], 0);
+                    __syncwarp();
+                }
                 const uint32_t d_tmem = tmem_base + (uint32_t)((s * nbt + b) * LT_BN);
                 const uint32_t a_hi = ((sa_u + (uint32_t)(b * a_tile)) >> 4) | A_HI, a_lo = a_hi + (uint32_t)(a_tile >> 5);
                 if (leader) {
@@ -289,45 +341,28 @@ __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftPar
                 }
             }
             if (leader) tc_commit(&empty[s]);    // E stage free when these MMAs retire
+            if (lane == 0) LT_STAMP(1, it, 1);
             __syncwarp();
         }
     } else if (warp >= LT_EPI_WARPS) {
-        // ===================== producers.  Thread (f, cg): frame f of the tile, K chunks cg, cg + 5, ... (8 mel rows each).
+        // ===================== producers (thread (f, cg), see the top of the kernel).
         // A warp's 32 lanes are 32 consecutive frames of one mel row: every global load is one 128-byte line, every
         // shared-memory store 32 consecutive 16-byte core-matrix rows.  Loads run one tile ahead of the conversion.
-        const int ptid = threadIdx.x - 32 * LT_EPI_WARPS;
-        const int f = ptid & (LT_BN - 1), cg = ptid / LT_BN;
-        constexpr int NX = CPT * 8;
-        constexpr bool AHEAD = CPT <= 2;                 // the prefetched tile lives in registers
         float wreg[NX];                                  // this thread's entries of the pseudo-inverse's Nyquist row
 #pragma unroll
         for (int j = 0; j < CPT; j++)
 #pragma unroll
             for (int r = 0; r < 8; r++) wreg[8 * j + r] = (cg + LT_PGROUPS * j) < p.kchunks ? wn[(cg + LT_PGROUPS * j) * 8 + r] : 0.f;
-        auto issue_loads = [&](int it_, float* x) {
-            const int4 tl = tile_rec(it_);
-            const int T = tl.y;
-            const bool fv = tl.z + f < T;
-            const float* src = p.mel_arena + (size_t)tl.x * p.n_mels + tl.z + f;   // row 0 of the utterance, this thread's frame
-#pragma unroll
-            for (int j = 0; j < CPT; j++)
-#pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    const int m = (cg + LT_PGROUPS * j) * 8 + r;   // 32-bit offsets: a plan holds fewer than 2^31 / K frames
-                    x[8 * j + r] = (fv && m < p.n_mels) ? __ldg(src + m * T) : -INFINITY;   // -inf: no sample
-                }
-        };
-        float xq[NX];
-        if (AHEAD && my_tiles > 0) issue_loads(0, xq);
+        auto issue_loads = [&](int it_, float* x) { issue_loads_rec(tile_rec(it_), x); };
         float nq_prev = 0.f, sh_prev = 0.f;   // cg == 0: the Nyquist partial sum and 2^shift of the previous tile
         int4 tl_prev = make_int4(0, 0, 0, 0);
         auto finish_nyquist = [&](int it_prev) {   // after the producers' barrier that follows tile it_prev
-            if (part == 0 && cg == 0 && tl_prev.z + f < tl_prev.y) {
+            if (part == 0 && cg == 0 && f < tl_prev.w && tl_prev.z + f < tl_prev.y) {
                 float v = nq_prev;
                 const float* pp = nqp + (it_prev & 1) * LT_PGROUPS * LT_BN + f;
 #pragma unroll
                 for (int c = 1; c < LT_PGROUPS; c++) v += pp[c * LT_BN];
-                p.S[((size_t)tl_prev.x + tl_prev.z + f) * p.ld + p.n_mt * LT_BM] =
+                p.S[((size_t)tl_prev.x + tl_prev.z + f) * ld + p.n_mt * LT_BM] =
                     p.power == 1.0f ? fmaxf(v * sh_prev, 0.f) : pow_pos(v * sh_prev, p.power);
             }
         };
@@ -356,7 +391,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftPar
             shift = fminf(fmaxf(shift, -100.f), 118.f) - (float)LT_E_SHIFT;
             const float sc = __int_as_float((127 - (int)shift) << 23);   // 2^-shift
             if (it > 0) finish_nyquist(it - 1);
+            if (ptid == 0) LT_STAMP(0, it, 0);
+            if (ptid == 0 && it == 0) LT_GSTAMP(1, 1);
             mbar_wait(&empty[s], (uint32_t)((it / LT_STAGES) & 1) ^ 1u);
+            if (ptid == 0) LT_STAMP(3, it, 0);
             uint8_t* ehi = se + s * 2 * e_plane + f * 16;
             float nq = 0.f;
 #pragma unroll
@@ -385,6 +423,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftPar
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async proxy
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[s]);
+            if (ptid == 0) LT_STAMP(0, it, 1);
             if (cg == 0) {
                 nq_prev = nq;
                 sh_prev = exp2_int((int)shift);
@@ -398,57 +437,59 @@ __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftPar
             finish_nyquist(my_tiles - 1);
         }
     } else {
-        // ===================== epilogue: TMEM lane quarter q <-> bins bt*128 + 32 q + lane; column half ch
-        const int q = warp & 3, ch = warp >> 2;
-        constexpr int CW = LT_BN / (LT_EPI_WARPS / 4);
-        const bool plain = p.power == 1.0f;
+        // ===================== epilogue: TMEM lane quarter q <-> bins bt*128 + 32 q + lane.  A work item is (bin tile, half of the
+        // tile's 64 columns); the four warps of a quarter take items j, j + 4, ...  Four epilogue warps per scheduler, not two:
+        // the special-function unit (two operations per value) is the unit to keep fed, and a warp is in order.
+        const int q = warp & 3, j = warp >> 2;
+        constexpr int CW = 32;
+        const bool plain = (XDTTS_LIFT_SKIP & 16) ? true : p.power == 1.0f;
         for (int it = 0; it < my_tiles; it++) {
             const int s = it % LT_STAGES;
             const uint32_t ph = (uint32_t)((it / LT_STAGES) & 1);
             const int4 tl = tile_rec(it);
-            const int nf = min(LT_BN, tl.y - tl.z) - ch * CW;   // frames of this warp's columns that exist
-            const bool full_tile = nf >= CW;                    // all but an utterance's last tile
-            float* out0 = p.S + ((size_t)tl.x + tl.z + ch * CW) * p.ld + (part * nbt) * LT_BM + q * 32 + lane;
-            const float4* cf4 = reinterpret_cast<const float4*>(cfac + (it % LT_CF_RING) * LT_BN + ch * CW);
-            for (int b = 0; b < nbt; b++) {
+            for (int item = j; item < 2 * nbt; item += LT_EPI_WARPS / 4) {
+                const int b = item >> 1, ch = item & 1;
+                const int nf = min(tl.w, tl.y - tl.z) - ch * CW;    // frames of these columns that exist
+                if (nf <= 0 || (XDTTS_LIFT_SKIP & 2)) continue;
+                const bool full_tile = nf >= CW;
+                float* out = p.S + ((size_t)tl.x + tl.z + ch * CW) * ld + (part * nbt + b) * LT_BM + q * 32 + lane;
+                const float4* cf4 = reinterpret_cast<const float4*>(cfac + (it % LT_CF_RING) * LT_BN + ch * CW);
                 mbar_wait(&tfull[s * LT_MAX_BT + b], ph);
                 tc_fence_after();
+                if (threadIdx.x == 0 && item == j) LT_STAMP(2, it, 0);
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((s * nbt + b) * LT_BN + ch * CW);
-                float* out = out0 + b * LT_BM;
+                uint32_t v[CW];
+                if (XDTTS_LIFT_SKIP & 32) {
 #pragma unroll
-                for (int c0 = 0; c0 < ((XDTTS_LIFT_SKIP & 2) ? 0 : CW); c0 += 16) {
-                    uint32_t v[16];
-                    tc_ld16(taddr + (uint32_t)c0, v);
-                    float cf[16];
+                    for (int i = 0; i < CW; i++) v[i] = 0x3f800000u + lane + i;
+                } else {
+                    tc_ld32(taddr, v);
+                    tc_wait_ld();
+                }
+#pragma unroll
+                for (int c0 = 0; c0 < CW; c0 += 4) {
+                    const float4 c = cf4[c0 >> 2];   // the frames' powers of two (a broadcast read)
+                    const float cf[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        const float4 c = cf4[(c0 >> 2) + i];
-                        cf[4 * i] = c.x; cf[4 * i + 1] = c.y; cf[4 * i + 2] = c.z; cf[4 * i + 3] = c.w;
-                    }
-                    tc_wait_ld();
-                    float r[16];
-#pragma unroll
-                    for (int i = 0; i < 16; i++)
-                        r[i] = plain ? fmaxf(__uint_as_float(v[i]) * cf[i], 0.f) : pow_pos(__uint_as_float(v[i]) * cf[i], p.power);
-                    // 32 lanes = 32 consecutive bins of one frame: every store is one 128-byte line
-                    if (full_tile) {
-#pragma unroll
-                        for (int i = 0; i < 16; i++) __stcs(out + (c0 + i) * p.ld, r[i]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; i++)
-                            if (c0 + i < nf) __stcs(out + (c0 + i) * p.ld, r[i]);
+                        const float x = __uint_as_float(v[c0 + i]) * cf[i];
+                        const float r = plain ? fmaxf(x, 0.f) : pow_pos(x, p.power);
+                        // 32 lanes = 32 consecutive bins of one frame: every store is one 128-byte line
+                        if ((XDTTS_LIFT_SKIP & 8) ? r == 123456.789f : (full_tile || c0 + i < nf)) __stcs(out + (c0 + i) * ld, r);
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[s]);
+            if (threadIdx.x == 0) LT_STAMP(2, it, 1);
         }
     }
 
+    if (threadIdx.x == 0) LT_GSTAMP(2, 0);
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) LT_GSTAMP(0, 1);
     if (warp == LT_EPI_WARPS + LT_PRO_WARPS)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
 }
@@ -526,7 +567,27 @@ std::vector<float> gl_lift_build_image(const float* pinv, int K, int n_mels, flo
     return img;
 }
 
-int gl_lift_tile_frames() { return LT_BN; }
+static int lift_bin_tiles_per_cta(int n_mt, int kchunks);
+bool gl_lift_uses_tensor_cores(int n_mels, int K);
+
+// frames per tile for a plan: the extent (a multiple of 8, at most 64) whose tile count fills the CTAs' last round best.
+// 32 x 1000 frames in tiles of 64 are 500 tiles = 3.4 rounds of 148 CTAs, paid as 4; tiles of 56 are 576 = 3.9 rounds, 12% less
+// work on the longest CTA.  The cost model is rounds x (extent + 8): a tile has a fixed cost of about 8 frames' worth.
+int gl_lift_tile_frames(const int* Ts, int B, int n_mels, int K, int sm_count) {
+    if (!gl_lift_uses_tensor_cores(n_mels, K)) return LT_BN;
+    const int n_mt = (K - 1) / LT_BM, kchunks = 2 * ((n_mels + 15) / 16);
+    const int n_part = n_mt / lift_bin_tiles_per_cta(n_mt, kchunks);
+    const int groups = std::max(1, sm_count / n_part);
+    int best = LT_BN;
+    long best_cost = -1;
+    for (int bn = LT_BN; bn >= 16; bn -= 8) {
+        long tiles = 0;
+        for (int b = 0; b < B; b++) tiles += (Ts[b] + bn - 1) / bn;
+        const long rounds = (tiles + groups - 1) / groups, cost = rounds * (bn + 8);
+        if (best_cost < 0 || cost < best_cost) best = bn, best_cost = cost;
+    }
+    return best;
+}
 
 // bin tiles one CTA keeps resident: the largest of 4, 2, 1 that divides the tile count and fits shared memory
 static int lift_bin_tiles_per_cta(int n_mt, int kchunks) {
@@ -543,7 +604,11 @@ bool gl_lift_uses_tensor_cores(int n_mels, int K) {
 
 template <int DELOG, int CPT>
 static cudaError_t lift_attr(int bytes) {
-    return cudaFuncSetAttribute(gl_lift_tc_kernel<DELOG, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaError_t e = cudaFuncSetAttribute(gl_lift_tc_kernel<DELOG, CPT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gl_lift_tc_kernel<DELOG, CPT, 772>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gl_lift_tc_kernel<DELOG, CPT, 1540>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gl_lift_tc_kernel<DELOG, CPT, 3076>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    return e;
 }
 
 cudaError_t gl_lift_prepare(int n_mels) {
@@ -558,9 +623,20 @@ cudaError_t gl_lift_prepare(int n_mels) {
     return e;
 }
 
+template <int DELOG, int CPT>
+static void lift_launch(const LiftParams& p, int grid, int sm, cudaStream_t s) {
+    switch (p.ld) {   // the record strides of n_fft 512 / 1024 / 2048 (3 n_fft / 2 + 4 floats) as compile-time constants
+        case 772: gl_lift_tc_kernel<DELOG, CPT, 772><<<grid, LT_THREADS, sm, s>>>(p); break;
+        case 1540: gl_lift_tc_kernel<DELOG, CPT, 1540><<<grid, LT_THREADS, sm, s>>>(p); break;
+        case 3076: gl_lift_tc_kernel<DELOG, CPT, 3076><<<grid, LT_THREADS, sm, s>>>(p); break;
+        default: gl_lift_tc_kernel<DELOG, CPT, 0><<<grid, LT_THREADS, sm, s>>>(p);
+    }
+}
+
 // S[(foff + t) * ld + k] = max(0, sum_m pinv[k][m] delog(mel[m][t])) ^ power for k = 0..M (k = M: the Nyquist slot).
-// pinvT: [n_mels][K] (the transposed pseudo-inverse); a_image, p_exp: gl_lift_build_image.  *n_kernels: launches made.
-cudaError_t gl_launch_lift(const float* mel_arena, const float* a_image, float p_exp, const float* pinvT, const int4* tiles, int n_tiles,
+// pinvT: [n_mels][K] (the transposed pseudo-inverse); a_image, p_exp: gl_lift_build_image; tiles: records of at most
+// tile_frames frames (gl_lift_tile_frames).  *n_kernels: launches made.
+cudaError_t gl_launch_lift(const float* mel_arena, const float* a_image, float p_exp, const float* pinvT, const int4* tiles, int n_tiles, int tile_frames,
                            const int* utt_T, const int* utt_foff, int n_utt, int max_T, int n_mels, int K, int ld, float power,
                            int delog, int sm_count, float* S, cudaStream_t s, int* n_kernels) {
     const int M = K - 1;
@@ -586,15 +662,40 @@ cudaError_t gl_launch_lift(const float* mel_arena, const float* a_image, float p
     p.pinv_nyq = pinvT + M; p.pinv_ld = K;
     const int grid = p.n_part * p.groups, sm = LiftSmem::total(p.nbt, p.kchunks);
     const bool wide = p.kchunks > 2 * LT_PGROUPS;   // more than two K chunks per producer thread
-#define XDTTS_LIFT_LAUNCH(D)                                                              \
-    do {                                                                                  \
-        if (wide) gl_lift_tc_kernel<D, 4><<<grid, LT_THREADS, sm, s>>>(p);                \
-        else gl_lift_tc_kernel<D, 2><<<grid, LT_THREADS, sm, s>>>(p);                     \
-    } while (0)
-    if (delog == 0) XDTTS_LIFT_LAUNCH(0);
-    else if (delog == 1) XDTTS_LIFT_LAUNCH(1);
-    else XDTTS_LIFT_LAUNCH(2);
-#undef XDTTS_LIFT_LAUNCH
+    p.mma_n = std::min(LT_BN, (std::max(tile_frames, 1) + 15) & ~15);
+#ifdef XDTTS_LIFT_TRACE
+    static long long* d_trace = nullptr;
+    const size_t tr_n = (size_t)grid * 4 * 32 * 2;
+    if (!d_trace) cudaMalloc(&d_trace, 296 * 4 * 32 * 2 * 8);
+    cudaMemsetAsync(d_trace, 0, tr_n * 8, s);
+    p.trace = d_trace;
+#endif
+    if (delog == 0) wide ? lift_launch<0, 4>(p, grid, sm, s) : lift_launch<0, 2>(p, grid, sm, s);
+    else if (delog == 1) wide ? lift_launch<1, 4>(p, grid, sm, s) : lift_launch<1, 2>(p, grid, sm, s);
+    else wide ? lift_launch<2, 4>(p, grid, sm, s) : lift_launch<2, 2>(p, grid, sm, s);
+#ifdef XDTTS_LIFT_TRACE
+    if (getenv("XDTTS_LIFT_TRACE_PRINT")) {
+        cudaStreamSynchronize(s);
+        std::vector<long long> tr(tr_n);
+        cudaMemcpy(tr.data(), d_trace, tr_n * 8, cudaMemcpyDeviceToHost);
+        for (int cta : {0, grid - 1}) {
+            long long t0 = 0;
+            for (size_t i = 0; i < 4 * 32 * 2; i++) { long long v = tr[(size_t)cta * 256 + i]; if (v && (!t0 || v < t0)) t0 = v; }
+            fprintf(stderr, "lift trace cta %d (cycles from first stamp): it | prod start, slot free, done | mma start, issued | epi start, done\n", cta);
+            {
+                auto G = [&](int role, int k) { return tr[(((size_t)cta * 4 + role) * 32 + 31) * 2 + k]; };
+                long long e0 = 0, e1 = 0;
+                for (int c = 0; c < grid; c++) { long long a = tr[(((size_t)c * 4 + 0) * 32 + 31) * 2], b = tr[(((size_t)c * 4 + 0) * 32 + 31) * 2 + 1]; if (!e0 || a < e0) e0 = a; if (b > e1) e1 = b; }
+                fprintf(stderr, "  ns: all CTAs entry..exit %lld | this CTA entry +%lld, setup done +%lld, first tile loaded +%lld, epilogue warp 0 done +%lld, exit +%lld\n", e1 - e0, G(0, 0) - e0, G(1, 0) - e0, G(1, 1) - e0, G(2, 0) - e0, G(0, 1) - e0);
+            }
+            for (int it = 0; it < 31; it++) {
+                auto g = [&](int role, int k) { long long v = tr[(((size_t)cta * 4 + role) * 32 + it) * 2 + k]; return v ? v - t0 : -1; };
+                if (g(0, 0) < 0) break;
+                fprintf(stderr, "  %2d | %7lld %7lld %7lld | %7lld %7lld | %7lld %7lld\n", it, g(0, 0), g(3, 0), g(0, 1), g(1, 0), g(1, 1), g(2, 0), g(2, 1));
+            }
+        }
+    }
+#endif
     return cudaGetLastError();
 }
 

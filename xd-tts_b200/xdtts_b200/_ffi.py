@@ -76,6 +76,7 @@ SIGNATURES = {
     "xdtts_gl_infer_batch_pcm16": (ctypes.c_int, [_vp, _fpp, _ip, ctypes.c_int, _fpp, _spp]),
     "xdtts_gl_plan_download_pcm16": (ctypes.c_int, [_vp, _spp]),
     "xdtts_gl_plan_lift_ms": (ctypes.c_int, [_vp, _fp]),
+    "xdtts_gl_plan_time_lift": (ctypes.c_int, [_vp, ctypes.c_int, _fp]),
     "xdtts_pool_create": (ctypes.c_int, [_fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
                                          ctypes.c_float, ctypes.POINTER(GlOpts), _ip, ctypes.c_int, ctypes.POINTER(_vp)]),
     "xdtts_pool_destroy": (None, [_vp]),

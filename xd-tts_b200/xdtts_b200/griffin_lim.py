@@ -189,6 +189,12 @@ class GlPlan:
         check(load_library().xdtts_gl_plan_lift_ms(self._p, ctypes.byref(ms)))
         return ms.value
 
+    def time_lift(self, reps=20):
+        """Device time per launch (ms) of the mel -> linear step, launched reps times back to back after a warm-up."""
+        ms = ctypes.c_float()
+        check(load_library().xdtts_gl_plan_time_lift(self._p, int(reps), ctypes.byref(ms)))
+        return ms.value
+
     def is_persistent(self):
         """True when run() vocodes the plan with the single cooperative launch (all runs resident at once)."""
         rc = load_library().xdtts_gl_plan_is_persistent(self._p)
