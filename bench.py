@@ -482,7 +482,8 @@ def measure(ctx, cfg, utt_ids, steps, warmup, *, kernel=True, blocking=True, pip
             iter_n += n
             lift.append(plan.lift_ms())
         r["kern_stream_ms"] = iter_ms / max(iter_n, 1)
-        r["lift_ms"] = min(lift)
+        r["lift_single_ms"] = min(lift)                      # one launch bracketed by two events (+ launch / event latency)
+        r["lift_ms"] = min(plan.time_lift(20) for _ in range(3))   # a train of 20 launches after a warm-up, per launch
         it_half = it // 2
         voc_half = griffin_lim.GriffinLim.new(basis, n_fft - hop, POWER, it_half, MOMENTUM, seed=shard.rank_seed(0, ctx.rank),
                                               device=ctx.local_rank)
@@ -682,7 +683,7 @@ def run_gpu(args):
         fr, la, vals = shard.reduce_counters(r["frames"], r.get("launches", 0), vals, device="cuda")   # the job's single collective
         return fr, la, dict(zip(keys, vals))
 
-    keys = ["dev_ms", "wall_ms", "e2e_ms", "kern_ms", "call_ms", "call_pageable_ms", "kern_stream_ms", "lift_ms"]
+    keys = ["dev_ms", "wall_ms", "e2e_ms", "kern_ms", "call_ms", "call_pageable_ms", "kern_stream_ms", "lift_ms", "lift_single_ms"]
     total_frames, total_launches, red = reduce(main, keys)
 
     # ---- every N: the other scaling mode as a sub-object (resident + streaming e2e only), so that one run per N gives both
@@ -728,9 +729,12 @@ def run_gpu(args):
         def lift_obj(r, lift_ms):
             alg = r["frames"] * 4 * (N_MELS + r["k"])            # 4 (80 + K) bytes per frame
             ach = alg / (lift_ms * 1e-3) / 1e9
-            return {"bound": "hbm", "kernel": "gl_lift_tc_kernel (tcgen05 kind::tf32, hi/lo split, 3 passes; exp prologue, clamp + ^1.7 epilogue)",
+            return {"bound": "hbm", "kernel": "gl_lift_tc_kernel (tcgen05 kind::f16, fp16 hi/lo split, 3 passes; exp prologue, clamp + ^1.7 epilogue)",
                     "ms": lift_ms, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
-                    "algorithmic_bytes": alg, "how": "CUDA events around the launch in a kernel-by-kernel pass (best of 5)"}
+                    "algorithmic_bytes": alg, "ms_single_bracketed_launch": r.get("lift_single_ms"),
+                    "how": "CUDA events around a train of 20 launches on the library's stream after a warm-up, per launch (best of 3); "
+                           "ms_single_bracketed_launch is one launch between two events in a kernel-by-kernel pass (best of 5) and "
+                           "carries that pair's launch and event latency"}
 
         def postnet_obj(r):
             tpeak, tsrc = measured_tensor_peak()

@@ -34,6 +34,8 @@
 // bits), hence never travel.  All cross-CTA state is read through L2 (ld.global.cg).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "decoder.h"
 #include "gl_core.cuh"   // phase_turn: the counter-based generator shared with the vocoder's phase init
 
@@ -82,9 +84,11 @@ struct GateAcc {
 // segment).  The loads of BOTH rows are issued before either is used (these products are latency-bound: a slice is
 // 2-4 float4 per lane and row, so everything that can be in flight must be).  Rows past the end (last CTAs, second
 // row of warps 12..15) are clamped to a valid row and dropped in lstm_finish.
+// cache: this CTA's 28 rows of exactly these columns in shared memory ([row][128 NC4], filled once in the prologue), or
+// null -- the same values in the same order either way, so the result does not depend on what is cached.
 template <int NB, int NC4>
 __device__ __forceinline__ void lstm_partial(GateAcc<NB>& acc, const float* __restrict__ W, int ld, int col0, const float* zs,
-                                             int zld, int unit0) {
+                                             int zld, int unit0, const float* cache) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int WARPS = DC_THREADS / 32;
     const int r0 = warp, r1 = warp + WARPS < 4 * DC_UNITS ? warp + WARPS : 4 * DC_UNITS - 1;
@@ -92,10 +96,17 @@ __device__ __forceinline__ void lstm_partial(GateAcc<NB>& acc, const float* __re
     const float* wr0 = W + (size_t)((r0 / DC_UNITS) * DC_RNN + u0) * ld + col0 + lane * 4;
     const float* wr1 = W + (size_t)((r1 / DC_UNITS) * DC_RNN + u1) * ld + col0 + lane * 4;
     float4 w0[NC4], w1[NC4];
+    if (cache) {   // CTA-uniform
 #pragma unroll
-    for (int c = 0; c < NC4; c++) w0[c] = __ldg(reinterpret_cast<const float4*>(wr0 + 128 * c));
+        for (int c = 0; c < NC4; c++) w0[c] = *reinterpret_cast<const float4*>(cache + r0 * (128 * NC4) + lane * 4 + 128 * c);
 #pragma unroll
-    for (int c = 0; c < NC4; c++) w1[c] = __ldg(reinterpret_cast<const float4*>(wr1 + 128 * c));
+        for (int c = 0; c < NC4; c++) w1[c] = *reinterpret_cast<const float4*>(cache + r1 * (128 * NC4) + lane * 4 + 128 * c);
+    } else {
+#pragma unroll
+        for (int c = 0; c < NC4; c++) w0[c] = __ldg(reinterpret_cast<const float4*>(wr0 + 128 * c));
+#pragma unroll
+        for (int c = 0; c < NC4; c++) w1[c] = __ldg(reinterpret_cast<const float4*>(wr1 + 128 * c));
+    }
 #pragma unroll
     for (int c = 0; c < NC4; c++) {
 #pragma unroll
@@ -159,9 +170,26 @@ __device__ __forceinline__ float keep_scale(const DecParams& p, int b, int step,
 }
 
 // shared memory of one CTA (floats)
+// LSTM weight slices a CTA may keep in shared memory for the whole loop instead of re-reading them from the L2 every step, in
+// the order they are granted while shared memory lasts (dec_cache_mask): first the two slices that sit ON the critical path
+// of a step (their inputs arrive with the barrier they follow, so their L2 latency cannot hide behind one), then slices
+// streamed behind barriers (less L2 traffic per step: at batch 1 the step is bound by the 72.7 MB it reads from the L2).
+// A slice is this CTA's 28 gate rows x 128 nc4 columns.
+struct DecSlice { int mat, col0, nc4; };   // mat 0: attention LSTM (Wa), 1: decoder LSTM (Wd)
+constexpr int DC_NSLICES = 6;
+__host__ __device__ constexpr DecSlice dec_slice(int id) {
+    return id == 0 ? DecSlice{0, DC_ENC + DC_RNN, 2}     // stage A2: prenet columns of the attention LSTM
+         : id == 1 ? DecSlice{1, 2 * DC_RNN, 4}          // stage D2: context columns of the decoder LSTM
+         : id == 2 ? DecSlice{0, 0, 4}                   // behind D2's barrier: context columns of the attention LSTM
+         : id == 3 ? DecSlice{1, 768, 2}                 // behind C's barrier
+         : id == 4 ? DecSlice{1, 384, 3}                 // behind E's barrier
+         :           DecSlice{1, 0, 3};                  // behind Q's barrier
+}
+__host__ __device__ constexpr int dec_slice_floats(int id) { return 4 * DC_UNITS * 128 * dec_slice(id).nc4; }
+
 template <int NB>
 struct DecSmem {
-    static constexpr int a4(int x) { return (x + 3) & ~3; }  // regions start on 16-byte boundaries (float4 reads)
+    __host__ __device__ static constexpr int a4(int x) { return (x + 3) & ~3; }  // regions start on 16-byte boundaries (float4 reads)
     static constexpr int ZA_LD = DC_ENC + DC_RNN;                  // [ctx | h_att]: attention-LSTM columns streamed ahead
     static constexpr int ZD_LD = 2 * DC_RNN;                       // [h_att | h_dec]: decoder-LSTM columns streamed ahead
     static constexpr int ZA = 0;
@@ -176,7 +204,13 @@ struct DecSmem {
     static constexpr int XIN = a4(CST_D + DC_UNITS * NB);          // [NB][80]
     static constexpr int VS = a4(XIN + NB * DC_MEL);               // [128]
     static constexpr int DYN = a4(VS + DC_ATT);                    // then [NB][t_enc] new weights, [NB][2][t_enc + 30] padded w / w_cum
-    static size_t bytes(int t_enc) { return sizeof(float) * (size_t)(DYN + NB * t_enc + NB * 2 * (t_enc + 30) + 8); }
+    __host__ __device__ static constexpr int cache_off(int t_enc) { return a4(DYN + NB * t_enc + NB * 2 * (t_enc + 30) + 8); }   // the weight cache follows
+    static size_t bytes(int t_enc, unsigned cache_mask) {
+        size_t f = (size_t)cache_off(t_enc);
+        for (int id = 0; id < DC_NSLICES; id++)
+            if (cache_mask >> id & 1) f += (size_t)dec_slice_floats(id);
+        return sizeof(float) * f;
+    }
 };
 
 // Split-phase grid barrier.  A stage publishes its results, ARRIVES, then streams LSTM weight columns whose
@@ -220,6 +254,15 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
     const int t_enc = p.t_enc, wld = t_enc + 2 * (DC_LOCK / 2);
     float* wnew = sm + S::DYN;                 // [NB][t_enc]
     float* wpad = wnew + NB * t_enc;           // [NB][2][wld]
+    const float* wc[DC_NSLICES];               // cached weight slices (null: streamed from the L2)
+    {
+        float* cp = sm + S::cache_off(t_enc);
+#pragma unroll
+        for (int id = 0; id < DC_NSLICES; id++) {
+            wc[id] = (p.cache_mask >> id & 1) ? cp : nullptr;
+            if (p.cache_mask >> id & 1) cp += dec_slice_floats(id);
+        }
+    }
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = gridDim.x, cta = blockIdx.x, nb = p.nb;
@@ -232,6 +275,20 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
     for (int i = tid; i < DC_ATT * (2 * DC_LOCK); i += DC_THREADS)
         weff[(i / (2 * DC_LOCK)) * DC_WEFF_LD + i % (2 * DC_LOCK)] = p.Weff[i];
     for (int i = tid; i < DC_ATT; i += DC_THREADS) vs[i] = p.v[i];
+#pragma unroll
+    for (int id = 0; id < DC_NSLICES; id++) {
+        if (!(p.cache_mask >> id & 1)) continue;
+        const DecSlice sl = dec_slice(id);
+        const float* W = sl.mat ? p.Wd : p.Wa;
+        const int ld = sl.mat ? DC_ZD : DC_ZA;
+        float* dst = const_cast<float*>(wc[id]);
+        for (int i = tid; i < 4 * DC_UNITS * 32 * sl.nc4; i += DC_THREADS) {   // row r = gate * 7 + unit, as lstm_partial indexes it
+            const int r = i / (32 * sl.nc4), c4 = i % (32 * sl.nc4);
+            const int u = min(cta * DC_UNITS + r % DC_UNITS, DC_RNN - 1);
+            *reinterpret_cast<float4*>(dst + r * (128 * sl.nc4) + 4 * c4) =
+                __ldg(reinterpret_cast<const float4*>(W + (size_t)((r / DC_UNITS) * DC_RNN + u) * ld + sl.col0 + 4 * c4));
+        }
+    }
     for (int i = tid; i < NB * 2 * wld; i += DC_THREADS) wpad[i] = 0.f;
     for (int i = tid; i < NB * (ZA_LD + ZD_LD); i += DC_THREADS) zA[i] = 0.f;   // zA and zD are adjacent
     for (int i = tid; i < DC_UNITS * NB; i += DC_THREADS) { cst_a[i] = 0.f; cst_d[i] = 0.f; }
@@ -289,18 +346,18 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
             }
         }
         bar_arrive(p.barrier);
-        if (step) lstm_partial<NB, 4>(acc_a, p.Wa, DC_ZA, DC_ENC + DC_RNN / 2, zA + DC_ENC + DC_RNN / 2, ZA_LD, unit0);
+        if (step) lstm_partial<NB, 4>(acc_a, p.Wa, DC_ZA, DC_ENC + DC_RNN / 2, zA + DC_ENC + DC_RNN / 2, ZA_LD, unit0, nullptr);
         bar_wait(p.barrier, epoch, G);
 
         // ================= stage A2: attention LSTM, prenet columns + cell update  ||  decoder LSTM, second half of h_dec columns
         for (int i = tid; i < nb * DC_PRE; i += DC_THREADS) x2s[i] = __ldcg(p.x2 + i);
         __syncthreads();
-        lstm_partial<NB, 2>(acc_a, p.Wa, DC_ZA, DC_ENC + DC_RNN, x2s, DC_PRE, unit0);
+        lstm_partial<NB, 2>(acc_a, p.Wa, DC_ZA, DC_ENC + DC_RNN, x2s, DC_PRE, unit0, wc[0]);
         lstm_finish<NB>(acc_a, unit0, part_a, p.ba);
         __syncthreads();
         lstm_cell<NB>(part_a, cst_a, unit0, nb, p.h_a + (size_t)nxt * nb * DC_RNN);
         bar_arrive(p.barrier);
-        if (step) lstm_partial<NB, 4>(acc_d, p.Wd, DC_ZD, DC_RNN + DC_RNN / 2, zD + DC_RNN + DC_RNN / 2, ZD_LD, unit0);
+        if (step) lstm_partial<NB, 4>(acc_d, p.Wd, DC_ZD, DC_RNN + DC_RNN / 2, zD + DC_RNN + DC_RNN / 2, ZD_LD, unit0, nullptr);
         bar_wait(p.barrier, epoch, G);
 
         // ================= stage Q: query rows  ||  decoder LSTM, h_att columns [0, 384)
@@ -319,7 +376,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
             }
         }
         bar_arrive(p.barrier);
-        lstm_partial<NB, 3>(acc_d, p.Wd, DC_ZD, 0, zD, ZD_LD, unit0);
+        lstm_partial<NB, 3>(acc_d, p.Wd, DC_ZD, 0, zD, ZD_LD, unit0, wc[5]);
         bar_wait(p.barrier, epoch, G);
 
         // ================= stage E: energies e[b][t] = v . tanh(pq + Weff * [w; w_cum](t-15..t+15) + pm[t])  ||  h_att columns [384, 768)
@@ -394,7 +451,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
             }
         }
         bar_arrive(p.barrier);
-        lstm_partial<NB, 3>(acc_d, p.Wd, DC_ZD, 384, zD + 384, ZD_LD, unit0);
+        lstm_partial<NB, 3>(acc_d, p.Wd, DC_ZD, 384, zD + 384, ZD_LD, unit0, wc[4]);
         bar_wait(p.barrier, epoch, G);
 
         // ================= stage C: softmax (every CTA keeps w / w_cum itself) + context chunks  ||  h_att columns [768, 1024)
@@ -493,7 +550,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
             }
         }
         bar_arrive(p.barrier);
-        lstm_partial<NB, 2>(acc_d, p.Wd, DC_ZD, 768, zD + 768, ZD_LD, unit0);
+        lstm_partial<NB, 2>(acc_d, p.Wd, DC_ZD, 768, zD + 768, ZD_LD, unit0, wc[3]);
         bar_wait(p.barrier, epoch, G);
 
         // ================= stage D2: decoder LSTM, context columns + cell update  ||  attention LSTM of the NEXT step, context columns
@@ -501,12 +558,12 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
         for (int i = tid; i < nb * DC_RNN; i += DC_THREADS)
             zA[(i / DC_RNN) * ZA_LD + DC_ENC + i % DC_RNN] = zD[(i / DC_RNN) * ZD_LD + i % DC_RNN];   // h_att of this step
         __syncthreads();
-        lstm_partial<NB, 4>(acc_d, p.Wd, DC_ZD, 2 * DC_RNN, zA, ZA_LD, unit0);
+        lstm_partial<NB, 4>(acc_d, p.Wd, DC_ZD, 2 * DC_RNN, zA, ZA_LD, unit0, wc[1]);
         lstm_finish<NB>(acc_d, unit0, part_d, p.bd);
         __syncthreads();
         lstm_cell<NB>(part_d, cst_d, unit0, nb, p.h_d + (size_t)nxt * nb * DC_RNN);
         bar_arrive(p.barrier);
-        lstm_partial<NB, 4>(acc_a, p.Wa, DC_ZA, 0, zA, ZA_LD, unit0);
+        lstm_partial<NB, 4>(acc_a, p.Wa, DC_ZA, 0, zA, ZA_LD, unit0, wc[2]);
         bar_wait(p.barrier, epoch, G);
 
         // ================= stage R: projection + gate rows  ||  next step: attention LSTM h_att columns (first half),
@@ -532,8 +589,8 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
             }
         }
         bar_arrive(p.barrier);
-        lstm_partial<NB, 4>(acc_a, p.Wa, DC_ZA, DC_ENC, zA + DC_ENC, ZA_LD, unit0);
-        lstm_partial<NB, 4>(acc_d, p.Wd, DC_ZD, DC_RNN, zD + DC_RNN, ZD_LD, unit0);
+        lstm_partial<NB, 4>(acc_a, p.Wa, DC_ZA, DC_ENC, zA + DC_ENC, ZA_LD, unit0, nullptr);
+        lstm_partial<NB, 4>(acc_d, p.Wd, DC_ZD, DC_RNN, zD + DC_RNN, ZD_LD, unit0, nullptr);
         bar_wait(p.barrier, epoch, G);
 
         // ================= stop rule (src/tacotron2/mod.rs:319-324): every CTA takes the same decision
@@ -587,10 +644,22 @@ cudaError_t dec_launch_transpose(const float* mel_frames, const int* n_frames, i
     return cudaGetLastError();
 }
 
+constexpr int DC_SMEM_MAX = 232448;   // 227 KB
+
+// the weight slices that fit beside the kernel's own shared memory, in dec_slice's order of preference
+template <int NB>
+static unsigned cache_mask_nb(int t_enc) {
+    static const bool off = getenv("XDTTS_DEC_NO_CACHE") != nullptr;   // measurement: stream everything from the L2
+    unsigned mask = 0;
+    if (off) return 0;
+    for (int id = 0; id < DC_NSLICES; id++)
+        if (DecSmem<NB>::bytes(t_enc, mask | 1u << id) <= (size_t)DC_SMEM_MAX) mask |= 1u << id;
+    return mask;
+}
+
 template <int NB>
 static cudaError_t prepare_nb() {
-    return cudaFuncSetAttribute(dec_persist_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)DecSmem<NB>::bytes(DC_MAX_TENC));
+    return cudaFuncSetAttribute(dec_persist_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, DC_SMEM_MAX);
 }
 
 cudaError_t dec_prepare(int* grid_out) {
@@ -603,7 +672,7 @@ cudaError_t dec_prepare(int* grid_out) {
     e = cudaGetDevice(&dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dec_persist_kernel<8>, DC_THREADS, DecSmem<8>::bytes(DC_MAX_TENC));
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dec_persist_kernel<8>, DC_THREADS, DC_SMEM_MAX);
     if (e != cudaSuccess) return e;
     const int need = (DC_RNN + DC_UNITS - 1) / DC_UNITS;   // CTAs that own hidden units
     if (per_sm < 1 || sms < need) return cudaErrorInvalidConfiguration;
@@ -614,9 +683,10 @@ cudaError_t dec_prepare(int* grid_out) {
 template <int NB>
 static cudaError_t launch_nb(const DecParams& p, int grid, cudaStream_t s) {
     DecParams q = p;
+    q.cache_mask = cache_mask_nb<NB>(p.t_enc);
     void* args[1] = {&q};
     return cudaLaunchCooperativeKernel((const void*)dec_persist_kernel<NB>, dim3(grid), dim3(DC_THREADS), args,
-                                       DecSmem<NB>::bytes(p.t_enc), s);
+                                       DecSmem<NB>::bytes(p.t_enc, q.cache_mask), s);
 }
 
 cudaError_t dec_launch(const DecParams& p, int grid, cudaStream_t s) {

@@ -53,6 +53,7 @@ struct DecParams {
     unsigned long long seed;
     int utt_base;           // global index of utterance 0 of this launch (dropout stream)
     int dropout;            // 1: prenet dropout on (the exported graph's behaviour), 0: off
+    unsigned cache_mask;    // set by dec_launch: LSTM weight slices kept in shared memory (decoder.cu dec_slice)
 };
 
 cudaError_t dec_prepare(int* grid_out);
