@@ -139,13 +139,16 @@ DEC_BARRIERS_PER_STEP, DEC_BARRIER_US = 7, 1.23   # grid barriers per decoder st
 def decoder_leg(ctx, with_cpu):
     """The decoder loop: 1000 steps of the Tacotron2 decoder in one persistent kernel, for one
     utterance (the reference's shape) and for 8 in lockstep.  Device time = CUDA events around the launch.
-    Its 72.7 MB of weights stay in the L2 (ncu: 0.15% DRAM throughput, 93% L2 hits), so it is reported against (i) weights /
-    measured L2 read bandwidth -- the bound it sits under -- and (ii) the grid-barrier floor, not against HBM."""
+    Its 72.7 MB of weights stay in the L2 (ncu: 0.15% DRAM throughput, 93% L2 hits) and up to a third of them in shared memory,
+    so it is reported against (i) the grid-barrier floor -- the loop is a chain of 7 dependent grid-wide hops per step, and
+    keeping a third of the LSTM weights in shared memory moved the step by only 2.5% -- and (ii) weights / measured L2 read
+    bandwidth (an upper bound on the L2 time now), not against HBM."""
     tacotron2 = ctx.tacotron2
     device = ctx.local_rank
     wt = synth_decoder_weights()
     dec = tacotron2.Decoder.from_weights(wt, gate_threshold=0.999999, max_steps=DEC_STEPS, seed=1, device=device)
-    out = {"bound": "l2 (the 72.7 MB of weights are re-read from the L2 every step; %d dependent grid-wide hops per step)" % DEC_BARRIERS_PER_STEP,
+    out = {"bound": "latency (%d dependent grid-wide barriers per step and the serial stages between them; L2 reads are not the limiter: "
+                    "with a third of the LSTM weights resident in shared memory the step moved 2.5%%, XDTTS_DEC_NO_CACHE=1 reproduces)" % DEC_BARRIERS_PER_STEP,
            "kernel": "dec_persist_kernel (one cooperative launch = %d decoder steps, %d grid barriers per step)" % (DEC_STEPS, DEC_BARRIERS_PER_STEP),
            "workload": "Tacotron2 decoder loop, t_enc=%d (%d unpadded), %d steps, fp32, synthetic weights" % (DEC_T_ENC, DEC_UNPADDED, DEC_STEPS),
            "weight_bytes_per_step": DEC_WEIGHT_BYTES}
@@ -165,12 +168,13 @@ def decoder_leg(ctx, with_cpu):
     out["floors"] = {"l2_read_gbs_measured": l2, "l2_us_per_step": l2_floor, "barrier_us_per_step": bar_floor,
                      "how": "L2: 64 MB torch reduction repeated in this process; barrier: %d x %.2f us, this kernel's barrier with "
                             "the stage bodies compiled out (DESIGN.md 3.4)" % (DEC_BARRIERS_PER_STEP, DEC_BARRIER_US)}
-    out["frac"] = l2_floor / us                     # of the L2-read floor: the roofline this loop is actually under
+    out["frac"] = bar_floor / us                    # of the barrier floor: the chain of grid-wide hops is what a step cannot go below
+    out["frac_of_l2_floor"] = l2_floor / us         # all 72.7 MB from the L2 at the measured L2 rate (the cached slices no longer are)
     out["achieved"] = DEC_WEIGHT_BYTES / (us * 1e-6) / 1e9
     out["peak"] = l2
-    out["unit"] = "GB/s (L2 read, measured live)"
-    out["frac_of_barrier_floor"] = bar_floor / us
-    out["note"] = "achieved / peak are L2 figures, NOT HBM: the weights never leave the L2 (ncu: DRAM throughput 0.15%, L2 hit rate 93%)"
+    out["unit"] = "GB/s (weight bytes per step / step time against the measured L2 read rate)"
+    out["note"] = ("achieved / peak are L2 figures, NOT HBM: the weights never leave the chip (ncu: DRAM throughput 0.15%, L2 hit rate "
+                   "93%); frac is against the barrier floor")
     if with_cpu:
         from oracle import decoder_oracle as d   # CPU baseline leg only
 
