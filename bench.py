@@ -133,7 +133,7 @@ def measured_l2_read_gbs(torch, device):
     return x.numel() * 4 / (best * 1e-3) / 1e9
 
 
-DEC_BARRIERS_PER_STEP, DEC_BARRIER_US = 7, 1.23   # grid barriers per decoder step; one barrier with empty stages (DESIGN.md 3.4)
+DEC_BARRIERS_PER_STEP, DEC_BARRIER_US = 7, 1.23   # grid barriers per decoder step; one barrier with empty stages (DESIGN.md 3.5)
 
 
 def decoder_leg(ctx, with_cpu):
@@ -167,7 +167,7 @@ def decoder_leg(ctx, with_cpu):
     bar_floor = DEC_BARRIERS_PER_STEP * DEC_BARRIER_US
     out["floors"] = {"l2_read_gbs_measured": l2, "l2_us_per_step": l2_floor, "barrier_us_per_step": bar_floor,
                      "how": "L2: 64 MB torch reduction repeated in this process; barrier: %d x %.2f us, this kernel's barrier with "
-                            "the stage bodies compiled out (DESIGN.md 3.4)" % (DEC_BARRIERS_PER_STEP, DEC_BARRIER_US)}
+                            "the stage bodies compiled out (DESIGN.md 3.5)" % (DEC_BARRIERS_PER_STEP, DEC_BARRIER_US)}
     out["frac"] = bar_floor / us                    # of the barrier floor: the chain of grid-wide hops is what a step cannot go below
     out["frac_of_l2_floor"] = l2_floor / us         # all 72.7 MB from the L2 at the measured L2 rate (the cached slices no longer are)
     out["achieved"] = DEC_WEIGHT_BYTES / (us * 1e-6) / 1e9
