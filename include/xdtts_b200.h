@@ -29,7 +29,7 @@ extern "C" {
 #define XDTTS_ERR_SHAPE (-2)       /* T < 4, K != n_fft/2+1, wrong out_len ... */
 #define XDTTS_ERR_CUDA (-3)        /* CUDA runtime error, no usable sm_100 device */
 #define XDTTS_ERR_OOM (-4)
-#define XDTTS_ERR_UNSUPPORTED (-5) /* n_fft not in {512,1024,2048}, hop != n_fft/4, n_mels > 256 */
+#define XDTTS_ERR_UNSUPPORTED (-5) /* n_fft not a power of two in [64, 4096], n_mels > 256, a graph that is not the expected network */
 
 /* Options whose value the un-vendored crate fixes internally (SURVEY.md section 7 "unknowns");
  * defaults (all zero) are the librosa-0.9.2 behaviour the crate ports -- WITH ONE DELIBERATE EXCEPTION:
@@ -78,8 +78,10 @@ int xdtts_mel_filter_bank(float sr, int n_fft, int n_mels, float fmin, float fma
 int xdtts_pinv(const float* a, int rows, int cols, float* out);
 
 /* GriffinLim::new(mel_basis, noverlap, power, iter, momentum) (call site src/tacotron2/mod.rs:456).
- * mel_basis: [n_mels, K] row-major; n_fft = 2 (K-1); hop = n_fft - noverlap.  Builds the
- * pseudo-inverse of the basis once (host, fp64) and uploads constants to `device`. */
+ * mel_basis: [n_mels, K] row-major; n_fft = 2 (K-1), a power of two in [64, 4096]; hop = n_fft - noverlap, any value in
+ * [1, n_fft].  hop == n_fft / 4 at n_fft 512 / 1024 / 2048 (the shipped call: 1024 / 768) runs the fused kernel -- one
+ * launch per iteration -- every other geometry the un-fused kernels (two launches per iteration, same results contract).
+ * Builds the pseudo-inverse of the basis once (host, fp64) and uploads constants to `device`. */
 int xdtts_gl_create(const float* mel_basis, int n_mels, int K, int noverlap, float power, int n_iter, float momentum,
                     const xdtts_gl_opts* opts_or_null, int device, xdtts_gl** out);
 void xdtts_gl_destroy(xdtts_gl* h);

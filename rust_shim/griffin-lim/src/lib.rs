@@ -5,8 +5,10 @@
 //! Differences from the crate this replaces, all reachable through `GriffinLim::with_options`:
 //!  * the mel -> linear lift is `max(0, pinv(basis) . exp(mel)) ^ power` by default; `Lift::Nnls` (or the cargo feature
 //!    `nnls-lift`, or XDTTS_B200_LIFT=nnls) selects the non-negative least-squares lift librosa's `mel_to_stft` performs;
-//!  * `noverlap` must leave hop == n_fft / 4 and n_fft must be 512, 1024 or 2048 (what `create_griffin_lim` configures:
-//!    1024 / 768); anything else fails in `new` with the library's message ("the fused kernel needs hop == n_fft/4 ...").
+//!  * n_fft = 2 (K - 1) must be a power of two in [64, 4096] (anything else fails in `new` with the library's message); any
+//!    `noverlap` in [0, n_fft) is taken.  hop == n_fft / 4 at n_fft 512 / 1024 / 2048 -- what `create_griffin_lim` configures,
+//!    1024 / 768 -- runs the fused one-launch-per-iteration kernel, every other geometry the un-fused kernels (same results
+//!    contract, ~6x the memory traffic).
 use anyhow::{bail, Result};
 use ndarray::{Array1, Array2};
 use std::ffi::CStr;

@@ -36,6 +36,12 @@ for n_fft, ts in ((1024, [37, 4, 150]), (2048, [21, 9]), (512, [30])):
         got = [r for r in (pipe.push(mels) for _ in range(3)) if r is not None] + pipe.flush()
         assert len(got) == 3 and all(np.array_equal(a, b) for a, b in zip(got[0], w))
         pipe.close()
+# the un-fused path (gl_generic.cu): a hop that is not n_fft / 4, and an n_fft outside the fused kernel's
+for n_fft, hop, ts in ((1024, 200, [9, 31]), (256, 64, [12])):
+    basis = o.create_mel_filter_bank(22050.0, n_fft, 40, 0.0, 8000.0)
+    voc = griffin_lim.GriffinLim.new(basis, n_fft - hop, 1.7, 2, 0.99, fixed_seed=True)
+    ys = voc.infer_batch([o.synth_mel(i, 40, t) for i, t in enumerate(ts)])
+    assert all(y.shape == (hop * (t - 1),) and np.isfinite(y).all() for y, t in zip(ys, ts))
 # decoder loop: batch of 3 (template NB = 4), 6 steps, spin barriers under the sanitizer are slow but finite
 from oracle import decoder_oracle as d  # noqa: E402
 

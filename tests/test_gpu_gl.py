@@ -541,3 +541,53 @@ def test_lift_other_geometries_and_ragged_tiles(gl, n_fft):
         ref = o.lift_pinv_clamp(mw, wide, 1.7, dtype=np.float64)
         got = np.concatenate([pw.peek(0).T, pw.peek(1)[None, :]], 0)
         assert np.abs(got - ref).max() / ref.max() < 1e-5, rows
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_fft,hop", [(1024, 200), (1024, 512), (1024, 1024), (512, 100), (256, 64), (64, 16), (4096, 1024), (2048, 300)])
+def test_any_hop_any_power_of_two_n_fft(gl, n_fft, hop):
+    """GriffinLim::new(mel_basis, noverlap, ...) (src/tacotron2/mod.rs:456) takes any overlap; geometries outside the fused
+    kernel's (hop == n_fft/4 at 512 / 1024 / 2048) run the un-fused kernels of gl_generic.cu: same librosa semantics, checked
+    against the fp64 oracle from the same magnitudes and initial phase."""
+    k = n_fft // 2 + 1
+    ts = [5, 23, 40]
+    basis = o.create_mel_filter_bank(22050.0, n_fft, 40, 0.0, 8000.0)
+    mags = [o.synth_speech_like_mag(60 + i, n_fft, hop, t) for i, t in enumerate(ts)]
+    turns = [o.phase_turns(9, i, k, t) for i, t in enumerate(ts)]
+    for n_iter, pad in ((0, None), (3, None), (3, gl.PAD_CONSTANT)):
+        kw = dict(normalise=gl.NORM_NONE)
+        if pad is not None:
+            kw["pad_mode"] = pad
+        voc = gl.GriffinLim.new(basis, n_fft - hop, 1.7, n_iter, 0.99, **kw)
+        ys = voc.from_magnitude_batch(mags, turns)
+        for i, (s, tu, y) in enumerate(zip(mags, turns, ys)):
+            ref = o.griffin_lim(s, tu, n_iter, 0.99, n_fft, hop, pad_mode=o.PAD_CONSTANT if pad is not None else o.PAD_REFLECT,
+                                dtype=np.float64)
+            assert y.shape == ref.shape == (hop * (ts[i] - 1),)
+            # the CPU fp32 oracle itself is 2e-8 .. 2e-6 from the fp64 one after 3 iterations of these geometries
+            assert rel_rms(y, ref) < (2e-6 if n_iter == 0 else 2e-5), (n_fft, hop, n_iter, i, rel_rms(y, ref))
+        (single,) = voc.from_magnitude_batch([mags[1]], [turns[1]])
+        assert np.array_equal(single, ys[1])                       # a batch returns the bits of single calls
+    # from the mel: lift + seeded phase (== the oracle's phase_turns) + peak normalisation, 8 iterations
+    voc = gl.GriffinLim.new(basis, n_fft - hop, 1.7, 8, 0.99, seed=21, fixed_seed=1)
+    mel = o.synth_mel(3, 40, 30)
+    y = voc.infer(mel)
+    ref = o.infer(mel, basis, n_fft - hop, 1.7, 8, 0.99, o.phase_turns(21, 0, k, 30), dtype=np.float64)
+    assert y.shape == ref.shape and abs(np.abs(y).max() - 1.0) < 1e-6
+    assert rel_rms(y, ref) < 1e-4
+
+
+@pytest.mark.gpu
+def test_unfused_path_agrees_with_the_fused_kernel(gl, monkeypatch):
+    """XDTTS_GL_GENERIC=1 sends the shipped geometry (n_fft 1024, hop 256) through the un-fused kernels: two independent device
+    implementations of the same iteration, compared with each other and with the oracle at 30 iterations."""
+    s = o.synth_speech_like_mag(7, 1024, 256, 120)
+    tu = o.phase_turns(5, 0, 513, 120)
+    fused = make(gl, 1024, 30, normalise=gl.NORM_NONE)
+    (yf,) = fused.from_magnitude_batch([s], [tu])
+    monkeypatch.setenv("XDTTS_GL_GENERIC", "1")
+    unfused = make(gl, 1024, 30, normalise=gl.NORM_NONE)
+    monkeypatch.delenv("XDTTS_GL_GENERIC")
+    (yg,) = unfused.from_magnitude_batch([s], [tu])
+    ref = o.griffin_lim(s, tu, 30, 0.99, 1024, 256, dtype=np.float64)
+    assert rel_rms(yf, ref) < 1e-4 and rel_rms(yg, ref) < 1e-4 and rel_rms(yf, yg) < 1e-4

@@ -117,12 +117,13 @@ def test_pinv_matches_numpy(lib):
 
 def test_argument_validation_without_gpu(lib):
     from xdtts_b200 import griffin_lim
-    from xdtts_b200._ffi import ERR_BAD_ARG, ERR_SHAPE, ERR_UNSUPPORTED, XdttsError
+    from xdtts_b200._ffi import ERR_BAD_ARG, ERR_CUDA, ERR_SHAPE, ERR_UNSUPPORTED, XdttsError
 
     basis = o.create_mel_filter_bank(22050.0, 1024, 80, 0.0, 8000.0)
-    with pytest.raises(XdttsError) as e:
-        griffin_lim.GriffinLim.new(basis, 1024 - 200, 1.7, 30, 0.99)    # hop != n_fft/4
-    assert e.value.code == ERR_UNSUPPORTED
+    try:                                                                # hop != n_fft/4: the un-fused path takes it -- the only
+        griffin_lim.GriffinLim.new(basis, 1024 - 200, 1.7, 30, 0.99)    # way this call fails is the missing GPU
+    except XdttsError as err:
+        assert err.code == ERR_CUDA
     with pytest.raises(XdttsError) as e:
         griffin_lim.GriffinLim.new(basis[:, :400], 768, 1.7, 30, 0.99)  # n_fft = 798
     assert e.value.code == ERR_UNSUPPORTED

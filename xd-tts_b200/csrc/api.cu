@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "api_internal.h"
+#include "gl_generic.h"
 #include "gl_host.h"
 #include "gl_tables.h"
 #include "host_copy.h"
@@ -204,11 +205,13 @@ extern "C" int xdtts_gl_create(const float* mel_basis, int n_mels, int K, int no
     if (n_mels < 1 || K < 2) return fail(XDTTS_ERR_SHAPE, "gl_create: mel_basis must be [n_mels >= 1, K >= 2], got [%d, %d]", n_mels, K);
     if (n_mels > 256) return fail(XDTTS_ERR_UNSUPPORTED, "gl_create: n_mels = %d > 256", n_mels);
     const int n_fft = 2 * (K - 1);
-    if (n_fft != 512 && n_fft != 1024 && n_fft != 2048)
-        return fail(XDTTS_ERR_UNSUPPORTED, "gl_create: n_fft = 2*(K-1) = %d, supported: 512, 1024, 2048", n_fft);
+    if (n_fft < 64 || n_fft > 4096 || (n_fft & (n_fft - 1)))
+        return fail(XDTTS_ERR_UNSUPPORTED, "gl_create: n_fft = 2*(K-1) = %d, supported: the powers of two from 64 to 4096", n_fft);
     if (noverlap < 0 || noverlap >= n_fft) return fail(XDTTS_ERR_BAD_ARG, "gl_create: noverlap = %d not in [0, n_fft = %d)", noverlap, n_fft);
     const int hop = n_fft - noverlap;
-    if (hop * 4 != n_fft) return fail(XDTTS_ERR_UNSUPPORTED, "gl_create: hop = n_fft - noverlap = %d, the fused kernel needs hop == n_fft/4 = %d", hop, n_fft / 4);
+    // the fused one-launch-per-iteration kernel covers hop == n_fft / 4 at n_fft 512 / 1024 / 2048 (the shipped configuration and
+    // its neighbours); every other geometry of GriffinLim::new's signature takes the un-fused kernels of gl_generic.cu
+    const bool generic = !((n_fft == 512 || n_fft == 1024 || n_fft == 2048) && hop * 4 == n_fft) || getenv("XDTTS_GL_GENERIC") != nullptr;
     if (!(power > 0.f) || !std::isfinite(power)) return fail(XDTTS_ERR_BAD_ARG, "gl_create: power must be finite and > 0");
     if (n_iter < 0) return fail(XDTTS_ERR_BAD_ARG, "gl_create: iter must be >= 0");
     if (!(momentum >= 0.f) || !std::isfinite(momentum)) return fail(XDTTS_ERR_BAD_ARG, "gl_create: momentum must be finite and >= 0");
@@ -234,6 +237,7 @@ extern "C" int xdtts_gl_create(const float* mel_basis, int n_mels, int K, int no
     xdtts_gl* h = new (std::nothrow) xdtts_gl();
     if (!h) return fail(XDTTS_ERR_OOM, "gl_create: out of host memory");
     h->device = device; h->n_mels = n_mels; h->K = K; h->n_fft = n_fft; h->hop = hop; h->n_iter = n_iter;
+    h->generic = generic;
     h->power = power; h->momentum = momentum; h->sm_count = prop.multiProcessorCount;
     if (opts) h->opts = *opts;
     if (h->opts.exponent == 1) h->power = 1.0f / power;   // librosa's mel_to_stft convention: S = x ^ (1 / power)
@@ -319,8 +323,11 @@ extern "C" int xdtts_gl_create(const float* mel_basis, int n_mels, int K, int no
         delete h;
         return fail(XDTTS_ERR_BAD_ARG, "gl_create: the NNLS lift needs a non-zero mel basis");
     }
-    std::vector<float2> tab = n_fft == 512 ? build_tables<4>() : (n_fft == 1024 ? build_tables<8>() : build_tables<16>());
-    std::vector<float> edge = build_edge_scale(n_fft);
+    const bool fused_size = n_fft == 512 || n_fft == 1024 || n_fft == 2048;
+    std::vector<float2> tab = !fused_size ? std::vector<float2>(1) : (n_fft == 512 ? build_tables<4>() : (n_fft == 1024 ? build_tables<8>() : build_tables<16>()));
+    std::vector<float> edge = fused_size ? build_edge_scale(n_fft) : std::vector<float>(1);
+    std::vector<float2> gtw = glg_build_twiddles(n_fft);
+    std::vector<float> gwin = glg_build_window(n_fft);
     cudaError_t e = cudaSuccess;
     std::vector<float> img = gl_lift_build_image(h->pinv.data(), K, n_mels, &h->lift_p_exp);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_lift_img, img.size() * 4);
@@ -350,8 +357,15 @@ extern "C" int xdtts_gl_create(const float* mel_basis, int n_mels, int K, int no
     if (e == cudaSuccess) e = cudaMemcpy(h->d_pinvT, pT.data(), pT.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_tables, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_edge, edge.data(), edge.size() * 4, cudaMemcpyHostToDevice);
+    if (generic) {
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_gtw, gtw.size() * sizeof(float2));
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_gwin, gwin.size() * 4);
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_gtw, gtw.data(), gtw.size() * sizeof(float2), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_gwin, gwin.data(), gwin.size() * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = glg_prepare(n_fft);
+    }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = gl_prepare(n_fft);
+    if (e == cudaSuccess && !generic) e = gl_prepare(n_fft);
     if (e != cudaSuccess) {
         xdtts_gl_destroy(h);
         return fail(e == cudaErrorMemoryAllocation ? XDTTS_ERR_OOM : XDTTS_ERR_CUDA, "gl_create: %s", cudaGetErrorString(e));
@@ -368,6 +382,8 @@ extern "C" void xdtts_gl_destroy(xdtts_gl* h) {
     cudaFree(h->d_lift_img);
     cudaFree(h->d_tables);
     cudaFree(h->d_edge);
+    cudaFree(h->d_gtw);
+    cudaFree(h->d_gwin);
     cudaFree(h->d_csr); cudaFree(h->d_csc); cudaFree(h->d_csr_val); cudaFree(h->d_csc_val);
     cudaFree(h->d_band_lo); cudaFree(h->d_bandT); cudaFree(h->d_ell_row); cudaFree(h->d_ell_val);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -395,7 +411,7 @@ extern "C" void xdtts_gl_plan_destroy(xdtts_gl_plan* p) {
     for (auto& e : p->ev)
         if (e) cudaEventDestroy(e);
     cudaFree(p->d_runs); cudaFree(p->d_T); cudaFree(p->d_foff); cudaFree(p->d_out_off);
-    cudaFree(p->d_mel); cudaFree(p->d_in_mag); cudaFree(p->d_in_phase); cudaFree(p->d_turns); cudaFree(p->d_lift_tiles); cudaFree(p->d_seed);
+    cudaFree(p->d_mel); cudaFree(p->d_in_mag); cudaFree(p->d_in_phase); cudaFree(p->d_turns); cudaFree(p->d_lift_tiles); cudaFree(p->d_seed); cudaFree(p->d_frames);
     if (p->h_seed) cudaFreeHost(p->h_seed);
     for (cudaEvent_t e : p->out_ev)
         if (e) cudaEventDestroy(e);
@@ -430,6 +446,7 @@ int xdtts::gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out)
     // duration (256 x 1000 frames as 4000 runs of 64 = 2.25 waves; as 5328 runs of 48 = 3 full waves).
     int rf = h->opts.run_frames;
     if (const char* env = getenv("XDTTS_GL_RUN_FRAMES")) rf = atoi(env);
+    if (h->generic) rf = 64;   // the un-fused path has no runs; the table only carries the frame offsets
     if (rf > 0) {
         if (rf < 4) rf = 4;
         build_runs(Ts, B, rf, &p->runs, &p->foff);
@@ -465,9 +482,9 @@ int xdtts::gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out)
     p->run_frames = rf;
     {   // persistent single-launch path: every run must be resident at once (checked again at launch)
         const char* env = getenv("XDTTS_GL_PERSISTENT");
-        const long long resident = (long long)h->sm_count * gl_resident_warps_per_sm(h->n_fft);
+        const long long resident = h->generic ? 0 : (long long)h->sm_count * gl_resident_warps_per_sm(h->n_fft);
         const bool want = env ? atoi(env) != 0 : h->opts.persistent != 0;
-        p->use_persistent = want && (long long)p->runs.size() <= resident;
+        p->use_persistent = !h->generic && want && (long long)p->runs.size() <= resident;
     }
     p->out_off.resize(B);
     for (int b = 0; b < B; b++) {
@@ -492,6 +509,7 @@ int xdtts::gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out)
     }
     ALLOC(p->d_lift_tiles, p->lift_tiles.size() * sizeof(int4));
     ALLOC(p->d_seed, 8 + (size_t)B * sizeof(int));   // [u64 phase seed][int stream index of each utterance]
+    if (h->generic) ALLOC(p->d_frames, TT * (size_t)h->n_fft * 4);
     ALLOC(p->d_y[0], TT * H * 4);
     ALLOC(p->d_y[1], TT * H * 4);
     ALLOC(p->d_halo, nr * 6 * H * 4);
@@ -686,6 +704,33 @@ static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid, cud
         CU(gl_launch_to_frame_major(p->d_in_phase, p->d_T, p->d_foff, p->B, p->max_T, h->K, p->d_turns, h->K, s));
         launched++;
     }
+    if (h->generic) {   // any hop / any power-of-two n_fft: un-fused kernels, two launches per iteration (gl_generic.cu)
+        GlgParams q;
+        memset(&q, 0, sizeof(q));
+        q.n_fft = h->n_fft; q.hop = h->hop; q.n_utt = p->B;
+        for (q.log_n = 0; (1 << q.log_n) < h->n_fft; q.log_n++) {}
+        q.utt_T = p->d_T; q.utt_foff = p->d_foff; q.state = p->d_state; q.rec_f = p->rec_f; q.frames = p->d_frames; q.y = p->d_y[0];
+        q.turns = use_phase ? p->d_turns : nullptr;
+        q.seed = reinterpret_cast<const unsigned long long*>(p->d_seed);
+        q.utt_seed_id = reinterpret_cast<const int*>(p->d_seed + 8);
+        q.tw = h->d_gtw; q.win = h->d_gwin; q.amax = p->d_amax;
+        q.alpha = h->momentum / (1.0f + h->momentum);
+        q.pad_mode = h->opts.pad_mode;
+        int mids = 0;
+        for (int it = 0; it <= h->n_iter; it++) {
+            if (timed && it == 2) CU(cudaEventRecord(p->ev[1], s));
+            CU(glg_launch_frames(q, it == 0 ? 0 : 1, p->total_T, s));
+            CU(glg_launch_ola(q, it == h->n_iter, p->max_T, s));
+            launched += 2;
+            if (it >= 2 && it < h->n_iter) mids++;
+            if (timed && it == h->n_iter - 1 && it >= 2) CU(cudaEventRecord(p->ev[2], s));
+        }
+        CU(glg_launch_finish(p->d_y[0], p->d_T, p->d_foff, p->d_out_off, p->d_amax, p->B, p->max_T, h->hop, h->opts.normalise == 0, p->d_out, s));
+        launched++;
+        if (n_mid) *n_mid = mids;
+        if (!capturing) g_launches += launched;
+        return XDTTS_OK;
+    }
     GlParams gp;
     memset(&gp, 0, sizeof(gp));
     gp.n_runs = (int)p->runs.size();
@@ -757,7 +802,7 @@ static int plan_launch_graph(xdtts_gl_plan* p, int flags, cudaStream_t s) {
         if (e != cudaSuccess) return fail(XDTTS_ERR_CUDA, "plan_run: graph instantiate: %s", cudaGetErrorString(e));
     }
     CU(cudaGraphLaunch(p->graphs[gi], s));
-    g_launches += (unsigned long long)(h->n_iter + 3 + ((!(flags & XDTTS_RUN_FROM_MAG) && h->opts.lift == 1) ? 1 : 0) + ((flags & XDTTS_RUN_USE_PHASE) ? 1 : 0));
+    g_launches += (unsigned long long)((h->generic ? 2 * h->n_iter + 4 : h->n_iter + 3) + ((!(flags & XDTTS_RUN_FROM_MAG) && h->opts.lift == 1) ? 1 : 0) + ((flags & XDTTS_RUN_USE_PHASE) ? 1 : 0));
     return XDTTS_OK;
 }
 

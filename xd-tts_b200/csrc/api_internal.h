@@ -44,6 +44,9 @@ struct xdtts_gl {
     std::vector<float> pinv;        // [K][n_mels] host copy
     float* d_pinvT = nullptr;       // [n_mels][K]
     float* d_lift_img = nullptr;    // fp16 hi/lo tiles of the scaled pseudo-inverse in the MMA's operand layout (gl_lift.cu)
+    float2* d_gtw = nullptr;        // un-fused path (gl_generic.cu): FFT twiddles and the Hann window
+    float* d_gwin = nullptr;
+    bool generic = false;           // geometry outside the fused kernel's: any hop, any power-of-two n_fft
     float lift_p_exp = 0.f;         // ... which holds pinv * 2^lift_p_exp
     float2* d_tables = nullptr;
     float* d_edge = nullptr;
@@ -79,6 +82,7 @@ struct xdtts_gl_plan {
     std::vector<int4> lift_tiles;    // (frame row of the utterance, its T, first frame, 0) of every frame tile of the lift
     int4* d_lift_tiles = nullptr;
     int lift_tile_frames = 64;
+    float* d_frames = nullptr;       // un-fused path: [total frames][n_fft] windowed inverse transforms
     unsigned char *d_seed = nullptr, *h_seed = nullptr;   // [u64 phase seed][int stream index per utterance], device + pinned
     short* d_pcm = nullptr;          // 16-bit PCM copy of d_out (allocated on first use)
     short* h_pcm = nullptr;
