@@ -6,12 +6,13 @@
 // One step of the exported graph (NVIDIA Tacotron2 Decoder.decode, oracle/decoder_oracle.py):
 //   prenet (2 x linear+relu+dropout) -> attention LSTM -> location-sensitive attention -> decoder LSTM
 //   -> linear projection (mel frame) + gate.
-// At batch 1 this is a chain of matrix-vector products: 18.2 M weights = 72.7 MB fp32 are read once per
-// step (they stay in the 126 MB L2) and everything else is latency, so the design is about (1) streaming the two LSTM matrices with
-// every SM at once, (2) keeping all state on chip or in L2 between steps, (3) as few grid-wide barriers as
-// the data dependences allow, with the weight streaming placed so that it overlaps the small serial stages:
+// At batch 1 this is a chain of matrix-vector products: 18.2 M weights = 72.7 MB fp32 are read once per step (they stay
+// in the 126 MB L2, a third of a CTA's share in its shared memory) and everything else is latency, so the design is about
+// (1) streaming the two LSTM matrices with every SM at once, (2) keeping all state on chip or in L2 between steps,
+// (3) making the seven hand-overs between CTAs that a step needs as short as the hardware allows, with the weight
+// streaming placed so that it overlaps the small serial stages:
 //
-//   stage     on the critical path (published before the barrier)            streamed behind the barrier
+//   stage     on the critical path (published for the next stage)               streamed while the cells travel
 //   P   prenet layer 1 (every CTA, redundantly) + layer 2 rows (one per CTA)    att. LSTM, h_att columns (2nd half)
 //   A2  attention LSTM: the 256 prenet columns + cell update                    dec. LSTM, h_dec columns (2nd half)
 //   Q   query rows (one per CTA)                                                dec. LSTM, h_att columns [0, 384)
@@ -20,19 +21,22 @@
 //   D2  decoder LSTM: the 512 context columns + cell update                     NEXT step's att. LSTM, ctx columns
 //   R   projection + gate rows (one per CTA)                                    NEXT step: att. LSTM h_att (1st half),
 //                                                                               dec. LSTM h_dec (1st half)
-// Every barrier is split-phase: a stage publishes its small result, arrives, streams LSTM weight columns whose
-// input vectors are already known (82% of the bytes of a step) and only then waits, so the barrier latency and
-// the serial stages overlap the weight traffic instead of adding to it.
+// There is NO grid barrier: a stage publishes each of its results as a 64-bit cell {value, step tag} -- one store that
+// carries the data and its own "ready" flag -- then streams LSTM weight columns whose input vectors are already known
+// (82% of the bytes of a step), and the next stage polls exactly the cells it consumes (cell_put / cell_get below).
+// Round 1 and most of round 2 used split-phase grid barriers (arrive -> stream -> wait); stamps around them showed
+// ~1000 cycles per arrival spent waiting for the CTA's stores to be acknowledged before the release could go out, the
+// arrival's own trip to the L2, the poll, and then one more L2 round trip to load the data: 19.2 us per step, 17.3 with cells.
 //
 // CTA c owns hidden units [7c, 7c+7) of both LSTMs: their four gate rows, the partial gate sums (per lane, in
-// registers, across slices and barriers) and the cell state never leave the SM.  A warp computes two weight rows
+// registers, across slices and stages) and the cell state never leave the SM.  A warp computes two weight rows
 // at a time against up to 8 utterances' input vectors held in shared memory (float4 loads, all loads of a slice in
 // flight; one shuffle reduction per row and step), so the weights are read once per step however many utterances
-// decode in lockstep.  Measured (B200): 19.2 us per step at batch 1, of which 8.6 us are the seven barriers; the rest is
-// dependent instruction chains in the serial stages, NOT weight traffic: keeping a third of a CTA's LSTM rows in shared memory
-// for the whole loop (dec_slice below) moved the step from 19.7 to 19.2 us.
+// decode in lockstep.  What bounds the step is dependent instruction chains and L2 latency in the serial stages, NOT
+// weight traffic: keeping a third of a CTA's LSTM rows in shared memory for the whole loop (dec_slice below) moved
+// the step by 2.5%.
 // Attention weights / cumulative weights are kept by every CTA in shared memory (same instructions, same
-// bits), hence never travel.  All cross-CTA state is read through L2 (ld.global.cg).
+// bits), hence never travel.
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -43,6 +47,108 @@
 namespace xdtts {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// Cross-CTA hand-over without barriers.  Every value one stage publishes for the next (a prenet output, a hidden unit, a
+// query entry, an energy, a context dimension, a mel bin) travels as ONE 64-bit cell {value, tag}, tag = step + 1: a single
+// store, atomic by size, carries the data and its own "ready" flag, and a consumer polls the cells it needs until their
+// tag is this step's.  Against a grid barrier this removes, per stage, the release (~700 cycles waiting for the CTA's
+// stores to be acknowledged before the arrival may be sent), the arrival's trip to the L2, and the separate load of the
+// data after the wait: store -> L2 -> poll is the whole critical path (measured: 19.2 -> see DESIGN.md 3.5 us per step).
+// A cell is rewritten one step later; by then every reader of the old value has published something that needed it
+// (the stages of a step form one dependence chain through all CTAs), so one buffer per stage is enough.
+// Polling is bounded: a cooperative launch keeps all CTAs resident, so a cell is only ever late, never lost, but a bound
+// turns any mistake into an error code instead of a hung GPU.
+constexpr unsigned DC_SPIN_LIMIT = 1u << 24;
+
+__device__ __forceinline__ void cell_put(dc_cell* c, float v, unsigned tag) {
+    const dc_cell w = ((dc_cell)tag << 32) | (dc_cell)__float_as_uint(v);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(c), "l"(w) : "memory");
+}
+__device__ __forceinline__ dc_cell cell_peek(const dc_cell* c) {
+    dc_cell w;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(c) : "memory");
+    return w;
+}
+__device__ __forceinline__ float cell_wait(const dc_cell* c, dc_cell w, unsigned tag, int* err) {   // w: a first peek
+    unsigned spins = 0;
+    while ((unsigned)(w >> 32) != tag) {
+        if (++spins > DC_SPIN_LIMIT) {
+            *err = 1;
+            break;
+        }
+        __nanosleep(32);
+        w = cell_peek(c);
+    }
+    return __uint_as_float((unsigned)w);
+}
+// POLL = false: the batch-of-4-and-more form, where a grid barrier stands between producer and consumer and the cells are
+// read once, unchecked (see hand_over below)
+template <bool POLL>
+__device__ __forceinline__ float cell_get(const dc_cell* c, unsigned tag, int* err) {
+    const dc_cell w = cell_peek(c);
+    return POLL ? cell_wait(c, w, tag, err) : __uint_as_float((unsigned)w);
+}
+
+// n <= PER * DC_THREADS cells -> shared memory, dst[(i / row) * ld + i % row].  All of a thread's peeks are in flight before
+// the first is checked (one L2 round trip for the whole vector when the values are already there); cells that are not,
+// are peeked again together after a short sleep -- 75 k threads re-polling without one flood the L2 the producers write through.
+template <int PER, bool POLL>
+__device__ __forceinline__ void cells_to_smem(const dc_cell* src, int n, int row, float* dst, int ld, unsigned tag, int* err) {
+    if (!POLL) {
+#pragma unroll 4
+        for (int i = threadIdx.x; i < n; i += DC_THREADS) dst[(i / row) * ld + i % row] = __uint_as_float((unsigned)cell_peek(src + i));
+        return;
+    }
+    unsigned pending = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++)
+        if ((int)threadIdx.x + k * DC_THREADS < n) pending |= 1u << k;
+    unsigned spins = 0;
+    while (pending) {
+        dc_cell w[PER];
+#pragma unroll
+        for (int k = 0; k < PER; k++)
+            if (pending >> k & 1) w[k] = cell_peek(src + threadIdx.x + k * DC_THREADS);
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            if ((pending >> k & 1) && (unsigned)(w[k] >> 32) == tag) {
+                const int i = threadIdx.x + k * DC_THREADS;
+                dst[(i / row) * ld + i % row] = __uint_as_float((unsigned)w[k]);
+                pending &= ~(1u << k);
+            }
+        }
+        if (pending) {
+            if (++spins > (DC_SPIN_LIMIT >> 4)) {
+                *err = 1;
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+}
+
+// The grid barrier of the batch >= 4 form (split-phase: arrive -> stream weight columns -> wait).  With 4 or 8 utterances in
+// lockstep a stage hands over 4-8 k values per vector; polling each of them costs more (register-resident peeks, twice the
+// bytes in flight) than the barrier's fixed ~1 us, so large batches keep the barrier and read the cells once, unchecked.
+__device__ __forceinline__ void bar_arrive(unsigned* counter) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // release at gpu scope: cumulative over the CTA's stores ordered before it by the barrier above.  (A
+        // __threadfence() here compiles to MEMBAR.SC + an L1 invalidate and costs a fifth of the barrier.)
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    }
+}
+__device__ __forceinline__ void bar_wait(unsigned* counter, unsigned& epoch, unsigned n_ctas) {
+    epoch += n_ctas;
+    if (threadIdx.x == 0) {
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < epoch);
+    }
+    __syncthreads();
+}
+
 
 // dot products of `ncols` consecutive weights (a multiple of 128) with NB vectors in shared memory
 // (vector b starts at zs + b * zld); every lane ends up with the full sums added to acc[]
@@ -151,7 +257,7 @@ __device__ __forceinline__ void lstm_finish(GateAcc<NB>& acc, int unit0, float* 
 
 // LSTM cell update of this CTA's units from the finished gate sums; h goes to global memory
 template <int NB>
-__device__ __forceinline__ void lstm_cell(const float* part, float* cst, int unit0, int nb, float* h_out) {
+__device__ __forceinline__ void lstm_cell(const float* part, float* cst, int unit0, int nb, dc_cell* h_out, unsigned tag) {
     const int t = threadIdx.x;
     if (t < DC_UNITS * NB) {
         const int u = t / NB, b = t % NB, unit = unit0 + u;
@@ -160,7 +266,7 @@ __device__ __forceinline__ void lstm_cell(const float* part, float* cst, int uni
             const float gg = part[(2 * DC_UNITS + u) * NB + b], go = part[(3 * DC_UNITS + u) * NB + b];
             const float c = sigmoidf_(gf) * cst[u * NB + b] + sigmoidf_(gi) * tanhf(gg);
             cst[u * NB + b] = c;
-            h_out[(size_t)b * DC_RNN + unit] = sigmoidf_(go) * tanhf(c);
+            cell_put(h_out + (size_t)b * DC_RNN + unit, sigmoidf_(go) * tanhf(c), tag);
         }
     }
 }
@@ -214,28 +320,6 @@ struct DecSmem {
     }
 };
 
-// Split-phase grid barrier.  A stage publishes its results, ARRIVES, then streams LSTM weight columns whose
-// inputs were already known, and only then WAITS: the barrier's latency (two L2 round trips) is hidden
-// behind useful memory traffic instead of being paid seven times per step.
-__device__ __forceinline__ void bar_arrive(unsigned* counter) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        // release at gpu scope: cumulative over the CTA's stores ordered before it by the barrier above.  (A
-        // __threadfence() here compiles to MEMBAR.SC + an L1 invalidate and costs a fifth of the barrier.)
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
-    }
-}
-__device__ __forceinline__ void bar_wait(unsigned* counter, unsigned& epoch, unsigned n_ctas) {
-    epoch += n_ctas;
-    if (threadIdx.x == 0) {
-        unsigned v;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-        } while (v < epoch);
-    }
-    __syncthreads();
-}
-
 template <int NB>
 __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecParams p) {
     extern __shared__ __align__(16) float sm[];
@@ -269,8 +353,19 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
     const int G = gridDim.x, cta = blockIdx.x, nb = p.nb;
     const int unit0 = cta * DC_UNITS;
     constexpr int WARPS = DC_THREADS / 32;
-    constexpr int LIGHT_WARP = WARPS - 1;      // has one LSTM row where most warps have two
+    constexpr bool POLL = NB <= 2;             // hand-over by polled cells (batch 1-2) or by grid barrier (batch 4-8)
     unsigned epoch = 0;
+    // between publishing a stage's results and consuming the next stage's inputs: a CTA-wide sync (the stages reuse shared
+    // scratch) and, in the barrier form, the split-phase grid barrier around the streamed weight columns
+    auto hand_over_publish = [&]() {
+        if (POLL) __syncthreads();
+        else bar_arrive(p.barrier);
+    };
+    auto hand_over_consume = [&]() {
+        if (POLL) __syncthreads();
+        else bar_wait(p.barrier, epoch, G);
+    };
+    constexpr int LIGHT_WARP = WARPS - 1;      // has one LSTM row where most warps have two
 
     // ---- prologue: constants and the all-zero DecoderState (src/tacotron2/mod.rs:212-236)
     for (int i = tid; i < DC_ATT * (2 * DC_LOCK); i += DC_THREADS)
@@ -304,10 +399,11 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
     int step = 0;
     for (; step < p.max_steps; step++) {
         const int cur = step & 1, nxt = cur ^ 1;
+        const unsigned tag = (unsigned)step + 1u;   // of everything this step publishes
         // ================= stage P: prenet of this step  ||  attention LSTM, second half of its h_att columns
         for (int i = tid; i < nb * DC_MEL; i += DC_THREADS) {
             const int b = i / DC_MEL, k = i % DC_MEL;
-            xin[b * DC_MEL + k] = step ? __ldcg(p.mel_out + ((size_t)b * p.max_steps + (step - 1)) * DC_MEL + k) : 0.f;
+            xin[b * DC_MEL + k] = step ? cell_get<POLL>(p.melt + b * (DC_MEL + 1) + k, tag - 1u, p.err) : 0.f;   // the previous step's frame
         }
         __syncthreads();
         {   // layer 1: thread = (output row, half of the 80 inputs); the 40 weight loads of a thread are all in flight
@@ -343,27 +439,26 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
             if (lane == 0) {
 #pragma unroll
                 for (int b = 0; b < NB; b++)
-                    if (b < nb) p.x2[b * DC_PRE + r] = fmaxf(acc[b], 0.f) * keep_scale(p, b, step, 1, r);
+                    if (b < nb) cell_put(p.x2 + b * DC_PRE + r, fmaxf(acc[b], 0.f) * keep_scale(p, b, step, 1, r), tag);
             }
         }
-        bar_arrive(p.barrier);
+        hand_over_publish();
         if (step) lstm_partial<NB, 4>(acc_a, p.Wa, DC_ZA, DC_ENC + DC_RNN / 2, zA + DC_ENC + DC_RNN / 2, ZA_LD, unit0, nullptr);
-        bar_wait(p.barrier, epoch, G);
+        hand_over_consume();
 
         // ================= stage A2: attention LSTM, prenet columns + cell update  ||  decoder LSTM, second half of h_dec columns
-        for (int i = tid; i < nb * DC_PRE; i += DC_THREADS) x2s[i] = __ldcg(p.x2 + i);
+        cells_to_smem<(NB * DC_PRE + DC_THREADS - 1) / DC_THREADS, POLL>(p.x2, nb * DC_PRE, DC_PRE, x2s, DC_PRE, tag, p.err);
         __syncthreads();
         lstm_partial<NB, 2>(acc_a, p.Wa, DC_ZA, DC_ENC + DC_RNN, x2s, DC_PRE, unit0, wc[0]);
         lstm_finish<NB>(acc_a, unit0, part_a, p.ba);
         __syncthreads();
-        lstm_cell<NB>(part_a, cst_a, unit0, nb, p.h_a + (size_t)nxt * nb * DC_RNN);
-        bar_arrive(p.barrier);
+        lstm_cell<NB>(part_a, cst_a, unit0, nb, p.h_a + (size_t)nxt * nb * DC_RNN, tag);
+        hand_over_publish();
         if (step) lstm_partial<NB, 4>(acc_d, p.Wd, DC_ZD, DC_RNN + DC_RNN / 2, zD + DC_RNN + DC_RNN / 2, ZD_LD, unit0, nullptr);
-        bar_wait(p.barrier, epoch, G);
+        hand_over_consume();
 
         // ================= stage Q: query rows  ||  decoder LSTM, h_att columns [0, 384)
-        for (int i = tid; i < nb * DC_RNN; i += DC_THREADS)
-            zD[(i / DC_RNN) * ZD_LD + i % DC_RNN] = __ldcg(p.h_a + (size_t)nxt * nb * DC_RNN + i);
+        cells_to_smem<(NB * DC_RNN + DC_THREADS - 1) / DC_THREADS, POLL>(p.h_a + (size_t)nxt * nb * DC_RNN, nb * DC_RNN, DC_RNN, zD, ZD_LD, tag, p.err);
         __syncthreads();
         if (warp == LIGHT_WARP && cta < DC_ATT) {
             float acc[NB];
@@ -373,12 +468,12 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
             if (lane == 0) {
 #pragma unroll
                 for (int b = 0; b < NB; b++)
-                    if (b < nb) p.pq[b * DC_ATT + cta] = acc[b];
+                    if (b < nb) cell_put(p.pq + b * DC_ATT + cta, acc[b], tag);
             }
         }
-        bar_arrive(p.barrier);
+        hand_over_publish();
         lstm_partial<NB, 3>(acc_d, p.Wd, DC_ZD, 0, zD, ZD_LD, unit0, wc[5]);
-        bar_wait(p.barrier, epoch, G);
+        hand_over_consume();
 
         // ================= stage E: energies e[b][t] = v . tanh(pq + Weff * [w; w_cum](t-15..t+15) + pm[t])  ||  h_att columns [384, 768)
         if (nb * t_enc <= G) {
@@ -400,7 +495,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
             }
             float q = 0.f, m = 0.f;
             if (have && tid < DC_ATT) {
-                q = __ldcg(p.pq + b * DC_ATT + tid);
+                q = cell_get<POLL>(p.pq + b * DC_ATT + tid, tag, p.err);
                 m = __ldg(p.pm + ((size_t)b * t_enc + t) * DC_ATT + tid);
             }
             __syncthreads();
@@ -416,7 +511,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
                 for (int j = 0; j < DC_ATT / 32; j++) s = fmaf(vs[lane + 32 * j], scratch[lane + 32 * j], s);
 #pragma unroll
                 for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (lane == 0) p.e[b * t_enc + t] = s;
+                if (lane == 0) cell_put(p.e + b * t_enc + t, s, tag);
             }
         } else {
             for (int item = cta + G * warp; item < nb * t_enc; item += G * WARPS) {
@@ -442,18 +537,18 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
                         }
                     }
                     const float pa = (pa0 + pa1) + (pa2 + pa3);
-                    const float q = __ldcg(p.pq + b * DC_ATT + a);
+                    const float q = cell_get<POLL>(p.pq + b * DC_ATT + a, tag, p.err);
                     const float m = __ldg(p.pm + ((size_t)b * t_enc + t) * DC_ATT + a);
                     s = fmaf(vs[a], tanhf(q + pa + m), s);
                 }
 #pragma unroll
                 for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (lane == 0) p.e[b * t_enc + t] = s;
+                if (lane == 0) cell_put(p.e + b * t_enc + t, s, tag);
             }
         }
-        bar_arrive(p.barrier);
+        hand_over_publish();
         lstm_partial<NB, 3>(acc_d, p.Wd, DC_ZD, 384, zD + 384, ZD_LD, unit0, wc[4]);
-        bar_wait(p.barrier, epoch, G);
+        hand_over_consume();
 
         // ================= stage C: softmax (every CTA keeps w / w_cum itself) + context chunks  ||  h_att columns [768, 1024)
         if (NB <= 2) {
@@ -464,7 +559,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
             const int nj = (t_enc + 31) / 32;
             for (int b = 0; b < nb; b++) {
                 const int tl = p.t_len[b];
-                const float ev = tid < tl ? __ldcg(p.e + b * t_enc + tid) : -INFINITY;
+                const float ev = tid < tl ? cell_get<POLL>(p.e + b * t_enc + tid, tag, p.err) : -INFINITY;
                 float m = ev;
 #pragma unroll
                 for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -501,7 +596,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
             for (int j = 0; j < DC_MAX_TENC / 32; j++) {
                 if (j >= nj) break;
                 const int t = lane + 32 * j;
-                ev[j] = t < tl ? __ldcg(p.e + b * t_enc + t) : -INFINITY;
+                ev[j] = t < tl ? cell_get<POLL>(p.e + b * t_enc + t, tag, p.err) : -INFINITY;
                 m = fmaxf(m, ev[j]);
             }
 #pragma unroll
@@ -545,32 +640,31 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
                     float sum = 0.f;
 #pragma unroll
                     for (int w = 0; w < WARPS; w++) sum += scratch[w * 32 + tid];
-                    p.ctx[b * DC_ENC + d0 + tid] = sum;   // read by every CTA after the barrier
+                    cell_put(p.ctx + b * DC_ENC + d0 + tid, sum, tag);   // read by every CTA in stage D2
                 }
                 __syncthreads();
             }
         }
-        bar_arrive(p.barrier);
+        hand_over_publish();
         lstm_partial<NB, 2>(acc_d, p.Wd, DC_ZD, 768, zD + 768, ZD_LD, unit0, wc[3]);
-        bar_wait(p.barrier, epoch, G);
+        hand_over_consume();
 
         // ================= stage D2: decoder LSTM, context columns + cell update  ||  attention LSTM of the NEXT step, context columns
-        for (int i = tid; i < nb * DC_ENC; i += DC_THREADS) zA[(i / DC_ENC) * ZA_LD + i % DC_ENC] = __ldcg(p.ctx + i);
+        cells_to_smem<(NB * DC_ENC + DC_THREADS - 1) / DC_THREADS, POLL>(p.ctx, nb * DC_ENC, DC_ENC, zA, ZA_LD, tag, p.err);
         for (int i = tid; i < nb * DC_RNN; i += DC_THREADS)
             zA[(i / DC_RNN) * ZA_LD + DC_ENC + i % DC_RNN] = zD[(i / DC_RNN) * ZD_LD + i % DC_RNN];   // h_att of this step
         __syncthreads();
         lstm_partial<NB, 4>(acc_d, p.Wd, DC_ZD, 2 * DC_RNN, zA, ZA_LD, unit0, wc[1]);
         lstm_finish<NB>(acc_d, unit0, part_d, p.bd);
         __syncthreads();
-        lstm_cell<NB>(part_d, cst_d, unit0, nb, p.h_d + (size_t)nxt * nb * DC_RNN);
-        bar_arrive(p.barrier);
+        lstm_cell<NB>(part_d, cst_d, unit0, nb, p.h_d + (size_t)nxt * nb * DC_RNN, tag);
+        hand_over_publish();
         lstm_partial<NB, 4>(acc_a, p.Wa, DC_ZA, 0, zA, ZA_LD, unit0, wc[2]);
-        bar_wait(p.barrier, epoch, G);
+        hand_over_consume();
 
         // ================= stage R: projection + gate rows  ||  next step: attention LSTM h_att columns (first half),
         //                   decoder LSTM h_dec columns (first half)
-        for (int i = tid; i < nb * DC_RNN; i += DC_THREADS)
-            zD[(i / DC_RNN) * ZD_LD + DC_RNN + i % DC_RNN] = __ldcg(p.h_d + (size_t)nxt * nb * DC_RNN + i);
+        cells_to_smem<(NB * DC_RNN + DC_THREADS - 1) / DC_THREADS, POLL>(p.h_d + (size_t)nxt * nb * DC_RNN, nb * DC_RNN, DC_RNN, zD + DC_RNN, ZD_LD, tag, p.err);
         __syncthreads();
         if (warp == LIGHT_WARP && cta <= DC_MEL) {
             float acc[NB];
@@ -586,20 +680,21 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
                     if (b >= nb) continue;
                     if (cta < DC_MEL) p.mel_out[((size_t)b * p.max_steps + step) * DC_MEL + cta] = acc[b] + bias;
                     else p.gate_out[(size_t)b * p.max_steps + step] = acc[b] + bias;
+                    cell_put(p.melt + b * (DC_MEL + 1) + cta, acc[b] + bias, tag);   // the in-loop copy: next step's prenet, the stop rule
                 }
             }
         }
-        bar_arrive(p.barrier);
+        hand_over_publish();
         lstm_partial<NB, 4>(acc_a, p.Wa, DC_ZA, DC_ENC, zA + DC_ENC, ZA_LD, unit0, nullptr);
         lstm_partial<NB, 4>(acc_d, p.Wd, DC_ZD, DC_RNN, zD + DC_RNN, ZD_LD, unit0, nullptr);
-        bar_wait(p.barrier, epoch, G);
+        hand_over_consume();
 
         // ================= stop rule (src/tacotron2/mod.rs:319-324): every CTA takes the same decision
         bool all = true;
 #pragma unroll
         for (int b = 0; b < NB; b++) {
             if (b < nb && !done[b]) {
-                const float g = __ldcg(p.gate_out + (size_t)b * p.max_steps + step);
+                const float g = cell_get<POLL>(p.melt + b * (DC_MEL + 1) + DC_MEL, tag, p.err);
                 // the reference's sigmoid (src/tacotron2/mod.rs:126-133)
                 const float sg = g >= 0.f ? 1.0f / (1.0f + expf(-g)) : expf(g) / (1.0f + expf(g));
                 if (sg > p.gate_threshold) {

@@ -17,6 +17,8 @@ constexpr int DC_MAX_TENC = 512;
 constexpr int DC_MAX_NB = 8;                       // utterances decoded in lockstep by one launch
 constexpr int DC_WEFF_LD = 2 * DC_LOCK + 1;        // padded row of the fused location filter (bank-conflict free)
 
+typedef unsigned long long dc_cell;   // {value, tag}: a float and the step that published it (decoder.cu)
+
 struct DecParams {
     // weights, re-laid out on the host (decoder_api.cu)
     const float* p1T;    // [80][256]     prenet layer 1, transposed
@@ -36,18 +38,20 @@ struct DecParams {
     const float* memory;    // [nb][t_enc][512]
     const float* pm;        // [nb][t_enc][128]  processed_memory
     const int* t_len;       // [nb] unpadded lengths (mask: t >= t_len)
-    // cross-CTA state in global memory
-    float* x2;              // [nb][256]           prenet output of the current step
-    float* h_a;             // [2][nb][1024]       attention LSTM hidden state, double buffered by step parity
-    float* h_d;             // [2][nb][1024]
-    float* ctx;             // [nb][512]           attention context of the current step
-    float* pq;              // [nb][128]           processed query
-    float* e;               // [nb][t_enc]         attention energies
+    // cross-CTA state in global memory: cells {value, tag = step + 1}, all zero at launch
+    dc_cell* x2;            // [nb][256]           prenet output of the current step
+    dc_cell* h_a;           // [2][nb][1024]       attention LSTM hidden state, double buffered by step parity
+    dc_cell* h_d;           // [2][nb][1024]
+    dc_cell* ctx;           // [nb][512]           attention context of the current step
+    dc_cell* pq;            // [nb][128]           processed query
+    dc_cell* e;             // [nb][t_enc]         attention energies
+    dc_cell* melt;          // [nb][81]            the step's mel frame and gate logit (the in-loop copy of mel_out / gate_out)
+    int* err;               // set to 1 if a poll ran into its bound (never, unless the kernel is wrong)
+    unsigned* barrier;      // grid barrier counter of the batch >= 4 form, zero at launch
     float* mel_out;         // [nb][max_steps][80] decoder outputs, frame major (also the next step's input)
     float* gate_out;        // [nb][max_steps]     gate logits
     float* align_out;       // [nb][max_steps][t_enc] attention weights, or null
     int* n_frames;          // [nb] frames produced (the frame whose gate fired is kept)
-    unsigned* barrier;      // grid barrier counter, zero at launch
     int max_steps;
     float gate_threshold;   // stop when sigmoid(gate) > threshold
     unsigned long long seed;

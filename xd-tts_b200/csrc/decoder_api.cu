@@ -25,10 +25,11 @@ struct xdtts_decoder {
           *Wd = nullptr, *bd = nullptr, *Wp = nullptr, *bp = nullptr;
     // workspace for one group of DC_MAX_NB utterances
     int ws_t_enc = 0;
-    float *memory = nullptr, *pm = nullptr, *state = nullptr, *mel_out = nullptr, *gate_out = nullptr, *align_out = nullptr,
+    dc_cell* state = nullptr;
+    float *memory = nullptr, *pm = nullptr, *mel_out = nullptr, *gate_out = nullptr, *align_out = nullptr,
           *mel_T = nullptr;
     int *t_len = nullptr, *n_frames = nullptr;
-    unsigned* barrier = nullptr;
+    int* err = nullptr;             // [0] poll error flag, [1] grid barrier counter
     float *h_stage = nullptr;          // pinned staging for pageable callers / results
     size_t h_stage_floats = 0;
     cudaStream_t stream = nullptr;
@@ -49,9 +50,10 @@ extern "C" void xdtts_decoder_destroy(xdtts_decoder* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     float* bufs[] = {h->p1T, h->p2, h->Wa, h->ba, h->Wq, h->v, h->Weff, h->Wd, h->bd, h->Wp, h->bp,
-                     h->memory, h->pm, h->state, h->mel_out, h->gate_out, h->align_out, h->mel_T};
+                     h->memory, h->pm, h->mel_out, h->gate_out, h->align_out, h->mel_T};
     for (float* b : bufs) cudaFree(b);
-    cudaFree(h->t_len); cudaFree(h->n_frames); cudaFree(h->barrier);
+    cudaFree(h->state);
+    cudaFree(h->t_len); cudaFree(h->n_frames); cudaFree(h->err);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
@@ -150,14 +152,14 @@ extern "C" int xdtts_decoder_create(const xdtts_decoder_weights* w, const xdtts_
     if (e == cudaSuccess) e = upload(&h->Wp, Wp);
     if (e == cudaSuccess) e = upload(&h->bp, bp);
     const size_t nb = DC_MAX_NB, ms = (size_t)h->max_steps;
-    const size_t state_floats = nb * (DC_PRE + 4 * DC_RNN + DC_ENC + DC_ATT + DC_MAX_TENC);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&h->state, state_floats * 4);
+    const size_t state_cells = nb * (DC_PRE + 4 * DC_RNN + DC_ENC + DC_ATT + DC_MAX_TENC + DC_MEL + 1);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->state, state_cells * sizeof(dc_cell));
     if (e == cudaSuccess) e = cudaMalloc((void**)&h->mel_out, nb * ms * DC_MEL * 4);
     if (e == cudaSuccess) e = cudaMalloc((void**)&h->mel_T, nb * ms * DC_MEL * 4);
     if (e == cudaSuccess) e = cudaMalloc((void**)&h->gate_out, nb * ms * 4);
     if (e == cudaSuccess) e = cudaMalloc((void**)&h->t_len, nb * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void**)&h->n_frames, nb * sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&h->barrier, sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->err, 2 * sizeof(int));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreate(&h->ev[i]);
     if (e == cudaSuccess) e = dec_prepare(&h->grid);
@@ -238,24 +240,25 @@ extern "C" int xdtts_decoder_infer_batch(xdtts_decoder* h, const float* const* m
         CU(cudaMemcpyAsync(h->memory, sm, (size_t)nb * t_enc * DC_ENC * 4, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(h->pm, sp, (size_t)nb * t_enc * DC_ATT * 4, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(h->t_len, unpadded_len + b0, nb * sizeof(int), cudaMemcpyHostToDevice, s));
-        const size_t state_floats = nbmax * (DC_PRE + 4 * DC_RNN + DC_ENC + DC_ATT + DC_MAX_TENC);
-        CU(cudaMemsetAsync(h->state, 0, state_floats * 4, s));
-        CU(cudaMemsetAsync(h->barrier, 0, sizeof(unsigned), s));
+        const size_t state_cells = nbmax * (DC_PRE + 4 * DC_RNN + DC_ENC + DC_ATT + DC_MAX_TENC + DC_MEL + 1);
+        CU(cudaMemsetAsync(h->state, 0, state_cells * sizeof(dc_cell), s));   // tag 0: nothing published yet
+        CU(cudaMemsetAsync(h->err, 0, 2 * sizeof(int), s));
         CU(cudaMemsetAsync(h->n_frames, 0, nbmax * sizeof(int), s));
         DecParams p;
         memset(&p, 0, sizeof(p));
         p.p1T = h->p1T; p.p2 = h->p2; p.Wa = h->Wa; p.ba = h->ba; p.Wq = h->Wq; p.v = h->v; p.Weff = h->Weff;
         p.Wd = h->Wd; p.bd = h->bd; p.Wp = h->Wp; p.bp = h->bp;
         p.nb = nb; p.t_enc = t_enc; p.memory = h->memory; p.pm = h->pm; p.t_len = h->t_len;
-        float* st = h->state;
+        dc_cell* st = h->state;
         p.x2 = st; st += (size_t)nb * DC_PRE;
         p.h_a = st; st += (size_t)2 * nb * DC_RNN;
         p.h_d = st; st += (size_t)2 * nb * DC_RNN;
         p.ctx = st; st += (size_t)nb * DC_ENC;
         p.pq = st; st += (size_t)nb * DC_ATT;
+        p.melt = st; st += (size_t)nb * (DC_MEL + 1);
         p.e = st;
         p.mel_out = h->mel_out; p.gate_out = h->gate_out; p.align_out = out_align ? h->align_out : nullptr;
-        p.n_frames = h->n_frames; p.barrier = h->barrier;
+        p.n_frames = h->n_frames; p.err = h->err; p.barrier = reinterpret_cast<unsigned*>(h->err + 1);
         p.max_steps = h->max_steps; p.gate_threshold = h->gate_threshold; p.seed = h->seed; p.utt_base = b0; p.dropout = h->dropout;
         CU(cudaEventRecord(h->ev[0], s));
         CU(dec_launch(p, h->grid, s));
@@ -264,9 +267,11 @@ extern "C" int xdtts_decoder_infer_batch(xdtts_decoder* h, const float* const* m
         CU(dec_launch_transpose(h->mel_out, h->n_frames, nb, h->max_steps, h->mel_T, s));
         g_launches++;
         // ---- results
-        int nf[DC_MAX_NB];
+        int nf[DC_MAX_NB], poll_err = 0;
         CU(cudaMemcpyAsync(nf, h->n_frames, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(&poll_err, h->err, sizeof(int), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
+        if (poll_err) return fail(XDTTS_ERR_CUDA, "decoder_infer: a stage waited for another CTA's result beyond its bound (internal error)");
         float ms_chunk = 0.f;
         CU(cudaEventElapsedTime(&ms_chunk, h->ev[0], h->ev[1]));
         h->last_ms += ms_chunk;
