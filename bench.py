@@ -133,25 +133,26 @@ def measured_l2_read_gbs(torch, device):
     return x.numel() * 4 / (best * 1e-3) / 1e9
 
 
-DEC_BARRIERS_PER_STEP, DEC_BARRIER_US = 7, 1.23   # grid barriers per decoder step; one barrier with empty stages
+DEC_HANDOVER_US = 0.55    # one hand-over between CTAs through the L2: a store's trip there + one poll round trip (~1050 cycles)
+DEC_BARRIER_US = 1.23     # one split-phase grid barrier of this kernel with empty stages
 
 
 def decoder_leg(ctx, with_cpu):
     """The decoder loop: 1000 steps of the Tacotron2 decoder in one persistent kernel, for one
     utterance (the reference's shape) and for 8 in lockstep.  Device time = CUDA events around the launch.
-    Its 72.7 MB of weights stay in the L2 (ncu: 0.15% DRAM throughput, 93% L2 hits) and up to a third of them in shared memory,
-    so it is reported against (i) the grid-barrier floor -- the loop is a chain of 7 dependent grid-wide hops per step, and
-    keeping a third of the LSTM weights in shared memory moved the step by only 2.5% -- and (ii) weights / measured L2 read
-    bandwidth (an upper bound on the L2 time now), not against HBM."""
+    Its 72.7 MB of weights never leave the chip (ncu: 0.15% DRAM throughput; a third of them stay in shared memory, the rest is
+    re-read from the L2 every step) and a step is a chain of 7 dependent hand-overs between CTAs, so it is reported against
+    (i) the hand-over floor and (ii) the bytes it reads from the L2 / the measured L2 read bandwidth -- not against HBM."""
     tacotron2 = ctx.tacotron2
     device = ctx.local_rank
     wt = synth_decoder_weights()
     dec = tacotron2.Decoder.from_weights(wt, gate_threshold=0.999999, max_steps=DEC_STEPS, seed=1, device=device)
-    out = {"bound": "latency (%d dependent grid-wide barriers per step and the serial stages between them; L2 reads are not the limiter: "
-                    "with a third of the LSTM weights resident in shared memory the step moved 2.5%%, XDTTS_DEC_NO_CACHE=1 reproduces)" % DEC_BARRIERS_PER_STEP,
-           "kernel": "dec_persist_kernel (one cooperative launch = %d decoder steps, %d grid barriers per step)" % (DEC_STEPS, DEC_BARRIERS_PER_STEP),
+    info = dec.info(1, DEC_T_ENC)
+    out = {"bound": "latency: a step is a chain of %d dependent hand-overs between CTAs (polled {value, tag} cells through the L2 at batch "
+                    "1-2, split-phase grid barriers at batch 4-8) and the serial stages between them; neither L2 nor HBM bandwidth" % info["handovers_per_step"],
+           "kernel": "dec_persist_kernel (one cooperative launch = %d decoder steps)" % DEC_STEPS,
            "workload": "Tacotron2 decoder loop, t_enc=%d (%d unpadded), %d steps, fp32, synthetic weights" % (DEC_T_ENC, DEC_UNPADDED, DEC_STEPS),
-           "weight_bytes_per_step": DEC_WEIGHT_BYTES}
+           "weight_bytes_per_step": info["weight_bytes_per_step"], "weight_bytes_resident_in_smem": info["smem_resident_bytes"]}
     for nb in (1, 8):
         enc = [synth_encoder_outputs(100 + i, DEC_T_ENC) for i in range(nb)]
         best = None
@@ -160,21 +161,24 @@ def decoder_leg(ctx, with_cpu):
             ms, steps = dec.last_timing()
             best = ms if best is None or ms < best else best
         assert steps == DEC_STEPS and all(m.shape == (80, DEC_STEPS) and np.isfinite(m).all() for m in mels)
-        out["b%d" % nb] = {"ms": best, "us_per_step": best * 1e3 / DEC_STEPS, "frames_per_s": nb * DEC_STEPS / (best * 1e-3)}
+        out["b%d" % nb] = {"ms": best, "us_per_step": best * 1e3 / DEC_STEPS, "frames_per_s": nb * DEC_STEPS / (best * 1e-3),
+                           "handover": "polled cells" if dec.info(nb, DEC_T_ENC)["polled_cells"] else "grid barriers"}
     l2 = measured_l2_read_gbs(ctx.torch, device)
     us = out["b1"]["us_per_step"]
-    l2_floor = DEC_WEIGHT_BYTES / (l2 * 1e9) * 1e6
-    bar_floor = DEC_BARRIERS_PER_STEP * DEC_BARRIER_US
-    out["floors"] = {"l2_read_gbs_measured": l2, "l2_us_per_step": l2_floor, "barrier_us_per_step": bar_floor,
-                     "how": "L2: 64 MB torch reduction repeated in this process; barrier: %d x %.2f us, this kernel's barrier with "
-                            "the stage bodies compiled out (DESIGN.md 3.5)" % (DEC_BARRIERS_PER_STEP, DEC_BARRIER_US)}
-    out["frac"] = bar_floor / us                    # of the barrier floor: the chain of grid-wide hops is what a step cannot go below
-    out["frac_of_l2_floor"] = l2_floor / us         # all 72.7 MB from the L2 at the measured L2 rate (the cached slices no longer are)
-    out["achieved"] = DEC_WEIGHT_BYTES / (us * 1e-6) / 1e9
+    l2_bytes = info["weight_bytes_per_step"] - info["smem_resident_bytes"]
+    l2_floor = l2_bytes / (l2 * 1e9) * 1e6
+    ho_floor = info["handovers_per_step"] * DEC_HANDOVER_US
+    out["floors"] = {"l2_read_gbs_measured": l2, "l2_bytes_per_step": l2_bytes, "l2_us_per_step": l2_floor, "handover_us_per_step": ho_floor,
+                     "how": "L2: 64 MB torch reduction repeated in this process; hand-over: %d x %.2f us (a store's trip to the L2 + one poll "
+                            "round trip; the grid barrier it replaced at batch 1-2 cost %.2f us with empty stages)" % (
+                                info["handovers_per_step"], DEC_HANDOVER_US, DEC_BARRIER_US)}
+    out["frac"] = l2_floor / us                     # the larger of the two floors: the bytes the step still reads from the L2
+    out["frac_of_handover_floor"] = ho_floor / us
+    out["achieved"] = l2_bytes / (us * 1e-6) / 1e9
     out["peak"] = l2
-    out["unit"] = "GB/s (weight bytes per step / step time against the measured L2 read rate)"
-    out["note"] = ("achieved / peak are L2 figures, NOT HBM: the weights never leave the chip (ncu: DRAM throughput 0.15%, L2 hit rate "
-                   "93%); frac is against the barrier floor")
+    out["unit"] = "GB/s (bytes read from the L2 per step / step time against the measured L2 read rate)"
+    out["note"] = ("achieved / peak are L2 figures, NOT HBM: the weights never leave the chip (ncu: DRAM throughput 0.15%, L2 hit rate 93%).  "
+                   "The step is latency-bound: with and without the shared-memory weight cache it differs by 1-2% (XDTTS_DEC_NO_CACHE=1).")
     if with_cpu:
         from oracle import decoder_oracle as d   # CPU baseline leg only
 

@@ -271,6 +271,10 @@ int xdtts_onnx_decoder_dims(const xdtts_onnx_decoder* m, int* dims10);
 long long xdtts_onnx_decoder_tensor(const xdtts_onnx_decoder* m, int which, float* out_or_null, long long capacity);
 /* device time (CUDA events around the persistent kernel launches) and steps executed by the last call */
 int xdtts_decoder_last_timing(const xdtts_decoder* h, float* ms, int* steps);
+/* measurement: what a launch for nb utterances in lockstep at encoder length t_enc reads and how its CTAs hand results over.
+ * info[0] = weight bytes one decoder step reads, [1] = of those, bytes kept in shared memory for the whole loop (the rest
+ * comes from the L2 every step), [2] = hand-overs between CTAs per step, [3] = 1: polled {value, tag} cells, 0: grid barriers */
+int xdtts_decoder_info(const xdtts_decoder* h, int nb, int t_enc, long long* info);
 
 /* ---- Streaming: the same tail for a sequence of batches of one shape, copies overlapped with kernels.
  * XdTts::infer returns host samples per call (src/lib.rs:141-157) and the binary loops over chunks

@@ -22,7 +22,7 @@ for c in ("cfg3", "cfg5"):
     if c in d: show(c, d[c])
 if "strong_scaling" in d: print("strong", json.dumps(d["strong_scaling"])[:400])
 if "dropin" in d: print("dropin", json.dumps(d["dropin"]["cases"])[:900])
-if "decoder" in d: print("decoder", {k: d["decoder"][k] for k in ("b1", "b8", "floors", "frac", "frac_of_l2_floor")})
+if "decoder" in d: print("decoder", {k: d["decoder"][k] for k in ("b1", "b8", "floors", "frac", "frac_of_handover_floor")})
 if "postnet" in d.get("cfg3", {}): print("postnet", {k: d["cfg3"]["postnet"][k] for k in ("ms", "frac", "frac_executed")})
 print("cpu", d.get("cpu_baseline", {}).get("value"), d.get("cpu_baseline", {}).get("candidates"))
 print("clocks", d["clocks"], "launches", d["gpu_launches"])

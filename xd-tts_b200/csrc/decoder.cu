@@ -39,6 +39,7 @@
 // bits), hence never travel.
 #include <cuda_runtime.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "decoder.h"
@@ -76,7 +77,6 @@ __device__ __forceinline__ float cell_wait(const dc_cell* c, dc_cell w, unsigned
             *err = 1;
             break;
         }
-        __nanosleep(32);
         w = cell_peek(c);
     }
     return __uint_as_float((unsigned)w);
@@ -122,7 +122,7 @@ __device__ __forceinline__ void cells_to_smem(const dc_cell* src, int n, int row
                 *err = 1;
                 break;
             }
-            __nanosleep(64);
+            if (PER > 4) __nanosleep(64);   // (batch 1-2: a few cells per thread, re-polled at once)
         }
     }
 }
@@ -320,6 +320,14 @@ struct DecSmem {
     }
 };
 
+// timing experiments (-DXDTTS_DEC_TRACE): clock stamps of one CTA's thread 0 at every hand-over of steps 100..102
+#ifdef XDTTS_DEC_TRACE
+__device__ long long g_dec_trace[2][4][32];
+#define DC_STAMP(i) do { if ((blockIdx.x == 0 || blockIdx.x == 140) && threadIdx.x == 0 && step >= 100 && step < 104) g_dec_trace[blockIdx.x ? 1 : 0][step - 100][i] = clock64(); } while (0)
+#else
+#define DC_STAMP(i) do { } while (0)
+#endif
+
 template <int NB>
 __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecParams p) {
     extern __shared__ __align__(16) float sm[];
@@ -400,6 +408,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
     for (; step < p.max_steps; step++) {
         const int cur = step & 1, nxt = cur ^ 1;
         const unsigned tag = (unsigned)step + 1u;   // of everything this step publishes
+        DC_STAMP(30);
         // ================= stage P: prenet of this step  ||  attention LSTM, second half of its h_att columns
         for (int i = tid; i < nb * DC_MEL; i += DC_THREADS) {
             const int b = i / DC_MEL, k = i % DC_MEL;
@@ -442,9 +451,12 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
                     if (b < nb) cell_put(p.x2 + b * DC_PRE + r, fmaxf(acc[b], 0.f) * keep_scale(p, b, step, 1, r), tag);
             }
         }
+        DC_STAMP(0);
         hand_over_publish();
         if (step) lstm_partial<NB, 4>(acc_a, p.Wa, DC_ZA, DC_ENC + DC_RNN / 2, zA + DC_ENC + DC_RNN / 2, ZA_LD, unit0, nullptr);
+        DC_STAMP(1);
         hand_over_consume();
+        DC_STAMP(2);
 
         // ================= stage A2: attention LSTM, prenet columns + cell update  ||  decoder LSTM, second half of h_dec columns
         cells_to_smem<(NB * DC_PRE + DC_THREADS - 1) / DC_THREADS, POLL>(p.x2, nb * DC_PRE, DC_PRE, x2s, DC_PRE, tag, p.err);
@@ -453,9 +465,12 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
         lstm_finish<NB>(acc_a, unit0, part_a, p.ba);
         __syncthreads();
         lstm_cell<NB>(part_a, cst_a, unit0, nb, p.h_a + (size_t)nxt * nb * DC_RNN, tag);
+        DC_STAMP(3);
         hand_over_publish();
         if (step) lstm_partial<NB, 4>(acc_d, p.Wd, DC_ZD, DC_RNN + DC_RNN / 2, zD + DC_RNN + DC_RNN / 2, ZD_LD, unit0, nullptr);
+        DC_STAMP(4);
         hand_over_consume();
+        DC_STAMP(5);
 
         // ================= stage Q: query rows  ||  decoder LSTM, h_att columns [0, 384)
         cells_to_smem<(NB * DC_RNN + DC_THREADS - 1) / DC_THREADS, POLL>(p.h_a + (size_t)nxt * nb * DC_RNN, nb * DC_RNN, DC_RNN, zD, ZD_LD, tag, p.err);
@@ -471,9 +486,12 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
                     if (b < nb) cell_put(p.pq + b * DC_ATT + cta, acc[b], tag);
             }
         }
+        DC_STAMP(6);
         hand_over_publish();
         lstm_partial<NB, 3>(acc_d, p.Wd, DC_ZD, 0, zD, ZD_LD, unit0, wc[5]);
+        DC_STAMP(7);
         hand_over_consume();
+        DC_STAMP(8);
 
         // ================= stage E: energies e[b][t] = v . tanh(pq + Weff * [w; w_cum](t-15..t+15) + pm[t])  ||  h_att columns [384, 768)
         if (nb * t_enc <= G) {
@@ -546,9 +564,12 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
                 if (lane == 0) cell_put(p.e + b * t_enc + t, s, tag);
             }
         }
+        DC_STAMP(9);
         hand_over_publish();
         lstm_partial<NB, 3>(acc_d, p.Wd, DC_ZD, 384, zD + 384, ZD_LD, unit0, wc[4]);
+        DC_STAMP(10);
         hand_over_consume();
+        DC_STAMP(11);
 
         // ================= stage C: softmax (every CTA keeps w / w_cum itself) + context chunks  ||  h_att columns [768, 1024)
         if (NB <= 2) {
@@ -645,9 +666,12 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
                 __syncthreads();
             }
         }
+        DC_STAMP(12);
         hand_over_publish();
         lstm_partial<NB, 2>(acc_d, p.Wd, DC_ZD, 768, zD + 768, ZD_LD, unit0, wc[3]);
+        DC_STAMP(13);
         hand_over_consume();
+        DC_STAMP(14);
 
         // ================= stage D2: decoder LSTM, context columns + cell update  ||  attention LSTM of the NEXT step, context columns
         cells_to_smem<(NB * DC_ENC + DC_THREADS - 1) / DC_THREADS, POLL>(p.ctx, nb * DC_ENC, DC_ENC, zA, ZA_LD, tag, p.err);
@@ -658,9 +682,12 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
         lstm_finish<NB>(acc_d, unit0, part_d, p.bd);
         __syncthreads();
         lstm_cell<NB>(part_d, cst_d, unit0, nb, p.h_d + (size_t)nxt * nb * DC_RNN, tag);
+        DC_STAMP(15);
         hand_over_publish();
         lstm_partial<NB, 4>(acc_a, p.Wa, DC_ZA, 0, zA, ZA_LD, unit0, wc[2]);
+        DC_STAMP(16);
         hand_over_consume();
+        DC_STAMP(17);
 
         // ================= stage R: projection + gate rows  ||  next step: attention LSTM h_att columns (first half),
         //                   decoder LSTM h_dec columns (first half)
@@ -684,10 +711,13 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dec_persist_kernel(const DecPar
                 }
             }
         }
+        DC_STAMP(18);
         hand_over_publish();
         lstm_partial<NB, 4>(acc_a, p.Wa, DC_ZA, DC_ENC, zA + DC_ENC, ZA_LD, unit0, nullptr);
         lstm_partial<NB, 4>(acc_d, p.Wd, DC_ZD, DC_RNN, zD + DC_RNN, ZD_LD, unit0, nullptr);
+        DC_STAMP(19);
         hand_over_consume();
+        DC_STAMP(20);
 
         // ================= stop rule (src/tacotron2/mod.rs:319-324): every CTA takes the same decision
         bool all = true;
@@ -781,8 +811,43 @@ static cudaError_t launch_nb(const DecParams& p, int grid, cudaStream_t s) {
     DecParams q = p;
     q.cache_mask = cache_mask_nb<NB>(p.t_enc);
     void* args[1] = {&q};
-    return cudaLaunchCooperativeKernel((const void*)dec_persist_kernel<NB>, dim3(grid), dim3(DC_THREADS), args,
-                                       DecSmem<NB>::bytes(p.t_enc, q.cache_mask), s);
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)dec_persist_kernel<NB>, dim3(grid), dim3(DC_THREADS), args,
+                                                DecSmem<NB>::bytes(p.t_enc, q.cache_mask), s);
+#ifdef XDTTS_DEC_TRACE
+    if (e == cudaSuccess && p.max_steps > 104) {
+        cudaStreamSynchronize(s);
+        static long long tr[2][4][32];
+        cudaMemcpyFromSymbol(tr, g_dec_trace, sizeof(tr));
+        static const char* names[7] = {"P", "A2", "Q", "E", "C", "D2", "R"};
+        for (int c = 0; c < 2; c++) {
+            fprintf(stderr, "decoder trace, CTA %d, step 101 (cycles): stage: inputs + work until published | streamed columns | wait\n", c ? 140 : 0);
+            long long t = tr[c][1][30];
+            for (int k = 0; k < 7; k++) {
+                fprintf(stderr, "  %-2s %6lld | %6lld | %6lld\n", names[k], tr[c][1][3 * k] - t, tr[c][1][3 * k + 1] - tr[c][1][3 * k],
+                        tr[c][1][3 * k + 2] - tr[c][1][3 * k + 1]);
+                t = tr[c][1][3 * k + 2];
+            }
+            fprintf(stderr, "  stop rule %lld, step total %lld\n", tr[c][2][30] - t, tr[c][2][30] - tr[c][1][30]);
+        }
+    }
+#endif
+    return e;
+}
+
+// how a launch for nb utterances at t_enc hands over and what it keeps on chip: info[0] = LSTM / projection / prenet weight bytes a
+// step reads (grid-wide), [1] = of those, bytes resident in shared memory for the whole loop, [2] = hand-overs between CTAs per
+// step, [3] = 1 when they are polled cells, 0 when grid barriers
+void dec_info(int nb, int t_enc, int grid, long long* info) {
+    unsigned mask = nb == 1 ? cache_mask_nb<1>(t_enc) : nb == 2 ? cache_mask_nb<2>(t_enc) : nb <= 4 ? cache_mask_nb<4>(t_enc) : cache_mask_nb<8>(t_enc);
+    long long cached = 0;
+    for (int id = 0; id < DC_NSLICES; id++)
+        if (mask >> id & 1) cached += (long long)dec_slice_floats(id) * 4;
+    const long long owners = (DC_RNN + DC_UNITS - 1) / DC_UNITS;   // CTAs that own hidden units (the last one fewer than 7)
+    info[0] = 4ll * ((long long)DC_MEL * DC_PRE + (long long)DC_PRE * DC_PRE + 4ll * DC_RNN * (DC_ZA + DC_ZD) + (long long)DC_ATT * DC_RNN +
+                     (long long)(DC_MEL + 1) * DC_ZP);
+    info[1] = cached * (owners < grid ? owners : grid);
+    info[2] = 7;
+    info[3] = nb <= 2 ? 1 : 0;
 }
 
 cudaError_t dec_launch(const DecParams& p, int grid, cudaStream_t s) {

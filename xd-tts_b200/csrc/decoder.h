@@ -63,6 +63,7 @@ struct DecParams {
 cudaError_t dec_prepare(int* grid_out);
 // one cooperative launch: the whole decoder loop for p.nb utterances
 cudaError_t dec_launch(const DecParams& p, int grid, cudaStream_t s);
+void dec_info(int nb, int t_enc, int grid, long long* info);
 // [nb][max_steps][80] frame-major decoder output -> per utterance [80][n_frames[b]] row-major at dst + b * 80 * max_steps
 cudaError_t dec_launch_transpose(const float* mel_frames, const int* n_frames, int nb, int max_steps, float* dst, cudaStream_t s);
 

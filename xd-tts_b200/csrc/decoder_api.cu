@@ -185,6 +185,13 @@ extern "C" int xdtts_decoder_last_timing(const xdtts_decoder* h, float* ms, int*
     return XDTTS_OK;
 }
 
+extern "C" int xdtts_decoder_info(const xdtts_decoder* h, int nb, int t_enc, long long* info) {
+    if (!h || !info) return fail(XDTTS_ERR_BAD_ARG, "decoder_info: null argument");
+    if (nb < 1 || nb > DC_MAX_NB || t_enc < 1 || t_enc > DC_MAX_TENC) return fail(XDTTS_ERR_SHAPE, "decoder_info: nb = %d, t_enc = %d out of range", nb, t_enc);
+    dec_info(nb, t_enc, h->grid, info);
+    return XDTTS_OK;
+}
+
 static int ensure_stage(xdtts_decoder* h, size_t floats) {
     if (h->h_stage_floats >= floats) return XDTTS_OK;
     if (h->h_stage) cudaFreeHost(h->h_stage);

@@ -122,6 +122,7 @@ SIGNATURES = {
     "xdtts_decoder_max_steps": (ctypes.c_int, [_vp]),
     "xdtts_decoder_infer_batch": (ctypes.c_int, [_vp, _fpp, _fpp, ctypes.c_int, _ip, ctypes.c_int, _fpp, _ip, _fpp, _fpp]),
     "xdtts_decoder_last_timing": (ctypes.c_int, [_vp, _fp, _ip]),
+    "xdtts_decoder_info": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]),
     "xdtts_pipe_create": (ctypes.c_int, [_vp, _vp, _ip, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]),
     "xdtts_pipe_push": (ctypes.c_int, [_vp, _fpp, _fpp, _fpp, _fpp]),
     "xdtts_pipe_pop": (ctypes.c_int, [_vp]),

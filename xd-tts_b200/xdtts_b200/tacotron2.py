@@ -210,6 +210,12 @@ class Decoder:
         """Tacotron2::run_decoder up to the postnet (src/tacotron2/mod.rs:272-345): -> [80, T]."""
         return self.run_batch([memory], [processed_memory], [unpadded_len])[0]
 
+    def info(self, nb, t_enc):
+        """-> dict(weight_bytes_per_step, smem_resident_bytes, handovers_per_step, polled_cells) of a launch for nb utterances"""
+        a = (ctypes.c_longlong * 4)()
+        check(load_library().xdtts_decoder_info(self._h, int(nb), int(t_enc), a))
+        return dict(weight_bytes_per_step=a[0], smem_resident_bytes=a[1], handovers_per_step=a[2], polled_cells=bool(a[3]))
+
     def last_timing(self):
         """-> (device milliseconds of the decoder kernel, steps executed) of the last call"""
         ms, steps = ctypes.c_float(), ctypes.c_int()
