@@ -47,5 +47,6 @@ print("# SASS evidence, %s (`cuobjdump -sass`, sm_100a)\n" % os.path.relpath(g.L
 print("| kernel | SASS instr | regs | " + " | ".join(PAT) + " |")
 print("|---|---|---|" + "---|" * len(PAT))
 for (k, c), d in zip(rows.items(), dem):
-    name = re.sub(r"\(.*", "", d).replace("xdtts::", "").replace("(anonymous namespace)::", "")
+    d = d.replace("(anonymous namespace)::", "").replace("xdtts::", "")   # before cutting the parameter list at its "("
+    name = re.sub(r"^void ", "", re.sub(r"\(.*", "", d))
     print("| `%s` | %d | %s | " % (name[:70], c["instr"], regs.get(k, "?")) + " | ".join(str(c[n]) for n in PAT) + " |")
