@@ -26,7 +26,7 @@ extern "C" {
 
 #define XDTTS_OK 0
 #define XDTTS_ERR_BAD_ARG (-1)     /* null pointer, non-finite or out-of-range parameter */
-#define XDTTS_ERR_SHAPE (-2)       /* T < 4, K != n_fft/2+1, wrong out_len ... */
+#define XDTTS_ERR_SHAPE (-2)       /* T < 2, K != n_fft/2+1, wrong out_len ... */
 #define XDTTS_ERR_CUDA (-3)        /* CUDA runtime error, no usable sm_100 device */
 #define XDTTS_ERR_OOM (-4)
 #define XDTTS_ERR_UNSUPPORTED (-5) /* n_fft not a power of two in [64, 4096], n_mels > 256, a graph that is not the expected network */

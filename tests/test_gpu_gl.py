@@ -182,7 +182,7 @@ def test_zero_input_and_errors(gl):
     (y,) = voc.from_magnitude_batch([np.zeros((513, 10), np.float32)])
     assert y.shape == (256 * 9,) and (y == 0).all()           # silence stays silence, no NaN from 0/0
     with pytest.raises(XdttsError) as e:
-        voc.infer(np.zeros((80, 3), np.float32))               # T < 4
+        voc.infer(np.zeros((80, 1), np.float32))               # one frame = 0 samples
     assert e.value.code == ERR_SHAPE
     with pytest.raises(XdttsError) as e:
         voc.infer(np.zeros((79, 30), np.float32))
@@ -591,3 +591,23 @@ def test_unfused_path_agrees_with_the_fused_kernel(gl, monkeypatch):
     (yg,) = unfused.from_magnitude_batch([s], [tu])
     ref = o.griffin_lim(s, tu, 30, 0.99, 1024, 256, dtype=np.float64)
     assert rel_rms(yf, ref) < 1e-4 and rel_rms(yg, ref) < 1e-4 and rel_rms(yf, yg) < 1e-4
+
+
+@pytest.mark.gpu
+def test_utterances_of_two_and_three_frames(gl):
+    """The fused kernel needs 4 frames per utterance (its runs); a batch with a shorter one runs the un-fused kernels.  Reflect
+    padding of n_fft/2 = 512 samples over a 256- or 512-sample signal folds more than once, as numpy's does."""
+    ts = [2, 3, 25, 4]
+    mags = [o.synth_speech_like_mag(80 + i, 1024, 256, t) for i, t in enumerate(ts)]
+    turns = [o.phase_turns(4, i, 513, t) for i, t in enumerate(ts)]
+    for pad in (gl.PAD_REFLECT, gl.PAD_CONSTANT):
+        voc = make(gl, 1024, 3, normalise=gl.NORM_NONE, pad_mode=pad)
+        ys = voc.from_magnitude_batch(mags, turns)
+        for i, (s, tu, y) in enumerate(zip(mags, turns, ys)):
+            ref = o.griffin_lim(s, tu, 3, 0.99, 1024, 256, pad_mode=pad, dtype=np.float64)
+            assert y.shape == ref.shape == (256 * (ts[i] - 1),)
+            assert rel_rms(y, ref) < 2e-5, (pad, i, rel_rms(y, ref))
+    voc = make(gl, 1024, 5, seed=3, fixed_seed=True)
+    y = voc.infer(o.synth_mel(1, 80, 3))
+    ref = o.infer(o.synth_mel(1, 80, 3), basis_for(1024), 768, 1.7, 5, 0.99, o.phase_turns(3, 0, 513, 3), dtype=np.float64)
+    assert y.shape == (512,) and rel_rms(y, ref) < 1e-4

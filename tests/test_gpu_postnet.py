@@ -201,7 +201,7 @@ def test_pipe_equals_blocking_calls_bitwise(taco, layers, built):
     assert lib.xdtts_pipe_push(q, fptr_array(batches[0]), None, fptr_array(outs), fptr_array(outs)) == ERR_BAD_ARG  # out_mels without postnet
     lib.xdtts_pipe_destroy(q)
     with pytest.raises(XdttsError) as e:
-        voc.pipe([33, 2], depth=2)          # T < 4
+        voc.pipe([33, 1], depth=2)          # one frame = no samples
     assert e.value.code == ERR_SHAPE
     with pytest.raises(XdttsError) as e:
         voc.pipe(ts, depth=0)

@@ -357,7 +357,7 @@ extern "C" int xdtts_gl_create(const float* mel_basis, int n_mels, int K, int no
     if (e == cudaSuccess) e = cudaMemcpy(h->d_pinvT, pT.data(), pT.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_tables, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_edge, edge.data(), edge.size() * 4, cudaMemcpyHostToDevice);
-    if (generic) {
+    {   // the un-fused path's tables, for every handle: utterances shorter than 4 frames take it on any geometry
         if (e == cudaSuccess) e = cudaMalloc(&h->d_gtw, gtw.size() * sizeof(float2));
         if (e == cudaSuccess) e = cudaMalloc(&h->d_gwin, gwin.size() * 4);
         if (e == cudaSuccess) e = cudaMemcpy(h->d_gtw, gtw.data(), gtw.size() * sizeof(float2), cudaMemcpyHostToDevice);
@@ -392,7 +392,7 @@ extern "C" void xdtts_gl_destroy(xdtts_gl* h) {
 
 extern "C" int xdtts_gl_out_len(const xdtts_gl* h, int T) {
     if (!h) return fail(XDTTS_ERR_BAD_ARG, "gl_out_len: handle is null");
-    if (T < 4) return fail(XDTTS_ERR_SHAPE, "gl_out_len: T = %d, need >= 4 frames (reflect padding of n_fft/2 needs hop*(T-1) > n_fft/2)", T);
+    if (T < 2) return fail(XDTTS_ERR_SHAPE, "gl_out_len: T = %d, need >= 2 frames (one frame is hop * (T - 1) = 0 samples)", T);
     return h->hop * (T - 1);
 }
 
@@ -429,7 +429,7 @@ int xdtts::gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out)
     if (!Ts || B < 1) return fail(XDTTS_ERR_BAD_ARG, "plan: need B >= 1 utterances");
     long long total = 0;
     for (int b = 0; b < B; b++) {
-        if (Ts[b] < 4) return fail(XDTTS_ERR_SHAPE, "plan: utterance %d has T = %d frames, need >= 4", b, Ts[b]);
+        if (Ts[b] < 2) return fail(XDTTS_ERR_SHAPE, "plan: utterance %d has T = %d frames, need >= 2", b, Ts[b]);
         total += Ts[b];
     }
     if (total * (long long)(h->K - 1) >= (1ll << 31)) return fail(XDTTS_ERR_SHAPE, "plan: %lld frames in one batch is too many (split it)", total);
@@ -438,6 +438,10 @@ int xdtts::gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out)
     xdtts_gl_plan* p = new (std::nothrow) xdtts_gl_plan();
     if (!p) return fail(XDTTS_ERR_OOM, "plan: out of host memory");
     p->h = h; p->B = B; p->Ts.assign(Ts, Ts + B); p->total_T = (int)total;
+    // the fused kernel splits an utterance into runs of >= 4 frames (a hop block is shared by at most two runs): a batch with a
+    // shorter utterance runs the un-fused kernels, like the geometries the fused kernel does not cover
+    p->generic = h->generic;
+    for (int b = 0; b < B; b++) p->generic = p->generic || Ts[b] < 4;
     for (int b = 0; b < B; b++) p->max_T = Ts[b] > p->max_T ? Ts[b] : p->max_T;
     // Runs: one warp each.  A fixed run length (option / environment) gives results that do not depend on
     // the batch; the automatic choice fills the resident warp slots of the device a whole number of times
@@ -446,7 +450,7 @@ int xdtts::gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out)
     // duration (256 x 1000 frames as 4000 runs of 64 = 2.25 waves; as 5328 runs of 48 = 3 full waves).
     int rf = h->opts.run_frames;
     if (const char* env = getenv("XDTTS_GL_RUN_FRAMES")) rf = atoi(env);
-    if (h->generic) rf = 64;   // the un-fused path has no runs; the table only carries the frame offsets
+    if (p->generic) rf = 64;   // the un-fused path has no runs; the table only carries the frame offsets
     if (rf > 0) {
         if (rf < 4) rf = 4;
         build_runs(Ts, B, rf, &p->runs, &p->foff);
@@ -482,9 +486,9 @@ int xdtts::gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out)
     p->run_frames = rf;
     {   // persistent single-launch path: every run must be resident at once (checked again at launch)
         const char* env = getenv("XDTTS_GL_PERSISTENT");
-        const long long resident = h->generic ? 0 : (long long)h->sm_count * gl_resident_warps_per_sm(h->n_fft);
+        const long long resident = p->generic ? 0 : (long long)h->sm_count * gl_resident_warps_per_sm(h->n_fft);
         const bool want = env ? atoi(env) != 0 : h->opts.persistent != 0;
-        p->use_persistent = !h->generic && want && (long long)p->runs.size() <= resident;
+        p->use_persistent = !p->generic && want && (long long)p->runs.size() <= resident;
     }
     p->out_off.resize(B);
     for (int b = 0; b < B; b++) {
@@ -509,7 +513,7 @@ int xdtts::gl_plan_build(xdtts_gl* h, const int* Ts, int B, xdtts_gl_plan** out)
     }
     ALLOC(p->d_lift_tiles, p->lift_tiles.size() * sizeof(int4));
     ALLOC(p->d_seed, 8 + (size_t)B * sizeof(int));   // [u64 phase seed][int stream index of each utterance]
-    if (h->generic) ALLOC(p->d_frames, TT * (size_t)h->n_fft * 4);
+    if (p->generic) ALLOC(p->d_frames, TT * (size_t)h->n_fft * 4);
     ALLOC(p->d_y[0], TT * H * 4);
     ALLOC(p->d_y[1], TT * H * 4);
     ALLOC(p->d_halo, nr * 6 * H * 4);
@@ -704,7 +708,7 @@ static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid, cud
         CU(gl_launch_to_frame_major(p->d_in_phase, p->d_T, p->d_foff, p->B, p->max_T, h->K, p->d_turns, h->K, s));
         launched++;
     }
-    if (h->generic) {   // any hop / any power-of-two n_fft: un-fused kernels, two launches per iteration (gl_generic.cu)
+    if (p->generic) {   // any hop / any power-of-two n_fft / utterances of 2-3 frames: un-fused kernels, two launches per iteration (gl_generic.cu)
         GlgParams q;
         memset(&q, 0, sizeof(q));
         q.n_fft = h->n_fft; q.hop = h->hop; q.n_utt = p->B;
@@ -802,7 +806,7 @@ static int plan_launch_graph(xdtts_gl_plan* p, int flags, cudaStream_t s) {
         if (e != cudaSuccess) return fail(XDTTS_ERR_CUDA, "plan_run: graph instantiate: %s", cudaGetErrorString(e));
     }
     CU(cudaGraphLaunch(p->graphs[gi], s));
-    g_launches += (unsigned long long)((h->generic ? 2 * h->n_iter + 4 : h->n_iter + 3) + ((!(flags & XDTTS_RUN_FROM_MAG) && h->opts.lift == 1) ? 1 : 0) + ((flags & XDTTS_RUN_USE_PHASE) ? 1 : 0));
+    g_launches += (unsigned long long)((p->generic ? 2 * h->n_iter + 4 : h->n_iter + 3) + ((!(flags & XDTTS_RUN_FROM_MAG) && h->opts.lift == 1) ? 1 : 0) + ((flags & XDTTS_RUN_USE_PHASE) ? 1 : 0));
     return XDTTS_OK;
 }
 
@@ -1040,7 +1044,7 @@ extern "C" int xdtts_gl_from_mag_batch(xdtts_gl* h, const float* const* mags, co
 extern "C" int xdtts_gl_infer(xdtts_gl* h, const float* mel, int T, const float* init_phase, float* out, int out_len) {
     if (!h) return fail(XDTTS_ERR_BAD_ARG, "infer: handle is null");
     if (!mel || !out) return fail(XDTTS_ERR_BAD_ARG, "infer: null argument");
-    if (T < 4) return fail(XDTTS_ERR_SHAPE, "infer: T = %d, need >= 4 frames", T);
+    if (T < 2) return fail(XDTTS_ERR_SHAPE, "infer: T = %d, need >= 2 frames", T);
     if (out_len != h->hop * (T - 1)) return fail(XDTTS_ERR_SHAPE, "infer: out_len = %d, expected hop*(T-1) = %d", out_len, h->hop * (T - 1));
     const float* mels[1] = {mel};
     const float* ph[1] = {init_phase};

@@ -83,6 +83,7 @@ struct xdtts_gl_plan {
     int4* d_lift_tiles = nullptr;
     int lift_tile_frames = 64;
     float* d_frames = nullptr;       // un-fused path: [total frames][n_fft] windowed inverse transforms
+    bool generic = false;            // this plan runs the un-fused kernels (the handle's geometry, or an utterance of 2-3 frames)
     unsigned char *d_seed = nullptr, *h_seed = nullptr;   // [u64 phase seed][int stream index per utterance], device + pinned
     short* d_pcm = nullptr;          // 16-bit PCM copy of d_out (allocated on first use)
     short* h_pcm = nullptr;
