@@ -611,3 +611,28 @@ def test_utterances_of_two_and_three_frames(gl):
     y = voc.infer(o.synth_mel(1, 80, 3))
     ref = o.infer(o.synth_mel(1, 80, 3), basis_for(1024), 768, 1.7, 5, 0.99, o.phase_turns(3, 0, 513, 3), dtype=np.float64)
     assert y.shape == (512,) and rel_rms(y, ref) < 1e-4
+
+
+@pytest.mark.gpu
+def test_unfused_path_random_geometries(gl):
+    """Thirty seeded random (n_fft, hop, T) triples -- hops that do not divide n_fft, hop = 1, hop = n_fft (frames that do not
+    overlap: the window sum-square has zeros the division must skip), utterances of two frames -- against the fp64 oracle."""
+    rng = np.random.default_rng(2024)
+    for case in range(30):
+        n_fft = int(rng.choice([64, 128, 256, 512, 1024]))
+        hop = int(rng.choice([1, n_fft, n_fft // 2 + 1, int(rng.integers(1, n_fft + 1))]))
+        if hop * 4 == n_fft and n_fft >= 512:
+            hop += 1                                      # (that one is the fused kernel's)
+        ts = [int(x) for x in rng.integers(2, 12, size=int(rng.integers(1, 4)))]
+        k = n_fft // 2 + 1
+        basis = o.create_mel_filter_bank(22050.0, n_fft, 20, 0.0, 8000.0)
+        mags = [o.synth_speech_like_mag(300 + case * 7 + i, n_fft, hop, t) for i, t in enumerate(ts)]
+        turns = [o.phase_turns(case, i, k, t) for i, t in enumerate(ts)]
+        pad = gl.PAD_CONSTANT if case % 3 == 0 else gl.PAD_REFLECT
+        voc = gl.GriffinLim.new(basis, n_fft - hop, 1.7, 2, 0.99, normalise=gl.NORM_NONE, pad_mode=pad)
+        ys = voc.from_magnitude_batch(mags, turns)
+        for s, tu, y, t in zip(mags, turns, ys, ts):
+            ref = o.griffin_lim(s, tu, 2, 0.99, n_fft, hop, pad_mode=pad, dtype=np.float64)
+            assert y.shape == ref.shape == (hop * (t - 1),)
+            scale = max(float(np.abs(ref).max()), 1e-30)
+            assert float(np.sqrt(np.mean((y - ref) ** 2))) / scale < 2e-5, (case, n_fft, hop, t)
