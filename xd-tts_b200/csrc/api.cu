@@ -712,7 +712,6 @@ static int plan_enqueue(xdtts_gl_plan* p, int flags, bool timed, int* n_mid, cud
         GlgParams q;
         memset(&q, 0, sizeof(q));
         q.n_fft = h->n_fft; q.hop = h->hop; q.n_utt = p->B;
-        for (q.log_n = 0; (1 << q.log_n) < h->n_fft; q.log_n++) {}
         q.utt_T = p->d_T; q.utt_foff = p->d_foff; q.state = p->d_state; q.rec_f = p->rec_f; q.frames = p->d_frames; q.y = p->d_y[0];
         q.turns = use_phase ? p->d_turns : nullptr;
         q.seed = reinterpret_cast<const unsigned long long*>(p->d_seed);

@@ -7,7 +7,7 @@
 namespace xdtts {
 
 struct GlgParams {
-    int n_fft, log_n, hop, n_utt;
+    int n_fft, hop, n_utt;
     const int* utt_T;        // [n_utt] frames per utterance
     const int* utt_foff;     // [n_utt] first frame row of each utterance
     float* state;            // per-frame records [R: M float2, slot 0 = (Re R[0], Re R[M]) | S: M floats | S_nyq | pad], rec_f floats apart
