@@ -438,8 +438,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftPar
         }
     } else {
         // ===================== epilogue: TMEM lane quarter q <-> bins bt*128 + 32 q + lane.  A work item is (bin tile, half of the
-        // tile's 64 columns); the four warps of a quarter take items j, j + 4, ...  Four epilogue warps per scheduler, not two:
-        // the special-function unit (two operations per value) is the unit to keep fed, and a warp is in order.
+        // tile's 64 columns); the four warps of a quarter take items j, j + 4, ...  Four epilogue warps per scheduler: six
+        // instructions per value over 16.4 M values make this role the one that sets the tile time (it is issue-bound).
         const int q = warp & 3, j = warp >> 2;
         constexpr int CW = 32;
         const bool plain = (XDTTS_LIFT_SKIP & 16) ? true : p.power == 1.0f;
