@@ -358,7 +358,8 @@ def test_nnls_lift_matches_oracle(gl):
         f = lambda x: 0.5 * ((a @ x - b) ** 2).sum(0)   # noqa: E731
         assert (x_gpu >= 0).all() and np.isfinite(x_gpu).all()
         assert np.all(f(x_gpu) <= f(x_ref) * 1.01 + 1e-9 * (b ** 2).sum(0))
-        assert np.all(f(x_gpu) <= f(x0) * (1 + 1e-5) + 1e-12)
+        # (the start is the fp32 lift: where the fp64 start fits the mel exactly, the objective is the fp32 rounding of b, ~1e-13 b^2)
+        assert np.all(f(x_gpu) <= f(x0) * (1 + 1e-5) + 1e-11 * (b ** 2).sum(0) + 1e-12)
         img_err = np.abs(a @ x_gpu - a @ x_ref).max() / np.abs(a @ x_ref).max()
         assert img_err < 2e-4, img_err
         assert np.linalg.norm(x_gpu - x_ref) / np.linalg.norm(x_ref) < 2e-2

@@ -17,8 +17,9 @@
 // each of the four bin-tile CTAs of a frame tile repeated the exp / split / store of the same mel tile and the
 // kernel was issue-bound on exactly that work (45 us; now one conversion per frame).
 // fp16 has 5 exponent bits, so both operands are scaled by exact powers of two: P once on the host (largest entry
-// into [2^12, 2^13)), every frame of E by its own 2^(8 - ceil(log2 max_m E[m])) (a frame is a column of the GEMM, so
-// a per-frame factor commutes with it); the epilogue folds both exponents into the log2 it takes for ^power anyway.
+// into [4, 8)), every frame of E by its own 2^-ceil(log2 max_m E[m]) (a frame is a column of the GEMM, so a per-frame
+// factor commutes with it).  The accumulator is then O(1) -- its log2 keeps full precision -- and ^power turns the two
+// exponents into an addend of the epilogue's 2^(power * log2 x): one FFMA.
 //
 // One tile of the GEMM is D[bin 0..127][frame 0..63] = sum_m P[bin][m] E[frame][m] (UMMA M = 128 bins, N = 64
 // frames, K = 16 per instruction), both operands K-major in the un-swizzled core-matrix layout (8 rows x 16 bytes
@@ -77,7 +78,7 @@ constexpr int LT_PRO_WARPS = 10;
 constexpr int LT_PGROUPS = LT_PRO_WARPS * 32 / LT_BN;   // producer thread (frame f, chunk group cg): chunks cg, cg + 5, ...
 constexpr int LT_THREADS = 32 * (LT_EPI_WARPS + LT_PRO_WARPS + 1);
 constexpr int LT_CF_RING = 2 * LT_STAGES;   // per-frame exponents: written up to 2 stages ahead of the epilogue that reads them
-constexpr int LT_E_SHIFT = 8;    // a frame's largest de-logged value lands in (2^7, 2^8]
+constexpr int LT_E_SHIFT = 0;    // a frame's largest de-logged value lands in (1/2, 1]
 constexpr int LT_SMEM_MAX = 232448;   // 227 KB
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -183,6 +184,13 @@ __device__ __forceinline__ float pow_pos(float s, float power) {
     float l, r;   // max(s, 0) -> log2 = -inf at 0 -> 2^-inf = 0: the clamp needs no select
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(fmaxf(s, 0.f)));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * power));
+    return r;
+}
+// (s 2^e) ^ power with the addend a = power * e supplied: 2^(power * log2 s + a), the factor rides in the FFMA
+__device__ __forceinline__ float pow_pos_add(float s, float power, float a) {
+    float l, r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(fmaxf(s, 0.f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(l, power, a)));
     return r;
 }
 __device__ __forceinline__ float exp2_int(int e) {   // 2^e, e clamped to the normal range
@@ -417,9 +425,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftPar
                     *reinterpret_cast<uint4*>(ehi + e_plane + c * (LT_BN * 16)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                 }
             }
-            // D = (P 2^p_exp)(E 2^-shift): the accumulator owes 2^(shift - p_exp).  A factor, not an exponent added to the
-            // epilogue's log2: log2 of the raw accumulator (~2^20) would be rounded at 2^-19, 1e-6 of the result after ^power
-            if (cg == 0) cfac[(it % LT_CF_RING) * LT_BN + f] = exp2_int((int)shift - (int)p.p_exp);
+            // D = (P 2^p_exp)(E 2^-shift): the accumulator owes 2^(shift - p_exp).  ^power turns that into the ADDEND power * (shift -
+            // p_exp) of the epilogue's 2^(power * log2 x): one FFMA instead of two multiplies per value.  (The operands are scaled
+            // so that the accumulator is O(1): the log2 of a value around 2^20 is rounded at 2^-19, 1e-6 of the result.)
+            if (cg == 0) cfac[(it % LT_CF_RING) * LT_BN + f] = p.power == 1.0f ? exp2_int((int)shift - (int)p.p_exp) : p.power * (shift - p.p_exp);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async proxy
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[s]);
@@ -472,8 +481,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) gl_lift_tc_kernel(const LiftPar
                     const float cf[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        const float x = __uint_as_float(v[c0 + i]) * cf[i];
-                        const float r = plain ? fmaxf(x, 0.f) : pow_pos(x, p.power);
+                        const float r = plain ? fmaxf(__uint_as_float(v[c0 + i]) * cf[i], 0.f) : pow_pos_add(__uint_as_float(v[c0 + i]), p.power, cf[i]);
                         // 32 lanes = 32 consecutive bins of one frame: every store is one 128-byte line
                         if ((XDTTS_LIFT_SKIP & 8) ? r == 123456.789f : (full_tile || c0 + i < nf)) __stcs(out + (c0 + i) * ld, r);
                     }
@@ -541,7 +549,7 @@ __global__ void __launch_bounds__(128) gl_lift_f32_kernel(const float* __restric
 // host: the device image of the pseudo-inverse for gl_lift_tc_kernel.  pinv: [K][n_mels] row-major (K = M + 1; the
 // last row is the Nyquist bin and is not part of the image).  Layout [bin tile][plane hi, lo][K chunk][row 0..127][8 fp16]
 // (core matrices of 8 rows x 16 bytes, un-swizzled); values are pinv * 2^(*p_exp), the power of two that brings the
-// largest entry into [2^12, 2^13) -- fp16 has 5 exponent bits, and the low halves should stay out of its subnormals.
+// largest entry into [4, 8) -- fp16 has 5 exponent bits, and the low halves should stay out of its subnormals.
 std::vector<float> gl_lift_build_image(const float* pinv, int K, int n_mels, float* p_exp) {
     const int M = K - 1, n_mt = (M + LT_BM - 1) / LT_BM, kchunks = 2 * ((n_mels + 15) / 16);
     float amax = 0.f;
@@ -549,7 +557,7 @@ std::vector<float> gl_lift_build_image(const float* pinv, int K, int n_mels, flo
         if (std::isfinite(pinv[i])) amax = std::max(amax, std::fabs(pinv[i]));
     int ex = 0;
     if (amax > 0.f) std::frexp(amax, &ex);   // amax in [2^(ex-1), 2^ex)
-    const int pe = amax > 0.f ? 13 - ex : 0;
+    const int pe = amax > 0.f ? 3 - ex : 0;
     *p_exp = (float)pe;
     std::vector<float> img((size_t)n_mt * 2 * kchunks * LT_BM * 8 / 2, 0.f);   // fp16 pairs in float-sized slots
     uint16_t* h16 = reinterpret_cast<uint16_t*>(img.data());
