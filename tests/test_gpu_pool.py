@@ -59,7 +59,7 @@ def test_pool_equals_single_device_bitwise(gl, n_dev):
     from xdtts_b200._ffi import ERR_SHAPE, XdttsError
 
     with pytest.raises(XdttsError) as e:
-        pool.infer_batch([o.synth_mel(1, 80, 3)])
+        pool.infer_batch([o.synth_mel(1, 80, 1)])                 # one frame = no samples
     assert e.value.code == ERR_SHAPE
     pool.close()
     one.close()

@@ -266,3 +266,37 @@ def test_load_files_written_by_pytorch(taco, golden_dir):
         assert y.shape == g["y"].shape
         assert np.abs(y - g["y"]).max() < 2e-4, tag
         post.close()
+
+
+@pytest.mark.gpu
+def test_tail_pipe_and_pool_on_the_unfused_path(taco, layers, built):
+    """The callers of the vocoder do not care which kernels a plan runs: the fused tail call, the streaming pipe and the
+    multi-GPU pool give the bits of the plain calls on a geometry the fused kernel does not cover (hop 200) and on a batch
+    with a three-frame utterance (which sends the shipped geometry through the un-fused kernels too)."""
+    from xdtts_b200 import griffin_lim
+
+    basis = o.create_mel_filter_bank(22050.0, 1024, 80, 0.0, 8000.0)
+    post = taco.Postnet.from_layers(layers, precision=0)
+    for hop, ts in ((200, [12, 30]), (256, [3, 25])):
+        voc = griffin_lim.GriffinLim.new(basis, 1024 - hop, 1.7, 3, 0.99)
+        mels = [o.synth_mel(500 + i, 80, t) for i, t in enumerate(ts)]
+        phs = [o.phase_turns(6, i, 513, t) for i, t in enumerate(ts)]
+        waves, pmels = taco.infer_tail_batch(post, voc, mels, phs, return_mels=True)
+        chained = voc.infer_batch(post.run_batch(mels), phs)
+        for a, b, t in zip(waves, chained, ts):
+            assert a.shape == (hop * (t - 1),) and np.array_equal(a, b)
+        pm = po.postnet(mels[1], layers, dtype=np.float64).astype(np.float32)
+        ref = o.infer(pm, basis, 1024 - hop, 1.7, 3, 0.99, phs[1], dtype=np.float64)
+        assert float(np.sqrt(np.mean((waves[1] - ref) ** 2))) < 1e-3
+        pipe = voc.pipe(ts, depth=2)
+        fixed = griffin_lim.GriffinLim.new(basis, 1024 - hop, 1.7, 3, 0.99, seed=9, fixed_seed=True)
+        want = fixed.infer_batch(mels)
+        pipe2 = fixed.pipe(ts, depth=2)
+        got = [r for r in (pipe2.push(mels) for _ in range(2)) if r is not None] + pipe2.flush()
+        assert len(got) == 2 and all(np.array_equal(a, b) for a, b in zip(got[0], want))
+        pipe.close()
+        pipe2.close()
+        pool = griffin_lim.GriffinLimPool.new(basis, 1024 - hop, 1.7, 3, 0.99, seed=9, fixed_seed=True)
+        for a, b in zip(pool.infer_batch(mels), want):
+            assert np.array_equal(a, b)
+        pool.close()

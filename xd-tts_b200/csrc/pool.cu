@@ -174,7 +174,7 @@ static int pool_run(xdtts_pool* p, int kind, const float* const* ins, const int*
     if (B < 1) return fail(XDTTS_ERR_BAD_ARG, "pool_infer: B = %d", B);
     for (int b = 0; b < B; b++) {
         if (!ins[b] || !outs[b] || (phases && !phases[b])) return fail(XDTTS_ERR_BAD_ARG, "pool_infer: null buffer for utterance %d", b);
-        if (Ts[b] < 4) return fail(XDTTS_ERR_SHAPE, "pool_infer: utterance %d has T = %d frames, need >= 4", b, Ts[b]);
+        if (Ts[b] < 2) return fail(XDTTS_ERR_SHAPE, "pool_infer: utterance %d has T = %d frames, need >= 2", b, Ts[b]);
     }
     std::lock_guard<std::mutex> call(p->call_mu);
     const int nd = (int)p->workers.size();

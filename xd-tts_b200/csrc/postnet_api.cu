@@ -490,7 +490,7 @@ extern "C" int xdtts_tail_infer_batch(xdtts_postnet* pn, xdtts_gl* gl, const flo
     xdtts_gl_plan* gp = nullptr;
     int rc = pn_cached_plan(pn, Ts, B, &pp);
     if (rc) return rc;
-    rc = gl_cached_plan(gl, Ts, B, &gp);      // also rejects T < 4
+    rc = gl_cached_plan(gl, Ts, B, &gp);      // also rejects T < 2
     if (rc) return rc;
     float* arena = nullptr;
     rc = gl_plan_mel_arena(gp, &arena);
@@ -605,7 +605,7 @@ extern "C" int xdtts_pipe_create(xdtts_gl* gl, xdtts_postnet* pn, const int* Ts,
         xdtts_pipe::Slot& sl = q->slots[i];
         {
             std::lock_guard<std::mutex> lk(gl->mu);
-            rc = gl_plan_build(gl, Ts, B, &sl.gp);      // also rejects T < 4
+            rc = gl_plan_build(gl, Ts, B, &sl.gp);      // also rejects T < 2
         }
         if (rc == XDTTS_OK && pn) {
             std::lock_guard<std::mutex> lk(pn->mu);
