@@ -343,9 +343,9 @@ def synthesize_batch(decoder, post, vocoder, memories, processed_memories, unpad
     decoder loop -> postnet -> mel-to-linear lift -> Griffin-Lim -> float32 samples.  The frame counts come out of
     the decoder's stop rule, so the tail runs as one batch of ragged lengths."""
     mels = decoder.run_batch(memories, processed_memories, unpadded_lens)
-    short = [i for i, m in enumerate(mels) if m.shape[1] < 4]
+    short = [i for i, m in enumerate(mels) if m.shape[1] < 2]
     if short:
-        raise XdttsError(_ffi.ERR_SHAPE, "utterances %s stopped after fewer than 4 frames: too short to vocode" % short)
+        raise XdttsError(_ffi.ERR_SHAPE, "utterances %s stopped after one frame: no samples to vocode" % short)
     return infer_tail_batch(post, vocoder, mels, init_phases, return_mels=return_mels)
 
 
