@@ -637,3 +637,29 @@ def test_unfused_path_random_geometries(gl):
             assert y.shape == ref.shape == (hop * (t - 1),)
             scale = max(float(np.abs(ref).max()), 1e-30)
             assert float(np.sqrt(np.mean((y - ref) ** 2))) / scale < 2e-5, (case, n_fft, hop, t)
+
+
+@pytest.mark.gpu
+def test_lift_wide_dynamic_range(gl):
+    """The tensor-core lift carries fp16 operands, so every frame is scaled by its own power of two: frames whose ln-mel peaks
+    anywhere from -60 to +25 (magnitudes from 1e-26 to 7e10), next to each other in one tile, each come out to 1e-5 of THEIR
+    OWN full scale -- the gate of test_lift_matches_oracle, per frame; a frame of -200 everywhere is zero, as exp(-200) is in fp32."""
+    basis = basis_for(1024)
+    rng = np.random.default_rng(7)
+    t = 150
+    mel = rng.uniform(-8.0, 0.0, size=(80, t)).astype(np.float32)
+    mel += rng.uniform(-52.0, 25.0, size=(1, t)).astype(np.float32)      # a different level per frame
+    mel[:, 17] = -200.0
+    mel[5, 40] = -np.inf                                                  # a single silent band
+    voc = make(gl, 1024, 0)
+    plan = voc.plan([t])
+    plan.upload(0, [mel])
+    plan.run(0)
+    got = np.concatenate([plan.peek(0).T, plan.peek(1)[None, :]], 0).astype(np.float64)
+    ref = o.lift_pinv_clamp(mel, basis, 1.7, dtype=np.float64)
+    assert np.isfinite(got).all()
+    scale = ref.max(0)
+    assert (got[:, 17] == 0).all() and scale[17] < 1e-140
+    ok = scale > 1e-30                                                    # (what fp32 can hold)
+    err = np.abs(got - ref).max(0)[ok] / scale[ok]
+    assert err.max() < 1e-5, (int(np.argmax(err)), float(err.max()))
